@@ -1,0 +1,120 @@
+/* pfft.h -- C ABI of the B200-native FFT library that stands in for portFFT's descriptor/commit/compute path.
+ *
+ * portFFT is header-only C++/SYCL, so it has no FFI of its own; these entry points are what a binding of its public
+ * API binds to (all citations relative to the reference checkout):
+ *
+ *   pfft_desc              <- struct portfft::descriptor<Scalar, Domain>      src/portfft/descriptor.hpp:43-129
+ *   pfft_validate          <- detail::validate::validate_descriptor           src/portfft/descriptor_validation.hpp:264-281
+ *   pfft_commit            <- descriptor::commit(sycl::queue&)                src/portfft/descriptor.hpp:152-156
+ *                             + committed_descriptor_impl ctor                src/portfft/committed_descriptor_impl.hpp:716-768
+ *   pfft_compute           <- committed_descriptor::compute_forward/backward  src/portfft/committed_descriptor.hpp:171-310
+ *                             (USM overloads; dispatch_direction              src/portfft/committed_descriptor_impl.hpp:852-878)
+ *   pfft_destroy           <- ~committed_descriptor_impl                      src/portfft/committed_descriptor_impl.hpp:825-828
+ *   pfft_get_buffer_count  <- descriptor::get_input_count / get_output_count  src/portfft/descriptor.hpp:172-183,262-270
+ *   pfft_get_layout        <- detail::get_layout                              src/portfft/utils.hpp:237-246
+ *   status codes           <- exception classes                               src/portfft/common/exceptions.hpp:32-77
+ *
+ * `sycl::queue` becomes a CUDA stream (passed as void* so that this header needs no CUDA include); USM pointers
+ * become plain device pointers.  All strides / distances / offsets count complex elements for interleaved storage
+ * and scalars-per-array for split storage, exactly as in the reference (committed_descriptor_impl.hpp:1105-1110).
+ * The header-only C++ mirror of the reference API (include/portfft/portfft.hpp) is a thin layer over these calls.
+ */
+#ifndef PFFT_H_
+#define PFFT_H_
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum pfft_status {
+  PFFT_OK = 0,
+  PFFT_INVALID_CONFIGURATION = 1,     /* portfft::invalid_configuration     */
+  PFFT_UNSUPPORTED_CONFIGURATION = 2, /* portfft::unsupported_configuration */
+  PFFT_OUT_OF_LOCAL_MEMORY = 3,       /* portfft::out_of_local_memory_error */
+  PFFT_INTERNAL_ERROR = 4,            /* portfft::internal_error            */
+  PFFT_CUDA_ERROR = 5,
+  PFFT_NCCL_ERROR = 6
+} pfft_status;
+
+/* enumerator order follows src/portfft/enums.hpp:26-39 */
+enum { PFFT_DOMAIN_REAL = 0, PFFT_DOMAIN_COMPLEX = 1 };
+enum { PFFT_INTERLEAVED_COMPLEX = 0, PFFT_SPLIT_COMPLEX = 1 };
+enum { PFFT_IN_PLACE = 0, PFFT_OUT_OF_PLACE = 1 };
+enum { PFFT_FORWARD = 0, PFFT_BACKWARD = 1 };
+enum { PFFT_FLOAT = 0, PFFT_DOUBLE = 1 };
+/* src/portfft/enums.hpp:44 and :46-69 */
+enum { PFFT_LEVEL_WORKITEM = 0, PFFT_LEVEL_SUBGROUP = 1, PFFT_LEVEL_WORKGROUP = 2, PFFT_LEVEL_GLOBAL = 3 };
+enum { PFFT_LAYOUT_PACKED = 0, PFFT_LAYOUT_UNPACKED = 1, PFFT_LAYOUT_BATCH_INTERLEAVED = 2 };
+
+/* POD mirror of portfft::descriptor (src/portfft/descriptor.hpp:59-129). `lengths`, `forward_strides` and
+ * `backward_strides` point at `rank` entries each (stride arrays may carry a different count through
+ * `n_forward_strides` / `n_backward_strides` so that the "mismatching strides length" check can be exercised). */
+typedef struct pfft_desc {
+  int precision; /* PFFT_FLOAT / PFFT_DOUBLE  (template parameter Scalar) */
+  int domain;    /* PFFT_DOMAIN_*             (template parameter Domain) */
+  size_t rank;
+  const size_t* lengths;
+  double forward_scale;
+  double backward_scale;
+  size_t number_of_transforms;
+  int complex_storage;
+  int placement;
+  size_t n_forward_strides;
+  const size_t* forward_strides;
+  size_t n_backward_strides;
+  const size_t* backward_strides;
+  size_t forward_distance;
+  size_t backward_distance;
+  size_t forward_offset;
+  size_t backward_offset;
+} pfft_desc;
+
+typedef struct pfft_plan pfft_plan;
+
+/* Host-only: the reference's commit-time validation. Never touches the GPU. */
+pfft_status pfft_validate(const pfft_desc* desc);
+
+/* Host-only helpers of the descriptor. `direction` selects the forward or backward domain. */
+size_t pfft_get_flattened_length(const pfft_desc* desc);
+size_t pfft_get_buffer_count(const pfft_desc* desc, int direction);
+int pfft_get_layout(const pfft_desc* desc, int direction);
+
+/* Host-only: run the planner without allocating device memory and describe the resulting passes (levels, radices,
+ * launch geometry) as text. Returns the number of characters that the full description needs. */
+pfft_status pfft_plan_describe(const pfft_desc* desc, int direction, char* buf, size_t buf_len, size_t* needed);
+
+/* validate + plan + build device-resident twiddle tables and workspace on `device`. `stream` (cudaStream_t) is the
+ * queue the plan is committed to; it is used for the one-off table uploads and as default stream of pfft_compute. */
+pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_plan** plan_out);
+
+/* Asynchronous, stream-ordered transform on device pointers. Interleaved storage: `in` / `out` point at complex
+ * arrays and the *_imag pointers must be NULL. Split storage: real and imaginary arrays. in == out is the in-place
+ * call. A storage mismatch with the descriptor returns PFFT_INVALID_CONFIGURATION
+ * (committed_descriptor_impl.hpp:862-871). `stream` may be NULL to use the commit stream. */
+pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                         void* out_imag, void* stream);
+
+/* End-to-end convenience for callers holding HOST buffers: H2D of the input, pfft_compute, D2H of the output, one
+ * stream synchronisation. Buffers are sized by pfft_get_buffer_count (elements) and staged through plan-owned
+ * device buffers that persist between calls. */
+pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                              void* out_imag);
+
+pfft_status pfft_destroy(pfft_plan* plan);
+
+/* Introspection. */
+size_t pfft_workspace_bytes(const pfft_plan* plan);
+int pfft_plan_level(const pfft_plan* plan, size_t dimension); /* PFFT_LEVEL_* of one dimension, -1 if out of range */
+size_t pfft_plan_num_launches(const pfft_plan* plan, int direction); /* kernel launches per compute call */
+unsigned long long pfft_total_launches(void);                        /* kernels launched by this process so far */
+
+/* Thread-local message of the last non-OK status returned on this thread. */
+const char* pfft_last_error(void);
+const char* pfft_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PFFT_H_ */

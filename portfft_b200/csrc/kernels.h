@@ -1,0 +1,19 @@
+// Host-side launch entry points of the CUDA kernels (one per level) used by the planner.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstddef>
+
+#include "pass.h"
+
+namespace pfft {
+
+inline size_t wg_generic_smem_bytes(int ffts_per_block, int pitch, size_t scalar_bytes) {
+  return (size_t)2 * ffts_per_block * pitch * 2 * scalar_bytes + (size_t)3 * ffts_per_block * sizeof(long long);
+}
+
+// WORKGROUP level, generic (wg_generic.cu)
+cudaError_t launch_wg_generic(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid,
+                              cudaStream_t stream);
+
+}  // namespace pfft

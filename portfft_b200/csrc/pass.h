@@ -1,0 +1,62 @@
+// One kernel launch of a plan ("pass"): a batched, strided 1-D DFT with optional inter-factor twiddle on store.
+//
+//   for every batch multi-index b = (b0, b1, b2, b3), 0 <= b_d < nb[d]:
+//     out[ooff + sum_d b_d*obd[d] + k*os] = scale * gtw(b, k) * sum_j in[ioff + sum_d b_d*ibd[d] + j*is] * w_n^{jk}
+//
+// Every algorithm of the library is a sequence of such passes: a plain batched 1-D transform is one pass; an N-D
+// transform is one pass per dimension (the reference instead loops over `batch*outer` separate launches,
+// /root/reference/src/portfft/committed_descriptor_impl.hpp:899-950); the GLOBAL level (four-step) is one pass per
+// factor with gtw = w_{gtw_n}^{b[gtw_dim]*k} fused on store and the transposition fused into (os, obd)
+// (the reference: one launch per factor per batch plus a chain of transpose kernels,
+// /root/reference/src/portfft/dispatcher/global_dispatcher.hpp:312-412).
+#pragma once
+#include <cstdint>
+
+namespace pfft {
+
+constexpr int kMaxBatchDims = 4;
+constexpr int kMaxRadices = 12;
+
+enum IoMode : int {
+  IO_DIRECT = 0,       // butterfly-owning threads access global memory directly (coalesced when stride == 1)
+  IO_STAGED_ELEM = 1,  // cooperative tile copy through shared memory, lanes run along the element index
+  IO_STAGED_BATCH = 2  // cooperative tile copy through shared memory, lanes run along the batch index
+};
+
+enum Level : int { LEVEL_WORKITEM = 0, LEVEL_SUBGROUP = 1, LEVEL_WORKGROUP = 2, LEVEL_GLOBAL = 3 };
+
+struct PassParams {
+  // data pointers (scalar arrays). Interleaved storage: *_im == nullptr and *_re points at (re,im) pairs.
+  const void* in_re;
+  const void* in_im;
+  void* out_re;
+  void* out_im;
+  // transform
+  int n;
+  int num_radices;
+  int radix[kMaxRadices];
+  int threads_per_fft;  // T
+  int ffts_per_block;   // F
+  int pitch;            // shared-memory pitch (complex elements) of one transform
+  // batch geometry (in complex elements)
+  long long batch_total;
+  long long nb[kMaxBatchDims];
+  long long ibd[kMaxBatchDims];
+  long long obd[kMaxBatchDims];
+  long long is, os;
+  long long ioff, ooff;
+  int in_mode, out_mode;
+  // twiddles w_n^k, k in [0, n), complex<T>, device resident
+  const void* tw;
+  // inter-factor twiddle on store (GLOBAL level): w_{gtw_n}^{b[gtw_dim] * k} = hi[m >> gtw_bits] * lo[m & mask]
+  int gtw_dim;  // -1: none
+  int gtw_bits;
+  long long gtw_n;
+  const void* gtw_lo;
+  const void* gtw_hi;
+  // scale applied on store (only when apply_scale != 0)
+  double scale;
+  int apply_scale;
+};
+
+}  // namespace pfft

@@ -1,0 +1,538 @@
+// Host planner. See plan.h for the reference counterparts.
+#include "plan.h"
+
+#include <algorithm>
+#include <cmath>
+#include <map>
+#include <numeric>
+#include <sstream>
+
+namespace pfft {
+
+// ---------------------------------------------------------------------------------------------------------------
+// descriptor helpers (src/portfft/descriptor.hpp:161-183,262-270; src/portfft/utils.hpp:190-246)
+// ---------------------------------------------------------------------------------------------------------------
+size_t DescHost::flattened_length() const {
+  size_t t = 1;
+  for (size_t l : lengths) t *= l;
+  return t;
+}
+
+size_t DescHost::buffer_count(int dir) const {
+  const auto& s = strides(dir);
+  size_t last = (number_of_transforms - 1) * distance(dir);
+  for (size_t i = 0; i < lengths.size() && i < s.size(); ++i) last += (lengths[i] - 1) * s[i];
+  return offset(dir) + last + 1;
+}
+
+std::vector<size_t> default_strides(const std::vector<size_t>& lengths) {
+  std::vector<size_t> s(lengths.size());
+  size_t total = 1;
+  for (size_t i = lengths.size(); i > 0; --i) {
+    s[i - 1] = total;
+    total *= lengths[i - 1];
+  }
+  return s;
+}
+
+int get_layout(const DescHost& d, int dir) {
+  if (d.strides(dir) == default_strides(d.lengths) && d.distance(dir) == d.flattened_length())
+    return PFFT_LAYOUT_PACKED;
+  if (d.lengths.size() == 1 && d.distance(dir) == 1 && d.strides(dir).back() == d.number_of_transforms)
+    return PFFT_LAYOUT_BATCH_INTERLEAVED;
+  return PFFT_LAYOUT_UNPACKED;
+}
+
+DescHost desc_from_c(const pfft_desc* c) {
+  if (c == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null descriptor");
+  DescHost d;
+  d.is_double = c->precision == PFFT_DOUBLE;
+  d.domain = c->domain;
+  if (c->rank > 0 && c->lengths == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null lengths");
+  d.lengths.assign(c->lengths, c->lengths + c->rank);
+  d.forward_scale = c->forward_scale;
+  d.backward_scale = c->backward_scale;
+  d.number_of_transforms = c->number_of_transforms;
+  d.complex_storage = c->complex_storage;
+  d.placement = c->placement;
+  if (c->forward_strides) d.forward_strides.assign(c->forward_strides, c->forward_strides + c->n_forward_strides);
+  if (c->backward_strides) d.backward_strides.assign(c->backward_strides, c->backward_strides + c->n_backward_strides);
+  d.forward_distance = c->forward_distance;
+  d.backward_distance = c->backward_distance;
+  d.forward_offset = c->forward_offset;
+  d.backward_offset = c->backward_offset;
+  return d;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// validation: same accept / reject set for *invalid* configurations as descriptor_validation.hpp
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+template <typename... Ts>
+[[noreturn]] void invalid(const Ts&... args) {
+  std::stringstream ss;
+  (ss << ... << args);
+  throw PlanError(PFFT_INVALID_CONFIGURATION, ss.str());
+}
+template <typename... Ts>
+[[noreturn]] void unsupported(const Ts&... args) {
+  std::stringstream ss;
+  (ss << ... << args);
+  throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION, ss.str());
+}
+
+// descriptor_validation.hpp:92-111
+void check_basic(const std::vector<size_t>& lengths, size_t batch, const std::vector<size_t>& strides, size_t distance,
+                 const char* dom) {
+  if (strides.size() != lengths.size())
+    invalid("Mismatching ", dom, " strides length got ", strides.size(), " expected ", lengths.size());
+  for (size_t i = 0; i < strides.size(); ++i)
+    if (strides[i] == 0) invalid("Invalid ", dom, " stride[", i, "]=", strides[i], ", must be positive");
+  if (batch > 1 && distance == 0) invalid("Invalid ", dom, " distance ", distance, ", must be positive for batched FFTs");
+}
+
+// descriptor_validation.hpp:123-151
+void check_multidim(const std::vector<size_t>& lengths, size_t batch, const std::vector<size_t>& strides,
+                    size_t distance, const char* dom) {
+  std::vector<size_t> gs = strides, gn = lengths;
+  if (batch > 1) {
+    gs.push_back(distance);
+    gn.push_back(batch);
+  }
+  std::vector<size_t> idx(gn.size());
+  std::iota(idx.begin(), idx.end(), 0);
+  std::stable_sort(idx.begin(), idx.end(), [&](size_t a, size_t b) { return gs[a] < gs[b]; });
+  for (size_t i = 1; i < idx.size(); ++i)
+    if (!(gs[idx[i - 1]] * gn[idx[i - 1]] <= gs[idx[i]]))
+      invalid("Domain ", dom, ": multi-dimension strides are not large enough to avoid overlap");
+}
+
+// descriptor_validation.hpp:162-204 -- sub-linear in the batch count
+void check_1d(const std::vector<size_t>& lengths, size_t batch, const std::vector<size_t>& strides, size_t distance,
+              const char* dom) {
+  const size_t fft_size = lengths[0], stride = strides[0];
+  const size_t first_batch_limit = stride * fft_size;
+  const size_t first_length_limit = distance * batch;
+  if ((stride <= distance && first_batch_limit <= distance) || (distance <= stride && first_length_limit <= stride))
+    return;
+  for (size_t b = 1; b < batch;) {
+    const size_t first = b * distance;
+    const size_t column = first % stride;
+    if (column == 0) {
+      if (first >= first_batch_limit) return;
+      invalid("Domain ", dom, ": batch ", b, " collides with first batch at index ", first);
+    }
+    size_t skip = (stride - column) / distance;
+    if ((stride - column) % distance != 0) skip += 1;
+    b += skip;
+  }
+}
+
+void check_strides_distance(const std::vector<size_t>& lengths, size_t batch, const std::vector<size_t>& strides,
+                            size_t distance, const char* dom) {
+  check_basic(lengths, batch, strides, distance, dom);
+  if (lengths.size() > 1)
+    check_multidim(lengths, batch, strides, distance, dom);
+  else
+    check_1d(lengths, batch, strides, distance, dom);
+}
+
+}  // namespace
+
+void validate_descriptor(const DescHost& d) {
+  // descriptor_validation.hpp:268-270
+  if (d.domain == PFFT_DOMAIN_REAL) unsupported("REAL domain is unsupported");
+  if (d.number_of_transforms == 0) invalid("Invalid number of transform ", d.number_of_transforms, ", must be positive");
+  // :38-47
+  if (d.lengths.empty()) invalid("Invalid lengths, must have at least 1 dimension");
+  for (size_t i = 0; i < d.lengths.size(); ++i)
+    if (d.lengths[i] == 0) invalid("Invalid lengths[", i, "]=", d.lengths[i], ", must be positive");
+  // :237-253
+  if (d.placement == PFFT_IN_PLACE) {
+    if (d.forward_strides != d.backward_strides)
+      invalid("Invalid forward and backward strides must match for in-place configurations");
+    if (d.forward_distance != d.backward_distance)
+      invalid("Invalid forward and backward distances must match for in-place configurations");
+    check_strides_distance(d.lengths, d.number_of_transforms, d.forward_strides, d.forward_distance, "forward");
+  } else {
+    check_strides_distance(d.lengths, d.number_of_transforms, d.forward_strides, d.forward_distance, "forward");
+    check_strides_distance(d.lengths, d.number_of_transforms, d.backward_strides, d.backward_distance, "backward");
+  }
+  // validate_layout (:57-81) only raises *unsupported*; those restrictions (N-D non-default strides, arbitrary
+  // strides beyond one sub-group) do not exist in this implementation.
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// factorisation
+// ---------------------------------------------------------------------------------------------------------------
+namespace {
+
+const int kRadixSet[] = {16, 13, 12, 11, 10, 9, 8, 7, 6, 5, 4, 3, 2, 17, 19, 23, 29, 31};
+
+bool smooth31(size_t n) {
+  for (int p : {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31})
+    while (n % p == 0) n /= p;
+  return n == 1;
+}
+
+struct RadixChoice {
+  long cost;
+  int radix;
+};
+
+RadixChoice best_radix(size_t n, std::map<size_t, RadixChoice>& memo) {
+  if (n == 1) return {0, 1};
+  auto it = memo.find(n);
+  if (it != memo.end()) return it->second;
+  RadixChoice best{1L << 60, 0};
+  for (int r : kRadixSet) {
+    if (n % r != 0) continue;
+    RadixChoice sub = best_radix(n / r, memo);
+    if (sub.cost >= (1L << 60)) continue;
+    long c = 1000 + r + sub.cost;
+    if (c < best.cost) best = {c, r};
+  }
+  memo[n] = best;
+  return best;
+}
+
+int pad_index(int i, bool dbl) { return i + (i >> (dbl ? 3 : 4)); }
+int pitch_for(int n, bool dbl) { return (pad_index(n - 1, dbl) + 1) | 1; }
+
+int pow2_floor(long long v) {
+  int r = 1;
+  while ((long long)r * 2 <= v) r *= 2;
+  return r;
+}
+int pow2_ceil(long long v) {
+  int r = 1;
+  while (r < v) r *= 2;
+  return r;
+}
+
+constexpr size_t kSoftSmem = 72 * 1024;  // three CTAs per SM
+
+struct BDim {
+  long long n, in, out;
+};
+
+// merge adjacent batch dimensions that are contiguous in both domains; drop unit dimensions
+std::vector<BDim> merge_dims(std::vector<BDim> dims, size_t keep_front) {
+  std::vector<BDim> head(dims.begin(), dims.begin() + keep_front), rest;
+  for (size_t i = keep_front; i < dims.size(); ++i)
+    if (dims[i].n > 1) rest.push_back(dims[i]);
+  std::stable_sort(rest.begin(), rest.end(),
+                   [](const BDim& a, const BDim& b) { return std::min(a.in, a.out) < std::min(b.in, b.out); });
+  std::vector<BDim> merged;
+  for (const BDim& d : rest) {
+    if (!merged.empty() && d.in == merged.back().n * merged.back().in && d.out == merged.back().n * merged.back().out)
+      merged.back().n *= d.n;
+    else
+      merged.push_back(d);
+  }
+  head.insert(head.end(), merged.begin(), merged.end());
+  return head;
+}
+
+}  // namespace
+
+std::vector<int> choose_radices(size_t n) {
+  if (n == 1) return {1};
+  if (!smooth31(n)) return {};
+  std::map<size_t, RadixChoice> memo;
+  std::vector<int> out;
+  while (n > 1) {
+    RadixChoice c = best_radix(n, memo);
+    out.push_back(c.radix);
+    n /= c.radix;
+  }
+  std::sort(out.begin(), out.end(), std::greater<int>());
+  return out;
+}
+
+static size_t wg_smem(int F, int pitch, bool dbl) { return (size_t)2 * F * pitch * (dbl ? 16 : 8) + (size_t)24 * F; }
+
+size_t max_workgroup_length(bool is_double, const DeviceLimits& lim) {
+  // largest n whose ping-pong buffers fit one CTA (F = 1)
+  size_t n = 1;
+  while (wg_smem(1, pitch_for((int)(n * 2), is_double), is_double) <= lim.max_smem_per_block - 1024) n *= 2;
+  return n;  // 8192 (fp32) / 4096 (fp64) with 227 KB
+}
+
+namespace {
+
+void set_batch_dims(PassParams& p, const std::vector<BDim>& dims) {
+  if (dims.size() > (size_t)kMaxBatchDims)
+    unsupported("transform needs ", dims.size(), " independent batch dimensions in one pass; at most ", kMaxBatchDims,
+                " are supported");
+  p.batch_total = 1;
+  for (int d = 0; d < kMaxBatchDims; ++d) {
+    if ((size_t)d < dims.size()) {
+      p.nb[d] = dims[d].n;
+      p.ibd[d] = dims[d].in;
+      p.obd[d] = dims[d].out;
+      p.batch_total *= dims[d].n;
+    } else {
+      p.nb[d] = 1;
+      p.ibd[d] = 0;
+      p.obd[d] = 0;
+    }
+  }
+}
+
+// launch geometry, shared-memory pitch and I/O modes of the generic block-level kernel
+void configure_wg_generic(PassHost& ps, bool dbl, const DeviceLimits& lim, bool force_stage) {
+  PassParams& p = ps.pp;
+  const int n = p.n;
+  const int elem = dbl ? 16 : 8;
+  const int max_threads = dbl ? 256 : 512;
+  int rmax = 1;
+  for (int i = 0; i < p.num_radices; ++i) rmax = std::max(rmax, p.radix[i]);
+  const int t_nat = std::max(1, n / rmax);
+  p.pitch = pitch_for(n, dbl);
+
+  const bool in_batch = (p.is != 1 && p.nb[0] > 1 && p.ibd[0] < p.is) || (force_stage && p.is != 1);
+  const bool out_batch = (p.os != 1 && p.nb[0] > 1 && p.obd[0] < p.os) || (force_stage && p.os != 1);
+  int F, T;
+  if (in_batch || out_batch) {
+    F = 128 / elem;
+    while (F > 32 / elem && wg_smem(F, p.pitch, dbl) > kSoftSmem) F /= 2;
+    while (F > 1 && wg_smem(F, p.pitch, dbl) > lim.max_smem_per_block - 1024) F /= 2;
+    while (F > 1 && F / 2 >= p.nb[0] && F / 2 >= 1) F /= 2;
+    T = std::max(1, std::min(t_nat, max_threads / F));
+  } else {
+    T = std::min(t_nat, max_threads);
+    F = std::min(64, pow2_floor(std::max(1, 256 / T)));
+    while (F > 1 && wg_smem(F, p.pitch, dbl) > kSoftSmem) F /= 2;
+    while (F > 1 && F / 2 >= p.batch_total) F /= 2;
+  }
+  if (wg_smem(F, p.pitch, dbl) > lim.max_smem_per_block - 1024)
+    throw PlanError(PFFT_OUT_OF_LOCAL_MEMORY, "transform does not fit shared memory");
+  p.threads_per_fft = T;
+  p.ffts_per_block = F;
+  p.in_mode = in_batch ? IO_STAGED_BATCH : IO_DIRECT;
+  p.out_mode = out_batch ? IO_STAGED_BATCH : IO_DIRECT;
+  // tiny transforms: one thread owns a whole transform; stage the contiguous tile so that global access coalesces
+  if (p.in_mode == IO_DIRECT && p.is == 1 && T * elem < 32 && F > 1 && p.ibd[0] == n) p.in_mode = IO_STAGED_ELEM;
+  if (p.out_mode == IO_DIRECT && p.os == 1 && T * elem < 32 && F > 1 && p.obd[0] == n) p.out_mode = IO_STAGED_ELEM;
+  ps.block = F * T;
+  ps.smem = wg_smem(F, p.pitch, dbl);
+  const long long blocks = (p.batch_total + F - 1) / F;
+  ps.grid = (int)std::min<long long>(blocks, (long long)lim.num_sms * 16);
+  ps.kernel = KERNEL_WG_GENERIC;
+  ps.tw_n = n;
+}
+
+void set_radices(PassParams& p, size_t n) {
+  std::vector<int> r = choose_radices(n);
+  if (r.empty()) unsupported("FFT size ", n, " has a prime factor larger than 31, which is not supported");
+  if (r.size() > (size_t)kMaxRadices) unsupported("FFT size ", n, " needs too many radix passes");
+  p.n = (int)n;
+  p.num_radices = (int)r.size();
+  for (size_t i = 0; i < r.size(); ++i) p.radix[i] = r[i];
+}
+
+// split n into k factors, each <= fmax, as balanced as possible
+bool split_factors(size_t n, int k, size_t fmax, std::vector<size_t>& out) {
+  if (k == 1) {
+    if (n > fmax) return false;
+    out.push_back(n);
+    return true;
+  }
+  const double target = std::pow((double)n, 1.0 / k);
+  std::vector<size_t> cands;
+  for (size_t a = 2; a <= fmax && a <= n; ++a)
+    if (n % a == 0) cands.push_back(a);
+  std::sort(cands.begin(), cands.end(), [&](size_t a, size_t b) {
+    return std::fabs(std::log((double)a) - std::log(target)) < std::fabs(std::log((double)b) - std::log(target));
+  });
+  for (size_t a : cands) {
+    std::vector<size_t> sub;
+    if (split_factors(n / a, k - 1, fmax, sub)) {
+      out.push_back(a);
+      out.insert(out.end(), sub.begin(), sub.end());
+      return true;
+    }
+  }
+  return false;
+}
+
+struct Domain {
+  std::vector<size_t> strides;
+  size_t distance, offset;
+};
+
+void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
+  const DescHost& d = plan.desc;
+  const bool dbl = d.is_double;
+  const Domain in{d.strides(dir), d.distance(dir), d.offset(dir)};
+  const int odir = dir == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
+  const Domain out{d.strides(odir), d.distance(odir), d.offset(odir)};
+  const size_t D = d.lengths.size();
+  const size_t wg_max = max_workgroup_length(dbl, lim);
+  const size_t col_max = 1024;  // longest factor of a multi-pass (GLOBAL) transform: keeps >= 64 B per row segment
+  std::vector<PassHost>& passes = plan.passes[dir];
+  if (plan.dim_level.size() != D) plan.dim_level.assign(D, PFFT_LEVEL_WORKGROUP);
+
+  for (size_t step = 0; step < D; ++step) {
+    const size_t dim = D - 1 - step;
+    const bool first = step == 0;
+    const size_t L = d.lengths[dim];
+    // batch dimensions seen by this dimension's transform (fastest first)
+    std::vector<BDim> outer;
+    for (size_t e = D; e > 0; --e) {
+      if (e - 1 == dim) continue;
+      outer.push_back({(long long)d.lengths[e - 1], (long long)(first ? in.strides[e - 1] : out.strides[e - 1]),
+                       (long long)out.strides[e - 1]});
+    }
+    outer.push_back({(long long)d.number_of_transforms, (long long)(first ? in.distance : out.distance),
+                     (long long)out.distance});
+    const long long es_in = (long long)(first ? in.strides[dim] : out.strides[dim]);
+    const long long es_out = (long long)out.strides[dim];
+    const long long off_in = (long long)(first ? in.offset : out.offset);
+    const long long off_out = (long long)out.offset;
+    const int src0 = first ? BUF_IN : BUF_OUT;
+
+    if (L <= wg_max && !choose_radices(L).empty()) {
+      PassHost ps;
+      set_radices(ps.pp, L);
+      ps.pp.is = es_in;
+      ps.pp.os = es_out;
+      ps.pp.ioff = off_in;
+      ps.pp.ooff = off_out;
+      ps.pp.gtw_dim = -1;
+      set_batch_dims(ps.pp, merge_dims(outer, 0));
+      ps.src = src0;
+      ps.dst = BUF_OUT;
+      ps.level = LEVEL_WORKGROUP;
+      configure_wg_generic(ps, dbl, lim, false);
+      passes.push_back(ps);
+      plan.dim_level[dim] = PFFT_LEVEL_WORKGROUP;
+      continue;
+    }
+
+    // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
+    if (!smooth31(L)) unsupported("FFT size ", L, " has a prime factor larger than 31, which is not supported");
+    std::vector<size_t> factors;
+    for (int k = 2; k <= 4 && factors.empty(); ++k) {
+      std::vector<size_t> f;
+      if (split_factors(L, k, col_max, f)) factors = f;
+    }
+    if (factors.empty()) unsupported("FFT size ", L, " is too large");
+    std::sort(factors.begin(), factors.end(), std::greater<size_t>());
+    const size_t k = factors.size();
+    plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
+    // scratch: one packed length-L row per outer batch element
+    std::vector<BDim> outer_m = merge_dims(outer, 0);
+    long long outer_total = 1;
+    for (const BDim& b : outer_m) outer_total *= b.n;
+    plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * L);
+    // scratch distance of every outer batch dimension (packed in merge order)
+    std::vector<long long> sdist(outer_m.size());
+    {
+      long long acc = (long long)L;
+      for (size_t i = 0; i < outer_m.size(); ++i) {
+        sdist[i] = acc;
+        acc *= outer_m[i].n;
+      }
+    }
+    long long M = (long long)L;  // M_{p-1}
+    long long done = 1;          // N_1 * ... * N_{p-1}
+    for (size_t pi = 0; pi < k; ++pi) {
+      const long long Np = (long long)factors[pi];
+      const long long Mp = M / Np;
+      const bool pfirst = pi == 0, plast = pi + 1 == k;
+      PassHost ps;
+      set_radices(ps.pp, (size_t)Np);
+      ps.level = LEVEL_GLOBAL;
+      std::vector<BDim> dims;
+      if (!plast) {
+        // columns c' (dim 0, carries the twiddle index), combined earlier digits K, outer batches
+        const long long in_unit = pfirst ? es_in : 1;
+        dims.push_back({Mp, in_unit, 1});
+        if (done > 1) dims.push_back({done, M, M});  // only for pi >= 1, scratch -> scratch
+        for (size_t i = 0; i < outer_m.size(); ++i)
+          dims.push_back({outer_m[i].n, pfirst ? outer_m[i].in : sdist[i], sdist[i]});
+        ps.pp.is = Mp * in_unit;
+        ps.pp.os = Mp;
+        ps.pp.ioff = pfirst ? off_in : 0;
+        ps.pp.ooff = 0;
+        ps.pp.gtw_dim = 0;
+        ps.pp.gtw_n = M;
+        ps.src = pfirst ? src0 : BUF_SCRATCH;
+        ps.dst = BUF_SCRATCH;
+        std::vector<BDim> md = merge_dims(dims, 1);
+        set_batch_dims(ps.pp, md);
+      } else {
+        // last factor: contiguous rows of the scratch, output digit-reversed into the user layout
+        // rows are indexed by digits k_1..k_{k-1}: scratch distance M_q, output distance N_1..N_{q-1}
+        long long mq = (long long)L, prod = 1;
+        for (size_t q = 0; q + 1 < k; ++q) {
+          mq /= (long long)factors[q];
+          dims.push_back({(long long)factors[q], mq, prod * es_out});
+          prod *= (long long)factors[q];
+        }
+        for (size_t i = 0; i < outer_m.size(); ++i) dims.push_back({outer_m[i].n, sdist[i], outer_m[i].out});
+        ps.pp.is = 1;
+        ps.pp.os = done * es_out;
+        ps.pp.ioff = 0;
+        ps.pp.ooff = off_out;
+        ps.pp.gtw_dim = -1;
+        ps.src = BUF_SCRATCH;
+        ps.dst = BUF_OUT;
+        // dim 0 must be the unit-output-distance digit (k_1) so that the staged store coalesces along it
+        std::vector<BDim> md = merge_dims(dims, 1);
+        set_batch_dims(ps.pp, md);
+      }
+      configure_wg_generic(ps, dbl, lim, true);
+      passes.push_back(ps);
+      M = Mp;
+      done *= Np;
+    }
+  }
+  // scale on the last pass executed (committed_descriptor_impl.hpp:473-474)
+  const double scale = d.scale(dir);
+  PassHost& last = passes.back();
+  last.pp.scale = d.is_double ? scale : (double)(float)scale;
+  last.pp.apply_scale = (d.is_double ? scale : (double)(float)scale) != 1.0;
+}
+
+}  // namespace
+
+PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
+  validate_descriptor(d);
+  PlanHost plan;
+  plan.desc = d;
+  build_direction(plan, PFFT_FORWARD, lim);
+  build_direction(plan, PFFT_BACKWARD, lim);
+  return plan;
+}
+
+std::string describe_plan(const PlanHost& plan, int direction) {
+  static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_pow2"};
+  static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
+  static const char* buf_names[] = {"in", "out", "scratch"};
+  std::stringstream ss;
+  ss << "levels:";
+  for (int l : plan.dim_level) ss << " " << level_names[l];
+  ss << "; scratch_elems=" << plan.scratch_elems << "\n";
+  for (const PassHost& ps : plan.passes[direction]) {
+    const PassParams& p = ps.pp;
+    ss << "pass kernel=" << kernel_names[ps.kernel] << " level=" << level_names[ps.level] << " n=" << p.n << " radices=";
+    for (int i = 0; i < p.num_radices; ++i) ss << (i ? "x" : "") << p.radix[i];
+    ss << " T=" << p.threads_per_fft << " F=" << p.ffts_per_block << " block=" << ps.block << " grid=" << ps.grid
+       << " smem=" << ps.smem << " " << buf_names[ps.src] << "->" << buf_names[ps.dst] << " in=" << mode_names[p.in_mode]
+       << " out=" << mode_names[p.out_mode] << " is=" << p.is << " os=" << p.os << " batch=[";
+    for (int dd = 0; dd < kMaxBatchDims; ++dd)
+      if (p.nb[dd] > 1 || dd == 0) ss << (dd ? " " : "") << p.nb[dd] << ":" << p.ibd[dd] << ":" << p.obd[dd];
+    ss << "] gtw_dim=" << p.gtw_dim;
+    if (p.gtw_dim >= 0) ss << " gtw_n=" << p.gtw_n;
+    if (p.apply_scale) ss << " scale=" << p.scale;
+    ss << "\n";
+  }
+  return ss.str();
+}
+
+}  // namespace pfft

@@ -1,0 +1,85 @@
+// Host-side planner: descriptor validation, layout classification, level selection, factorisation into passes.
+// Pure C++17 (no CUDA calls) so that it can be exercised on a machine without a GPU.
+//
+// Counterpart of the reference's commit-time logic:
+//   /root/reference/src/portfft/descriptor_validation.hpp (whole file)
+//   /root/reference/src/portfft/utils.hpp:94-132,190-246
+//   /root/reference/src/portfft/committed_descriptor_impl.hpp:210-313 (prepare_implementation), :448-532
+#pragma once
+#include <cstddef>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/pfft.h"
+#include "pass.h"
+
+namespace pfft {
+
+// Error carrying a pfft_status; the C ABI maps it to status + thread-local message, the C++ header back to the
+// reference's exception types (src/portfft/common/exceptions.hpp:32-77).
+struct PlanError : std::runtime_error {
+  pfft_status status;
+  PlanError(pfft_status s, const std::string& m) : std::runtime_error(m), status(s) {}
+};
+
+struct DescHost {
+  bool is_double = false;
+  int domain = PFFT_DOMAIN_COMPLEX;
+  std::vector<size_t> lengths;
+  double forward_scale = 1.0, backward_scale = 1.0;
+  size_t number_of_transforms = 1;
+  int complex_storage = PFFT_INTERLEAVED_COMPLEX;
+  int placement = PFFT_OUT_OF_PLACE;
+  std::vector<size_t> forward_strides, backward_strides;
+  size_t forward_distance = 1, backward_distance = 1;
+  size_t forward_offset = 0, backward_offset = 0;
+
+  const std::vector<size_t>& strides(int dir) const { return dir == PFFT_FORWARD ? forward_strides : backward_strides; }
+  size_t distance(int dir) const { return dir == PFFT_FORWARD ? forward_distance : backward_distance; }
+  size_t offset(int dir) const { return dir == PFFT_FORWARD ? forward_offset : backward_offset; }
+  double scale(int dir) const { return dir == PFFT_FORWARD ? forward_scale : backward_scale; }
+  size_t flattened_length() const;
+  size_t buffer_count(int dir) const;
+};
+
+DescHost desc_from_c(const pfft_desc* d);
+std::vector<size_t> default_strides(const std::vector<size_t>& lengths);
+int get_layout(const DescHost& d, int dir);
+void validate_descriptor(const DescHost& d);  // throws PlanError
+
+enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
+
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_POW2 = 3 };
+
+// One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
+struct PassHost {
+  PassParams pp{};
+  int kernel = KERNEL_WG_GENERIC;
+  int level = LEVEL_WORKGROUP;
+  int src = BUF_IN, dst = BUF_OUT;
+  int grid = 1;
+  int block = 1;
+  size_t smem = 0;
+  long long tw_n = 0;  // per-pass twiddle table w_n^k (0: none)
+};
+
+struct PlanHost {
+  DescHost desc;
+  std::vector<PassHost> passes[2];  // [direction]
+  std::vector<int> dim_level;       // per dimension, PFFT_LEVEL_*
+  size_t scratch_elems = 0;         // complex elements of plan-owned workspace
+};
+
+struct DeviceLimits {
+  int num_sms = 148;
+  size_t max_smem_per_block = 227 * 1024;
+};
+
+// radix sequence (largest first) for a block-level transform of length n; empty when n has a prime factor > 31
+std::vector<int> choose_radices(size_t n);
+size_t max_workgroup_length(bool is_double, const DeviceLimits& lim);
+PlanHost build_plan(const DescHost& d, const DeviceLimits& lim);  // validates first; throws PlanError
+std::string describe_plan(const PlanHost& plan, int direction);
+
+}  // namespace pfft

@@ -1,0 +1,357 @@
+// Runtime of a committed plan + the C ABI (include/pfft.h).
+//
+// Owns what the reference's committed_descriptor_impl owns (twiddles, scratch, kernel parameters;
+// /root/reference/src/portfft/committed_descriptor_impl.hpp:716-768,579-708) and runs the pass list on a CUDA
+// stream.  Twiddle tables are built once per plan in extended precision on the host, rounded once to the plan's
+// scalar type and kept device resident (north_star: "device-resident twiddle tables" instead of
+// scripts/generate_twiddles.py + per-level device kernels, subgroup_dispatcher.hpp:666-693,
+// workgroup_dispatcher.hpp:382-443, global_dispatcher.hpp:107-256).
+#include <cuda_runtime.h>
+
+#include <atomic>
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/pfft.h"
+#include "kernels.h"
+#include "plan.h"
+
+namespace pfft {
+
+static thread_local std::string g_last_error;
+static std::atomic<unsigned long long> g_total_launches{0};
+
+#define PFFT_CUDA_CHECK(expr)                                                                         \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess)                                                                            \
+      throw PlanError(PFFT_CUDA_ERROR, std::string(#expr) + " failed: " + cudaGetErrorString(_e));    \
+  } while (0)
+
+// cos(2*pi*p/q), sin(2*pi*p/q) in long double with exact octant reduction
+static long double sin2pi_ld(long long p, long long q);
+static long double cos2pi_ld(long long p, long long q) {
+  p %= q;
+  if (p < 0) p += q;
+  if (2 * p > q) p = q - p;
+  if (4 * p > q) return -cos2pi_ld(q - 2 * p, 2 * q);
+  if (8 * p > q) return sin2pi_ld(q - 4 * p, 4 * q);
+  return cosl(6.283185307179586476925286766559L * (long double)p / (long double)q);
+}
+static long double sin2pi_ld(long long p, long long q) {
+  p %= q;
+  if (p < 0) p += q;
+  if (2 * p > q) return -sin2pi_ld(q - p, q);
+  if (4 * p > q) return sin2pi_ld(q - 2 * p, 2 * q);
+  if (8 * p > q) return cos2pi_ld(q - 4 * p, 4 * q);
+  return sinl(6.283185307179586476925286766559L * (long double)p / (long double)q);
+}
+
+// table[i] = w_n^{i * mult} = exp(-2*pi*i * i*mult / n), i in [0, count)
+template <typename T>
+static std::vector<T> make_twiddles(long long n, long long count, long long mult) {
+  std::vector<T> t((size_t)count * 2);
+  for (long long i = 0; i < count; ++i) {
+    const long long k = (long long)(((__int128)i * mult) % n);
+    t[2 * i] = (T)cos2pi_ld(k, n);
+    t[2 * i + 1] = (T)(-sin2pi_ld(k, n));
+  }
+  return t;
+}
+
+struct GtwTable {
+  void* lo = nullptr;
+  void* hi = nullptr;
+  int bits = 0;
+};
+
+}  // namespace pfft
+
+using namespace pfft;
+
+struct pfft_plan {
+  PlanHost host;
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::map<long long, void*> tw;
+  std::map<long long, GtwTable> gtw;
+  void* scratch = nullptr;
+  size_t scratch_bytes = 0;
+  // device staging for pfft_compute_host
+  void* stage[2] = {nullptr, nullptr};
+  size_t stage_bytes[2] = {0, 0};
+  std::vector<void*> owned;
+
+  ~pfft_plan() {
+    for (void* p : owned) cudaFree(p);
+    if (scratch) cudaFree(scratch);
+    for (void* p : stage)
+      if (p) cudaFree(p);
+  }
+};
+
+namespace pfft {
+
+static void* upload(pfft_plan* plan, const void* host, size_t bytes) {
+  void* d = nullptr;
+  PFFT_CUDA_CHECK(cudaMalloc(&d, bytes));
+  plan->owned.push_back(d);
+  PFFT_CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, plan->stream));
+  PFFT_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+  return d;
+}
+
+template <typename T>
+static void build_tables(pfft_plan* plan) {
+  for (int dir = 0; dir < 2; ++dir) {
+    for (PassHost& ps : plan->host.passes[dir]) {
+      if (ps.tw_n > 0 && !plan->tw.count(ps.tw_n)) {
+        std::vector<T> t = make_twiddles<T>(ps.tw_n, ps.tw_n, 1);
+        plan->tw[ps.tw_n] = upload(plan, t.data(), t.size() * sizeof(T));
+      }
+      if (ps.pp.gtw_dim >= 0 && !plan->gtw.count(ps.pp.gtw_n)) {
+        const long long n = ps.pp.gtw_n;
+        int total_bits = 0;
+        while ((1LL << total_bits) < n) ++total_bits;
+        GtwTable g;
+        g.bits = (total_bits + 1) / 2;
+        const long long lo_count = 1LL << g.bits;
+        const long long hi_count = ((n - 1) >> g.bits) + 1;
+        std::vector<T> lo = make_twiddles<T>(n, lo_count, 1);
+        std::vector<T> hi = make_twiddles<T>(n, hi_count, lo_count);
+        g.lo = upload(plan, lo.data(), lo.size() * sizeof(T));
+        g.hi = upload(plan, hi.data(), hi.size() * sizeof(T));
+        plan->gtw[n] = g;
+      }
+    }
+  }
+}
+
+static void commit_device(pfft_plan* plan) {
+  PFFT_CUDA_CHECK(cudaSetDevice(plan->device));
+  if (plan->host.desc.is_double)
+    build_tables<double>(plan);
+  else
+    build_tables<float>(plan);
+  const size_t scalar = plan->host.desc.is_double ? 8 : 4;
+  plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
+  if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
+  for (int dir = 0; dir < 2; ++dir) {
+    for (PassHost& ps : plan->host.passes[dir]) {
+      ps.pp.tw = ps.tw_n > 0 ? plan->tw[ps.tw_n] : nullptr;
+      if (ps.pp.gtw_dim >= 0) {
+        const GtwTable& g = plan->gtw[ps.pp.gtw_n];
+        ps.pp.gtw_lo = g.lo;
+        ps.pp.gtw_hi = g.hi;
+        ps.pp.gtw_bits = g.bits;
+      }
+    }
+  }
+}
+
+static void execute(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
+                    cudaStream_t stream) {
+  const DescHost& d = plan->host.desc;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  // committed_descriptor_impl.hpp:862-871
+  if (il && (in_imag != nullptr || out_imag != nullptr))
+    throw PlanError(PFFT_INVALID_CONFIGURATION,
+                    "To use interleaved data layout, please set the storage in the descriptor to INTERLEAVED_COMPLEX");
+  if (!il && (in_imag == nullptr || out_imag == nullptr))
+    throw PlanError(PFFT_INVALID_CONFIGURATION,
+                    "To use split data layout, please set the storage in the descriptor to SPLIT_COMPLEX");
+  if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
+  const bool bwd = dir == PFFT_BACKWARD;
+  const size_t scalar = d.is_double ? 8 : 4;
+  // backward = forward transform of the (re <-> im)-swapped data, swapped back: free for split storage
+  const void* uin_re = in;
+  const void* uin_im = in_imag;
+  void* uout_re = out;
+  void* uout_im = out_imag;
+  if (!il && bwd) {
+    std::swap(uin_re, uin_im);
+    std::swap(uout_re, uout_im);
+  }
+  void* s_re = plan->scratch;
+  void* s_im = il ? nullptr : (void*)((char*)plan->scratch + plan->host.scratch_elems * scalar);
+  for (const PassHost& ps : plan->host.passes[dir]) {
+    PassParams p = ps.pp;
+    switch (ps.src) {
+      case BUF_IN: p.in_re = uin_re; p.in_im = uin_im; break;
+      case BUF_OUT: p.in_re = uout_re; p.in_im = uout_im; break;
+      default: p.in_re = s_re; p.in_im = s_im; break;
+    }
+    switch (ps.dst) {
+      case BUF_OUT: p.out_re = uout_re; p.out_im = uout_im; break;
+      default: p.out_re = s_re; p.out_im = s_im; break;
+    }
+    cudaError_t e = cudaSuccess;
+    switch (ps.kernel) {
+      case KERNEL_WG_GENERIC:
+        e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+        break;
+      default:
+        throw PlanError(PFFT_INTERNAL_ERROR, "unknown kernel kind");
+    }
+    if (e != cudaSuccess) throw PlanError(PFFT_CUDA_ERROR, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+    g_total_launches.fetch_add(1, std::memory_order_relaxed);
+  }
+}
+
+template <typename F>
+static pfft_status guarded(F&& f) {
+  try {
+    f();
+    return PFFT_OK;
+  } catch (const PlanError& e) {
+    g_last_error = e.what();
+    return e.status;
+  } catch (const std::exception& e) {
+    g_last_error = e.what();
+    return PFFT_INTERNAL_ERROR;
+  }
+}
+
+}  // namespace pfft
+
+extern "C" {
+
+pfft_status pfft_validate(const pfft_desc* desc) {
+  return guarded([&] { validate_descriptor(desc_from_c(desc)); });
+}
+
+size_t pfft_get_flattened_length(const pfft_desc* desc) {
+  size_t r = 0;
+  guarded([&] { r = desc_from_c(desc).flattened_length(); });
+  return r;
+}
+
+size_t pfft_get_buffer_count(const pfft_desc* desc, int direction) {
+  size_t r = 0;
+  guarded([&] { r = desc_from_c(desc).buffer_count(direction); });
+  return r;
+}
+
+int pfft_get_layout(const pfft_desc* desc, int direction) {
+  int r = -1;
+  guarded([&] { r = get_layout(desc_from_c(desc), direction); });
+  return r;
+}
+
+pfft_status pfft_plan_describe(const pfft_desc* desc, int direction, char* buf, size_t buf_len, size_t* needed) {
+  return guarded([&] {
+    PlanHost plan = build_plan(desc_from_c(desc), DeviceLimits{});
+    std::string s = describe_plan(plan, direction);
+    if (needed) *needed = s.size() + 1;
+    if (buf && buf_len) {
+      const size_t n = std::min(buf_len - 1, s.size());
+      std::memcpy(buf, s.data(), n);
+      buf[n] = 0;
+    }
+  });
+}
+
+pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_plan** plan_out) {
+  return guarded([&] {
+    if (plan_out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan_out");
+    *plan_out = nullptr;
+    DescHost d = desc_from_c(desc);
+    validate_descriptor(d);  // host-only errors first, before any CUDA call
+    PFFT_CUDA_CHECK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PFFT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+    DeviceLimits lim;
+    lim.num_sms = prop.multiProcessorCount;
+    lim.max_smem_per_block = prop.sharedMemPerBlockOptin;
+    std::unique_ptr<pfft_plan> plan(new pfft_plan);
+    plan->host = build_plan(d, lim);
+    plan->device = device;
+    plan->stream = (cudaStream_t)stream;
+    commit_device(plan.get());
+    *plan_out = plan.release();
+  });
+}
+
+pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                         void* out_imag, void* stream) {
+  return guarded([&] {
+    if (plan == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan");
+    if (direction != PFFT_FORWARD && direction != PFFT_BACKWARD)
+      throw PlanError(PFFT_INVALID_CONFIGURATION, "invalid direction");
+    cudaStream_t s = stream ? (cudaStream_t)stream : plan->stream;
+    execute(plan, direction, in, in_imag, out, out_imag, s);
+  });
+}
+
+pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                              void* out_imag) {
+  return guarded([&] {
+    if (plan == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan");
+    const DescHost& d = plan->host.desc;
+    const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+    const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
+    const size_t scalar = d.is_double ? 8 : 4;
+    const size_t in_elems = d.buffer_count(direction), out_elems = d.buffer_count(odir);
+    const size_t plane_in = in_elems * scalar * (il ? 2 : 1), plane_out = out_elems * scalar * (il ? 2 : 1);
+    const size_t planes = il ? 1 : 2;
+    const bool inplace = in == out;
+    PFFT_CUDA_CHECK(cudaSetDevice(plan->device));
+    const size_t need[2] = {plane_in * planes, inplace ? 0 : plane_out * planes};
+    for (int i = 0; i < 2; ++i) {
+      if (need[i] > plan->stage_bytes[i]) {
+        if (plan->stage[i]) PFFT_CUDA_CHECK(cudaFree(plan->stage[i]));
+        plan->stage[i] = nullptr;
+        PFFT_CUDA_CHECK(cudaMalloc(&plan->stage[i], need[i]));
+        plan->stage_bytes[i] = need[i];
+      }
+    }
+    cudaStream_t s = plan->stream;
+    char* din = (char*)plan->stage[0];
+    char* dout = inplace ? din : (char*)plan->stage[1];
+    PFFT_CUDA_CHECK(cudaMemcpyAsync(din, in, plane_in, cudaMemcpyHostToDevice, s));
+    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
+    // elements of the output buffer that the descriptor does not address must survive the round trip
+    const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
+    if (!inplace && !out_dense) {
+      PFFT_CUDA_CHECK(cudaMemcpyAsync(dout, out, plane_out, cudaMemcpyHostToDevice, s));
+      if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
+    }
+    execute(plan, direction, din, il ? nullptr : din + plane_in, dout, il ? nullptr : dout + plane_out, s);
+    PFFT_CUDA_CHECK(cudaMemcpyAsync(out, dout, plane_out, cudaMemcpyDeviceToHost, s));
+    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(out_imag, dout + plane_out, plane_out, cudaMemcpyDeviceToHost, s));
+    PFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+  });
+}
+
+pfft_status pfft_destroy(pfft_plan* plan) {
+  return guarded([&] {
+    if (plan == nullptr) return;
+    cudaSetDevice(plan->device);
+    cudaStreamSynchronize(plan->stream);  // committed_descriptor_impl.hpp:825-828
+    delete plan;
+  });
+}
+
+size_t pfft_workspace_bytes(const pfft_plan* plan) { return plan ? plan->scratch_bytes : 0; }
+
+int pfft_plan_level(const pfft_plan* plan, size_t dimension) {
+  if (!plan || dimension >= plan->host.dim_level.size()) return -1;
+  return plan->host.dim_level[dimension];
+}
+
+size_t pfft_plan_num_launches(const pfft_plan* plan, int direction) {
+  if (!plan || direction < 0 || direction > 1) return 0;
+  return plan->host.passes[direction].size();
+}
+
+unsigned long long pfft_total_launches(void) { return g_total_launches.load(); }
+
+const char* pfft_last_error(void) { return g_last_error.c_str(); }
+
+const char* pfft_version(void) { return "pfft_b200 0.1 (sm_100a)"; }
+
+}  // extern "C"
