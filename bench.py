@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the hot path (BASELINE.json): batched C2C FFT throughput on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config C2] [--impl reference]
+
+One "step" is one compute call of the hot path over the whole synthetic batch (steps alternate compute_forward and
+compute_backward with backward_scale = 1/N so that the in-place data stays bounded and the run ends with a
+full-size round-trip identity check).  Default workload = BASELINE.json configs[1] (C2): 1-D C2C fp32 N=4096,
+batch 65536, in place, interleaved -- 2 GiB per GPU, far larger than the 126 MB L2, so no flush is needed.
+
+Printed JSON line (rank 0): metric GFLOP/s = 5*N*log2(N)*batch/t (the reference's own model,
+/root/reference/test/bench/utils/ops_estimate.hpp:34-50), device-timed `value`, `e2e` through the C ABI with
+pinned HOST buffers (pfft_compute_host: H2D + compute + D2H per step), `roofline` for the dominant kernel against
+MEASURED_PEAKS.json, `cpu_baseline` = the C oracle port timed on a bounded sample on the host cores.
+Multi-GPU (torchrun): every rank transforms its own shard of the batch, no data-path collective ("weak").
+`--impl reference` times the reference's CPU algorithm (oracle port; the SYCL reference cannot be built here).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: lengths, batch, scalar, placement, storage
+    "C1": dict(lengths=[64], batch=1024, scalar="float", inplace=False, split=False,
+               desc="1D C2C fp32 N=64 batch=1024 interleaved out-of-place"),
+    "C2": dict(lengths=[4096], batch=65536, scalar="float", inplace=True, split=False,
+               desc="1D C2C fp32 N=4096 batch=65536 in-place interleaved"),
+    "C3": dict(lengths=[1000], batch=100000, scalar="float", inplace=False, split=True,
+               desc="1D C2C fp32 N=1000 batch=100000 split, fwd stride 2/dist 2048/off 7, bwd dist 1024/off 3, bwd scale 1e-3",
+               forward_strides=[2], forward_distance=2048, forward_offset=7, backward_strides=[1],
+               backward_distance=1024, backward_offset=3, backward_scale=1e-3),
+    "C4": dict(lengths=[1 << 24], batch=8, scalar="double", inplace=False, split=False,
+               desc="1D C2C fp64 N=2^24 batch=8 out-of-place (global level)"),
+    "C5": dict(lengths=[512, 512, 512], batch=1, scalar="float", inplace=False, split=False,
+               desc="3D C2C fp32 512^3 default strides out-of-place"),
+    "L1D": dict(lengths=[65536], batch=2048, scalar="float", inplace=False, split=False,
+                desc="1D C2C fp32 N=65536 batch=2048 out-of-place (reference bench_float large_1d)"),
+    "S16": dict(lengths=[16], batch=8 * 1024 * 1024, scalar="float", inplace=False, split=False,
+                desc="1D C2C fp32 N=16 batch=8Mi out-of-place (reference bench_float small_1d)"),
+    "M256": dict(lengths=[256], batch=512 * 1024, scalar="float", inplace=False, split=False,
+                 desc="1D C2C fp32 N=256 batch=512Ki out-of-place (reference bench_float medium_small_1d)"),
+}
+
+
+def flops_of(cfg) -> float:
+    n = 1
+    for l in cfg["lengths"]:
+        n *= l
+    return 5.0 * n * math.log2(n) * cfg["batch"]
+
+
+def bytes_of(cfg) -> float:
+    n = 1
+    for l in cfg["lengths"]:
+        n *= l
+    return 2.0 * n * cfg["batch"] * (16 if cfg["scalar"] == "double" else 8)
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+                for line in out.strip().splitlines():
+                    self.samples.append([x.strip() for x in line.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, val in zip(names, s[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def load_oracle():
+    lib = ctypes.CDLL(os.path.join(ROOT, "oracle", "liboracle.so"))
+    for name in ("pfft_oracle_fft_f32", "pfft_oracle_fft_f64"):
+        fn = getattr(lib, name)
+        fn.restype = ctypes.c_int
+        fn.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_longlong, ctypes.c_int,
+                       ctypes.c_double, ctypes.c_int]
+    return lib
+
+
+def cpu_port_time(cfg, sample_batch: int, repeats: int = 1):
+    """Time the C oracle (the reference's algorithm restated for the CPU) on `sample_batch` packed transforms of the
+    workload's flattened length, all host cores.  Returns (seconds per call, cores)."""
+    import numpy as np
+
+    lib = load_oracle()
+    n = 1
+    for l in cfg["lengths"]:
+        n *= l  # N-D is timed as the flattened 1-D length (same FLOP model as the reference's benches)
+    dbl = cfg["scalar"] == "double"
+    rng = np.random.Generator(np.random.SFC64(1))
+    x = rng.uniform(-1, 1, (sample_batch, n, 2)).astype(np.float64 if dbl else np.float32)
+    out = np.empty_like(x)
+    fn = lib.pfft_oracle_fft_f64 if dbl else lib.pfft_oracle_fft_f32
+    cores = len(os.sched_getaffinity(0))
+    fn(x.ctypes.data, out.ctypes.data, n, min(sample_batch, cores), 0, 1.0, cores)  # warm tables
+    best = float("inf")
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        rc = fn(x.ctypes.data, out.ctypes.data, n, sample_batch, 0, 1.0, cores)
+        best = min(best, time.perf_counter() - t0)
+        assert rc == 0
+    return best, cores
+
+
+def cpu_sample_batch(cfg) -> int:
+    """bounded sample: about 0.5 GFLOP-equivalents of the port's speed (~10-20 s on 8 cores)"""
+    per = flops_of(cfg) / cfg["batch"]
+    target_flops = 1.5e10
+    return int(max(1, min(cfg["batch"], target_flops // per)))
+
+
+def run_reference_arm(args, cfg, name):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = cpu_sample_batch(cfg)
+    per = flops_of(cfg) / cfg["batch"]
+    for _ in range(max(0, min(args.warmup, 1))):
+        cpu_port_time(cfg, min(sample, 64))
+    times = []
+    cores = 1
+    for _ in range(args.steps):
+        t, cores = cpu_port_time(cfg, sample)
+        times.append(t)
+    t = sum(times) / len(times)
+    val = per * sample / t / 1e9
+    line = {
+        "impl": "reference", "metric": "batched_c2c_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if cfg["scalar"] == "double" else "f32",
+        "data": "synthetic",
+        "config": {"workload": f"{name}: {cfg['desc']}", "sample": f"{sample} of {cfg['batch']} transforms per step"},
+        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} transforms of the workload per step, C oracle port of the reference "
+                                   f"algorithm (SYCL reference not buildable here)"},
+        "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, args.config)
+        return
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    import portfft_b200 as pf
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    # ---- descriptor (each rank owns an identical shard: batch-sharded, no data-path collective) ----------------
+    n_flat = 1
+    for l in cfg["lengths"]:
+        n_flat *= l
+    d = pf.descriptor(cfg["lengths"], cfg["scalar"])
+    d.number_of_transforms = cfg["batch"]
+    d.placement = pf.placement.IN_PLACE if cfg["inplace"] else pf.placement.OUT_OF_PLACE
+    d.complex_storage = pf.complex_storage.SPLIT_COMPLEX if cfg["split"] else pf.complex_storage.INTERLEAVED_COMPLEX
+    for k in ("forward_strides", "forward_distance", "forward_offset", "backward_strides", "backward_distance",
+              "backward_offset", "backward_scale"):
+        if k in cfg:
+            setattr(d, k, cfg[k])
+    if "backward_scale" not in cfg:
+        d.backward_scale = 1.0 / n_flat
+    stream = torch.cuda.current_stream(dev)
+    plan = d.commit(stream, local_rank)
+    fdt = torch.float64 if cfg["scalar"] == "double" else torch.float32
+    n_fwd, n_bwd = d.get_input_count(pf.direction.FORWARD), d.get_input_count(pf.direction.BACKWARD)
+    g = torch.Generator(device=dev)
+    g.manual_seed(1234 + rank)
+    planes = 2 if cfg["split"] else 1
+
+    def alloc(count):
+        if cfg["split"]:
+            return [torch.rand(count, dtype=fdt, device=dev, generator=g) * 2 - 1 for _ in range(2)]
+        return [torch.view_as_complex((torch.rand(count, 2, dtype=fdt, device=dev, generator=g) * 2 - 1))]
+
+    fwd_buf = alloc(n_fwd)
+    bwd_buf = fwd_buf if cfg["inplace"] else alloc(n_bwd)
+    orig = [t.clone() for t in fwd_buf] if n_fwd * (16 if fdt == torch.float64 else 8) <= (8 << 30) else None
+
+    def step(i):
+        if i % 2 == 0:
+            if cfg["inplace"]:
+                plan.compute_forward(*fwd_buf, queue=stream)
+            else:
+                plan.compute_forward(*fwd_buf, *bwd_buf, queue=stream)
+        else:
+            if cfg["inplace"]:
+                plan.compute_backward(*fwd_buf, queue=stream)
+            else:
+                plan.compute_backward(*bwd_buf, *fwd_buf, queue=stream)
+
+    total_steps = args.warmup + args.steps
+    if total_steps % 2 == 1:
+        args.warmup += 1  # even number of steps: the data ends where it started (round-trip check below)
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = pf.total_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for i in range(args.steps):
+        step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = pf.total_launches() - launches0
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+    tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    ms = float(tmax.item())
+    ms_per_step = ms / args.steps
+    flops_total = flops_of(cfg) * world
+    value = flops_total / (ms_per_step * 1e-3) / 1e9
+    hbm_gbs = bytes_of(cfg) * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- round-trip identity at full size (size-independent parity property) ------------------------------------
+    roundtrip = None
+    if orig is not None:
+        num = sum(float(torch.linalg.vector_norm((a - b).reshape(-1)).item()) ** 2 for a, b in zip(fwd_buf, orig))
+        den = sum(float(torch.linalg.vector_norm(b.reshape(-1)).item()) ** 2 for b in orig)
+        if "forward_strides" not in cfg:  # strided layouts hold untouched padding in between: norm still valid
+            pass
+        roundtrip = math.sqrt(num / den)
+        del orig
+
+    # ---- roofline of the dominant kernel (one launch per step for single-pass plans) ---------------------------
+    peak, peak_src = measured_peak()
+    per_launch_ms = ms_per_step / max(1, launches // args.steps)
+    n_pass = plan.num_launches(pf.direction.FORWARD)
+    achieved = bytes_of(cfg) / (per_launch_ms * 1e-3) / 1e9  # algorithmic bytes of ONE pass over the data / launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src, "kernel_launches_per_step": n_pass,
+                "note": "achieved = 1 read + 1 write of every element per launch / mean launch time (CUDA events)"}
+
+    # ---- e2e through the C ABI with pinned host buffers ----------------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        scalar_np = np.float64 if cfg["scalar"] == "double" else np.float32
+        esz = (2 if not cfg["split"] else 1)
+        h_in = [torch.empty(n_fwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
+        h_out = h_in if cfg["inplace"] else [torch.empty(n_bwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
+        for t in h_in:
+            t.uniform_(-1, 1)
+        for t in h_out:
+            if t is not h_in[0]:
+                t.zero_()
+        e_steps = max(1, min(args.steps, 4))
+
+        def e2e_step():
+            a = [t.data_ptr() for t in h_in] + [None] * (2 - planes)
+            b = [t.data_ptr() for t in h_out] + [None] * (2 - planes)
+            plan.compute_host(pf.direction.FORWARD, a[0], a[1], b[0], b[1])
+
+        e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e_steps):
+            e2e_step()
+        barrier()
+        te = (time.perf_counter() - t0) / e_steps
+        tt = torch.tensor([te], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        te = float(tt.item())
+        bpe = (16 if cfg["scalar"] == "double" else 8)
+        e2e = {"value": flops_total / te / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": n_fwd * bpe,
+               "d2h_bytes_per_step": n_bwd * bpe, "steps": e_steps, "ms_per_step": te * 1e3,
+               "api": "pfft_compute_host (C ABI, pinned host buffers)"}
+        del h_in, h_out
+
+    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample = cpu_sample_batch(cfg)
+        t, cores = cpu_port_time(cfg, sample)
+        cpu = {"value": flops_of(cfg) / cfg["batch"] * sample / t / 1e9, "unit": "GFLOP/s", "cores": cores,
+               "kind": "port", "sample": f"{sample} of {cfg['batch']} transforms, C oracle port of the reference "
+                                          f"algorithm, {t:.2f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": "batched_c2c_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64" if cfg["scalar"] == "double" else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.config}: {cfg['desc']}", "per_gpu_batch": cfg["batch"],
+                       "direction": "alternating compute_forward / compute_backward (backward_scale 1/N)",
+                       "l2": "per-GPU working set %.0f MiB >> 126 MB L2 (no flush needed)" % (bytes_of(cfg) / 2 / 2**20)
+                       if bytes_of(cfg) / 2 > 4 * 126e6 else "working set fits L2: launch-latency bound",
+                       "sharding": "batch-sharded, one plan per GPU, no collective"},
+            "hbm_gbs": hbm_gbs, "hbm_frac_of_measured": hbm_gbs / world / peak,
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
+            "clocks": sampler.summary(), "roundtrip_rel_l2": roundtrip,
+        }
+        print(json.dumps(line), flush=True)
+    plan.destroy()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -95,7 +95,7 @@ class OracleDescriptor:
         if not self.forward_strides:
             self.forward_strides = get_default_strides(self.lengths)
         if not self.backward_strides:
-            self.backward_strides = list(self.forward_strides)
+            self.backward_strides = get_default_strides(self.lengths)
         # ctor default: distance = flattened length (descriptor.hpp:141-143)
         if self.forward_distance is None:
             self.forward_distance = self.get_flattened_length()

@@ -21,7 +21,7 @@ P, BI, U = "PACKED", "BATCH_INTERLEAVED", "UNPACKED"
 
 
 @dataclass
-class TestParams:
+class CaseParams:
     lengths: Sequence[int]
     batch: int = 1
     placement: str = "OOP"          # "IP" / "OOP"
@@ -53,7 +53,7 @@ class TestParams:
         return s
 
 
-def make_descriptors(tp: TestParams):
+def make_descriptors(tp: CaseParams):
     """-> (portfft_b200.descriptor, oracle.OracleDescriptor), fields set as `get_descriptor` does."""
     d = pf.descriptor(list(tp.lengths), tp.scalar)
     d.number_of_transforms = tp.batch
@@ -99,7 +99,7 @@ def make_descriptors(tp: TestParams):
     return d, od
 
 
-def run_case(tp: TestParams, device: int = 0, rel_l2_tol: Optional[float] = None) -> float:
+def run_case(tp: CaseParams, device: int = 0, rel_l2_tol: Optional[float] = None) -> float:
     """Run one parity case on the GPU; returns the max relative L2 error.  Raises AssertionError on mismatch."""
     import torch
 

@@ -1,0 +1,101 @@
+"""GPU parity tests: the reference's FFT test grid (/root/reference/test/unit_test/instantiate_fft_tests.hpp:95-319,
+SURVEY.md App. B) re-expressed in pytest, run through the C ABI against the numpy oracle, for float and double."""
+import itertools
+
+import pytest
+
+from fft_check import BI, P, U, CaseParams, run_case
+
+pytestmark = pytest.mark.gpu
+
+# placement x layout sets (instantiate_fft_tests.hpp:37-85)
+ALL_LAYOUTS = [("IP", P, P), ("IP", BI, BI), ("OOP", P, P), ("OOP", P, BI), ("OOP", BI, BI), ("OOP", BI, P)]
+MD_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
+GLOBAL_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
+OOP_ALL = [l for l in ALL_LAYOUTS if l[0] == "OOP"]
+BOTH_DIR = ["fwd", "bwd"]
+STORAGES = ["interleaved", "split"]
+SCALARS = ["float", "double"]
+
+
+def basic(layouts, dirs, storages, batches, lengths):
+    out = []
+    for (pl, li, lo), dr, st, b, n, sc in itertools.product(layouts, dirs, storages, batches, lengths, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, b, pl, li, lo, dr, st, sc))
+    return out
+
+
+def layouts(placements, dirs, storages, batches, lps):
+    """layout_params = (len, fwd_stride, bwd_stride[, fwd_dist, bwd_dist]) (fft_test_utils.hpp:52-78)"""
+    out = []
+    for pl, dr, st, b, lp, sc in itertools.product(placements, dirs, storages, batches, lps, SCALARS):
+        fd, bd = (lp[3], lp[4]) if len(lp) == 5 else (None, None)
+        out.append(CaseParams([lp[0]], b, pl, U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
+                              forward_distance=fd, backward_distance=bd))
+    return out
+
+
+def offsets(layouts_, dirs, batches, lengths, offs):
+    out = []
+    for (pl, li, lo), dr, b, n, (fo, bo), sc in itertools.product(layouts_, dirs, batches, lengths, offs, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, b, pl, li, lo, dr, "interleaved", sc, forward_offset=fo, backward_offset=bo))
+    return out
+
+
+def scaled(dr, lengths, fs, bs):
+    out = []
+    for n, sc in itertools.product(lengths, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, 3, "OOP", P, P, dr, "interleaved", sc, forward_scale=fs, backward_scale=bs))
+    return out
+
+
+SUITES = {
+    "workItemTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 33000], [1, 2, 3, 4, 8]),
+    "workItemOrSubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [16, 32]),
+    "SubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [64, 96, 128]),
+    "SubgroupRegressionTest": basic([("IP", BI, BI)], ["fwd"], ["interleaved"], [44, 100], [80, 100]),
+    "SubgroupOrWorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 131], [256, 512, 1024]),
+    "SubgroupOrWorkgroupRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [1, 131], [1536]),
+    "WorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [2048, 3072, 4096]),
+    "WorkgroupOrGlobal": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 128], [8192, 16384]),
+    "GlobalTest": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [32768, 65536, 131072]),
+    "WorkgroupOrGlobalRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [3], [9800, 15360, 68640]),
+    "BackwardTest": basic(ALL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [8, 9, 16, 32, 64, 4096]),
+    "BackwardGlobalTest": basic(GLOBAL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [32768, 65536]),
+    "MultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                                  [[2, 4], [4, 2], [16, 512], [64, 2048], [2, 3, 6], [2, 3, 2, 3]]),
+    "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
+    "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
+    "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
+    "OffsetsWIErrorRegressionTest": offsets(OOP_ALL, BOTH_DIR, [33000], [8], [(0, 2049), (2049, 0), (2047, 2049)]),
+    "OffsetsMDErrorRegressionTest": offsets([("OOP", P, P)], ["fwd"], [2], [[4, 4]], [(2, 0)]),
+    "FwdScaledFFTTest": scaled("fwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
+    "BwdScaledFFTTest": scaled("bwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
+    "workItemStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
+                                         [(3, 4, 7), (8, 11, 2), (9, 3, 4, 30, 40)]),
+    "SubgroupStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
+                                         [(64, 1, 7), (64, 4, 7), (75, 3, 2, 300, 200), (104, 3, 4)]),
+    "workItemStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
+                                                      [(8, 33, 99, 1, 3), (8, 33, 2, 1, 16), (8, 2, 66, 16, 2)]),
+    "SubgroupStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
+                                                      [(64, 33, 99, 1, 3), (96, 33, 2, 1, 192), (70, 2, 66, 140, 2)]),
+    "workItemStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(3, 4, 4), (9, 3, 3, 25, 25)]),
+    "SubgroupStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(75, 4, 4), (96, 3, 3, 286, 286)]),
+    "workItemStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
+                                                     [(3, 66, 66, 2, 2), (6, 40, 40, 1, 1)]),
+    "SubgroupStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
+                                                     [(75, 66, 66, 2, 2), (96, 40, 40, 1, 1)]),
+    "StridedStrideEqualsDistance": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [1], [(8, 2, 2, 2, 2), (8, 1, 1, 1, 1)]),
+    "workItemStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [4], [(4, 4, 4, 3, 3)]),
+    "SubgroupStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [13], [(85, 13, 13, 12, 12)]),
+}
+
+CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.items() for tp in tps]
+
+
+@pytest.mark.parametrize("tp", CASES)
+def test_reference_grid(tp):
+    run_case(tp)
