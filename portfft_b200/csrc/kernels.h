@@ -16,4 +16,7 @@ inline size_t wg_generic_smem_bytes(int ffts_per_block, int pitch, size_t scalar
 cudaError_t launch_wg_generic(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid,
                               cudaStream_t stream);
 
+// WORKGROUP level, N = R^3 specialisation with TMA-fed persistent CTAs (wg_cube.cu). variant 0: TMA ring, 1: direct loads
+cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream);
+
 }  // namespace pfft

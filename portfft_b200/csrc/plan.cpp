@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <map>
 #include <numeric>
 #include <sstream>
@@ -333,6 +334,24 @@ void set_radices(PassParams& p, size_t n) {
   for (size_t i = 0; i < r.size(); ++i) p.radix[i] = r[i];
 }
 
+// Hot sizes: hand-specialised kernels (same numerics, compile-time geometry). The generic configuration stays in
+// the pass as the fallback for unaligned pointers.
+void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
+  const PassParams& p = ps.pp;
+  const char* env = std::getenv("PFFT_CUBE_VARIANT");
+  const int variant = env ? std::atoi(env) : 0;
+  if (variant < 0) return;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  bool single_batch_dim = true;
+  for (int i = 1; i < kMaxBatchDims; ++i) single_batch_dim = single_batch_dim && p.nb[i] == 1;
+  if (!d.is_double && p.n == 4096 && il && p.is == 1 && p.os == 1 && single_batch_dim && p.gtw_dim < 0 &&
+      p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0) {
+    ps.kernel = KERNEL_WG_CUBE;
+    ps.variant = variant;
+    ps.alt_grid = (int)std::min<long long>(p.batch_total, 2LL * lim.num_sms);
+  }
+}
+
 // split n into k factors, each <= fmax, as balanced as possible
 bool split_factors(size_t n, int k, size_t fmax, std::vector<size_t>& out) {
   if (k == 1) {
@@ -407,6 +426,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       ps.dst = BUF_OUT;
       ps.level = LEVEL_WORKGROUP;
       configure_wg_generic(ps, dbl, lim, false);
+      select_specialised(ps, d, lim);
       passes.push_back(ps);
       plan.dim_level[dim] = PFFT_LEVEL_WORKGROUP;
       continue;
@@ -511,7 +531,7 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_pow2"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
   static const char* buf_names[] = {"in", "out", "scratch"};
   std::stringstream ss;

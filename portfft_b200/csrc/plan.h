@@ -50,7 +50,7 @@ void validate_descriptor(const DescHost& d);  // throws PlanError
 
 enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_POW2 = 3 };
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -62,6 +62,8 @@ struct PassHost {
   int block = 1;
   size_t smem = 0;
   long long tw_n = 0;  // per-pass twiddle table w_n^k (0: none)
+  int alt_grid = 0;    // launch geometry of the specialised kernel (the generic geometry stays valid as fallback)
+  int variant = 0;
 };
 
 struct PlanHost {

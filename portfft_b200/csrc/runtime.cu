@@ -10,6 +10,7 @@
 
 #include <atomic>
 #include <cmath>
+#include <cstdint>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -193,6 +194,13 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     switch (ps.kernel) {
       case KERNEL_WG_GENERIC:
         e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+        break;
+      case KERNEL_WG_CUBE:
+        // cp.async.bulk needs 16-byte aligned global addresses; otherwise run the generic kernel
+        if (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0)
+          e = launch_wg_cube(p, d.is_double, bwd, ps.variant, ps.alt_grid, stream);
+        else
+          e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
         break;
       default:
         throw PlanError(PFFT_INTERNAL_ERROR, "unknown kernel kind");
