@@ -13,7 +13,7 @@ CPP_SRCS  := $(wildcard $(CSRC)/*.cpp)
 OBJS      := $(patsubst $(CSRC)/%.cu,$(BUILD)/%.o,$(CU_SRCS)) $(patsubst $(CSRC)/%.cpp,$(BUILD)/%.o,$(CPP_SRCS))
 HDRS      := $(wildcard $(CSRC)/*.h) $(wildcard $(CSRC)/*.cuh) include/pfft.h
 
-all: $(LIB) oracle
+all: $(LIB) oracle build/api_smoke
 
 $(BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
 	@mkdir -p $(BUILD)
@@ -35,3 +35,9 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all oracle clean
+
+# C++ smoke test of the header-only API mirror (include/portfft/portfft.hpp); run on the GPU by tests/test_cpp_api.py
+build/api_smoke: tests/cpp/api_smoke.cpp $(LIB) $(wildcard include/portfft/*.hpp)
+	@mkdir -p build
+	g++ -std=c++17 -O1 -Wall -Iinclude -I/usr/local/cuda/include $< -o $@ -Lportfft_b200/lib -lpfft_b200 \
+	  -L/usr/local/cuda/lib64 -lcudart -Wl,-rpath,'$$ORIGIN/../portfft_b200/lib'

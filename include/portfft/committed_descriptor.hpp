@@ -1,0 +1,109 @@
+// portfft::committed_descriptor<Scalar, Domain>: compute_forward / compute_backward on device (USM) pointers, the same
+// overload set as /root/reference/src/portfft/committed_descriptor.hpp:171-310.  The SYCL buffer overloads (:58-162)
+// have no CUDA meaning and are not provided.  A committed descriptor is copyable: copies share the plan.
+#ifndef PFFT_B200_PORTFFT_COMMITTED_DESCRIPTOR_HPP
+#define PFFT_B200_PORTFFT_COMMITTED_DESCRIPTOR_HPP
+
+#include <complex>
+#include <memory>
+#include <vector>
+
+#include "descriptor.hpp"
+
+namespace portfft {
+
+template <typename Scalar, domain Domain>
+class committed_descriptor {
+  friend struct descriptor<Scalar, Domain>;
+
+  struct state {
+    pfft_plan* plan = nullptr;
+    cudaEvent_t ring[16] = {};
+    unsigned next = 0;
+    ~state() {
+      if (plan) pfft_destroy(plan);
+      for (cudaEvent_t e : ring)
+        if (e) cudaEventDestroy(e);
+    }
+  };
+
+  descriptor<Scalar, Domain> params;
+  queue queue_;
+  std::shared_ptr<state> st_;
+
+  committed_descriptor(const descriptor<Scalar, Domain>& d, queue& q) : params(d), queue_(q), st_(new state) {
+    pfft_desc c = params.to_c();
+    detail::throw_on_status(pfft_commit(&c, q.device(), q.stream(), &st_->plan));
+  }
+
+  event run(direction dir, const void* in, const void* in_imag, void* out, void* out_imag,
+            const std::vector<event>& dependencies) {
+    for (const event& e : dependencies)
+      if (e.native()) cudaStreamWaitEvent(queue_.stream(), e.native(), 0);
+    detail::throw_on_status(
+        pfft_compute(st_->plan, static_cast<int>(dir), in, in_imag, out, out_imag, queue_.stream()));
+    cudaEvent_t& ev = st_->ring[st_->next++ % 16];
+    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+    cudaEventRecord(ev, queue_.stream());
+    return event(ev, queue_.stream());
+  }
+
+ public:
+  using scalar_type = Scalar;
+  using complex_type = std::complex<Scalar>;
+
+  static_assert(Domain == domain::COMPLEX || Domain == domain::REAL, "unknown domain");
+
+  const descriptor<Scalar, Domain>& get_descriptor() const noexcept { return params; }
+  /// Level chosen for one dimension (thread / warp / block / multi-kernel).
+  detail::level get_level(std::size_t dimension = 0) const {
+    return static_cast<detail::level>(pfft_plan_level(st_->plan, dimension));
+  }
+  std::size_t get_workspace_bytes() const { return pfft_workspace_bytes(st_->plan); }
+
+  // ---- in-place ------------------------------------------------------------------------------------------------
+  event compute_forward(complex_type* inout, const std::vector<event>& dependencies = {}) {
+    return compute_forward(inout, inout, dependencies);
+  }
+  event compute_forward(scalar_type* inout_real, scalar_type* inout_imag, const std::vector<event>& dependencies = {}) {
+    return compute_forward(inout_real, inout_imag, inout_real, inout_imag, dependencies);
+  }
+  event compute_backward(complex_type* inout, const std::vector<event>& dependencies = {}) {
+    return compute_backward(inout, inout, dependencies);
+  }
+  event compute_backward(scalar_type* inout_real, scalar_type* inout_imag,
+                         const std::vector<event>& dependencies = {}) {
+    return compute_backward(inout_real, inout_imag, inout_real, inout_imag, dependencies);
+  }
+  // ---- out-of-place ----------------------------------------------------------------------------------------------
+  event compute_forward(const complex_type* in, complex_type* out, const std::vector<event>& dependencies = {}) {
+    return run(direction::FORWARD, in, nullptr, out, nullptr, dependencies);
+  }
+  event compute_forward(const scalar_type* in_real, const scalar_type* in_imag, scalar_type* out_real,
+                        scalar_type* out_imag, const std::vector<event>& dependencies = {}) {
+    require_split();
+    return run(direction::FORWARD, in_real, in_imag, out_real, out_imag, dependencies);
+  }
+  event compute_backward(const complex_type* in, complex_type* out, const std::vector<event>& dependencies = {}) {
+    return run(direction::BACKWARD, in, nullptr, out, nullptr, dependencies);
+  }
+  event compute_backward(const scalar_type* in_real, const scalar_type* in_imag, scalar_type* out_real,
+                         scalar_type* out_imag, const std::vector<event>& dependencies = {}) {
+    require_split();
+    return run(direction::BACKWARD, in_real, in_imag, out_real, out_imag, dependencies);
+  }
+  // ---- real-to-complex stubs, as in the reference (:201-206, :273-278) --------------------------------------------
+  event compute_forward(const scalar_type* /*in*/, complex_type* /*out*/, const std::vector<event>& = {}) {
+    throw unsupported_configuration("Real to complex FFTs not yet implemented.");
+  }
+
+ private:
+  void require_split() const {
+    if (params.complex_storage != complex_storage::SPLIT_COMPLEX)
+      throw invalid_configuration(
+          "To use split data layout, please set the storage in the descriptor to SPLIT_COMPLEX");
+  }
+};
+
+}  // namespace portfft
+#endif

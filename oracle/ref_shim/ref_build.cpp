@@ -1,0 +1,77 @@
+// Builds oracle/_ref/libportfft_ref.so: the REFERENCE's own code, compiled from /root/reference where it lies
+// (nothing is copied), behind a C interface so that the tests can pin the oracle against it.
+//   wi_dft                 /root/reference/src/portfft/common/workitem.hpp:200-219
+//   sg_dft                 /root/reference/src/portfft/common/subgroup.hpp:271-291 (32 lock-step host threads)
+//   factorize, wi_temps, fits_in_wi, factorize_sg, fits_in_sg   workitem.hpp:135-185, subgroup.hpp:226-253
+// The SYCL runtime is replaced by oracle/ref_shim/sycl/sycl.hpp; the build defines are the reference's CMake
+// defaults (CMakeLists.txt:38-59).  TEST INFRASTRUCTURE ONLY.
+#define PORTFFT_REGISTERS_PER_WI 128
+#define PORTFFT_SUBGROUP_SIZES 32
+#define PORTFFT_VEC_LOAD_BYTES 16
+#define PORTFFT_SGS_IN_WG 2
+#define PORTFFT_MAX_CONCURRENT_KERNELS 16
+#define PORTFFT_SLOW_SG_SHUFFLES 0
+#define PORTFFT_UNROLL
+
+#include <portfft/common/subgroup.hpp>
+#include <portfft/common/workitem.hpp>
+
+#include <thread>
+#include <vector>
+
+namespace {
+
+template <typename T>
+void run_wi(const T* in, T* out, int n) {
+  std::vector<T> priv(in, in + 2 * n), scratch(4 * 2 * 64 + 8 * n);
+  portfft::wi_dft<0>(priv.data(), priv.data(), n, 1, 1, scratch.data());
+  for (int i = 0; i < 2 * n; ++i) out[i] = priv[i];
+}
+
+// one transform of size factor_sg * factor_wi held by lanes 0..factor_sg-1 (lane l, slot k <- x[l*factor_wi + k])
+template <typename T>
+void run_sg(const T* in, T* out, int factor_wi, int factor_sg) {
+  const int n = factor_wi * factor_sg;
+  std::vector<T> tw(2 * n);
+  for (int l = 0; l < factor_sg; ++l)
+    for (int k = 0; k < factor_wi; ++k) portfft::sg_calc_twiddles<T>(factor_sg, factor_wi, l, k, tw.data());
+  sycl::sg_shared_state state;
+  std::vector<std::vector<T>> priv(32, std::vector<T>(2 * factor_wi, T(0)));
+  for (int l = 0; l < factor_sg; ++l)
+    for (int k = 0; k < factor_wi; ++k) {
+      priv[l][2 * k] = in[2 * (l * factor_wi + k)];
+      priv[l][2 * k + 1] = in[2 * (l * factor_wi + k) + 1];
+    }
+  std::vector<std::thread> lanes;
+  for (int l = 0; l < 32; ++l)
+    lanes.emplace_back([&, l] {
+      sycl::sub_group sg(&state, static_cast<sycl::sub_group::linear_id_type>(l));
+      std::vector<T> scratch(4 * 2 * 64 + 8 * factor_wi);
+      portfft::sg_dft<32>(priv[l].data(), sg, factor_wi, factor_sg, tw.data(), scratch.data());
+    });
+  for (auto& t : lanes) t.join();
+  // output is transposed: lane l slot j holds X[j*factor_sg + l] (subgroup.hpp:262-263)
+  for (int l = 0; l < factor_sg; ++l)
+    for (int j = 0; j < factor_wi; ++j) {
+      out[2 * (j * factor_sg + l)] = priv[l][2 * j];
+      out[2 * (j * factor_sg + l) + 1] = priv[l][2 * j + 1];
+    }
+}
+
+}  // namespace
+
+extern "C" {
+void ref_wi_dft_f32(const float* in, float* out, int n) { run_wi<float>(in, out, n); }
+void ref_wi_dft_f64(const double* in, double* out, int n) { run_wi<double>(in, out, n); }
+void ref_sg_dft_f32(const float* in, float* out, int factor_wi, int factor_sg) { run_sg<float>(in, out, factor_wi, factor_sg); }
+void ref_sg_dft_f64(const double* in, double* out, int factor_wi, int factor_sg) { run_sg<double>(in, out, factor_wi, factor_sg); }
+long long refshim_factorize(long long n) { return portfft::detail::factorize<long long>(n); }
+long long refshim_wi_temps(long long n) { return portfft::detail::wi_temps<long long>(n); }
+int refshim_fits_in_wi(long long n, int is_double) {
+  return is_double ? portfft::detail::fits_in_wi<double>(n) : portfft::detail::fits_in_wi<float>(n);
+}
+long long refshim_factorize_sg(long long n, int sg) { return portfft::detail::factorize_sg<long long>(n, sg); }
+int refshim_fits_in_sg(long long n, int sg, int is_double) {
+  return is_double ? portfft::detail::fits_in_sg<double>(n, sg) : portfft::detail::fits_in_sg<float>(n, sg);
+}
+}

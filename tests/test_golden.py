@@ -1,0 +1,100 @@
+"""Committed golden fixtures (tests/golden, made by tools/make_golden.py in the authoring container):
+numpy_* = the reference test generator's input/expected pairs, refcode_* = outputs of the reference's own wi_dft /
+sg_dft code.  CPU tests keep the oracle honest on the GPU box; the GPU test runs the CUDA path against them."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+import portfft_oracle as o
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def _numpy_fixtures():
+    return sorted(glob.glob(os.path.join(GOLD, "numpy_*.npz")))
+
+
+def test_fixtures_present():
+    assert len(_numpy_fixtures()) == 12
+    assert os.path.exists(os.path.join(GOLD, "refcode_f32.npz")) and os.path.exists(os.path.join(GOLD, "refcode_f64.npz"))
+
+
+@pytest.mark.parametrize("path", _numpy_fixtures(), ids=os.path.basename)
+def test_oracle_reproduces_numpy_fixture(path):
+    """Same bytes for the input stream, same transform to rounding, whatever numpy this machine has."""
+    f = np.load(path)
+    x, y = f["input"], f["output"]
+    dbl = x.dtype == np.complex128
+    x2, y2 = o.gen_data(x.shape[0], list(x.shape[1:]), dbl)
+    assert np.array_equal(x, x2)
+    assert np.linalg.norm(y - y2) <= 4 * np.finfo(x.real.dtype).eps * np.linalg.norm(y)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_refcode_fixture_agrees_with_oracle(tag):
+    f = np.load(os.path.join(GOLD, f"refcode_{tag}.npz"))
+    dbl = tag == "f64"
+    pos = 0
+    for n in f["sizes"]:
+        n = int(n)
+        x = f["inputs"][pos:pos + n]
+        out = f["outputs"][pos:pos + n]
+        pos += n
+        x2, y2 = o.gen_data(1, [n], dbl)
+        assert np.array_equal(x, x2.reshape(-1))
+        assert np.linalg.norm(out - y2.reshape(-1)) <= o.rel_l2_bound(n, dbl) * np.linalg.norm(y2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_cuda_matches_reference_code_outputs(tag):
+    """CUDA path vs what the reference's own wi_dft / sg_dft code produced on the same inputs."""
+    import torch
+
+    import portfft_b200 as pf
+
+    f = np.load(os.path.join(GOLD, f"refcode_{tag}.npz"))
+    dbl = tag == "f64"
+    pos = 0
+    for n in f["sizes"]:
+        n = int(n)
+        x = f["inputs"][pos:pos + n]
+        ref = f["outputs"][pos:pos + n]
+        pos += n
+        d = pf.descriptor([n], "double" if dbl else "float")
+        c = d.commit(torch.cuda.current_stream(), 0)
+        tin = torch.from_numpy(x.copy()).cuda()
+        tout = torch.empty_like(tin)
+        c.compute_forward(tin, tout)
+        torch.cuda.synchronize()
+        got = tout.cpu().numpy()
+        assert np.linalg.norm(got - ref) <= o.rel_l2_bound(n, dbl) * np.linalg.norm(ref), n
+        c.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _numpy_fixtures(), ids=os.path.basename)
+def test_cuda_matches_numpy_fixture(path):
+    import torch
+
+    import portfft_b200 as pf
+
+    f = np.load(path)
+    x, y = f["input"], f["output"]
+    dbl = x.dtype == np.complex128
+    d = pf.descriptor(list(x.shape[1:]), "double" if dbl else "float")
+    d.number_of_transforms = x.shape[0]
+    c = d.commit(torch.cuda.current_stream(), 0)
+    tin = torch.from_numpy(x.reshape(-1).copy()).cuda()
+    tout = torch.empty_like(tin)
+    c.compute_forward(tin, tout)
+    torch.cuda.synchronize()
+    n = int(np.prod(x.shape[1:]))
+    got = tout.cpu().numpy().reshape(x.shape[0], -1)
+    yy = y.reshape(x.shape[0], -1)
+    err = np.max(np.linalg.norm(got - yy, axis=1) / np.linalg.norm(yy, axis=1))
+    assert err <= o.rel_l2_bound(n, dbl)
+    c.destroy()
