@@ -8,9 +8,11 @@
 // workgroup_dispatcher.hpp:382-443, global_dispatcher.hpp:107-256).
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -86,8 +88,17 @@ struct pfft_plan {
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
   std::vector<void*> owned;
+  // pfft_compute_host pipeline: copy streams, per-chunk events, sub-batch plans (number_of_transforms -> plan)
+  cudaStream_t copy_stream[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> chunk_up, chunk_done;
+  std::map<size_t, pfft_plan*> child;
 
   ~pfft_plan() {
+    for (auto& kv : child) delete kv.second;
+    for (cudaEvent_t e : chunk_up) cudaEventDestroy(e);
+    for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
+    for (cudaStream_t s : copy_stream)
+      if (s) cudaStreamDestroy(s);
     for (void* p : owned) cudaFree(p);
     if (scratch) cudaFree(scratch);
     for (void* p : stage)
@@ -210,6 +221,117 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   }
 }
 
+static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream) {
+  PFFT_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PFFT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  DeviceLimits lim;
+  lim.num_sms = prop.multiProcessorCount;
+  lim.max_smem_per_block = prop.sharedMemPerBlockOptin;
+  std::unique_ptr<pfft_plan> plan(new pfft_plan);
+  plan->host = build_plan(d, lim);
+  plan->device = device;
+  plan->stream = stream;
+  commit_device(plan.get());
+  return plan.release();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// pfft_compute_host: batch-chunked pipeline.  Chunk c is copied to the device on copy stream 0, transformed on the
+// plan's stream and copied back on copy stream 1, so that H2D of chunk c+1, the kernels of chunk c and D2H of
+// chunk c-1 overlap (PCIe is full duplex; the kernels are ~50x shorter than either copy).
+// ---------------------------------------------------------------------------------------------------------------
+struct HostDomain {
+  size_t dist, off, extent, count;
+};
+
+static HostDomain host_domain(const DescHost& d, int dir) {
+  HostDomain h;
+  h.dist = d.distance(dir);
+  h.off = d.offset(dir);
+  h.extent = 1;
+  for (size_t i = 0; i < d.lengths.size(); ++i) h.extent += (d.lengths[i] - 1) * d.strides(dir)[i];
+  h.count = d.buffer_count(dir);
+  return h;
+}
+
+static void compute_host_monolithic(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                                    void* out_imag, char* din, char* dout, size_t plane_in, size_t plane_out) {
+  const DescHost& d = plan->host.desc;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
+  const bool inplace = in == out;
+  cudaStream_t s = plan->stream;
+  PFFT_CUDA_CHECK(cudaMemcpyAsync(din, in, plane_in, cudaMemcpyHostToDevice, s));
+  if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
+  // elements of the output buffer that the descriptor does not address must survive the round trip
+  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
+  if (!inplace && !out_dense) {
+    PFFT_CUDA_CHECK(cudaMemcpyAsync(dout, out, plane_out, cudaMemcpyHostToDevice, s));
+    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
+  }
+  execute(plan, direction, din, il ? nullptr : din + plane_in, dout, il ? nullptr : dout + plane_out, s);
+  PFFT_CUDA_CHECK(cudaMemcpyAsync(out, dout, plane_out, cudaMemcpyDeviceToHost, s));
+  if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(out_imag, dout + plane_out, plane_out, cudaMemcpyDeviceToHost, s));
+  PFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
+static void compute_host_pipelined(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
+                                   void* out_imag, char* din, char* dout, size_t plane_in, size_t plane_out,
+                                   size_t chunks) {
+  const DescHost& d = plan->host.desc;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
+  const bool inplace = in == out;
+  const size_t esz = (d.is_double ? 8 : 4) * (il ? 2 : 1);  // bytes of one addressed unit of a plane
+  const HostDomain hi = host_domain(d, direction), ho = host_domain(d, odir);
+  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
+  const size_t batch = d.number_of_transforms;
+  const size_t per = (batch + chunks - 1) / chunks;
+  chunks = (batch + per - 1) / per;
+  for (int i = 0; i < 2; ++i)
+    if (!plan->copy_stream[i]) PFFT_CUDA_CHECK(cudaStreamCreateWithFlags(&plan->copy_stream[i], cudaStreamNonBlocking));
+  while (plan->chunk_up.size() < chunks) {
+    cudaEvent_t a, b;
+    PFFT_CUDA_CHECK(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+    PFFT_CUDA_CHECK(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+    plan->chunk_up.push_back(a);
+    plan->chunk_done.push_back(b);
+  }
+  cudaStream_t s_up = plan->copy_stream[0], s_dn = plan->copy_stream[1], s = plan->stream;
+  for (size_t c = 0; c < chunks; ++c) {
+    const size_t b0 = c * per, b1 = std::min(batch, b0 + per), nb = b1 - b0;
+    pfft_plan*& sub = plan->child[nb];
+    if (sub == nullptr) {
+      DescHost dc = d;
+      dc.number_of_transforms = nb;
+      sub = make_plan(dc, plan->device, s);
+    }
+    // byte ranges of this chunk in the input and output planes
+    const size_t i0 = c == 0 ? 0 : (hi.off + b0 * hi.dist) * esz, i1 = b1 == batch ? plane_in : (hi.off + b1 * hi.dist) * esz;
+    const size_t o0 = c == 0 ? 0 : (ho.off + b0 * ho.dist) * esz, o1 = b1 == batch ? plane_out : (ho.off + b1 * ho.dist) * esz;
+    PFFT_CUDA_CHECK(cudaMemcpyAsync(din + i0, (const char*)in + i0, i1 - i0, cudaMemcpyHostToDevice, s_up));
+    if (!il)
+      PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in + i0, (const char*)in_imag + i0, i1 - i0, cudaMemcpyHostToDevice, s_up));
+    if (!inplace && !out_dense) {
+      PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + o0, (const char*)out + o0, o1 - o0, cudaMemcpyHostToDevice, s_up));
+      if (!il)
+        PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out + o0, (const char*)out_imag + o0, o1 - o0, cudaMemcpyHostToDevice, s_up));
+    }
+    PFFT_CUDA_CHECK(cudaEventRecord(plan->chunk_up[c], s_up));
+    PFFT_CUDA_CHECK(cudaStreamWaitEvent(s, plan->chunk_up[c], 0));
+    const size_t pi = b0 * hi.dist * esz, po = b0 * ho.dist * esz;  // the sub-plan keeps the descriptor's offsets
+    execute(sub, direction, din + pi, il ? nullptr : din + plane_in + pi, dout + po, il ? nullptr : dout + plane_out + po, s);
+    PFFT_CUDA_CHECK(cudaEventRecord(plan->chunk_done[c], s));
+    PFFT_CUDA_CHECK(cudaStreamWaitEvent(s_dn, plan->chunk_done[c], 0));
+    PFFT_CUDA_CHECK(cudaMemcpyAsync((char*)out + o0, dout + o0, o1 - o0, cudaMemcpyDeviceToHost, s_dn));
+    if (!il)
+      PFFT_CUDA_CHECK(cudaMemcpyAsync((char*)out_imag + o0, dout + plane_out + o0, o1 - o0, cudaMemcpyDeviceToHost, s_dn));
+  }
+  PFFT_CUDA_CHECK(cudaStreamSynchronize(s_dn));
+  PFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+}
+
 template <typename F>
 static pfft_status guarded(F&& f) {
   try {
@@ -269,18 +391,7 @@ pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_pl
     *plan_out = nullptr;
     DescHost d = desc_from_c(desc);
     validate_descriptor(d);  // host-only errors first, before any CUDA call
-    PFFT_CUDA_CHECK(cudaSetDevice(device));
-    cudaDeviceProp prop;
-    PFFT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    DeviceLimits lim;
-    lim.num_sms = prop.multiProcessorCount;
-    lim.max_smem_per_block = prop.sharedMemPerBlockOptin;
-    std::unique_ptr<pfft_plan> plan(new pfft_plan);
-    plan->host = build_plan(d, lim);
-    plan->device = device;
-    plan->stream = (cudaStream_t)stream;
-    commit_device(plan.get());
-    *plan_out = plan.release();
+    *plan_out = make_plan(d, device, (cudaStream_t)stream);
   });
 }
 
@@ -317,21 +428,22 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
         plan->stage_bytes[i] = need[i];
       }
     }
-    cudaStream_t s = plan->stream;
     char* din = (char*)plan->stage[0];
     char* dout = inplace ? din : (char*)plan->stage[1];
-    PFFT_CUDA_CHECK(cudaMemcpyAsync(din, in, plane_in, cudaMemcpyHostToDevice, s));
-    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
-    // elements of the output buffer that the descriptor does not address must survive the round trip
-    const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
-    if (!inplace && !out_dense) {
-      PFFT_CUDA_CHECK(cudaMemcpyAsync(dout, out, plane_out, cudaMemcpyHostToDevice, s));
-      if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
+    // Chunk along the batch when both domains are batch-major (every transform lives inside its own
+    // [offset + b*distance, offset + (b+1)*distance) window); otherwise one H2D / compute / D2H sequence.
+    const HostDomain hi = host_domain(d, direction), ho = host_domain(d, odir);
+    const size_t batch = d.number_of_transforms;
+    size_t chunks = 1;
+    if (batch >= 2 && hi.extent <= hi.dist && ho.extent <= ho.dist) {
+      const char* env = std::getenv("PFFT_HOST_CHUNK_BYTES");
+      const size_t target = env ? (size_t)std::atoll(env) : ((size_t)32 << 20);
+      chunks = std::min<size_t>(std::min<size_t>(batch, 64), std::max<size_t>(1, (plane_in * planes) / std::max<size_t>(1, target)));
     }
-    execute(plan, direction, din, il ? nullptr : din + plane_in, dout, il ? nullptr : dout + plane_out, s);
-    PFFT_CUDA_CHECK(cudaMemcpyAsync(out, dout, plane_out, cudaMemcpyDeviceToHost, s));
-    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(out_imag, dout + plane_out, plane_out, cudaMemcpyDeviceToHost, s));
-    PFFT_CUDA_CHECK(cudaStreamSynchronize(s));
+    if (chunks <= 1)
+      compute_host_monolithic(plan, direction, in, in_imag, out, out_imag, din, dout, plane_in, plane_out);
+    else
+      compute_host_pipelined(plan, direction, in, in_imag, out, out_imag, din, dout, plane_in, plane_out, chunks);
   });
 }
 

@@ -13,6 +13,7 @@
 //   * backward = swap(re, im) on load and store (no conjugation pass), scale fused on store.
 // Hot sizes have fully specialised kernels (wg_pow2.cu); this one guarantees coverage.
 #include "device_utils.cuh"
+#include "io.cuh"
 #include "kernels.h"
 #include "pass.h"
 
@@ -21,43 +22,6 @@ namespace pfft {
 template <typename T>
 __device__ __forceinline__ int padidx(int i) {
   return i + (i >> (sizeof(T) == 4 ? 4 : 3));
-}
-
-struct IoFlags {
-  bool il;    // interleaved storage
-  bool swap;  // backward direction on interleaved storage (split storage swaps the pointers on the host)
-};
-
-template <typename T>
-__device__ __forceinline__ cx<T> gload(const PassParams& p, IoFlags fl, long long idx) {
-  cx<T> v;
-  if (fl.il) {
-    v = reinterpret_cast<const cx<T>*>(p.in_re)[idx];
-    if (fl.swap) {
-      T t = v.x;
-      v.x = v.y;
-      v.y = t;
-    }
-  } else {
-    v.x = reinterpret_cast<const T*>(p.in_re)[idx];
-    v.y = reinterpret_cast<const T*>(p.in_im)[idx];
-  }
-  return v;
-}
-
-template <typename T>
-__device__ __forceinline__ void gstore(const PassParams& p, IoFlags fl, long long idx, cx<T> v) {
-  if (fl.il) {
-    if (fl.swap) {
-      T t = v.x;
-      v.x = v.y;
-      v.y = t;
-    }
-    reinterpret_cast<cx<T>*>(p.out_re)[idx] = v;
-  } else {
-    reinterpret_cast<T*>(p.out_re)[idx] = v.x;
-    reinterpret_cast<T*>(p.out_im)[idx] = v.y;
-  }
 }
 
 // multiply by the inter-factor twiddle w_{gtw_n}^{c*k} and the scale (both optional), then store.

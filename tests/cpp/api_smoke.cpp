@@ -19,6 +19,9 @@ static double check(std::size_t n, std::size_t batch) {
   desc.backward_scale = T(1) / T(n);
   cudaStream_t s;
   cudaStreamCreate(&s);
+  double fwd_err = 0, err = 0, nrm = 0;
+  std::complex<T>* dev = nullptr;
+  {  // the committed descriptor must be gone before its stream is destroyed (its destructor synchronises the stream)
   queue q(s);
   auto committed = desc.commit(q);
   std::vector<std::complex<T>> host(n * batch), ref(n * batch), back(n * batch);
@@ -30,18 +33,16 @@ static double check(std::size_t n, std::size_t batch) {
         acc += std::complex<double>(host[b * n + j]) * std::polar(1.0, -2.0 * M_PI * double(j * k % n) / double(n));
       ref[b * n + k] = std::complex<T>(acc);
     }
-  std::complex<T>* dev;
   cudaMalloc(&dev, sizeof(std::complex<T>) * host.size());
   cudaMemcpyAsync(dev, host.data(), sizeof(std::complex<T>) * host.size(), cudaMemcpyHostToDevice, s);
   event e1 = committed.compute_forward(dev);
   e1.wait();
   cudaMemcpy(back.data(), dev, sizeof(std::complex<T>) * host.size(), cudaMemcpyDeviceToHost);
-  double err = 0, nrm = 0;
   for (std::size_t i = 0; i < host.size(); ++i) {
     err += std::norm(std::complex<double>(back[i]) - std::complex<double>(ref[i]));
     nrm += std::norm(std::complex<double>(ref[i]));
   }
-  double fwd_err = std::sqrt(err / nrm);
+  fwd_err = std::sqrt(err / nrm);
   event e2 = committed.compute_backward(dev, {e1});
   e2.wait();
   cudaMemcpy(back.data(), dev, sizeof(std::complex<T>) * host.size(), cudaMemcpyDeviceToHost);
@@ -49,6 +50,7 @@ static double check(std::size_t n, std::size_t batch) {
   for (std::size_t i = 0; i < host.size(); ++i) {
     err += std::norm(std::complex<double>(back[i]) - std::complex<double>(host[i]));
     nrm += std::norm(std::complex<double>(host[i]));
+  }
   }
   cudaFree(dev);
   cudaStreamDestroy(s);

@@ -139,3 +139,35 @@ def run_case(tp: CaseParams, device: int = 0, rel_l2_tol: Optional[float] = None
         actual = (out_re.cpu().numpy() + 1j * out_im.cpu().numpy()).astype(host_ref.dtype)
     committed.destroy()
     return oracle.verify_dft(od, dr, host_ref, actual, rel_l2_tol)
+
+
+def run_case_host(tp: CaseParams, device: int = 0) -> float:
+    """Same parity case through the end-to-end entry point `pfft_compute_host` (HOST buffers, H2D/D2H inside the
+    call; chunk-pipelined when the layout is batch-major).  The output buffer is pre-filled with the padding value,
+    which must survive wherever the descriptor addresses nothing."""
+    import torch
+
+    d, od = make_descriptors(tp)
+    dr = oracle.FORWARD if tp.dir == "fwd" else oracle.BACKWARD
+    host_in, host_ref = oracle.expected_io(od, dr)
+    in_place = tp.placement == "IP"
+    split = tp.storage == "split"
+    committed = d.commit(torch.cuda.current_stream(torch.device("cuda", device)), device)
+    pdir = pf.direction.FORWARD if tp.dir == "fwd" else pf.direction.BACKWARD
+    pad = oracle.PADDING_VALUE
+    if not split:
+        h_in = np.ascontiguousarray(host_in)
+        h_out = h_in if in_place else np.full(host_ref.shape, complex(pad, pad), dtype=host_ref.dtype)
+        committed.compute_host(pdir, h_in, None, h_out, None)
+        actual = h_out
+    else:
+        in_re, in_im = np.ascontiguousarray(host_in.real), np.ascontiguousarray(host_in.imag)
+        if in_place:
+            out_re, out_im = in_re, in_im
+        else:
+            out_re = np.full(host_ref.shape, pad, dtype=in_re.dtype)
+            out_im = np.full(host_ref.shape, pad, dtype=in_re.dtype)
+        committed.compute_host(pdir, in_re, in_im, out_re, out_im)
+        actual = (out_re + 1j * out_im).astype(host_ref.dtype)
+    committed.destroy()
+    return oracle.verify_dft(od, dr, host_ref, actual)
