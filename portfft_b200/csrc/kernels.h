@@ -5,6 +5,7 @@
 #include <cstddef>
 
 #include "pass.h"
+#include "plan.h"
 
 namespace pfft {
 
@@ -15,6 +16,19 @@ inline size_t wg_generic_smem_bytes(int ffts_per_block, int pitch, size_t scalar
 // WORKGROUP level, generic (wg_generic.cu)
 cudaError_t launch_wg_generic(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid,
                               cudaStream_t stream);
+
+// WORKITEM level (wi.cuh, wi_f32.cu, wi_f64.cu): one thread per transform, n <= kWiMaxN
+inline size_t wi_smem_bytes(int n, size_t scalar_bytes) {
+  return (size_t)kWiBlock * (n | 1) * 2 * scalar_bytes + (size_t)kWiBlock * sizeof(long long);
+}
+cudaError_t launch_wi_f32(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
+cudaError_t launch_wi_f64(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
+
+// SUBGROUP level (sg.cuh, sg_f32.cu, sg_f64.cu): n = lanes * m, `lanes` (power of two <= 32) threads per transform,
+// m <= kSgMaxM points per lane, cross-lane stages through __shfl_xor_sync
+inline size_t sg_smem_bytes(int m, size_t scalar_bytes) { return (size_t)kSgBlock * (m | 1) * 2 * scalar_bytes; }
+cudaError_t launch_sg_f32(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
+cudaError_t launch_sg_f64(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
 // WORKGROUP level, N = R^3 specialisation with TMA-fed persistent CTAs (wg_cube.cu). variant 0: TMA ring, 1: direct loads
 cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream);

@@ -214,6 +214,12 @@ int pow2_ceil(long long v) {
 
 constexpr size_t kSoftSmem = 72 * 1024;  // three CTAs per SM
 
+// PFFT_FORCE_LEVEL=0/1/2 restricts the single-pass kernel choice (testing / benchmarking); unset: automatic
+int force_level() {
+  const char* env = std::getenv("PFFT_FORCE_LEVEL");
+  return env ? std::atoi(env) : -1;
+}
+
 struct BDim {
   long long n, in, out;
 };
@@ -334,6 +340,69 @@ void set_radices(PassParams& p, size_t n) {
   for (size_t i = 0; i < r.size(); ++i) p.radix[i] = r[i];
 }
 
+// WORKITEM level (wi.cuh): one thread per transform.  Staged (coalesced tile copy through shared memory) on a side
+// whose elements lie closer together than its batches, direct (lanes along the batch) otherwise.
+bool configure_wi(PassHost& ps, bool dbl, const DeviceLimits& lim) {
+  PassParams& p = ps.pp;
+  if (p.n > (dbl ? kWiMaxNDouble : kWiMaxNFloat) || p.gtw_dim >= 0) return false;
+  p.threads_per_fft = 1;
+  p.ffts_per_block = kWiBlock;
+  p.pitch = p.n | 1;
+  p.num_radices = 1;
+  p.radix[0] = p.n;
+  p.in_mode = (p.n > 1 && p.is < p.ibd[0]) ? IO_STAGED_ELEM : IO_DIRECT;
+  p.out_mode = (p.n > 1 && p.os < p.obd[0]) ? IO_STAGED_ELEM : IO_DIRECT;
+  if (p.nb[0] == 1) {  // a single transform per row: no batch neighbour to coalesce with
+    if (p.n > 1) p.in_mode = p.out_mode = IO_STAGED_ELEM;
+  }
+  ps.block = kWiBlock;
+  const bool staged = p.in_mode == IO_STAGED_ELEM || p.out_mode == IO_STAGED_ELEM;
+  ps.smem = staged ? (size_t)kWiBlock * p.pitch * (dbl ? 16 : 8) + (size_t)kWiBlock * 8 : 0;
+  const long long blocks = (p.batch_total + kWiBlock - 1) / kWiBlock;
+  ps.grid = (int)std::min<long long>(blocks, (long long)lim.num_sms * 16);
+  ps.kernel = KERNEL_WI;
+  ps.level = LEVEL_WORKITEM;
+  ps.tw_n = 0;
+  return true;
+}
+
+// SUBGROUP level (sg.cuh): n = lanes * m with lanes a power of two <= 32 and m points per lane; unit element strides.
+bool configure_sg(PassHost& ps, bool dbl, const DeviceLimits& lim) {
+  PassParams& p = ps.pp;
+  if (p.is != 1 || p.os != 1 || p.gtw_dim >= 0) return false;
+  const int max_m = dbl ? kSgMaxMDouble : kSgMaxMFloat;
+  int best_l = 0, best_m = 0;
+  for (int l = 2; l <= 32; l *= 2) {
+    if (p.n % l != 0) continue;
+    const int m = p.n / l;
+    if (m < 2 || m > max_m || !sg_supports_m(m, dbl)) continue;
+    // prefer the largest m <= 16 (fewest shuffle stages per element at moderate register use), else the smallest m
+    const bool better = best_m == 0 || (m <= 16 && (best_m > 16 || m > best_m)) || (m > 16 && best_m > 16 && m < best_m);
+    if (better) {
+      best_l = l;
+      best_m = m;
+    }
+  }
+  if (best_m == 0) return false;
+  p.threads_per_fft = best_l;
+  p.ffts_per_block = kSgBlock / best_l;
+  p.pitch = best_m | 1;
+  p.num_radices = 2;
+  p.radix[0] = best_m;
+  p.radix[1] = best_l;
+  p.in_mode = IO_DIRECT;
+  p.out_mode = IO_STAGED_ELEM;
+  ps.block = kSgBlock;
+  ps.smem = (size_t)kSgBlock * p.pitch * (dbl ? 16 : 8);
+  const long long per_block = (long long)(kSgBlock / 32) * (32 / best_l);
+  const long long blocks = (p.batch_total + per_block - 1) / per_block;
+  ps.grid = (int)std::min<long long>(blocks, (long long)lim.num_sms * 4);
+  ps.kernel = KERNEL_SG;
+  ps.level = LEVEL_SUBGROUP;
+  ps.tw_n = p.n;
+  return true;
+}
+
 // Hot sizes: hand-specialised kernels (same numerics, compile-time geometry). The generic configuration stays in
 // the pass as the fallback for unaligned pointers.
 void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
@@ -425,10 +494,15 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       ps.src = src0;
       ps.dst = BUF_OUT;
       ps.level = LEVEL_WORKGROUP;
-      configure_wg_generic(ps, dbl, lim, false);
-      select_specialised(ps, d, lim);
+      const int force = force_level();
+      if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, lim)) {
+      } else if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) {
+      } else {
+        configure_wg_generic(ps, dbl, lim, false);
+        select_specialised(ps, d, lim);
+      }
       passes.push_back(ps);
-      plan.dim_level[dim] = PFFT_LEVEL_WORKGROUP;
+      plan.dim_level[dim] = ps.level;
       continue;
     }
 

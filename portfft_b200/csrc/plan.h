@@ -66,6 +66,11 @@ struct PassHost {
   int variant = 0;
 };
 
+// geometry limits of the thread- and warp-level kernels (wi.cuh, sg.cuh); sg_supports_m lives in sg_f32.cu
+constexpr int kWiMaxNFloat = 32, kWiMaxNDouble = 16, kWiBlock = 128;
+constexpr int kSgMaxMFloat = 32, kSgMaxMDouble = 16, kSgBlock = 256;
+bool sg_supports_m(int m, bool is_double);
+
 struct PlanHost {
   DescHost desc;
   std::vector<PassHost> passes[2];  // [direction]

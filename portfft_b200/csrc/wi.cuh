@@ -1,0 +1,111 @@
+// WORKITEM level: one CUDA thread computes one whole transform of compile-time length N <= 32 in registers.
+//
+// Reference counterpart: workitem_impl + wi_dft (/root/reference/src/portfft/dispatcher/workitem_dispatcher.hpp:
+// 99-350, /root/reference/src/portfft/common/workitem.hpp:64-219): run-time-sized recursive Cooley-Tukey on a
+// `priv[2*56]` array, sub-group cooperative global -> padded local -> private staging, store modifiers.  Here:
+//   * N is a template parameter: the transform is one DFT<N,T>::run on N complex registers (dft.cuh), no loops over
+//     run-time sizes, no private-memory indexing;
+//   * DIRECT I/O: the thread reads / writes its own elements; lanes run along the batch index, so batch-interleaved
+//     layouts (distance 1) and the outer dimensions of N-D transforms are perfectly coalesced and need no shared
+//     memory at all (the reference's `interleaved_transforms_input` path, workitem_dispatcher.hpp:215-229);
+//   * STAGED I/O (unit element stride): the CTA's tile of transforms is copied cooperatively with lanes along the
+//     element index (coalesced) through shared memory with an odd pitch, so that the per-thread strided reads are
+//     bank-conflict free (the reference pads with pad_local, memory_views.hpp:79-85);
+//   * backward = (re <-> im) swap, scale fused on store; all N loads of a thread are in flight together.
+#pragma once
+#include "io.cuh"
+#include "kernels.h"
+
+namespace pfft {
+
+constexpr int kWiThreads = kWiBlock;
+
+template <int N>
+__host__ __device__ constexpr int wi_pitch() {
+  return N | 1;
+}
+
+template <int N, typename T>
+__global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, const bool il, const bool swap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  constexpr int PITCH = wi_pitch<N>();
+  constexpr int F = kWiThreads;
+  cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
+  long long* s_base = reinterpret_cast<long long*>(buf + (size_t)F * PITCH);
+  const IoFlags fl{il, swap};
+  const int tid = threadIdx.x;
+  const bool one_dim = single_batch_dim(p);
+  const bool in_staged = p.in_mode == IO_STAGED_ELEM, out_staged = p.out_mode == IO_STAGED_ELEM;
+  const bool in_contig = one_dim && p.is == 1 && p.ibd[0] == N, out_contig = one_dim && p.os == 1 && p.obd[0] == N;
+  const T scale = T(p.scale);
+
+  for (long long g0 = (long long)blockIdx.x * F; g0 < p.batch_total; g0 += (long long)gridDim.x * F) {
+    const int nf = (int)min((long long)F, p.batch_total - g0);
+    const bool active = tid < nf;
+    long long ib = 0, ob = 0;
+    if (active) batch_bases(p, one_dim, g0 + tid, ib, ob);
+    cx<T> v[N];
+    if (in_staged) {
+      __syncthreads();  // previous iteration's staged stores have left the buffer
+      if (!in_contig) {
+        if (active) s_base[tid] = ib;
+        __syncthreads();
+      }
+      const long long tile0 = p.ioff + g0 * (long long)N;
+      const int total = nf * N;
+#pragma unroll 4
+      for (int e = tid; e < total; e += F) {
+        const int ff = e / N, i = e - ff * N;
+        buf[ff * PITCH + i] = gload<T>(p, fl, in_contig ? tile0 + e : s_base[ff] + i * p.is);
+      }
+      __syncthreads();
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = buf[tid * PITCH + j];
+      }
+    } else if (active) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = gload<T>(p, fl, ib + (long long)j * p.is);
+    }
+    if (active) {
+      DFT<N, T>::run(v);
+      if (p.apply_scale) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = cscale(v[j], scale);
+      }
+    }
+    if (out_staged) {
+      __syncthreads();  // every thread has read its staged input
+      if (active) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) buf[tid * PITCH + j] = v[j];
+        if (!out_contig) s_base[tid] = ob;
+      }
+      __syncthreads();
+      const long long tile0 = p.ooff + g0 * (long long)N;
+      const int total = nf * N;
+#pragma unroll 4
+      for (int e = tid; e < total; e += F) {
+        const int ff = e / N, i = e - ff * N;
+        gstore<T>(p, fl, out_contig ? tile0 + e : s_base[ff] + i * p.os, buf[ff * PITCH + i]);
+      }
+    } else if (active) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) gstore<T>(p, fl, ob + (long long)j * p.os, v[j]);
+    }
+  }
+}
+
+template <int N, typename T>
+cudaError_t launch_wi_n(const PassParams& p, bool il, bool swap, int grid, cudaStream_t stream) {
+  const bool staged = p.in_mode == IO_STAGED_ELEM || p.out_mode == IO_STAGED_ELEM;
+  const size_t smem = staged ? wi_smem_bytes(N, sizeof(T)) : 0;
+  if (smem > 48 * 1024) {
+    cudaError_t e = cudaFuncSetAttribute(wi_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+  }
+  wi_kernel<N, T><<<grid, kWiThreads, smem, stream>>>(p, il, swap);
+  return cudaGetLastError();
+}
+
+}  // namespace pfft
