@@ -73,6 +73,21 @@ typedef struct pfft_desc {
 
 typedef struct pfft_plan pfft_plan;
 
+/* One additional independent batch dimension (FFTW-guru style "howmany" dimension) on top of number_of_transforms.
+ * The reference has no counterpart (one batch dimension, one device: committed_descriptor_impl.hpp:109); these exist
+ * for the multi-GPU slab decomposition, whose local passes read x-slabs and write blocks addressed by
+ * (destination GPU, plane, row).  Distances count elements like forward_distance / backward_distance. */
+typedef struct pfft_batch_dim {
+  size_t count;
+  size_t forward_distance;
+  size_t backward_distance;
+} pfft_batch_dim;
+
+/* pfft_commit_guru flag: the LAST extra batch dimension does not address the output buffer by a distance but selects
+ * one of several output buffers (pfft_compute_peer): entry i of the pointer table receives the transforms whose
+ * index along that dimension is i.  With peer-mapped device memory the stores of the last pass ARE the exchange. */
+enum { PFFT_GURU_PEER_LAST_DIM = 1 };
+
 /* Host-only: the reference's commit-time validation. Never touches the GPU. */
 pfft_status pfft_validate(const pfft_desc* desc);
 
@@ -89,12 +104,22 @@ pfft_status pfft_plan_describe(const pfft_desc* desc, int direction, char* buf, 
  * queue the plan is committed to; it is used for the one-off table uploads and as default stream of pfft_compute. */
 pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_plan** plan_out);
 
+/* pfft_commit with `n_extra` additional batch dimensions (1-D descriptors only; at most 2). */
+pfft_status pfft_commit_guru(const pfft_desc* desc, size_t n_extra, const pfft_batch_dim* extra, int flags, int device,
+                             void* stream, pfft_plan** plan_out);
+
 /* Asynchronous, stream-ordered transform on device pointers. Interleaved storage: `in` / `out` point at complex
  * arrays and the *_imag pointers must be NULL. Split storage: real and imaginary arrays. in == out is the in-place
  * call. A storage mismatch with the descriptor returns PFFT_INVALID_CONFIGURATION
  * (committed_descriptor_impl.hpp:862-871). `stream` may be NULL to use the commit stream. */
 pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
                          void* out_imag, void* stream);
+
+/* pfft_compute for a plan committed with PFFT_GURU_PEER_LAST_DIM: `out[i]` (and `out_imag[i]` for split storage) is
+ * the output buffer for index i of the last extra batch dimension; n_peers must equal that dimension's count.  The
+ * buffers may live on other GPUs (peer access / symmetric memory). */
+pfft_status pfft_compute_peer(pfft_plan* plan, int direction, const void* in, const void* in_imag, size_t n_peers,
+                              void* const* out, void* const* out_imag, void* stream);
 
 /* End-to-end convenience for callers holding HOST buffers: H2D of the input, pfft_compute, D2H of the output, one
  * stream synchronisation. Buffers are sized by pfft_get_buffer_count (elements) and staged through plan-owned

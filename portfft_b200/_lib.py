@@ -33,6 +33,12 @@ class pfft_desc(ctypes.Structure):
     ]
 
 
+class pfft_batch_dim(ctypes.Structure):
+    """`pfft_batch_dim` (include/pfft.h): one extra batch dimension of pfft_commit_guru."""
+
+    _fields_ = [("count", c_size_t), ("forward_distance", c_size_t), ("backward_distance", c_size_t)]
+
+
 # every symbol include/pfft.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pfft_validate": (c_int, [POINTER(pfft_desc)]),
@@ -41,6 +47,10 @@ SYMBOLS = {
     "pfft_get_layout": (c_int, [POINTER(pfft_desc), c_int]),
     "pfft_plan_describe": (c_int, [POINTER(pfft_desc), c_int, c_char_p, c_size_t, POINTER(c_size_t)]),
     "pfft_commit": (c_int, [POINTER(pfft_desc), c_int, c_void_p, POINTER(c_void_p)]),
+    "pfft_commit_guru": (c_int, [POINTER(pfft_desc), c_size_t, POINTER(pfft_batch_dim), c_int, c_int, c_void_p,
+                                 POINTER(c_void_p)]),
+    "pfft_compute_peer": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_void_p),
+                                  c_void_p]),
     "pfft_compute": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfft_compute_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfft_destroy": (c_int, [c_void_p]),

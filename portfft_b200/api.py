@@ -210,11 +210,21 @@ class descriptor:
         _check(_lib.load().pfft_plan_describe(ctypes.byref(c), int(d), buf, needed.value, None))
         return buf.value.decode()
 
-    def commit(self, queue=None, device: int = 0) -> "committed_descriptor":
-        """descriptor::commit(sycl::queue&) (descriptor.hpp:152-156): validate, then build the plan on `device`."""
+    def commit(self, queue=None, device: int = 0, extra=None, peer_last: bool = False) -> "committed_descriptor":
+        """descriptor::commit(sycl::queue&) (descriptor.hpp:152-156): validate, then build the plan on `device`.
+
+        `extra` (no reference counterpart; used by portfft_b200.distributed): additional batch dimensions as
+        (count, forward_distance, backward_distance) tuples -> pfft_commit_guru; `peer_last`: the last one selects an
+        output buffer of compute_forward_peer."""
         c, keep = self._c_desc()
         handle = ctypes.c_void_p()
-        _check(_lib.load().pfft_commit(ctypes.byref(c), int(device), _stream_handle(queue), ctypes.byref(handle)))
+        if extra:
+            dims = (_lib.pfft_batch_dim * len(extra))(*[_lib.pfft_batch_dim(int(a), int(b), int(cc))
+                                                        for a, b, cc in extra])
+            _check(_lib.load().pfft_commit_guru(ctypes.byref(c), len(extra), dims, 1 if peer_last else 0, int(device),
+                                                _stream_handle(queue), ctypes.byref(handle)))
+        else:
+            _check(_lib.load().pfft_commit(ctypes.byref(c), int(device), _stream_handle(queue), ctypes.byref(handle)))
         return committed_descriptor(self, handle, device)
 
 
@@ -264,6 +274,15 @@ class committed_descriptor:
 
     def compute_backward(self, *args, queue=None):
         self._dispatch(direction.BACKWARD, args, queue)
+
+    def compute_forward_peer(self, in_, outs, in_imag=None, outs_imag=None, queue=None):
+        """pfft_compute_peer: `outs[i]` receives the transforms whose index along the last extra batch dimension is i
+        (buffers may be peer-mapped memory of other GPUs)."""
+        n = len(outs)
+        tab = (ctypes.c_void_p * n)(*[_ptr(o) for o in outs])
+        tab_im = (ctypes.c_void_p * n)(*[_ptr(o) for o in outs_imag]) if outs_imag is not None else None
+        _check(_lib.load().pfft_compute_peer(self._handle, int(direction.FORWARD), _ptr(in_), _ptr(in_imag), n, tab,
+                                             tab_im, _stream_handle(queue)))
 
     def compute_host(self, d: direction, in_, in_imag, out, out_imag):
         """End-to-end call on HOST (numpy) buffers: H2D + compute + D2H through pfft_compute_host."""

@@ -32,18 +32,26 @@ __device__ __forceinline__ cx<T> gload(const PassParams& p, IoFlags fl, long lon
   return v;
 }
 
+// `peer` < 0: the pass's own output buffer; otherwise entry `peer` of the peer table (memory of another GPU mapped
+// into this address space: the store itself is the NVLink transfer)
 template <typename T>
-__device__ __forceinline__ void gstore(const PassParams& p, IoFlags fl, long long idx, cx<T> v) {
+__device__ __forceinline__ void gstore(const PassParams& p, IoFlags fl, long long idx, cx<T> v, int peer = -1) {
+  void* re = p.out_re;
+  void* im = p.out_im;
+  if (peer >= 0) {
+    re = p.out_tab_re[peer];
+    im = p.out_tab_im[peer];
+  }
   if (fl.il) {
     if (fl.swap) {
       T t = v.x;
       v.x = v.y;
       v.y = t;
     }
-    reinterpret_cast<cx<T>*>(p.out_re)[idx] = v;
+    reinterpret_cast<cx<T>*>(re)[idx] = v;
   } else {
-    reinterpret_cast<T*>(p.out_re)[idx] = v.x;
-    reinterpret_cast<T*>(p.out_im)[idx] = v.y;
+    reinterpret_cast<T*>(re)[idx] = v.x;
+    reinterpret_cast<T*>(im)[idx] = v.y;
   }
 }
 
@@ -51,12 +59,14 @@ __device__ __forceinline__ bool single_batch_dim(const PassParams& p) {
   return p.nb[1] == 1 && p.nb[2] == 1 && p.nb[3] == 1;
 }
 
-// input / output base offsets (complex elements) of batch entry g
+// input / output base offsets (complex elements) of batch entry g; `peer` = index along p.peer_dim (or -1)
 __device__ __forceinline__ void batch_bases(const PassParams& p, bool one_dim, long long g, long long& ib,
-                                            long long& ob) {
+                                            long long& ob, int& peer) {
+  peer = -1;
   if (one_dim) {
     ib = p.ioff + g * p.ibd[0];
     ob = p.ooff + g * p.obd[0];
+    if (p.peer_dim == 0) peer = (int)g;
     return;
   }
   ib = p.ioff;
@@ -68,6 +78,7 @@ __device__ __forceinline__ void batch_bases(const PassParams& p, bool one_dim, l
     g = q;
     ib += b * p.ibd[d];
     ob += b * p.obd[d];
+    if (d == p.peer_dim) peer = (int)b;
   }
 }
 

@@ -10,7 +10,7 @@
 namespace pfft {
 
 inline size_t wg_generic_smem_bytes(int ffts_per_block, int pitch, size_t scalar_bytes) {
-  return (size_t)2 * ffts_per_block * pitch * 2 * scalar_bytes + (size_t)3 * ffts_per_block * sizeof(long long);
+  return (size_t)2 * ffts_per_block * pitch * 2 * scalar_bytes + (size_t)4 * ffts_per_block * sizeof(long long);
 }
 
 // WORKGROUP level, generic (wg_generic.cu)
@@ -19,7 +19,7 @@ cudaError_t launch_wg_generic(const PassParams& p, bool is_double, bool interlea
 
 // WORKITEM level (wi.cuh, wi_f32.cu, wi_f64.cu): one thread per transform, n <= kWiMaxN
 inline size_t wi_smem_bytes(int n, size_t scalar_bytes) {
-  return (size_t)kWiBlock * (n | 1) * 2 * scalar_bytes + (size_t)kWiBlock * sizeof(long long);
+  return (size_t)kWiBlock * (n | 1) * 2 * scalar_bytes + (size_t)kWiBlock * 2 * sizeof(long long);
 }
 cudaError_t launch_wi_f32(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
 cudaError_t launch_wi_f64(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);

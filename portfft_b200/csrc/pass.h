@@ -16,6 +16,7 @@ namespace pfft {
 
 constexpr int kMaxBatchDims = 4;
 constexpr int kMaxRadices = 12;
+constexpr int kMaxPeers = 16;
 
 enum IoMode : int {
   IO_DIRECT = 0,       // butterfly-owning threads access global memory directly (coalesced when stride == 1)
@@ -54,6 +55,11 @@ struct PassParams {
   long long gtw_n;
   const void* gtw_lo;
   const void* gtw_hi;
+  // peer output (multi-GPU slab exchange fused into the store): the index along batch dimension `peer_dim` selects
+  // the output base pointers from out_tab_* (peer-mapped device memory of the destination GPU) instead of out_re/im
+  int peer_dim;  // -1: none
+  void* out_tab_re[kMaxPeers];
+  void* out_tab_im[kMaxPeers];
   // scale applied on store (only when apply_scale != 0)
   double scale;
   int apply_scale;

@@ -23,6 +23,10 @@ size_t DescHost::buffer_count(int dir) const {
   const auto& s = strides(dir);
   size_t last = (number_of_transforms - 1) * distance(dir);
   for (size_t i = 0; i < lengths.size() && i < s.size(); ++i) last += (lengths[i] - 1) * s[i];
+  for (size_t i = 0; i < extra.size(); ++i) {
+    if (peer_last && i + 1 == extra.size() && dir == PFFT_BACKWARD) continue;  // selects a buffer, not an address
+    last += (extra[i].count - 1) * (dir == PFFT_FORWARD ? extra[i].forward_distance : extra[i].backward_distance);
+  }
   return offset(dir) + last + 1;
 }
 
@@ -160,6 +164,15 @@ void validate_descriptor(const DescHost& d) {
     check_strides_distance(d.lengths, d.number_of_transforms, d.forward_strides, d.forward_distance, "forward");
     check_strides_distance(d.lengths, d.number_of_transforms, d.backward_strides, d.backward_distance, "backward");
   }
+  // guru extension (no reference counterpart): plain sanity only, overlap is the caller's responsibility
+  if (!d.extra.empty()) {
+    if (d.lengths.size() != 1 || d.extra.size() > 2)
+      unsupported("extra batch dimensions need a 1-D descriptor and at most 2 extra dimensions");
+    for (const auto& e : d.extra)
+      if (e.count == 0) invalid("Invalid extra batch dimension count 0");
+    if (d.peer_last && d.extra.back().count > (size_t)kMaxPeers)
+      unsupported("at most ", kMaxPeers, " peer output buffers");
+  }
   // validate_layout (:57-81) only raises *unsupported*; those restrictions (N-D non-default strides, arbitrary
   // strides beyond one sub-group) do not exist in this implementation.
 }
@@ -222,18 +235,20 @@ int force_level() {
 
 struct BDim {
   long long n, in, out;
+  bool peer = false;  // selects an output buffer (never merged, may have n == 1)
 };
 
 // merge adjacent batch dimensions that are contiguous in both domains; drop unit dimensions
 std::vector<BDim> merge_dims(std::vector<BDim> dims, size_t keep_front) {
   std::vector<BDim> head(dims.begin(), dims.begin() + keep_front), rest;
   for (size_t i = keep_front; i < dims.size(); ++i)
-    if (dims[i].n > 1) rest.push_back(dims[i]);
+    if (dims[i].n > 1 || dims[i].peer) rest.push_back(dims[i]);
   std::stable_sort(rest.begin(), rest.end(),
                    [](const BDim& a, const BDim& b) { return std::min(a.in, a.out) < std::min(b.in, b.out); });
   std::vector<BDim> merged;
   for (const BDim& d : rest) {
-    if (!merged.empty() && d.in == merged.back().n * merged.back().in && d.out == merged.back().n * merged.back().out)
+    if (!merged.empty() && !d.peer && !merged.back().peer && d.in == merged.back().n * merged.back().in &&
+        d.out == merged.back().n * merged.back().out)
       merged.back().n *= d.n;
     else
       merged.push_back(d);
@@ -258,7 +273,7 @@ std::vector<int> choose_radices(size_t n) {
   return out;
 }
 
-static size_t wg_smem(int F, int pitch, bool dbl) { return (size_t)2 * F * pitch * (dbl ? 16 : 8) + (size_t)24 * F; }
+static size_t wg_smem(int F, int pitch, bool dbl) { return (size_t)2 * F * pitch * (dbl ? 16 : 8) + (size_t)32 * F; }
 
 size_t max_workgroup_length(bool is_double, const DeviceLimits& lim) {
   // largest n whose ping-pong buffers fit one CTA (F = 1)
@@ -274,8 +289,10 @@ void set_batch_dims(PassParams& p, const std::vector<BDim>& dims) {
     unsupported("transform needs ", dims.size(), " independent batch dimensions in one pass; at most ", kMaxBatchDims,
                 " are supported");
   p.batch_total = 1;
+  p.peer_dim = -1;
   for (int d = 0; d < kMaxBatchDims; ++d) {
     if ((size_t)d < dims.size()) {
+      if (dims[d].peer) p.peer_dim = d;
       p.nb[d] = dims[d].n;
       p.ibd[d] = dims[d].in;
       p.obd[d] = dims[d].out;
@@ -357,7 +374,7 @@ bool configure_wi(PassHost& ps, bool dbl, const DeviceLimits& lim) {
   }
   ps.block = kWiBlock;
   const bool staged = p.in_mode == IO_STAGED_ELEM || p.out_mode == IO_STAGED_ELEM;
-  ps.smem = staged ? (size_t)kWiBlock * p.pitch * (dbl ? 16 : 8) + (size_t)kWiBlock * 8 : 0;
+  ps.smem = staged ? (size_t)kWiBlock * p.pitch * (dbl ? 16 : 8) + (size_t)kWiBlock * 16 : 0;
   const long long blocks = (p.batch_total + kWiBlock - 1) / kWiBlock;
   ps.grid = (int)std::min<long long>(blocks, (long long)lim.num_sms * 16);
   ps.kernel = KERNEL_WI;
@@ -414,6 +431,7 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   bool single_batch_dim = true;
   for (int i = 1; i < kMaxBatchDims; ++i) single_batch_dim = single_batch_dim && p.nb[i] == 1;
   if (!d.is_double && p.n == 4096 && il && p.is == 1 && p.os == 1 && single_batch_dim && p.gtw_dim < 0 &&
+      p.peer_dim < 0 &&
       p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0) {
     ps.kernel = KERNEL_WG_CUBE;
     ps.variant = variant;
@@ -476,6 +494,16 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     }
     outer.push_back({(long long)d.number_of_transforms, (long long)(first ? in.distance : out.distance),
                      (long long)out.distance});
+    for (size_t e = 0; e < d.extra.size(); ++e) {
+      const long long fd = (long long)d.extra[e].forward_distance, bd = (long long)d.extra[e].backward_distance;
+      BDim b{(long long)d.extra[e].count, dir == PFFT_FORWARD ? fd : bd, dir == PFFT_FORWARD ? bd : fd};
+      // the peer dimension addresses the forward domain normally and selects a buffer in the backward domain
+      if (d.peer_last && e + 1 == d.extra.size() && dir == PFFT_FORWARD) {
+        b.peer = true;
+        b.out = 0;
+      }
+      outer.push_back(b);
+    }
     const long long es_in = (long long)(first ? in.strides[dim] : out.strides[dim]);
     const long long es_out = (long long)out.strides[dim];
     const long long off_in = (long long)(first ? in.offset : out.offset);
@@ -506,6 +534,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       continue;
     }
 
+    if (d.peer_last) unsupported("peer output buffers are supported for single-pass transform lengths only");
     // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
     if (!smooth31(L)) unsupported("FFT size ", L, " has a prime factor larger than 31, which is not supported");
     std::vector<size_t> factors;
@@ -622,6 +651,7 @@ std::string describe_plan(const PlanHost& plan, int direction) {
     for (int dd = 0; dd < kMaxBatchDims; ++dd)
       if (p.nb[dd] > 1 || dd == 0) ss << (dd ? " " : "") << p.nb[dd] << ":" << p.ibd[dd] << ":" << p.obd[dd];
     ss << "] gtw_dim=" << p.gtw_dim;
+    if (p.peer_dim >= 0) ss << " peer_dim=" << p.peer_dim;
     if (p.gtw_dim >= 0) ss << " gtw_n=" << p.gtw_n;
     if (p.apply_scale) ss << " scale=" << p.scale;
     ss << "\n";

@@ -34,6 +34,12 @@ struct DescHost {
   std::vector<size_t> forward_strides, backward_strides;
   size_t forward_distance = 1, backward_distance = 1;
   size_t forward_offset = 0, backward_offset = 0;
+  // guru extension (pfft_commit_guru): extra batch dimensions; peer_last: the last one selects an output buffer
+  struct ExtraDim {
+    size_t count, forward_distance, backward_distance;
+  };
+  std::vector<ExtraDim> extra;
+  bool peer_last = false;
 
   const std::vector<size_t>& strides(int dir) const { return dir == PFFT_FORWARD ? forward_strides : backward_strides; }
   size_t distance(int dir) const { return dir == PFFT_FORWARD ? forward_distance : backward_distance; }

@@ -165,8 +165,14 @@ static void commit_device(pfft_plan* plan) {
   }
 }
 
+struct PeerTable {
+  size_t n = 0;
+  void* const* re = nullptr;
+  void* const* im = nullptr;
+};
+
 static void execute(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const PeerTable* peers = nullptr) {
   const DescHost& d = plan->host.desc;
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
   // committed_descriptor_impl.hpp:862-871
@@ -200,6 +206,19 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     switch (ps.dst) {
       case BUF_OUT: p.out_re = uout_re; p.out_im = uout_im; break;
       default: p.out_re = s_re; p.out_im = s_im; break;
+    }
+    if (p.peer_dim >= 0) {
+      if (peers == nullptr || peers->n != (size_t)p.nb[p.peer_dim])
+        throw PlanError(PFFT_INVALID_CONFIGURATION,
+                        "plan committed with PFFT_GURU_PEER_LAST_DIM: call pfft_compute_peer with one output buffer "
+                        "per index of the last extra batch dimension");
+      for (size_t i = 0; i < peers->n; ++i) {
+        void* re = peers->re[i];
+        void* im = il ? nullptr : peers->im[i];
+        if (!il && bwd) std::swap(re, im);
+        p.out_tab_re[i] = re;
+        p.out_tab_im[i] = im;
+      }
     }
     cudaError_t e = cudaSuccess;
     switch (ps.kernel) {
@@ -409,6 +428,37 @@ pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const v
       throw PlanError(PFFT_INVALID_CONFIGURATION, "invalid direction");
     cudaStream_t s = stream ? (cudaStream_t)stream : plan->stream;
     execute(plan, direction, in, in_imag, out, out_imag, s);
+  });
+}
+
+pfft_status pfft_commit_guru(const pfft_desc* desc, size_t n_extra, const pfft_batch_dim* extra, int flags, int device,
+                             void* stream, pfft_plan** plan_out) {
+  return guarded([&] {
+    if (plan_out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan_out");
+    *plan_out = nullptr;
+    DescHost d = desc_from_c(desc);
+    if (n_extra > 0 && extra == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null extra batch dimensions");
+    for (size_t i = 0; i < n_extra; ++i)
+      d.extra.push_back({extra[i].count, extra[i].forward_distance, extra[i].backward_distance});
+    d.peer_last = (flags & PFFT_GURU_PEER_LAST_DIM) != 0;
+    if (d.peer_last && n_extra == 0) throw PlanError(PFFT_INVALID_CONFIGURATION, "PFFT_GURU_PEER_LAST_DIM needs an extra dimension");
+    validate_descriptor(d);
+    *plan_out = make_plan(d, device, (cudaStream_t)stream);
+  });
+}
+
+pfft_status pfft_compute_peer(pfft_plan* plan, int direction, const void* in, const void* in_imag, size_t n_peers,
+                              void* const* out, void* const* out_imag, void* stream) {
+  return guarded([&] {
+    if (plan == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan");
+    if (direction != PFFT_FORWARD) throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION, "peer output: forward direction only");
+    if (out == nullptr || n_peers == 0) throw PlanError(PFFT_INVALID_CONFIGURATION, "null peer table");
+    const bool il = plan->host.desc.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+    if (!il && out_imag == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null imaginary peer table");
+    PeerTable t{n_peers, out, out_imag};
+    cudaStream_t s = stream ? (cudaStream_t)stream : plan->stream;
+    // the "out" argument of execute only feeds its null checks and passes that do not write the final output
+    execute(plan, direction, in, in_imag, out[0], il ? nullptr : out_imag[0], s, &t);
   });
 }
 

@@ -67,7 +67,8 @@ __global__ void __launch_bounds__(kSgBlock) sg_kernel(const PassParams p, const 
     const long long g = tile * fpw + sub;
     const bool active = g < p.batch_total;
     long long ib = 0, ob = 0;
-    if (active) batch_bases(p, one_dim, g, ib, ob);
+    int peer = -1;
+    if (active) batch_bases(p, one_dim, g, ib, ob, peer);
     cx<T> v[M];
 #pragma unroll
     for (int r = 0; r < M; ++r) v[r] = active ? gload<T>(p, fl, ib + lrev + L * r) : cx<T>{T(0), T(0)};
@@ -105,12 +106,14 @@ __global__ void __launch_bounds__(kSgBlock) sg_kernel(const PassParams p, const 
       const int sub2 = c >> logL;
       const cx<T> val = wbuf[c * PM + (q - c * M)];
       long long ob2;
-      if (one_dim) {
+      int peer2 = -1;
+      if (one_dim && p.peer_dim < 0) {
         ob2 = p.ooff + (tile * fpw + sub2) * p.obd[0];
       } else {
         ob2 = __shfl_sync(0xffffffffu, ob, sub2 << logL);
+        peer2 = __shfl_sync(0xffffffffu, peer, sub2 << logL);
       }
-      if (tile * fpw + sub2 < p.batch_total) gstore<T>(p, fl, ob2 + (q - sub2 * N), val);
+      if (tile * fpw + sub2 < p.batch_total) gstore<T>(p, fl, ob2 + (q - sub2 * N), val, peer2);
     }
   }
 }

@@ -39,7 +39,7 @@ __device__ __forceinline__ cx<T> finalize(const PassParams& p, cx<T> v, long lon
 template <typename T, int R>
 __device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, int ns, bool src_global,
                                               bool dst_global, const cx<T>* __restrict__ src, cx<T>* __restrict__ dst,
-                                              long long ibase, long long obase, long long gtw_c, int tj) {
+                                              long long ibase, long long obase, long long gtw_c, int peer, int tj) {
   const int n = p.n;
   const int nbf = n / R;
   for (int j = tj; j < nbf; j += p.threads_per_fft) {
@@ -63,7 +63,7 @@ __device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, i
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int idx = ob + r * ns;
-        gstore<T>(p, fl, obase + (long long)idx * p.os, finalize<T>(p, v[r], gtw_c, idx));
+        gstore<T>(p, fl, obase + (long long)idx * p.os, finalize<T>(p, v[r], gtw_c, idx), peer);
       }
     } else {
 #pragma unroll
@@ -83,6 +83,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
   long long* s_ibase = reinterpret_cast<long long*>(buf1 + (size_t)F * pitch);
   long long* s_obase = s_ibase + F;
   long long* s_gtw = s_obase + F;
+  int* s_peer = reinterpret_cast<int*>(s_gtw + F);
   const IoFlags fl{il, swap};
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
@@ -95,6 +96,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
     __syncthreads();
     if (tid < nf) {
       long long g = g0 + tid, ib = p.ioff, ob = p.ooff, c = 0;
+      int peer = -1;
 #pragma unroll
       for (int d = 0; d < kMaxBatchDims; ++d) {
         const long long q = g / p.nb[d];
@@ -103,10 +105,12 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
         ib += b * p.ibd[d];
         ob += b * p.obd[d];
         if (d == p.gtw_dim) c = b;
+        if (d == p.peer_dim) peer = (int)b;
       }
       s_ibase[tid] = ib;
       s_obase[tid] = ob;
       s_gtw[tid] = c;
+      s_peer[tid] = peer;
     }
     __syncthreads();
     cx<T>* cur = buf0;
@@ -132,6 +136,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
     const long long ibase = active ? s_ibase[f] : 0;
     const long long obase = active ? s_obase[f] : 0;
     const long long gtw_c = active ? s_gtw[f] : 0;
+    const int peer = active ? s_peer[f] : -1;
     int ns = 1;
     for (int ps = 0; ps < p.num_radices; ++ps) {
       const bool src_global = (ps == 0) && (p.in_mode == IO_DIRECT);
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
         switch (R) {
 #define PFFT_CASE(RR)                                                                                         \
   case RR:                                                                                                    \
-    stockham_pass<T, RR>(p, fl, ns, src_global, dst_global, s, d, ibase, obase, gtw_c, tj);                   \
+    stockham_pass<T, RR>(p, fl, ns, src_global, dst_global, s, d, ibase, obase, gtw_c, peer, tj);                  \
     break;
           PFFT_CASE(1)
           PFFT_CASE(2)
@@ -183,7 +188,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
         const unsigned ff = e / (unsigned)n;
         const int i = (int)(e - ff * (unsigned)n);
         gstore<T>(p, fl, s_obase[ff] + (long long)i * p.os,
-                  finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i));
+                  finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i), s_peer[ff]);
       }
     } else if (p.out_mode == IO_STAGED_BATCH) {
       const unsigned total = (unsigned)F * (unsigned)n;
@@ -192,7 +197,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
         const int i = (int)(e / (unsigned)F);
         if (ff < nf)
           gstore<T>(p, fl, s_obase[ff] + (long long)i * p.os,
-                    finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i));
+                    finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i), s_peer[ff]);
       }
     }
   }

@@ -32,18 +32,21 @@ __global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, cons
   constexpr int F = kWiThreads;
   cx<T>* buf = reinterpret_cast<cx<T>*>(smem_raw);
   long long* s_base = reinterpret_cast<long long*>(buf + (size_t)F * PITCH);
+  int* s_peer = reinterpret_cast<int*>(s_base + F);
   const IoFlags fl{il, swap};
   const int tid = threadIdx.x;
   const bool one_dim = single_batch_dim(p);
   const bool in_staged = p.in_mode == IO_STAGED_ELEM, out_staged = p.out_mode == IO_STAGED_ELEM;
-  const bool in_contig = one_dim && p.is == 1 && p.ibd[0] == N, out_contig = one_dim && p.os == 1 && p.obd[0] == N;
+  const bool in_contig = one_dim && p.is == 1 && p.ibd[0] == N;
+  const bool out_contig = one_dim && p.os == 1 && p.obd[0] == N && p.peer_dim < 0;
   const T scale = T(p.scale);
 
   for (long long g0 = (long long)blockIdx.x * F; g0 < p.batch_total; g0 += (long long)gridDim.x * F) {
     const int nf = (int)min((long long)F, p.batch_total - g0);
     const bool active = tid < nf;
     long long ib = 0, ob = 0;
-    if (active) batch_bases(p, one_dim, g0 + tid, ib, ob);
+    int peer = -1;
+    if (active) batch_bases(p, one_dim, g0 + tid, ib, ob, peer);
     cx<T> v[N];
     if (in_staged) {
       __syncthreads();  // previous iteration's staged stores have left the buffer
@@ -79,7 +82,10 @@ __global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, cons
       if (active) {
 #pragma unroll
         for (int j = 0; j < N; ++j) buf[tid * PITCH + j] = v[j];
-        if (!out_contig) s_base[tid] = ob;
+        if (!out_contig) {
+          s_base[tid] = ob;
+          s_peer[tid] = peer;
+        }
       }
       __syncthreads();
       const long long tile0 = p.ooff + g0 * (long long)N;
@@ -87,11 +93,14 @@ __global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, cons
 #pragma unroll 4
       for (int e = tid; e < total; e += F) {
         const int ff = e / N, i = e - ff * N;
-        gstore<T>(p, fl, out_contig ? tile0 + e : s_base[ff] + i * p.os, buf[ff * PITCH + i]);
+        if (out_contig)
+          gstore<T>(p, fl, tile0 + e, buf[ff * PITCH + i]);
+        else
+          gstore<T>(p, fl, s_base[ff] + i * p.os, buf[ff * PITCH + i], s_peer[ff]);
       }
     } else if (active) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) gstore<T>(p, fl, ob + (long long)j * p.os, v[j]);
+      for (int j = 0; j < N; ++j) gstore<T>(p, fl, ob + (long long)j * p.os, v[j], peer);
     }
   }
 }
