@@ -33,4 +33,9 @@ cudaError_t launch_sg_f64(const PassParams& p, bool interleaved, bool swap, int 
 // WORKGROUP level, N = R^3 specialisation with TMA-fed persistent CTAs (wg_cube.cu). variant 0: TMA ring, 1: direct loads
 cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream);
 
+// WORKGROUP level, column tiles fed by TMA tensor copies (wg_col.cu): n in {64,128,256,512}; in_rows: contiguous input
+// rows (transposing pass).  *used == false with cudaSuccess: tensor map not encodable, run the generic kernel.
+cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, bool in_rows, int grid, cudaStream_t stream,
+                          bool* used);
+
 }  // namespace pfft

@@ -439,6 +439,39 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   }
 }
 
+// Column-tile kernel (wg_col.cu) for passes whose fastest batch dimension is contiguous on the output side: outer
+// dimensions of N-D transforms and every pass of the GLOBAL level.  The generic configuration stays valid as the
+// fallback (tensor map not encodable for the actual pointers).
+void select_col(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
+  const PassParams& p = ps.pp;
+  const char* env = std::getenv("PFFT_NO_COL");
+  if (env && std::atoi(env) != 0) return;
+  if (d.complex_storage != PFFT_INTERLEAVED_COMPLEX || p.peer_dim >= 0) return;
+  if (!col_supported(p.n, d.is_double, nullptr, nullptr)) return;
+  if (p.nb[0] < 2 || p.obd[0] != 1) return;
+  const long long esz = d.is_double ? 16 : 8;
+  bool in_rows;
+  if (p.ibd[0] == 1 && p.is != 1) {
+    in_rows = false;  // TMA: every stride a multiple of 16 bytes
+    if ((p.is * esz) % 16 != 0 || (p.ioff * esz) % 16 != 0) return;
+    for (int i = 1; i < kMaxBatchDims; ++i)
+      if (p.nb[i] > 1 && (p.ibd[i] * esz) % 16 != 0) return;
+    if (p.nb[0] * 2 > (1LL << 31) || p.nb[1] > (1LL << 31) || p.nb[2] > (1LL << 31) || p.nb[3] > (1LL << 31)) return;
+  } else if (p.is == 1) {
+    in_rows = true;
+  } else {
+    return;
+  }
+  const int c = (int)(128 / esz);
+  const size_t smem = col_smem_bytes(p.n, d.is_double, in_rows);
+  if (smem > lim.max_smem_per_block) return;
+  const long long tiles = ((p.nb[0] + c - 1) / c) * p.nb[1] * p.nb[2] * p.nb[3];
+  const int per_sm = std::max<int>(1, std::min<size_t>(8, (lim.max_smem_per_block + 1024) / (smem + 1024)));
+  ps.kernel = KERNEL_WG_COL;
+  ps.variant = in_rows ? 1 : 0;
+  ps.alt_grid = (int)std::min<long long>(tiles, (long long)lim.num_sms * per_sm);
+}
+
 // split n into k factors, each <= fmax, as balanced as possible
 bool split_factors(size_t n, int k, size_t fmax, std::vector<size_t>& out) {
   if (k == 1) {
@@ -477,7 +510,8 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   const Domain out{d.strides(odir), d.distance(odir), d.offset(odir)};
   const size_t D = d.lengths.size();
   const size_t wg_max = max_workgroup_length(dbl, lim);
-  const size_t col_max = 1024;  // longest factor of a multi-pass (GLOBAL) transform: keeps >= 64 B per row segment
+  // longest factor of a multi-pass (GLOBAL) transform; powers of two are cut into the column-tile kernel's lengths
+  const size_t col_max_any = 1024;
   std::vector<PassHost>& passes = plan.passes[dir];
   if (plan.dim_level.size() != D) plan.dim_level.assign(D, PFFT_LEVEL_WORKGROUP);
 
@@ -528,6 +562,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       } else {
         configure_wg_generic(ps, dbl, lim, false);
         select_specialised(ps, d, lim);
+        if (ps.kernel == KERNEL_WG_GENERIC) select_col(ps, d, lim);
       }
       passes.push_back(ps);
       plan.dim_level[dim] = ps.level;
@@ -540,6 +575,8 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     std::vector<size_t> factors;
     for (int k = 2; k <= 4 && factors.empty(); ++k) {
       std::vector<size_t> f;
+      const bool pow2 = (L & (L - 1)) == 0 && d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+      const size_t col_max = pow2 ? (dbl ? 256 : 512) : col_max_any;
       if (split_factors(L, k, col_max, f)) factors = f;
     }
     if (factors.empty()) unsupported("FFT size ", L, " is too large");
@@ -609,6 +646,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
         set_batch_dims(ps.pp, md);
       }
       configure_wg_generic(ps, dbl, lim, true);
+      select_col(ps, d, lim);
       passes.push_back(ps);
       M = Mp;
       done *= Np;
@@ -634,7 +672,7 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
   static const char* buf_names[] = {"in", "out", "scratch"};
   std::stringstream ss;

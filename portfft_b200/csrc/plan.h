@@ -56,7 +56,7 @@ void validate_descriptor(const DescHost& d);  // throws PlanError
 
 enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3 };
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -76,6 +76,10 @@ struct PassHost {
 constexpr int kWiMaxNFloat = 32, kWiMaxNDouble = 16, kWiBlock = 128;
 constexpr int kSgMaxMFloat = 32, kSgMaxMDouble = 16, kSgBlock = 256;
 bool sg_supports_m(int m, bool is_double);
+// column-tile kernel (wg_col.cu): supported lengths, shared memory and block size
+bool col_supported(int n, bool is_double, int* n1, int* n2);
+size_t col_smem_bytes(int n, bool is_double, bool in_rows);
+int col_threads(int n, bool is_double);
 
 struct PlanHost {
   DescHost desc;

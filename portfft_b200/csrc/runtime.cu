@@ -231,6 +231,12 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
       case KERNEL_SG:
         e = d.is_double ? launch_sg_f64(p, il, il && bwd, ps.grid, stream) : launch_sg_f32(p, il, il && bwd, ps.grid, stream);
         break;
+      case KERNEL_WG_COL: {
+        bool used = false;
+        e = launch_wg_col(p, d.is_double, il && bwd, ps.variant == 1, ps.alt_grid, stream, &used);
+        if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+        break;
+      }
       case KERNEL_WG_CUBE:
         // cp.async.bulk needs 16-byte aligned global addresses; otherwise run the generic kernel
         if (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0)

@@ -1,0 +1,347 @@
+// WORKGROUP level, column tiles: C adjacent columns (C * sizeof(complex) = 128 bytes) of a strided batch are
+// transformed together, N = N1 * N2 points each, persistent CTAs.  This kernel runs
+//   * the outer dimensions of N-D transforms (512^3: the y and x passes), and
+//   * every pass of the GLOBAL level (four-step for large N: strided column transforms with the inter-factor
+//     twiddle fused into the store, and the final row pass whose store performs the transposition).
+//
+// Reference counterparts: the per-plane launch loop of dispatch_dimensions
+// (/root/reference/src/portfft/committed_descriptor_impl.hpp:932-948: batch*outer separate BATCH_INTERLEAVED
+// launches), global_kernel / dispatch_level with store modifiers
+// (/root/reference/src/portfft/common/global.hpp:135-170,303-401) and the 16x16 transpose kernels
+// (/root/reference/src/portfft/common/transpose.hpp:44-100).  Here:
+//   * IN_COLS: the N x C tile (rows `is` elements apart) is fetched by TMA tensor copies
+//     (cp.async.bulk.tensor.5d, <= 256 rows per box) into a 2-stage shared-memory ring guarded by mbarriers, issued
+//     by one thread; the next tile streams in while this one is computed.  Every row segment is one full 128-byte
+//     line, so HBM sees only whole lines although the transform direction is strided;
+//   * IN_ROWS (last pass of the GLOBAL level): each of the C transforms is a contiguous row, read directly with
+//     lanes along the row; the stores below then write columns -> the transposition costs no extra pass;
+//   * two register-resident passes (radix N1, then radix N2; dft.cuh) with ONE exchange through a padded
+//     shared-memory buffer laid out [column][index] with odd pitch (conflict free for both access directions);
+//   * results leave straight from registers with lanes along the column index: 128-byte row segments, full lines;
+//     inter-factor twiddle w_M^{column * k} (two-level device table), scale and the backward (re <-> im) swap are
+//     fused into that store.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "device_utils.cuh"
+#include "io.cuh"
+#include "kernels.h"
+
+namespace pfft {
+
+namespace col {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// TMA tile load: box {C columns, rows, 1, 1, 1} at coordinates (c0, r0, b1, b2, b3)
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int r0, int b1, int b2, int b3,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
+      "%6}], [%7];" ::"r"(smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(b1), "r"(b2), "r"(b3), "r"(smem_u32(bar))
+      : "memory");
+}
+
+template <typename T>
+__host__ __device__ constexpr int pad(int i) {
+  return i + (i >> (sizeof(T) == 4 ? 4 : 3));
+}
+template <typename T>
+__host__ __device__ constexpr int pitch(int n) {
+  return (pad<T>(n - 1) + 1) | 1;
+}
+constexpr int cmin(int a, int b) { return a < b ? a : b; }
+
+}  // namespace col
+
+template <typename T, int N1, int N2, bool IN_ROWS>
+struct ColCfg {
+  static constexpr int N = N1 * N2;
+  static constexpr int C = 128 / (2 * (int)sizeof(T));  // columns per tile: 16 (fp32) / 8 (fp64)
+  static constexpr int TPC = col::cmin(col::cmin(N1, N2), 16);  // threads per column
+  static constexpr int NT = C * TPC;
+  static constexpr int PITCH = col::pitch<T>(N);
+  static constexpr int STAGES = IN_ROWS ? 0 : 2;
+  static constexpr size_t kStageBytes = (size_t)N * C * 2 * sizeof(T);
+  static constexpr size_t kSmem = STAGES * kStageBytes + (size_t)C * PITCH * 2 * sizeof(T) + 64;
+  static constexpr int kBoxRows = N < 256 ? N : 256;
+};
+
+template <typename T, int N1, int N2, bool IN_ROWS>
+__global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
+    wg_col_kernel(const PassParams p, const __grid_constant__ CUtensorMap tmap, const bool swap) {
+  using Cfg = ColCfg<T, N1, N2, IN_ROWS>;
+  constexpr int N = Cfg::N, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cx<T>* stage0 = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + Cfg::STAGES * Cfg::kStageBytes);
+  uint64_t* full = reinterpret_cast<uint64_t*>(E + (size_t)C * PITCH);
+  const IoFlags fl{true, swap};
+  const int tid = threadIdx.x;
+  // column-major mapping (stores, and loads from column tiles): lanes run along the column index
+  const int cc = tid % C, tc = tid / C;
+  // row-major mapping (IN_ROWS loads): lanes run along the row
+  const int cr = tid / TPC, tr = tid % TPC;
+  const long long tiles_c = (p.nb[0] + C - 1) / C;
+  const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
+  const T scale = T(p.scale);
+  const long long gmask = (1LL << p.gtw_bits) - 1;
+
+  auto decode = [&](long long tile, int& c0, int& b1, int& b2, int& b3) {
+    long long q = tile / tiles_c;
+    c0 = (int)(tile - q * tiles_c) * C;
+    long long q2 = q / p.nb[1];
+    b1 = (int)(q - q2 * p.nb[1]);
+    long long q3 = q2 / p.nb[2];
+    b2 = (int)(q2 - q3 * p.nb[2]);
+    b3 = (int)q3;
+  };
+  auto issue = [&](long long tile, int s) {
+    int c0, b1, b2, b3;
+    decode(tile, c0, b1, b2, b3);
+    col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
+#pragma unroll
+    for (int r0 = 0; r0 < N; r0 += Cfg::kBoxRows)
+      col::tma_load_5d(reinterpret_cast<unsigned char*>(stage0) + s * Cfg::kStageBytes + (size_t)r0 * C * sizeof(cx<T>),
+                       &tmap, 2 * c0, r0, b1, b2, b3, &full[s]);  // innermost coordinate counts scalars
+  };
+
+  if (!IN_ROWS) {
+    if (tid == 0) {
+      col::mbar_init(&full[0], 1);
+      col::mbar_init(&full[1], 1);
+      col::fence_mbar_init();
+      col::fence_proxy_async();
+    }
+    __syncthreads();
+    if (tid == 0) {
+      long long t0 = blockIdx.x;
+      if (t0 < total_tiles) issue(t0, 0);
+      t0 += gridDim.x;
+      if (t0 < total_tiles) issue(t0, 1);
+    }
+  }
+
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+    int c0, b1, b2, b3;
+    decode(tile, c0, b1, b2, b3);
+    // ---- pass 1: radix N1 over x[j + N2*r], result to E[column][pad(j*N1 + r)] ----------------------------------
+    if (!IN_ROWS) {
+      const cx<T>* S = reinterpret_cast<const cx<T>*>(reinterpret_cast<unsigned char*>(stage0) + (it & 1) * Cfg::kStageBytes);
+      col::mbar_wait(&full[it & 1], (it >> 1) & 1);
+#pragma unroll 1
+      for (int j = tc; j < N2; j += TPC) {
+        cx<T> v[N1];
+#pragma unroll
+        for (int r = 0; r < N1; ++r) v[r] = S[(j + N2 * r) * C + cc];
+        if (swap) {
+#pragma unroll
+          for (int r = 0; r < N1; ++r) {
+            const T t = v[r].x;
+            v[r].x = v[r].y;
+            v[r].y = t;
+          }
+        }
+        DFT<N1, T>::run(v);
+#pragma unroll
+        for (int r = 0; r < N1; ++r) E[cc * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+      }
+    } else {
+      const bool live = c0 + cr < p.nb[0];
+      const long long ib = p.ioff + (long long)(c0 + cr) * p.ibd[0] + (long long)b1 * p.ibd[1] +
+                           (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
+#pragma unroll 1
+      for (int j = tr; j < N2; j += TPC) {
+        cx<T> v[N1];
+#pragma unroll
+        for (int r = 0; r < N1; ++r) v[r] = live ? gload<T>(p, fl, ib + (j + N2 * r)) : cx<T>{T(0), T(0)};
+        DFT<N1, T>::run(v);
+#pragma unroll
+        for (int r = 0; r < N1; ++r) E[cr * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+      }
+    }
+    __syncthreads();
+    if (!IN_ROWS && tid == 0) {
+      // the stage just consumed is free: refill it with the tile two iterations ahead
+      const long long nxt = tile + 2LL * gridDim.x;
+      if (nxt < total_tiles) {
+        col::fence_proxy_async();
+        issue(nxt, it & 1);
+      }
+    }
+    // ---- pass 2: E[column][pad(j + N1*r)] * w_N^{j r}, radix N2, store out[(j + N1*r)*os + column] ---------------
+    {
+      const bool live = c0 + cc < p.nb[0];
+      const long long ob = p.ooff + (long long)(c0 + cc) * p.obd[0] + (long long)b1 * p.obd[1] +
+                           (long long)b2 * p.obd[2] + (long long)b3 * p.obd[3];
+      long long gidx = 0;
+      if (p.gtw_dim >= 0) gidx = p.gtw_dim == 0 ? c0 + cc : (p.gtw_dim == 1 ? b1 : (p.gtw_dim == 2 ? b2 : b3));
+#pragma unroll 1
+      for (int j = tc; j < N1; j += TPC) {
+        cx<T> v[N2];
+#pragma unroll
+        for (int r = 0; r < N2; ++r) v[r] = E[cc * PITCH + col::pad<T>(j + N1 * r)];
+#pragma unroll
+        for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
+        DFT<N2, T>::run(v);
+        if (live) {
+#pragma unroll
+          for (int r = 0; r < N2; ++r) {
+            const int k = j + N1 * r;
+            cx<T> o = v[r];
+            if (p.gtw_dim >= 0) {
+              const long long m = gidx * k;
+              o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & gmask)));
+            }
+            if (p.apply_scale) o = cscale(o, scale);
+            gstore<T>(p, fl, ob + (long long)k * p.os, o);
+          }
+        }
+      }
+    }
+    __syncthreads();  // E is rewritten by the next tile's pass 1
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+
+// 5-D view of the pass input: (column, row j, b1, b2, b3); element = one complex number described as 2 scalars
+// folded into the innermost dimension (so that fp32 and fp64 both use a native TMA data type)
+static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_rows, CUtensorMap* map) {
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return false;
+  const size_t sc = is_double ? 8 : 4, esz = 2 * sc;
+  const char* base = reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz;
+  if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return false;
+  cuuint64_t dims[5] = {(cuuint64_t)p.nb[0] * 2, (cuuint64_t)p.n, (cuuint64_t)p.nb[1], (cuuint64_t)p.nb[2],
+                        (cuuint64_t)p.nb[3]};
+  const long long st[4] = {p.is, p.nb[1] > 1 ? p.ibd[1] : p.is * p.n, p.nb[2] > 1 ? p.ibd[2] : p.is * p.n,
+                           p.nb[3] > 1 ? p.ibd[3] : p.is * p.n};
+  cuuint64_t strides[4];
+  for (int i = 0; i < 4; ++i) {
+    const unsigned long long bytes = (unsigned long long)st[i] * esz;
+    if (st[i] <= 0 || bytes % 16 != 0 || bytes >= (1ULL << 40)) return false;
+    strides[i] = bytes;
+  }
+  for (int i = 0; i < 5; ++i)
+    if (dims[i] == 0 || dims[i] > (1ULL << 32)) return false;
+  cuuint32_t box[5] = {(cuuint32_t)(2 * C), (cuuint32_t)box_rows, 1, 1, 1};
+  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  const CUresult r = enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
+                         const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <typename T, int N1, int N2>
+static cudaError_t launch_col_t(const PassParams& p, bool swap, bool in_rows, int grid, cudaStream_t stream, bool* used) {
+  *used = false;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (in_rows) {
+    using Cfg = ColCfg<T, N1, N2, true>;
+    auto kern = wg_col_kernel<T, N1, N2, true>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
+  } else {
+    using Cfg = ColCfg<T, N1, N2, false>;
+    if (!make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
+    auto kern = wg_col_kernel<T, N1, N2, false>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
+  }
+  *used = true;
+  return cudaGetLastError();
+}
+
+bool col_supported(int n, bool is_double, int* n1, int* n2) {
+  int a = 0, b = 0;
+  switch (n) {
+    case 64: a = 8; b = 8; break;
+    case 128: a = 16; b = 8; break;
+    case 256: a = 16; b = 16; break;
+    case 512: a = 16; b = 32; break;
+    default: return false;
+  }
+  if (is_double && n > 256) return false;
+  if (n1) *n1 = a;
+  if (n2) *n2 = b;
+  return true;
+}
+
+size_t col_smem_bytes(int n, bool is_double, bool in_rows) {
+  const size_t esz = is_double ? 16 : 8;
+  const int c = 128 / (int)esz;
+  const int pitch = is_double ? col::pitch<double>(n) : col::pitch<float>(n);
+  return (in_rows ? 0 : 2) * (size_t)n * c * esz + (size_t)c * pitch * esz + 64;
+}
+
+int col_threads(int n, bool is_double) {
+  int a, b;
+  if (!col_supported(n, is_double, &a, &b)) return 0;
+  const int tpc = a < b ? a : b;
+  return (128 / (is_double ? 16 : 8)) * (tpc < 16 ? tpc : 16);
+}
+
+// *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
+cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, bool in_rows, int grid, cudaStream_t stream,
+                          bool* used) {
+#define PFFT_COL(NN, A, B)                                                                  \
+  case NN:                                                                                  \
+    return is_double ? launch_col_t<double, A, B>(p, swap, in_rows, grid, stream, used)              \
+                     : launch_col_t<float, A, B>(p, swap, in_rows, grid, stream, used);
+  *used = false;
+  switch (p.n) {
+    PFFT_COL(64, 8, 8)
+    PFFT_COL(128, 16, 8)
+    PFFT_COL(256, 16, 16)
+    case 512:
+      return is_double ? cudaErrorInvalidValue : launch_col_t<float, 16, 32>(p, swap, in_rows, grid, stream, used);
+    default:
+      return cudaErrorInvalidValue;
+  }
+#undef PFFT_COL
+}
+
+}  // namespace pfft

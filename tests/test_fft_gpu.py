@@ -67,6 +67,10 @@ SUITES = {
     "BackwardGlobalTest": basic(GLOBAL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [32768, 65536]),
     "MultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
                                   [[2, 4], [4, 2], [16, 512], [64, 2048], [2, 3, 6], [2, 3, 2, 3]]),
+    # not in the reference grid: column-tile kernel (TMA tiles with ragged column counts, odd strides -> fallback)
+    "ColumnTileTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                            [[64, 100], [128, 24], [256, 20], [512, 36], [64, 33], [256, 256], [64, 64, 64]]),
+    "ColumnTileOffsetsTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
     "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
     "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
     "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
