@@ -33,9 +33,11 @@ cudaError_t launch_sg_f64(const PassParams& p, bool interleaved, bool swap, int 
 // WORKGROUP level, N = R^3 specialisation with TMA-fed persistent CTAs (wg_cube.cu). variant 0: TMA ring, 1: direct loads
 cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream);
 
-// WORKGROUP level, column tiles fed by TMA tensor copies (wg_col.cu): n in {64,128,256,512}; in_rows: contiguous input
-// rows (transposing pass).  *used == false with cudaSuccess: tensor map not encodable, run the generic kernel.
-cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, bool in_rows, int grid, cudaStream_t stream,
+// WORKGROUP level, tiles of 16 (fp32) / 8 (fp64) transforms fed by TMA (wg_col.cu): n in {64,128,256,512}.
+// variant bits 0-1: input mode (0 strided columns via TMA tensor tiles, 1 contiguous rows loaded directly, 2 contiguous
+// rows via cp.async.bulk), bit 2: contiguous output rows (else output columns).
+// *used == false with cudaSuccess: tensor map not encodable for these pointers, run the generic kernel.
+cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
                           bool* used);
 
 }  // namespace pfft

@@ -439,36 +439,47 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   }
 }
 
-// Column-tile kernel (wg_col.cu) for passes whose fastest batch dimension is contiguous on the output side: outer
-// dimensions of N-D transforms and every pass of the GLOBAL level.  The generic configuration stays valid as the
-// fallback (tensor map not encodable for the actual pointers).
+// Tile kernel (wg_col.cu): 16 (fp32) / 8 (fp64) transforms per CTA iteration, fed by TMA.  Input side: strided columns
+// whose fastest batch dimension is contiguous (TMA tensor tiles) or contiguous rows (cp.async.bulk / direct loads);
+// output side: columns (fastest batch dimension contiguous) or contiguous rows.  Covers the packed 1-D sizes
+// 64..512, the outer dimensions of N-D transforms and every pass of the GLOBAL level.  The generic configuration
+// stays valid as the fallback (tensor map not encodable for the actual pointers).
 void select_col(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   const PassParams& p = ps.pp;
   const char* env = std::getenv("PFFT_NO_COL");
   if (env && std::atoi(env) != 0) return;
   if (d.complex_storage != PFFT_INTERLEAVED_COMPLEX || p.peer_dim >= 0) return;
   if (!col_supported(p.n, d.is_double, nullptr, nullptr)) return;
-  if (p.nb[0] < 2 || p.obd[0] != 1) return;
   const long long esz = d.is_double ? 16 : 8;
-  bool in_rows;
-  if (p.ibd[0] == 1 && p.is != 1) {
-    in_rows = false;  // TMA: every stride a multiple of 16 bytes
-    if ((p.is * esz) % 16 != 0 || (p.ioff * esz) % 16 != 0) return;
-    for (int i = 1; i < kMaxBatchDims; ++i)
-      if (p.nb[i] > 1 && (p.ibd[i] * esz) % 16 != 0) return;
-    if (p.nb[0] * 2 > (1LL << 31) || p.nb[1] > (1LL << 31) || p.nb[2] > (1LL << 31) || p.nb[3] > (1LL << 31)) return;
-  } else if (p.is == 1) {
-    in_rows = true;
+  auto aligned = [&](bool need_is) {
+    if ((p.ioff * esz) % 16 != 0 || (need_is && (p.is * esz) % 16 != 0)) return false;
+    for (int i = need_is ? 1 : 0; i < kMaxBatchDims; ++i)
+      if (p.nb[i] > 1 && (p.ibd[i] * esz) % 16 != 0) return false;
+    return true;
+  };
+  int in_mode;
+  if (p.is == 1) {
+    in_mode = aligned(false) ? 2 : 1;
+  } else if (p.ibd[0] == 1 && p.nb[0] >= 2 && aligned(true) && p.nb[0] * 2 < (1LL << 31) && p.nb[1] < (1LL << 31) &&
+             p.nb[2] < (1LL << 31) && p.nb[3] < (1LL << 31)) {
+    in_mode = 0;
   } else {
     return;
   }
+  bool out_rows;
+  if (p.obd[0] == 1 && p.nb[0] >= 2 && p.os != 1)
+    out_rows = false;
+  else if (p.os == 1)
+    out_rows = true;
+  else
+    return;
   const int c = (int)(128 / esz);
-  const size_t smem = col_smem_bytes(p.n, d.is_double, in_rows);
+  const size_t smem = col_smem_bytes(p.n, d.is_double, in_mode != 1);
   if (smem > lim.max_smem_per_block) return;
   const long long tiles = ((p.nb[0] + c - 1) / c) * p.nb[1] * p.nb[2] * p.nb[3];
   const int per_sm = std::max<int>(1, std::min<size_t>(8, (lim.max_smem_per_block + 1024) / (smem + 1024)));
   ps.kernel = KERNEL_WG_COL;
-  ps.variant = in_rows ? 1 : 0;
+  ps.variant = in_mode | (out_rows ? 4 : 0);
   ps.alt_grid = (int)std::min<long long>(tiles, (long long)lim.num_sms * per_sm);
 }
 
@@ -558,11 +569,19 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       ps.level = LEVEL_WORKGROUP;
       const int force = force_level();
       if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, lim)) {
-      } else if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) {
       } else {
-        configure_wg_generic(ps, dbl, lim, false);
-        select_specialised(ps, d, lim);
-        if (ps.kernel == KERNEL_WG_GENERIC) select_col(ps, d, lim);
+        // block-level tile kernel first where it applies (it out-runs the warp-level kernel on B200: TMA-fed,
+        // persistent); the warp-level kernel takes the unit-stride sizes it does not cover
+        PassHost wg = ps;
+        configure_wg_generic(wg, dbl, lim, false);
+        select_specialised(wg, d, lim);
+        if (wg.kernel == KERNEL_WG_GENERIC) select_col(wg, d, lim);
+        if (force == LEVEL_WORKGROUP || (force < 0 && wg.kernel != KERNEL_WG_GENERIC)) {
+          ps = wg;
+        } else if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) {
+        } else {
+          ps = wg;
+        }
       }
       passes.push_back(ps);
       plan.dim_level[dim] = ps.level;
@@ -690,6 +709,11 @@ std::string describe_plan(const PlanHost& plan, int direction) {
       if (p.nb[dd] > 1 || dd == 0) ss << (dd ? " " : "") << p.nb[dd] << ":" << p.ibd[dd] << ":" << p.obd[dd];
     ss << "] gtw_dim=" << p.gtw_dim;
     if (p.peer_dim >= 0) ss << " peer_dim=" << p.peer_dim;
+    if (ps.kernel == KERNEL_WG_COL) {
+      static const char* in_names[] = {"cols_tma", "rows_direct", "rows_bulk", "?"};
+      ss << " tile_in=" << in_names[ps.variant & 3] << " tile_out=" << ((ps.variant & 4) ? "rows" : "cols")
+         << " tile_grid=" << ps.alt_grid << " (generic geometry above is the fallback)";
+    }
     if (p.gtw_dim >= 0) ss << " gtw_n=" << p.gtw_n;
     if (p.apply_scale) ss << " scale=" << p.scale;
     ss << "\n";

@@ -78,7 +78,7 @@ constexpr int kSgMaxMFloat = 32, kSgMaxMDouble = 16, kSgBlock = 256;
 bool sg_supports_m(int m, bool is_double);
 // column-tile kernel (wg_col.cu): supported lengths, shared memory and block size
 bool col_supported(int n, bool is_double, int* n1, int* n2);
-size_t col_smem_bytes(int n, bool is_double, bool in_rows);
+size_t col_smem_bytes(int n, bool is_double, bool ring);
 int col_threads(int n, bool is_double);
 
 struct PlanHost {

@@ -233,7 +233,7 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         break;
       case KERNEL_WG_COL: {
         bool used = false;
-        e = launch_wg_col(p, d.is_double, il && bwd, ps.variant == 1, ps.alt_grid, stream, &used);
+        e = launch_wg_col(p, d.is_double, il && bwd, ps.variant, ps.alt_grid, stream, &used);
         if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
         break;
       }

@@ -62,6 +62,13 @@ __device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, i
       : "memory");
 }
 
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 template <typename T>
 __host__ __device__ constexpr int pad(int i) {
   return i + (i >> (sizeof(T) == 4 ? 4 : 3));
@@ -74,38 +81,50 @@ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 
 }  // namespace col
 
-template <typename T, int N1, int N2, bool IN_ROWS>
+// IN: how a tile of C transforms reaches the CTA
+enum : int {
+  IN_COLS_TMA = 0,    // strided columns: TMA tensor tiles into the stage ring, stage layout [row j][column]
+  IN_ROWS_DIRECT = 1, // contiguous rows: direct global loads (no staging, latency hidden by resident CTAs)
+  IN_ROWS_BULK = 2    // contiguous rows, 16-byte aligned: cp.async.bulk (TMA 1-D) into the ring, layout [row][j]
+};
+
+template <typename T, int N1, int N2, int IN>
 struct ColCfg {
   static constexpr int N = N1 * N2;
-  static constexpr int C = 128 / (2 * (int)sizeof(T));  // columns per tile: 16 (fp32) / 8 (fp64)
-  static constexpr int TPC = col::cmin(col::cmin(N1, N2), 16);  // threads per column
+  static constexpr int C = 128 / (2 * (int)sizeof(T));  // transforms per tile: 16 (fp32) / 8 (fp64)
+  static constexpr int TPC = col::cmin(col::cmin(N1, N2), 16);  // threads per transform
   static constexpr int NT = C * TPC;
   static constexpr int PITCH = col::pitch<T>(N);
-  static constexpr int STAGES = IN_ROWS ? 0 : 2;
+  static constexpr int STAGES = IN == IN_ROWS_DIRECT ? 0 : 2;
   static constexpr size_t kStageBytes = (size_t)N * C * 2 * sizeof(T);
   static constexpr size_t kSmem = STAGES * kStageBytes + (size_t)C * PITCH * 2 * sizeof(T) + 64;
   static constexpr int kBoxRows = N < 256 ? N : 256;
 };
 
-template <typename T, int N1, int N2, bool IN_ROWS>
-__global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
+template <typename T, int N1, int N2, int IN, bool OUT_ROWS>
+__global__ void __launch_bounds__(ColCfg<T, N1, N2, IN>::NT)
     wg_col_kernel(const PassParams p, const __grid_constant__ CUtensorMap tmap, const bool swap) {
-  using Cfg = ColCfg<T, N1, N2, IN_ROWS>;
+  using Cfg = ColCfg<T, N1, N2, IN>;
   constexpr int N = Cfg::N, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH;
+  constexpr bool IN_ROWS = IN != IN_COLS_TMA;
+  constexpr bool RING = IN != IN_ROWS_DIRECT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  cx<T>* stage0 = reinterpret_cast<cx<T>*>(smem_raw);
+  unsigned char* stage0 = smem_raw;
   cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + Cfg::STAGES * Cfg::kStageBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(E + (size_t)C * PITCH);
   const IoFlags fl{true, swap};
   const int tid = threadIdx.x;
-  // column-major mapping (stores, and loads from column tiles): lanes run along the column index
+  // column mapping: lanes run along the transform index (used where memory is contiguous across transforms)
   const int cc = tid % C, tc = tid / C;
-  // row-major mapping (IN_ROWS loads): lanes run along the row
+  // row mapping: lanes run along the element index (used where each transform is contiguous)
   const int cr = tid / TPC, tr = tid % TPC;
+  const int c1 = IN_ROWS ? cr : cc, t1 = IN_ROWS ? tr : tc;     // pass 1
+  const int c2 = OUT_ROWS ? cr : cc, t2 = OUT_ROWS ? tr : tc;   // pass 2
   const long long tiles_c = (p.nb[0] + C - 1) / C;
   const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
   const T scale = T(p.scale);
   const long long gmask = (1LL << p.gtw_bits) - 1;
+  const bool in_contig = p.ibd[0] == N;  // IN_ROWS_BULK: the C rows of a tile are one contiguous run
 
   auto decode = [&](long long tile, int& c0, int& b1, int& b2, int& b3) {
     long long q = tile / tiles_c;
@@ -119,14 +138,29 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
   auto issue = [&](long long tile, int s) {
     int c0, b1, b2, b3;
     decode(tile, c0, b1, b2, b3);
-    col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
+    unsigned char* dst = stage0 + s * Cfg::kStageBytes;
+    if (IN == IN_COLS_TMA) {
+      col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
 #pragma unroll
-    for (int r0 = 0; r0 < N; r0 += Cfg::kBoxRows)
-      col::tma_load_5d(reinterpret_cast<unsigned char*>(stage0) + s * Cfg::kStageBytes + (size_t)r0 * C * sizeof(cx<T>),
-                       &tmap, 2 * c0, r0, b1, b2, b3, &full[s]);  // innermost coordinate counts scalars
+      for (int r0 = 0; r0 < N; r0 += Cfg::kBoxRows)
+        col::tma_load_5d(dst + (size_t)r0 * C * sizeof(cx<T>), &tmap, 2 * c0, r0, b1, b2, b3,
+                         &full[s]);  // innermost coordinate counts scalars
+    } else {
+      const int rows = (int)min((long long)C, p.nb[0] - c0);
+      const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in_re) + p.ioff + (long long)c0 * p.ibd[0] +
+                         (long long)b1 * p.ibd[1] + (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
+      col::mbar_expect_tx(&full[s], (uint32_t)(rows * N * sizeof(cx<T>)));
+      if (in_contig) {
+        col::bulk_g2s(dst, src, (uint32_t)(rows * N * sizeof(cx<T>)), &full[s]);
+      } else {
+        for (int r = 0; r < rows; ++r)
+          col::bulk_g2s(dst + (size_t)r * N * sizeof(cx<T>), src + (long long)r * p.ibd[0], (uint32_t)(N * sizeof(cx<T>)),
+                        &full[s]);
+      }
+    }
   };
 
-  if (!IN_ROWS) {
+  if (RING) {
     if (tid == 0) {
       col::mbar_init(&full[0], 1);
       col::mbar_init(&full[1], 1);
@@ -146,15 +180,27 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
     int c0, b1, b2, b3;
     decode(tile, c0, b1, b2, b3);
-    // ---- pass 1: radix N1 over x[j + N2*r], result to E[column][pad(j*N1 + r)] ----------------------------------
-    if (!IN_ROWS) {
-      const cx<T>* S = reinterpret_cast<const cx<T>*>(reinterpret_cast<unsigned char*>(stage0) + (it & 1) * Cfg::kStageBytes);
-      col::mbar_wait(&full[it & 1], (it >> 1) & 1);
+    // ---- pass 1: radix N1 over x[j + N2*r], result to E[transform][pad(j*N1 + r)] -------------------------------
+    {
+      const cx<T>* S = reinterpret_cast<const cx<T>*>(stage0 + (it & 1) * Cfg::kStageBytes);
+      const bool live = c0 + c1 < p.nb[0];
+      const long long ib = p.ioff + (long long)(c0 + c1) * p.ibd[0] + (long long)b1 * p.ibd[1] +
+                           (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
+      if (RING) col::mbar_wait(&full[it & 1], (it >> 1) & 1);
 #pragma unroll 1
-      for (int j = tc; j < N2; j += TPC) {
+      for (int j = t1; j < N2; j += TPC) {
         cx<T> v[N1];
+        if (IN == IN_COLS_TMA) {
 #pragma unroll
-        for (int r = 0; r < N1; ++r) v[r] = S[(j + N2 * r) * C + cc];
+          for (int r = 0; r < N1; ++r) v[r] = S[(j + N2 * r) * C + c1];
+        } else if (IN == IN_ROWS_BULK) {
+#pragma unroll
+          for (int r = 0; r < N1; ++r) v[r] = S[c1 * N + j + N2 * r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < N1; ++r)
+            v[r] = live ? reinterpret_cast<const cx<T>*>(p.in_re)[ib + (j + N2 * r)] : cx<T>{T(0), T(0)};
+        }
         if (swap) {
 #pragma unroll
           for (int r = 0; r < N1; ++r) {
@@ -165,24 +211,11 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
         }
         DFT<N1, T>::run(v);
 #pragma unroll
-        for (int r = 0; r < N1; ++r) E[cc * PITCH + col::pad<T>(j * N1 + r)] = v[r];
-      }
-    } else {
-      const bool live = c0 + cr < p.nb[0];
-      const long long ib = p.ioff + (long long)(c0 + cr) * p.ibd[0] + (long long)b1 * p.ibd[1] +
-                           (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
-#pragma unroll 1
-      for (int j = tr; j < N2; j += TPC) {
-        cx<T> v[N1];
-#pragma unroll
-        for (int r = 0; r < N1; ++r) v[r] = live ? gload<T>(p, fl, ib + (j + N2 * r)) : cx<T>{T(0), T(0)};
-        DFT<N1, T>::run(v);
-#pragma unroll
-        for (int r = 0; r < N1; ++r) E[cr * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+        for (int r = 0; r < N1; ++r) E[c1 * PITCH + col::pad<T>(j * N1 + r)] = v[r];
       }
     }
     __syncthreads();
-    if (!IN_ROWS && tid == 0) {
+    if (RING && tid == 0) {
       // the stage just consumed is free: refill it with the tile two iterations ahead
       const long long nxt = tile + 2LL * gridDim.x;
       if (nxt < total_tiles) {
@@ -190,18 +223,18 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN_ROWS>::NT)
         issue(nxt, it & 1);
       }
     }
-    // ---- pass 2: E[column][pad(j + N1*r)] * w_N^{j r}, radix N2, store out[(j + N1*r)*os + column] ---------------
+    // ---- pass 2: E[transform][pad(j + N1*r)] * w_N^{j r}, radix N2, store out[base + (j + N1*r)*os] --------------
     {
-      const bool live = c0 + cc < p.nb[0];
-      const long long ob = p.ooff + (long long)(c0 + cc) * p.obd[0] + (long long)b1 * p.obd[1] +
+      const bool live = c0 + c2 < p.nb[0];
+      const long long ob = p.ooff + (long long)(c0 + c2) * p.obd[0] + (long long)b1 * p.obd[1] +
                            (long long)b2 * p.obd[2] + (long long)b3 * p.obd[3];
       long long gidx = 0;
-      if (p.gtw_dim >= 0) gidx = p.gtw_dim == 0 ? c0 + cc : (p.gtw_dim == 1 ? b1 : (p.gtw_dim == 2 ? b2 : b3));
+      if (p.gtw_dim >= 0) gidx = p.gtw_dim == 0 ? c0 + c2 : (p.gtw_dim == 1 ? b1 : (p.gtw_dim == 2 ? b2 : b3));
 #pragma unroll 1
-      for (int j = tc; j < N1; j += TPC) {
+      for (int j = t2; j < N1; j += TPC) {
         cx<T> v[N2];
 #pragma unroll
-        for (int r = 0; r < N2; ++r) v[r] = E[cc * PITCH + col::pad<T>(j + N1 * r)];
+        for (int r = 0; r < N2; ++r) v[r] = E[c2 * PITCH + col::pad<T>(j + N1 * r)];
 #pragma unroll
         for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
         DFT<N2, T>::run(v);
@@ -272,27 +305,41 @@ static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_
   return r == CUDA_SUCCESS;
 }
 
+template <typename T, int N1, int N2, int IN, bool OUT_ROWS>
+static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, int grid, cudaStream_t stream) {
+  using Cfg = ColCfg<T, N1, N2, IN>;
+  auto kern = wg_col_kernel<T, N1, N2, IN, OUT_ROWS>;
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
+  return cudaGetLastError();
+}
+
+// variant: bits 0-1 = input mode, bit 2 = OUT_ROWS
 template <typename T, int N1, int N2>
-static cudaError_t launch_col_t(const PassParams& p, bool swap, bool in_rows, int grid, cudaStream_t stream, bool* used) {
+static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int grid, cudaStream_t stream, bool* used) {
   *used = false;
+  int in = variant & 3;
+  const bool out_rows = (variant & 4) != 0;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if (in_rows) {
-    using Cfg = ColCfg<T, N1, N2, true>;
-    auto kern = wg_col_kernel<T, N1, N2, true>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
-  } else {
-    using Cfg = ColCfg<T, N1, N2, false>;
+  if (in == IN_COLS_TMA) {
+    using Cfg = ColCfg<T, N1, N2, IN_COLS_TMA>;
     if (!make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
-    auto kern = wg_col_kernel<T, N1, N2, false>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
-    if (e != cudaSuccess) return e;
-    kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
+  }
+  if (in == IN_ROWS_BULK) {
+    const uintptr_t base = reinterpret_cast<uintptr_t>(p.in_re) + (size_t)p.ioff * 2 * sizeof(T);
+    if (base % 16 != 0) in = IN_ROWS_DIRECT;
   }
   *used = true;
-  return cudaGetLastError();
+  if (in == IN_COLS_TMA)
+    return out_rows ? launch_col_v<T, N1, N2, IN_COLS_TMA, true>(p, swap, map, grid, stream)
+                    : launch_col_v<T, N1, N2, IN_COLS_TMA, false>(p, swap, map, grid, stream);
+  if (in == IN_ROWS_BULK)
+    return out_rows ? launch_col_v<T, N1, N2, IN_ROWS_BULK, true>(p, swap, map, grid, stream)
+                    : launch_col_v<T, N1, N2, IN_ROWS_BULK, false>(p, swap, map, grid, stream);
+  return out_rows ? launch_col_v<T, N1, N2, IN_ROWS_DIRECT, true>(p, swap, map, grid, stream)
+                  : launch_col_v<T, N1, N2, IN_ROWS_DIRECT, false>(p, swap, map, grid, stream);
 }
 
 bool col_supported(int n, bool is_double, int* n1, int* n2) {
@@ -310,11 +357,11 @@ bool col_supported(int n, bool is_double, int* n1, int* n2) {
   return true;
 }
 
-size_t col_smem_bytes(int n, bool is_double, bool in_rows) {
+size_t col_smem_bytes(int n, bool is_double, bool ring) {
   const size_t esz = is_double ? 16 : 8;
   const int c = 128 / (int)esz;
   const int pitch = is_double ? col::pitch<double>(n) : col::pitch<float>(n);
-  return (in_rows ? 0 : 2) * (size_t)n * c * esz + (size_t)c * pitch * esz + 64;
+  return (ring ? 2 : 0) * (size_t)n * c * esz + (size_t)c * pitch * esz + 64;
 }
 
 int col_threads(int n, bool is_double) {
@@ -325,19 +372,19 @@ int col_threads(int n, bool is_double) {
 }
 
 // *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
-cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, bool in_rows, int grid, cudaStream_t stream,
+cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
                           bool* used) {
 #define PFFT_COL(NN, A, B)                                                                  \
   case NN:                                                                                  \
-    return is_double ? launch_col_t<double, A, B>(p, swap, in_rows, grid, stream, used)              \
-                     : launch_col_t<float, A, B>(p, swap, in_rows, grid, stream, used);
+    return is_double ? launch_col_t<double, A, B>(p, swap, variant, grid, stream, used)              \
+                     : launch_col_t<float, A, B>(p, swap, variant, grid, stream, used);
   *used = false;
   switch (p.n) {
     PFFT_COL(64, 8, 8)
     PFFT_COL(128, 16, 8)
     PFFT_COL(256, 16, 16)
     case 512:
-      return is_double ? cudaErrorInvalidValue : launch_col_t<float, 16, 32>(p, swap, in_rows, grid, stream, used);
+      return is_double ? cudaErrorInvalidValue : launch_col_t<float, 16, 32>(p, swap, variant, grid, stream, used);
     default:
       return cudaErrorInvalidValue;
   }

@@ -70,7 +70,8 @@ SUITES = {
     # not in the reference grid: column-tile kernel (TMA tiles with ragged column counts, odd strides -> fallback)
     "ColumnTileTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
                             [[64, 100], [128, 24], [256, 20], [512, 36], [64, 33], [256, 256], [64, 64, 64]]),
-    "ColumnTileOffsetsTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
+    "ColumnTileOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
+    "ColumnTileOffsetsMatchedTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(3, 3), (16, 16)]),
     "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
     "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
     "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
