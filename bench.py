@@ -78,7 +78,8 @@ def measured_peak():
 
 
 class ClockSampler(threading.Thread):
-    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+    """Samples SM clock / throttle reasons while the timed region runs (B200_PROFILING.md recipe).  NVML through
+    pynvml (~1 ms per sample, so that even a 10 ms timed region is covered); `nvidia-smi` as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
@@ -87,35 +88,70 @@ class ClockSampler(threading.Thread):
     def __init__(self, index: int):
         super().__init__(daemon=True)
         self.index = index
-        self.samples = []
+        self.samples = []  # (sm_mhz, max_mhz, set(reasons))
         self.stop_flag = threading.Event()
+        self.nvml = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index(index))
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
+
+    @staticmethod
+    def _physical_index(index: int) -> int:
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            try:
+                return int(vis.split(",")[index])
+            except Exception:
+                return index
+        return index
+
+    def _sample_nvml(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        mask = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        reasons = set()
+        for name, bit in (("hw_slowdown", n.nvmlClocksEventReasonHwSlowdown),
+                          ("hw_thermal_slowdown", n.nvmlClocksEventReasonHwThermalSlowdown),
+                          ("sw_thermal_slowdown", n.nvmlClocksEventReasonSwThermalSlowdown),
+                          ("sw_power_cap", n.nvmlClocksEventReasonSwPowerCap)):
+            if mask & bit:
+                reasons.add(name)
+        self.samples.append((mhz, self.max_mhz, reasons))
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            reasons = {nm for nm, val in zip(names, f[5:9]) if val.lower().startswith("active")}
+            self.samples.append((float(f[1]), float(f[2]), reasons))
 
     def run(self):
         while not self.stop_flag.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.index)], capture_output=True, text=True, timeout=5).stdout
-                for line in out.strip().splitlines():
-                    self.samples.append([x.strip() for x in line.split(",")])
+                if self.nvml is not None:
+                    self._sample_nvml()
+                else:
+                    self._sample_smi()
             except Exception:
                 pass
-            self.stop_flag.wait(0.1)
+            self.stop_flag.wait(0.002 if self.nvml is not None else 0.1)
 
     def summary(self):
-        sm, mx, reasons = [], 0.0, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        sm = sorted(s[0] for s in self.samples)
+        mx = max((s[1] for s in self.samples), default=0.0)
+        reasons = set()
         for s in self.samples:
-            try:
-                sm.append(float(s[1]))
-                mx = max(mx, float(s[2]))
-                for name, val in zip(names, s[5:9]):
-                    if val.lower().startswith("active"):
-                        reasons.add(name)
-            except Exception:
-                continue
-        sm.sort()
+            reasons |= s[2]
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvml" if self.nvml is not None else "nvidia-smi"}
 
 
 def load_oracle():
@@ -190,15 +226,105 @@ def run_reference_arm(args, cfg, name):
     print(json.dumps(line), flush=True)
 
 
+def run_slab(args, cfg, name, rank, local_rank, world, dev):
+    """--config C5 --gpus N>1: ONE 512^3 transform slab-decomposed over the N GPUs (strong scaling).  Local passes =
+    the C-ABI plans; exchange = FFT stores into peer memory (symmetric memory over NVLink) or NCCL all-to-all
+    (--exchange nccl).  The spectrum is left y-slab distributed (portfft_b200/distributed.py)."""
+    import torch
+    import torch.distributed as dist
+
+    import portfft_b200 as pf
+    from portfft_b200.distributed import slab_fft3d
+
+    n0, n1, n2 = cfg["lengths"]
+    plan = slab_fft3d(cfg["lengths"], cfg["scalar"], exchange=args.exchange, device=dev)
+    g = plan.geom
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(1234 + rank)
+    x = torch.view_as_complex(torch.rand(g.xl, n1, n2, 2, generator=gen, device=dev, dtype=torch.float32) * 2 - 1)
+
+    def barrier():
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    for _ in range(args.warmup):
+        out = plan.forward(x)
+    barrier()
+    e_in = (x.abs().double() ** 2).sum()
+    e_out = (out.abs().double() ** 2).sum()
+    t = torch.stack([e_in, e_out])
+    dist.all_reduce(t)
+    parseval = float(abs(t[1] / (t[0] * n0 * n1 * n2) - 1.0))
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    l0 = pf.total_launches()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record()
+    for _ in range(args.steps):
+        plan.forward(x)
+    ev1.record()
+    barrier()
+    launches = pf.total_launches() - l0
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join()
+    tm = torch.tensor([ev0.elapsed_time(ev1) / args.steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+    ms = float(tm.item())
+    # e2e: pinned host slab in, y-slab of the spectrum back to the host, every step
+    h_in = torch.empty(x.shape, dtype=x.dtype).pin_memory()
+    h_in.copy_(x)
+    h_out = torch.empty((n0, g.yb, n2), dtype=x.dtype).pin_memory()
+    xd = torch.empty_like(x)
+    e_steps = max(1, min(args.steps, 4))
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e_steps):
+        xd.copy_(h_in, non_blocking=True)
+        h_out.copy_(plan.forward(xd), non_blocking=True)
+        torch.cuda.synchronize(dev)
+    barrier()
+    te = torch.tensor([(time.perf_counter() - t0) / e_steps], dtype=torch.float64, device=dev)
+    dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    te = float(te.item())
+    if rank == 0:
+        flops = flops_of(cfg)
+        peak, peak_src = measured_peak()
+        nv_bytes = (world - 1) * g.block_elems * 8
+        line = {
+            "metric": "batched_c2c_gflops", "value": flops / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"{name}: {cfg['desc']}", "decomposition": f"x-slabs of {g.xl} planes per GPU, one "
+                       f"exchange step ({args.exchange}), spectrum left y-slab distributed",
+                       "l2": "per-GPU slab %.0f MiB" % (g.slab_elems * 8 / 2**20)},
+            "hbm_gbs": bytes_of(cfg) / (ms * 1e-3) / 1e9,
+            "roofline": {"bound": "nvlink", "achieved": nv_bytes / (ms * 1e-3) / 1e9, "peak": 770.0, "unit": "GB/s",
+                         "frac": nv_bytes / (ms * 1e-3) / 1e9 / 770.0, "traffic": None,
+                         "peak_source": "measured peer copy per direction per GPU (B200_PROFILING.md)",
+                         "note": "achieved = bytes each GPU sends over NVLink / whole step time (local passes included)"},
+            "cpu_baseline": None,
+            "e2e": {"value": flops / te / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": g.slab_elems * 8,
+                    "d2h_bytes_per_step": g.slab_elems * 8, "steps": e_steps, "ms_per_step": te * 1e3,
+                    "api": "slab_fft3d.forward with pinned host slabs"},
+            "gpu_launches": int(launches), "clocks": sampler.summary(), "parseval_rel": parseval,
+        }
+        print(json.dumps(line), flush=True)
+    plan.destroy()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="slab exchange (C5 at --gpus > 1)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
     if args.impl == "reference":
@@ -219,6 +345,11 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+
+    if args.config == "C5" and world > 1:
+        run_slab(args, cfg, args.config, rank, local_rank, world, dev)
+        dist.destroy_process_group()
+        return
 
     def barrier():
         if world > 1:
