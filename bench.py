@@ -324,6 +324,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the timed steps from one CUDA graph (launch-bound configs)")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="slab exchange (C5 at --gpus > 1)")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -331,6 +332,8 @@ def main():
         run_reference_arm(args, cfg, args.config)
         return
     args.warmup = max(args.warmup, 3)
+    if args.graph and args.steps % 2:
+        args.steps += 1  # a replay must leave the in-place data where it started
 
     import numpy as np
     import torch
@@ -410,14 +413,40 @@ def main():
         sampler.start()
     launches0 = pf.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph = None
+    if args.graph:
+        # launch-bound workloads: the K steps are captured once into a CUDA graph (stream capture of the same C-ABI
+        # calls) and the timed region replays it; the work on the device is identical
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(stream)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph, stream=side):
+            cap = torch.cuda.current_stream(dev)
+            for i in range(args.steps):
+                if i % 2 == 0:
+                    (plan.compute_forward(*fwd_buf, queue=cap) if cfg["inplace"]
+                     else plan.compute_forward(*fwd_buf, *bwd_buf, queue=cap))
+                else:
+                    (plan.compute_backward(*fwd_buf, queue=cap) if cfg["inplace"]
+                     else plan.compute_backward(*bwd_buf, *fwd_buf, queue=cap))
+        stream.wait_stream(side)
+        with torch.cuda.stream(stream):
+            graph.replay()  # warm replay
+        barrier()
     barrier()
     ev0.record(stream)
-    for i in range(args.steps):
-        step(args.warmup + i)
+    if graph is not None:
+        with torch.cuda.stream(stream):
+            graph.replay()
+    else:
+        for i in range(args.steps):
+            step(args.warmup + i)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = pf.total_launches() - launches0
+    if graph is not None:  # the replayed graph holds the launches counted at capture time
+        launches = args.steps * plan.num_launches(pf.direction.FORWARD)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
@@ -513,7 +542,7 @@ def main():
                        "sharding": "batch-sharded, one plan per GPU, no collective"},
             "hbm_gbs": hbm_gbs, "hbm_frac_of_measured": hbm_gbs / world / peak,
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "roundtrip_rel_l2": roundtrip,
+            "clocks": sampler.summary(), "roundtrip_rel_l2": roundtrip, "cuda_graph": bool(args.graph),
         }
         print(json.dumps(line), flush=True)
     plan.destroy()

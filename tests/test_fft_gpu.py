@@ -72,6 +72,8 @@ SUITES = {
                             [[64, 100], [128, 24], [256, 20], [512, 36], [64, 33], [256, 256], [64, 64, 64]]),
     "ColumnTileOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
     "ColumnTileOffsetsMatchedTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(3, 3), (16, 16)]),
+    # BASELINE config C4 at full length (one transform) and a 2^20 case: three / two column-tile passes
+    "LargeGlobalTest": basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [1], [1 << 20, 1 << 24]),
     "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
     "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
     "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
