@@ -40,4 +40,8 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
 cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
                           bool* used);
 
+// WORKGROUP level, three compile-time radix passes for any layout / storage (wg_r3.cu): n in {1000, 1024, 1536, 2048,
+// 3072, 4096}; geometry = p.ffts_per_block transforms per CTA, r3_supported's threads per transform
+cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
+
 }  // namespace pfft

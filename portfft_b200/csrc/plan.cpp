@@ -439,6 +439,32 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   }
 }
 
+// Three compile-time radix passes (wg_r3.cu) for layouts the tile kernels cannot take: replaces the generic kernel
+// when both sides are accessed directly by the butterfly threads.  Rewrites the pass geometry (no fallback needed:
+// the kernel takes every pointer alignment).
+void select_r3(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
+  PassParams& p = ps.pp;
+  const char* env = std::getenv("PFFT_NO_R3");
+  if (env && std::atoi(env) != 0) return;
+  int tpf = 0, pitch = 0;
+  if (p.gtw_dim >= 0 || p.in_mode != IO_DIRECT || p.out_mode != IO_DIRECT) return;
+  if (!r3_supported(p.n, d.is_double, &tpf, &pitch)) return;
+  const size_t esz = d.is_double ? 16 : 8;
+  int F = std::max(1, 256 / tpf);
+  while (F > 1 && (size_t)2 * F * pitch * esz > kSoftSmem) F /= 2;
+  while (F > 1 && F / 2 >= p.batch_total) F /= 2;
+  if (F * tpf > 512 || (size_t)2 * F * pitch * esz > lim.max_smem_per_block) return;
+  p.threads_per_fft = tpf;
+  p.ffts_per_block = F;
+  p.pitch = pitch;
+  ps.block = F * tpf;
+  ps.smem = (size_t)2 * F * pitch * esz;
+  const long long blocks = (p.batch_total + F - 1) / F;
+  const int per_sm = std::max<int>(1, std::min<int>(2048 / ps.block, (int)((lim.max_smem_per_block + 1024) / (ps.smem + 1024))));
+  ps.grid = (int)std::min<long long>(blocks, (long long)lim.num_sms * per_sm);
+  ps.kernel = KERNEL_WG_R3;
+}
+
 // Tile kernel (wg_col.cu): 16 (fp32) / 8 (fp64) transforms per CTA iteration, fed by TMA.  Input side: strided columns
 // whose fastest batch dimension is contiguous (TMA tensor tiles) or contiguous rows (cp.async.bulk / direct loads);
 // output side: columns (fastest batch dimension contiguous) or contiguous rows.  Covers the packed 1-D sizes
@@ -576,6 +602,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
         configure_wg_generic(wg, dbl, lim, false);
         select_specialised(wg, d, lim);
         if (wg.kernel == KERNEL_WG_GENERIC) select_col(wg, d, lim);
+        if (wg.kernel == KERNEL_WG_GENERIC) select_r3(wg, d, lim);
         if (force == LEVEL_WORKGROUP || (force < 0 && wg.kernel != KERNEL_WG_GENERIC)) {
           ps = wg;
         } else if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) {
@@ -691,7 +718,7 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
   static const char* buf_names[] = {"in", "out", "scratch"};
   std::stringstream ss;

@@ -56,7 +56,7 @@ void validate_descriptor(const DescHost& d);  // throws PlanError
 
 enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
 
-enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4 };
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -80,6 +80,8 @@ bool sg_supports_m(int m, bool is_double);
 bool col_supported(int n, bool is_double, int* n1, int* n2);
 size_t col_smem_bytes(int n, bool is_double, bool ring);
 int col_threads(int n, bool is_double);
+// three-radix kernel (wg_r3.cu)
+bool r3_supported(int n, bool is_double, int* threads_per_fft, int* pitch);
 
 struct PlanHost {
   DescHost desc;

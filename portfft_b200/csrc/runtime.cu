@@ -231,6 +231,9 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
       case KERNEL_SG:
         e = d.is_double ? launch_sg_f64(p, il, il && bwd, ps.grid, stream) : launch_sg_f32(p, il, il && bwd, ps.grid, stream);
         break;
+      case KERNEL_WG_R3:
+        e = launch_wg_r3(p, d.is_double, il, il && bwd, ps.grid, stream);
+        break;
       case KERNEL_WG_COL: {
         bool used = false;
         e = launch_wg_col(p, d.is_double, il && bwd, ps.variant, ps.alt_grid, stream, &used);
