@@ -78,6 +78,7 @@ __host__ __device__ constexpr int pitch(int n) {
   return (pad<T>(n - 1) + 1) | 1;
 }
 constexpr int cmin(int a, int b) { return a < b ? a : b; }
+constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 }  // namespace col
 

@@ -13,6 +13,8 @@
 //     bank-conflict free (the reference pads with pad_local, memory_views.hpp:79-85);
 //   * backward = (re <-> im) swap, scale fused on store; all N loads of a thread are in flight together.
 #pragma once
+#include <cstdint>
+
 #include "io.cuh"
 #include "kernels.h"
 
@@ -25,8 +27,26 @@ __host__ __device__ constexpr int wi_pitch() {
   return N | 1;
 }
 
+// one complex element global -> shared by cp.async: interleaved storage = one copy of sizeof(complex), split storage =
+// one copy per component (the element size is the alignment both sides are guaranteed to have)
+template <typename T>
+__device__ __forceinline__ void cp_async_cx(cx<T>* dst, const PassParams& p, bool il, long long idx) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+  if (il) {
+    const cx<T>* src = reinterpret_cast<const cx<T>*>(p.in_re) + idx;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(src), "n"(2 * sizeof(T)) : "memory");
+  } else {
+    const T* re = reinterpret_cast<const T*>(p.in_re) + idx;
+    const T* im = reinterpret_cast<const T*>(p.in_im) + idx;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d), "l"(re), "n"(sizeof(T)) : "memory");
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(d + (unsigned)sizeof(T)), "l"(im), "n"(sizeof(T))
+                 : "memory");
+  }
+}
+
 template <int N, typename T>
-__global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, const bool il, const bool swap) {
+__global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, const bool il, const bool swap,
+                                                        const bool use_async) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   constexpr int PITCH = wi_pitch<N>();
   constexpr int F = kWiThreads;
@@ -56,15 +76,37 @@ __global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, cons
       }
       const long long tile0 = p.ioff + g0 * (long long)N;
       const int total = nf * N;
+      if (use_async) {
+        // cp.async (LDGSTS): global -> shared without staging registers, all N copies of a thread in flight at once
+        // (rolled loop: the copies do not block, and unrolling only multiplies address registers)
+#pragma unroll 2
+        for (int i = 0; i < N; ++i) {
+          const int e = tid + i * F;
+          if (e < total) {
+            const int ff = e / N, k = e - ff * N;
+            cp_async_cx<T>(&buf[ff * PITCH + k], p, il, in_contig ? tile0 + e : s_base[ff] + k * p.is);
+          }
+        }
+        asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+      } else {
 #pragma unroll 4
-      for (int e = tid; e < total; e += F) {
-        const int ff = e / N, i = e - ff * N;
-        buf[ff * PITCH + i] = gload<T>(p, fl, in_contig ? tile0 + e : s_base[ff] + i * p.is);
+        for (int e = tid; e < total; e += F) {
+          const int ff = e / N, k = e - ff * N;
+          buf[ff * PITCH + k] = gload<T>(p, IoFlags{il, false}, in_contig ? tile0 + e : s_base[ff] + k * p.is);
+        }
       }
       __syncthreads();
       if (active) {
 #pragma unroll
         for (int j = 0; j < N; ++j) v[j] = buf[tid * PITCH + j];
+        if (swap) {
+#pragma unroll
+          for (int j = 0; j < N; ++j) {
+            const T tmp = v[j].x;
+            v[j].x = v[j].y;
+            v[j].y = tmp;
+          }
+        }
       }
     } else if (active) {
 #pragma unroll
@@ -91,12 +133,15 @@ __global__ void __launch_bounds__(kWiThreads) wi_kernel(const PassParams p, cons
       const long long tile0 = p.ooff + g0 * (long long)N;
       const int total = nf * N;
 #pragma unroll 4
-      for (int e = tid; e < total; e += F) {
-        const int ff = e / N, i = e - ff * N;
-        if (out_contig)
-          gstore<T>(p, fl, tile0 + e, buf[ff * PITCH + i]);
-        else
-          gstore<T>(p, fl, s_base[ff] + i * p.os, buf[ff * PITCH + i], s_peer[ff]);
+      for (int i = 0; i < N; ++i) {
+        const int e = tid + i * F;
+        if (e < total) {
+          const int ff = e / N, k = e - ff * N;
+          if (out_contig)
+            gstore<T>(p, fl, tile0 + e, buf[ff * PITCH + k]);
+          else
+            gstore<T>(p, fl, s_base[ff] + k * p.os, buf[ff * PITCH + k], s_peer[ff]);
+        }
       }
     } else if (active) {
 #pragma unroll
@@ -113,7 +158,11 @@ cudaError_t launch_wi_n(const PassParams& p, bool il, bool swap, int grid, cudaS
     cudaError_t e = cudaFuncSetAttribute(wi_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
   }
-  wi_kernel<N, T><<<grid, kWiThreads, smem, stream>>>(p, il, swap);
+  // cp.async needs the source aligned to the copy size: element alignment of the user's pointers
+  const size_t unit = il ? 2 * sizeof(T) : sizeof(T);
+  const bool use_async = reinterpret_cast<uintptr_t>(p.in_re) % unit == 0 &&
+                         (il || reinterpret_cast<uintptr_t>(p.in_im) % unit == 0);
+  wi_kernel<N, T><<<grid, kWiThreads, smem, stream>>>(p, il, swap, use_async);
   return cudaGetLastError();
 }
 

@@ -106,3 +106,27 @@ CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.i
 @pytest.mark.parametrize("tp", CASES)
 def test_reference_grid(tp):
     run_case(tp)
+
+
+# ---- every level's kernel stays under test: the planner's default choice prefers the TMA tile kernels, so the
+# ---- warp-level (SUBGROUP) kernel and the generic block-level kernel are forced for a slice of the grid
+FORCED = {
+    "subgroup": ({"PFFT_FORCE_LEVEL": "1"},
+                 basic(ALL_LAYOUTS[:3], BOTH_DIR, STORAGES, [1, 131], [64, 96, 128, 256, 512, 1024])),
+    "workgroup_generic": ({"PFFT_FORCE_LEVEL": "2", "PFFT_NO_COL": "1", "PFFT_NO_R3": "1", "PFFT_CUBE_VARIANT": "-1"},
+                          basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16, 64, 100, 512, 1000, 4096]) +
+                          basic(GLOBAL_LAYOUTS, ["fwd"], ["interleaved"], [3], [32768, 65536]) +
+                          basic(MD_LAYOUTS, ["fwd"], ["interleaved"], [3], [[16, 512], [64, 64, 64]])),
+    "cube_direct_loads": ({"PFFT_CUBE_VARIANT": "1"}, basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"],
+                                                            [5], [4096])),
+}
+FORCED_CASES = [pytest.param(env, tp, id=f"{name}-{tp.ident()}") for name, (env, tps) in FORCED.items() for tp in tps]
+
+
+@pytest.mark.parametrize("env,tp", FORCED_CASES)
+def test_forced_kernel_paths(env, tp, monkeypatch):
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    if env.get("PFFT_FORCE_LEVEL") == "1" and tp.scalar == "double" and max(tp.lengths) > 512:
+        pytest.skip("fp64 warp-level kernel covers N <= 512")
+    run_case(tp)
