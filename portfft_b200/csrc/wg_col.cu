@@ -23,6 +23,7 @@
 #include <cuda.h>
 
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 
 #include "device_utils.cuh"
@@ -89,11 +90,15 @@ enum : int {
   IN_ROWS_BULK = 2    // contiguous rows, 16-byte aligned: cp.async.bulk (TMA 1-D) into the ring, layout [row][j]
 };
 
-template <typename T, int N1, int N2, int IN>
+template <typename T, int N1, int N2, int N3, int IN>
 struct ColCfg {
-  static constexpr int N = N1 * N2;
+  static_assert(N3 == 1 || (N1 == N2 && N2 == N3), "three-pass variant: equal radices (one butterfly per thread)");
+  static constexpr int N = N1 * N2 * N3;
   static constexpr int C = 128 / (2 * (int)sizeof(T));  // transforms per tile: 16 (fp32) / 8 (fp64)
-  static constexpr int TPC = col::cmin(col::cmin(N1, N2), 16);  // threads per transform
+  static constexpr int NL = N3 > 1 ? N3 : N2;           // radix of the last pass
+  static constexpr int NS = N / NL;                     // butterflies of the last pass
+  // threads per transform: two-pass variants loop over their butterflies, the three-pass variant has one per thread
+  static constexpr int TPC = N3 > 1 ? N / N1 : col::cmin(col::cmin(N1, N2), 16);
   static constexpr int NT = C * TPC;
   static constexpr int PITCH = col::pitch<T>(N);
   static constexpr int STAGES = IN == IN_ROWS_DIRECT ? 0 : 2;
@@ -102,11 +107,12 @@ struct ColCfg {
   static constexpr int kBoxRows = N < 256 ? N : 256;
 };
 
-template <typename T, int N1, int N2, int IN, bool OUT_ROWS>
-__global__ void __launch_bounds__(ColCfg<T, N1, N2, IN>::NT)
+template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS>
+__global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
     wg_col_kernel(const PassParams p, const __grid_constant__ CUtensorMap tmap, const bool swap) {
-  using Cfg = ColCfg<T, N1, N2, IN>;
-  constexpr int N = Cfg::N, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH;
+  using Cfg = ColCfg<T, N1, N2, N3, IN>;
+  constexpr int N = Cfg::N, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH, NL = Cfg::NL, NS = Cfg::NS;
+  constexpr int B1 = N / N1;  // butterflies of pass 1
   constexpr bool IN_ROWS = IN != IN_COLS_TMA;
   constexpr bool RING = IN != IN_ROWS_DIRECT;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -189,18 +195,18 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN>::NT)
                            (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
       if (RING) col::mbar_wait(&full[it & 1], (it >> 1) & 1);
 #pragma unroll 1
-      for (int j = t1; j < N2; j += TPC) {
+      for (int j = t1; j < B1; j += TPC) {
         cx<T> v[N1];
         if (IN == IN_COLS_TMA) {
 #pragma unroll
-          for (int r = 0; r < N1; ++r) v[r] = S[(j + N2 * r) * C + c1];
+          for (int r = 0; r < N1; ++r) v[r] = S[(j + B1 * r) * C + c1];
         } else if (IN == IN_ROWS_BULK) {
 #pragma unroll
-          for (int r = 0; r < N1; ++r) v[r] = S[c1 * N + j + N2 * r];
+          for (int r = 0; r < N1; ++r) v[r] = S[c1 * N + j + B1 * r];
         } else {
 #pragma unroll
           for (int r = 0; r < N1; ++r)
-            v[r] = live ? reinterpret_cast<const cx<T>*>(p.in_re)[ib + (j + N2 * r)] : cx<T>{T(0), T(0)};
+            v[r] = live ? reinterpret_cast<const cx<T>*>(p.in_re)[ib + (j + B1 * r)] : cx<T>{T(0), T(0)};
         }
         if (swap) {
 #pragma unroll
@@ -224,7 +230,21 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN>::NT)
         issue(nxt, it & 1);
       }
     }
-    // ---- pass 2: E[transform][pad(j + N1*r)] * w_N^{j r}, radix N2, store out[base + (j + N1*r)*os] --------------
+    if (N3 > 1) {
+      // ---- middle pass (three-pass variant), in place on E: read, barrier, write --------------------------------
+      const int j = tc, k = j % N1;
+      cx<T> v[N2];
+#pragma unroll
+      for (int r = 0; r < N2; ++r) v[r] = E[cc * PITCH + col::pad<T>(j + (N / N2) * r)];
+#pragma unroll
+      for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, k * r * N3));  // w_{N1 N2}^{k r}
+      DFT<N2, T>::run(v);
+      __syncthreads();
+#pragma unroll
+      for (int r = 0; r < N2; ++r) E[cc * PITCH + col::pad<T>((j - k) * N2 + k + N1 * r)] = v[r];
+      __syncthreads();
+    }
+    // ---- last pass: E[transform][pad(j + NS*r)] * w_N^{j r}, radix NL, store out[base + (j + NS*r)*os] -----------
     {
       const bool live = c0 + c2 < p.nb[0];
       const long long ob = p.ooff + (long long)(c0 + c2) * p.obd[0] + (long long)b1 * p.obd[1] +
@@ -232,26 +252,26 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, IN>::NT)
       long long gidx = 0;
       if (p.gtw_dim >= 0) gidx = p.gtw_dim == 0 ? c0 + c2 : (p.gtw_dim == 1 ? b1 : (p.gtw_dim == 2 ? b2 : b3));
 #pragma unroll 1
-      for (int j = t2; j < N1; j += TPC) {
-        cx<T> v[N2];
+      for (int j = t2; j < NS; j += TPC) {
+        cx<T> v[NL];
 #pragma unroll
-        for (int r = 0; r < N2; ++r) v[r] = E[c2 * PITCH + col::pad<T>(j + N1 * r)];
+        for (int r = 0; r < NL; ++r) v[r] = E[c2 * PITCH + col::pad<T>(j + NS * r)];
 #pragma unroll
-        for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
-        DFT<N2, T>::run(v);
+        for (int r = 1; r < NL; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
+        DFT<NL, T>::run(v);
         if (live) {
-          // inter-factor twiddle w_M^{g*k}, k = j + N1*r.  fp64: two table look-ups (base w^{g*j}, step w^{g*N1}) and a
-          // running product (error ~ N2 * 1.1e-16, far inside the fp64 bound) instead of 2*N2 dependent L2 reads;
+          // inter-factor twiddle w_M^{g*k}, k = j + NS*r.  fp64: two table look-ups (base w^{g*j}, step w^{g*NS}) and a
+          // running product (error ~ NL * 1.1e-16, far inside the fp64 bound) instead of 2*NL dependent L2 reads;
           // fp32: the tables are small enough to stay in L1, every element is looked up exactly
           cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
           if (p.gtw_dim >= 0 && sizeof(T) == 8) {
-            const long long mb = gidx * j, ms = gidx * N1;
+            const long long mb = gidx * j, ms = gidx * NS;
             tw_run = cmul(ldg_cx<T>(p.gtw_hi, mb >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, mb & gmask));
             tw_step = cmul(ldg_cx<T>(p.gtw_hi, ms >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, ms & gmask));
           }
 #pragma unroll
-          for (int r = 0; r < N2; ++r) {
-            const int k = j + N1 * r;
+          for (int r = 0; r < NL; ++r) {
+            const int k = j + NS * r;
             cx<T> o = v[r];
             if (p.gtw_dim >= 0) {
               if (sizeof(T) == 8) {
@@ -320,10 +340,10 @@ static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_
   return r == CUDA_SUCCESS;
 }
 
-template <typename T, int N1, int N2, int IN, bool OUT_ROWS>
+template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS>
 static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, int grid, cudaStream_t stream) {
-  using Cfg = ColCfg<T, N1, N2, IN>;
-  auto kern = wg_col_kernel<T, N1, N2, IN, OUT_ROWS>;
+  using Cfg = ColCfg<T, N1, N2, N3, IN>;
+  auto kern = wg_col_kernel<T, N1, N2, N3, IN, OUT_ROWS>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
   if (e != cudaSuccess) return e;
   kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
@@ -331,7 +351,7 @@ static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMa
 }
 
 // variant: bits 0-1 = input mode, bit 2 = OUT_ROWS
-template <typename T, int N1, int N2>
+template <typename T, int N1, int N2, int N3>
 static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int grid, cudaStream_t stream, bool* used) {
   *used = false;
   int in = variant & 3;
@@ -339,7 +359,7 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
   if (in == IN_COLS_TMA) {
-    using Cfg = ColCfg<T, N1, N2, IN_COLS_TMA>;
+    using Cfg = ColCfg<T, N1, N2, N3, IN_COLS_TMA>;
     if (!make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
   }
   if (in == IN_ROWS_BULK) {
@@ -348,13 +368,13 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int
   }
   *used = true;
   if (in == IN_COLS_TMA)
-    return out_rows ? launch_col_v<T, N1, N2, IN_COLS_TMA, true>(p, swap, map, grid, stream)
-                    : launch_col_v<T, N1, N2, IN_COLS_TMA, false>(p, swap, map, grid, stream);
+    return out_rows ? launch_col_v<T, N1, N2, N3, IN_COLS_TMA, true>(p, swap, map, grid, stream)
+                    : launch_col_v<T, N1, N2, N3, IN_COLS_TMA, false>(p, swap, map, grid, stream);
   if (in == IN_ROWS_BULK)
-    return out_rows ? launch_col_v<T, N1, N2, IN_ROWS_BULK, true>(p, swap, map, grid, stream)
-                    : launch_col_v<T, N1, N2, IN_ROWS_BULK, false>(p, swap, map, grid, stream);
-  return out_rows ? launch_col_v<T, N1, N2, IN_ROWS_DIRECT, true>(p, swap, map, grid, stream)
-                  : launch_col_v<T, N1, N2, IN_ROWS_DIRECT, false>(p, swap, map, grid, stream);
+    return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, true>(p, swap, map, grid, stream)
+                    : launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, false>(p, swap, map, grid, stream);
+  return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, true>(p, swap, map, grid, stream)
+                  : launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, false>(p, swap, map, grid, stream);
 }
 
 bool col_supported(int n, bool is_double, int* n1, int* n2) {
@@ -366,7 +386,6 @@ bool col_supported(int n, bool is_double, int* n1, int* n2) {
     case 512: a = 16; b = 32; break;
     default: return false;
   }
-  if (is_double && n > 256) return false;
   if (n1) *n1 = a;
   if (n2) *n2 = b;
   return true;
@@ -382,24 +401,32 @@ size_t col_smem_bytes(int n, bool is_double, bool ring) {
 int col_threads(int n, bool is_double) {
   int a, b;
   if (!col_supported(n, is_double, &a, &b)) return 0;
-  const int tpc = a < b ? a : b;
-  return (128 / (is_double ? 16 : 8)) * (tpc < 16 ? tpc : 16);
+  const int tpc = n == 512 ? 64 : (a < b ? a : b);
+  return (128 / (is_double ? 16 : 8)) * (n == 512 ? tpc : (tpc < 16 ? tpc : 16));
 }
 
 // *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
 cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
                           bool* used) {
-#define PFFT_COL(NN, A, B)                                                                  \
-  case NN:                                                                                  \
-    return is_double ? launch_col_t<double, A, B>(p, swap, variant, grid, stream, used)              \
-                     : launch_col_t<float, A, B>(p, swap, variant, grid, stream, used);
+#define PFFT_COL(NN, A, B, CC)                                                                   \
+  case NN:                                                                                       \
+    return is_double ? launch_col_t<double, A, B, CC>(p, swap, variant, grid, stream, used)      \
+                     : launch_col_t<float, A, B, CC>(p, swap, variant, grid, stream, used);
   *used = false;
   switch (p.n) {
-    PFFT_COL(64, 8, 8)
-    PFFT_COL(128, 16, 8)
-    PFFT_COL(256, 16, 16)
-    case 512:
-      return is_double ? cudaErrorInvalidValue : launch_col_t<float, 16, 32>(p, swap, variant, grid, stream, used);
+    PFFT_COL(64, 8, 8, 1)
+    PFFT_COL(128, 16, 8, 1)
+    PFFT_COL(256, 16, 16, 1)
+    case 512: {
+      // three radix-8 passes (4x the threads, a third of the code) by default; PFFT_COL512=2: radix 16 x 32
+      static const int two_pass = [] {
+        const char* e = std::getenv("PFFT_COL512");
+        return e ? std::atoi(e) == 2 : 0;
+      }();
+      if (two_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, grid, stream, used);
+      return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, grid, stream, used)
+                       : launch_col_t<float, 8, 8, 8>(p, swap, variant, grid, stream, used);
+    }
     default:
       return cudaErrorInvalidValue;
   }
