@@ -499,7 +499,7 @@ void select_col(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
     out_rows = true;
   else
     return;
-  const int c = (int)(128 / esz);
+  const int c = col_tile_columns(p.n, d.is_double);
   const size_t smem = col_smem_bytes(p.n, d.is_double, in_mode != 1);
   if (smem > lim.max_smem_per_block) return;
   const long long tiles = ((p.nb[0] + c - 1) / c) * p.nb[1] * p.nb[2] * p.nb[3];

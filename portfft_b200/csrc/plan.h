@@ -80,6 +80,7 @@ bool sg_supports_m(int m, bool is_double);
 bool col_supported(int n, bool is_double, int* n1, int* n2);
 size_t col_smem_bytes(int n, bool is_double, bool ring);
 int col_threads(int n, bool is_double);
+int col_tile_columns(int n, bool is_double);
 // three-radix kernel (wg_r3.cu)
 bool r3_supported(int n, bool is_double, int* threads_per_fft, int* pitch);
 

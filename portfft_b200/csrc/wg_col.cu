@@ -94,7 +94,9 @@ template <typename T, int N1, int N2, int N3, int IN>
 struct ColCfg {
   static_assert(N3 == 1 || (N1 == N2 && N2 == N3), "three-pass variant: equal radices (one butterfly per thread)");
   static constexpr int N = N1 * N2 * N3;
-  static constexpr int C = 128 / (2 * (int)sizeof(T));  // transforms per tile: 16 (fp32) / 8 (fp64)
+  // transforms per tile: one 128-byte line per row segment (16 fp32 / 8 fp64).  Measured at N = 512: 64-byte segments
+  // (two CTAs per SM) are 15-20 % slower than full lines with one CTA per SM.
+  static constexpr int C = 128 / (2 * (int)sizeof(T));
   static constexpr int NL = N3 > 1 ? N3 : N2;           // radix of the last pass
   static constexpr int NS = N / NL;                     // butterflies of the last pass
   // threads per transform: two-pass variants loop over their butterflies, the three-pass variant has one per thread
@@ -391,9 +393,14 @@ bool col_supported(int n, bool is_double, int* n1, int* n2) {
   return true;
 }
 
+int col_tile_columns(int n, bool is_double) {
+  (void)n;
+  return 128 / (is_double ? 16 : 8);
+}
+
 size_t col_smem_bytes(int n, bool is_double, bool ring) {
   const size_t esz = is_double ? 16 : 8;
-  const int c = 128 / (int)esz;
+  const int c = col_tile_columns(n, is_double);
   const int pitch = is_double ? col::pitch<double>(n) : col::pitch<float>(n);
   return (ring ? 2 : 0) * (size_t)n * c * esz + (size_t)c * pitch * esz + 64;
 }
@@ -401,8 +408,8 @@ size_t col_smem_bytes(int n, bool is_double, bool ring) {
 int col_threads(int n, bool is_double) {
   int a, b;
   if (!col_supported(n, is_double, &a, &b)) return 0;
-  const int tpc = n == 512 ? 64 : (a < b ? a : b);
-  return (128 / (is_double ? 16 : 8)) * (n == 512 ? tpc : (tpc < 16 ? tpc : 16));
+  const int tpc = a < b ? a : b;  // (the three-pass N = 512 variant runs 64 threads per transform)
+  return col_tile_columns(n, is_double) * (n == 512 && is_double ? 64 : (tpc < 16 ? tpc : 16));
 }
 
 // *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
@@ -418,12 +425,13 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
     PFFT_COL(128, 16, 8, 1)
     PFFT_COL(256, 16, 16, 1)
     case 512: {
-      // three radix-8 passes (4x the threads, a third of the code) by default; PFFT_COL512=2: radix 16 x 32
-      static const int two_pass = [] {
+      // fp32: radix 16 x 32 (measured 1.41 ms on 512^3 against 1.45 ms for three radix-8 passes, PFFT_COL512=3);
+      // fp64: three radix-8 passes (a radix-32 fp64 butterfly does not fit the register file)
+      static const int three_pass = [] {
         const char* e = std::getenv("PFFT_COL512");
-        return e ? std::atoi(e) == 2 : 0;
+        return e ? std::atoi(e) == 3 : 0;
       }();
-      if (two_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, grid, stream, used);
+      if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, grid, stream, used);
       return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, grid, stream, used)
                        : launch_col_t<float, 8, 8, 8>(p, swap, variant, grid, stream, used);
     }
