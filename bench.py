@@ -40,6 +40,10 @@ CONFIGS = {
                desc="1D C2C fp32 N=1000 batch=100000 split, fwd stride 2/dist 2048/off 7, bwd dist 1024/off 3, bwd scale 1e-3",
                forward_strides=[2], forward_distance=2048, forward_offset=7, backward_strides=[1],
                backward_distance=1024, backward_offset=3, backward_scale=1e-3),
+    "C3B": dict(lengths=[1000], batch=100000, scalar="float", inplace=False, split=True,
+                desc="1D C2C fp32 N=1000 batch=100000 split, batch-interleaved both domains (stride 100000, distance 1), bwd scale 1e-3",
+                forward_strides=[100000], forward_distance=1, backward_strides=[100000], backward_distance=1,
+                backward_scale=1e-3),
     "C4": dict(lengths=[1 << 24], batch=8, scalar="double", inplace=False, split=False,
                desc="1D C2C fp64 N=2^24 batch=8 out-of-place (global level)"),
     "C5": dict(lengths=[512, 512, 512], batch=1, scalar="float", inplace=False, split=False,

@@ -77,3 +77,58 @@ def test_peer_plan_rejects_plain_compute():
     with pytest.raises(pf.invalid_configuration):
         plan.compute_forward(a, a.clone())
     plan.destroy()
+
+
+@pytest.mark.parametrize("world", [2, 3, 8])
+@pytest.mark.parametrize("kind", ["packed", "batch_interleaved", "strided"])
+def test_batch_sharding_virtual_ranks(world, kind):
+    """Batch sharding (portfft_b200.distributed.shard_descriptor) with the real CUDA plans: every virtual rank commits
+    its shard descriptor and transforms its slice; the reassembled result equals the un-sharded transform."""
+    import torch
+
+    import portfft_oracle as oracle
+    from portfft_b200.distributed import shard_descriptor
+
+    n, batch = 256, 37
+    d = pf.descriptor([n])
+    d.number_of_transforms = batch
+    if kind == "batch_interleaved":
+        d.forward_strides = d.backward_strides = [batch]
+        d.forward_distance = d.backward_distance = 1
+    elif kind == "strided":
+        d.forward_strides, d.forward_distance, d.forward_offset = [2], 2 * n + 3, 5
+        d.backward_strides, d.backward_distance, d.backward_offset = [1], n + 1, 2
+    od = oracle.OracleDescriptor(lengths=[n], number_of_transforms=batch, forward_strides=list(d.forward_strides),
+                                 backward_strides=list(d.backward_strides), forward_distance=d.forward_distance,
+                                 backward_distance=d.backward_distance, forward_offset=d.forward_offset,
+                                 backward_offset=d.backward_offset)
+    host_in, host_ref = oracle.expected_io(od, oracle.FORWARD)
+    dev = torch.device("cuda", 0)
+    out = np.full_like(host_ref, complex(oracle.PADDING_VALUE, oracle.PADDING_VALUE))
+    j = np.arange(n)
+    for r in range(world):
+        sh = shard_descriptor(d, world, r)
+        if sh.count == 0:
+            continue
+        b = np.arange(sh.first, sh.first + sh.count)
+        # host-side scatter: the shard's elements into a rank-local buffer laid out by the shard descriptor
+        loc = sh.desc
+        gin = d.forward_offset + b[:, None] * d.forward_distance + j[None, :] * d.forward_strides[0]
+        lb = np.arange(sh.count)
+        lin = loc.forward_offset + lb[:, None] * loc.forward_distance + j[None, :] * loc.forward_strides[0]
+        local_in = np.zeros(loc.get_input_count(pf.direction.FORWARD), dtype=host_in.dtype)
+        local_in[lin] = host_in[gin]
+        t_in = torch.from_numpy(local_in).to(dev)
+        t_out = torch.zeros(loc.get_output_count(pf.direction.FORWARD), dtype=t_in.dtype, device=dev)
+        plan = loc.commit(torch.cuda.current_stream(dev), 0)
+        plan.compute_forward(t_in, t_out)
+        torch.cuda.synchronize(dev)
+        plan.destroy()
+        lout = loc.backward_offset + lb[:, None] * loc.backward_distance + j[None, :] * loc.backward_strides[0]
+        gout = d.backward_offset + b[:, None] * d.backward_distance + j[None, :] * d.backward_strides[0]
+        out[gout] = t_out.cpu().numpy()[lout]
+    addressed = np.zeros(host_ref.shape, bool)
+    allb = np.arange(batch)
+    addressed[d.backward_offset + allb[:, None] * d.backward_distance + j[None, :] * d.backward_strides[0]] = True
+    rel = np.linalg.norm(out[addressed] - host_ref[addressed]) / np.linalg.norm(host_ref[addressed])
+    assert rel < 1e-5 * np.log2(n), rel
