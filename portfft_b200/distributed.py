@@ -147,7 +147,7 @@ class slab_fft3d:
     raises -- there is no silent fallback."""
 
     def __init__(self, lengths: Sequence[int], scalar: str = "float", group=None, device=None, exchange: str = "nccl",
-                 stream=None):
+                 stream=None, backward_scale: float = 1.0):
         import torch
         import torch.distributed as dist
 
@@ -181,7 +181,10 @@ class slab_fft3d:
         self.plans = []
         for pg in g.passes:
             d = _make_descriptor(pf, pg, scalar)
+            if pg.name == "y":
+                d.backward_scale = backward_scale  # the y pass runs last in the backward transform
             self.plans.append(d.commit(self.stream, self.device.index, extra=pg.extra, peer_last=pg.peer_last))
+        self._pz_back = None  # peer mode: the backward z pass reads an ordinary exchange buffer (built on first use)
 
     def forward(self, x_slab):
         import torch
@@ -204,7 +207,48 @@ class slab_fft3d:
             px.compute_forward(self.B, queue=self.stream)
         return self.B.view(g.lengths[0], g.yb, g.lengths[2])
 
+    def backward(self, y_slab, out=None):
+        """Inverse of `forward`: y-slab of the spectrum [n0, YB, n2] in, x-slab [XL, n1, n2] out (times
+        `backward_scale`).  Mirror image of the forward pipeline: x pass, one exchange step, z pass reading the
+        exchange layout through the same guru batch dimensions, y pass."""
+        import torch
+        import torch.distributed as dist
+
+        import portfft_b200 as pf
+
+        g = self.geom
+        assert y_slab.numel() == g.slab_elems and y_slab.dtype == self.cdtype
+        py, pz, px = self.plans
+        if out is None:
+            out = torch.empty(g.xl, g.lengths[1], g.lengths[2], dtype=self.cdtype, device=self.device)
+        if self.S is None:
+            self.S = torch.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
+        if self.exchange == "peer" and self._pz_back is None:
+            pg = slab_geometry(g.lengths, self.world, self.rank, peer=False).passes[1]
+            self._pz_back = _make_descriptor(pf, pg, self.scalar).commit(self.stream, self.device.index, extra=pg.extra)
+        with torch.cuda.stream(self.stream):
+            if y_slab.data_ptr() != self.B.data_ptr():
+                self.B.copy_(y_slab.reshape(-1))
+            px.compute_backward(self.B, queue=self.stream)
+            if self.exchange == "peer":
+                self._symm.barrier(channel=0)  # every rank's x pass is complete
+                for s in range(self.world):   # pull block `rank` of every peer's B over NVLink
+                    src = self._symm.get_buffer(s, (g.slab_elems,), self.cdtype)
+                    self.S[s * g.block_elems:(s + 1) * g.block_elems].copy_(
+                        src[self.rank * g.block_elems:(self.rank + 1) * g.block_elems], non_blocking=True)
+                self._symm.barrier(channel=1)  # nobody overwrites its B while peers still read it
+                self._pz_back.compute_backward(self.S, self.A, queue=self.stream)
+            else:
+                dist.all_to_all_single(torch.view_as_real(self.S).view(self.world, -1),
+                                       torch.view_as_real(self.B).view(self.world, -1), group=self.group)
+                pz.compute_backward(self.S, self.A, queue=self.stream)
+            py.compute_backward(self.A, out, queue=self.stream)
+        return out
+
     def destroy(self):
         for p in self.plans:
             p.destroy()
+        if self._pz_back is not None:
+            self._pz_back.destroy()
+            self._pz_back = None
         self.plans = []

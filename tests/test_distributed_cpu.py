@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 
 import portfft_oracle as oracle  # noqa: E402
-from pass_emulator import emulate_pass  # noqa: E402
+from pass_emulator import emulate_pass, emulate_pass_backward  # noqa: E402
 from portfft_b200.distributed import partition, shard_descriptor, slab_geometry  # noqa: E402
 
 
@@ -96,6 +96,20 @@ def _slab_single_process(lengths, world, peer):
         emulate_pass(g.passes[2], B[r], B[r])
         got = B[r].reshape(n0, g.yb, n2)
         np.testing.assert_allclose(got, ref[:, r * g.yb:(r + 1) * g.yb, :], rtol=0, atol=1e-3)
+    # backward pipeline (slab_fft3d.backward): x pass, exchange back, z pass, y pass; round trip = identity
+    gb = [slab_geometry(lengths, world, r, peer=False) for r in range(world)]
+    for r in range(world):
+        emulate_pass_backward(gb[r].passes[2], B[r], B[r])
+    S2 = [np.zeros(g0.slab_elems, np.complex64) for _ in range(world)]
+    for s in range(world):
+        for d in range(world):
+            S2[d][s * g0.block_elems:(s + 1) * g0.block_elems] = B[s][d * g0.block_elems:(d + 1) * g0.block_elems]
+    for r in range(world):
+        back_a = np.zeros(g0.slab_elems, np.complex64)
+        out = np.zeros(g0.slab_elems, np.complex64)
+        emulate_pass_backward(gb[r].passes[1], S2[r], back_a)
+        emulate_pass_backward(gb[r].passes[0], back_a, out, scale=1.0 / (n0 * n1 * n2))
+        np.testing.assert_allclose(out.reshape(gb[r].xl, n1, n2), x[r * gb[r].xl:(r + 1) * gb[r].xl], rtol=0, atol=1e-4)
 
 
 @pytest.mark.parametrize("peer", [False, True])

@@ -54,6 +54,22 @@ def _run(lengths, world, peer, scalar):
         want = ref[:, r * g.yb:(r + 1) * g.yb, :]
         rel = np.linalg.norm(got - want) / np.linalg.norm(want)
         assert rel <= bound, (r, rel, bound)
+    # backward pipeline of slab_fft3d.backward with the same plans run in the BACKWARD direction (non-peer z plan)
+    if not peer:
+        for r in range(world):
+            plans[r][2].compute_backward(B[r])
+        for s in range(world):
+            for d in range(world):
+                S[d][s * g0.block_elems:(s + 1) * g0.block_elems] = B[s][d * g0.block_elems:(d + 1) * g0.block_elems]
+        for r, g in enumerate(geoms):
+            out = torch.zeros(g0.slab_elems, dtype=cdt, device=dev)
+            plans[r][1].compute_backward(S[r], A[r])
+            plans[r][0].compute_backward(A[r], out)
+            torch.cuda.synchronize(dev)
+            got = out.cpu().numpy().reshape(g.xl, n1, n2) / nflat
+            want = x[r * g.xl:(r + 1) * g.xl]
+            rel = np.linalg.norm(got - want) / np.linalg.norm(want)
+            assert rel <= 2 * bound, (r, rel, bound)
     for ps in plans:
         for p in ps:
             p.destroy()

@@ -36,7 +36,8 @@ def main():
     dev = torch.device("cuda", local)
     dist.init_process_group("nccl", device_id=dev)
     n0, n1, n2 = args.lengths
-    plan = slab_fft3d(args.lengths, args.scalar, exchange=args.exchange, device=dev)
+    plan = slab_fft3d(args.lengths, args.scalar, exchange=args.exchange, device=dev,
+                      backward_scale=1.0 / (n0 * n1 * n2))
     g = plan.geom
     cdt = torch.complex128 if args.scalar == "double" else torch.complex64
     gen = torch.Generator(device=dev)
@@ -60,6 +61,14 @@ def main():
     t = torch.stack([e_in, e_out])
     dist.all_reduce(t)
     check["parseval_rel"] = float(abs(t[1] / (t[0] * n0 * n1 * n2) - 1.0))
+    # full-size round trip across the GPUs: backward(forward(x)) == x
+    back = plan.backward(plan.forward(x))
+    torch.cuda.synchronize()
+    num = ((back - x).abs().double() ** 2).sum()
+    den = (x.abs().double() ** 2).sum()
+    t2 = torch.stack([num, den])
+    dist.all_reduce(t2)
+    check["roundtrip_rel_l2"] = float((t2[0] / t2[1]).sqrt())
     for _ in range(args.warmup):
         plan.forward(x)
     torch.cuda.synchronize()
