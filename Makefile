@@ -4,7 +4,7 @@ NVCC      ?= nvcc
 CXX       ?= g++
 CC        ?= gcc
 ARCH      := -gencode arch=compute_100a,code=sm_100a
-NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -diag-suppress 20013
+NVFLAGS   := -std=c++17 -O3 $(ARCH) -lineinfo -Xcompiler -fPIC -Xcompiler -Wall -Xcompiler -Wno-unknown-pragmas -diag-suppress 20013
 CSRC      := portfft_b200/csrc
 BUILD     := build
 LIB       := portfft_b200/lib/libpfft_b200.so
@@ -21,7 +21,7 @@ $(BUILD)/%.o: $(CSRC)/%.cu $(HDRS)
 
 $(BUILD)/%.o: $(CSRC)/%.cpp $(HDRS)
 	@mkdir -p $(BUILD)
-	$(CXX) -std=c++17 -O2 -fPIC -Wall -I/usr/local/cuda/include -c $< -o $@
+	$(CXX) -std=c++17 -O2 -fPIC -Wall -Wno-unknown-pragmas -I/usr/local/cuda/include -c $< -o $@
 
 $(LIB): $(OBJS)
 	@mkdir -p portfft_b200/lib

@@ -219,11 +219,6 @@ int pow2_floor(long long v) {
   while ((long long)r * 2 <= v) r *= 2;
   return r;
 }
-int pow2_ceil(long long v) {
-  int r = 1;
-  while (r < v) r *= 2;
-  return r;
-}
 
 constexpr size_t kSoftSmem = 72 * 1024;  // three CTAs per SM
 
