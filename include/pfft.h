@@ -100,6 +100,16 @@ int pfft_get_layout(const pfft_desc* desc, int direction);
  * launch geometry) as text. Returns the number of characters that the full description needs. */
 pfft_status pfft_plan_describe(const pfft_desc* desc, int direction, char* buf, size_t buf_len, size_t* needed);
 
+/* Host-only: the pass list of the plan as JSON (one object per kernel launch: transform length, element strides,
+ * offsets, batch dimensions, buffers, inter-factor twiddle, element-wise modifiers, scale).  tests/plan_emulator.py
+ * evaluates it with numpy to check the planner without a GPU.  Same buffer convention as pfft_plan_describe. */
+pfft_status pfft_plan_export(const pfft_desc* desc, int direction, char* buf, size_t buf_len, size_t* needed);
+
+/* Host-only: copy of a device-resident modifier table as the plan builds it (csrc/tables.h ModTable kinds: 1 chirp
+ * exp(-i pi j^2 / L), 2 chirp / M, 3 FFT_M of the conjugate chirp) into `out` (interleaved complex of the given
+ * precision; L entries for kinds 1 and 2, M entries for kind 3). */
+pfft_status pfft_table_host(int precision, int kind, size_t transform_length, size_t convolution_length, void* out);
+
 /* validate + plan + build device-resident twiddle tables and workspace on `device`. `stream` (cudaStream_t) is the
  * queue the plan is committed to; it is used for the one-off table uploads and as default stream of pfft_compute. */
 pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_plan** plan_out);

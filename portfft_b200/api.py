@@ -210,6 +210,17 @@ class descriptor:
         _check(_lib.load().pfft_plan_describe(ctypes.byref(c), int(d), buf, needed.value, None))
         return buf.value.decode()
 
+    def export_plan(self, d=direction.FORWARD) -> dict:
+        """Planner dry run (host only): the pass list as a dict (pfft_plan_export JSON)."""
+        import json
+
+        c, keep = self._c_desc()
+        needed = ctypes.c_size_t(0)
+        _check(_lib.load().pfft_plan_export(ctypes.byref(c), int(d), None, 0, ctypes.byref(needed)))
+        buf = ctypes.create_string_buffer(needed.value)
+        _check(_lib.load().pfft_plan_export(ctypes.byref(c), int(d), buf, needed.value, None))
+        return json.loads(buf.value.decode())
+
     def commit(self, queue=None, device: int = 0, extra=None, peer_last: bool = False) -> "committed_descriptor":
         """descriptor::commit(sycl::queue&) (descriptor.hpp:152-156): validate, then build the plan on `device`.
 
@@ -298,6 +309,17 @@ class committed_descriptor:
 
     def num_launches(self, d=direction.FORWARD) -> int:
         return int(_lib.load().pfft_plan_num_launches(self._handle, int(d)))
+
+
+def mod_table(scalar: str, kind: int, transform_length: int, convolution_length: int):
+    """Host copy of a modifier table as the plan builds it (pfft_table_host; kinds: csrc/tables.h ModTable)."""
+    import numpy as np
+
+    n = convolution_length if kind == 3 else transform_length
+    out = np.empty(n, dtype=np.complex128 if scalar == "double" else np.complex64)
+    _check(_lib.load().pfft_table_host(1 if scalar == "double" else 0, int(kind), int(transform_length),
+                                       int(convolution_length), out.ctypes.data))
+    return out
 
 
 def total_launches() -> int:

@@ -44,4 +44,7 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
 // 3072, 4096}; geometry = p.ffts_per_block transforms per CTA, r3_supported's threads per transform
 cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
+// element-wise pass with modifiers (ew.cu): n == 1, modifier index = index along batch dimension 0
+cudaError_t launch_ew(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
+
 }  // namespace pfft

@@ -63,6 +63,22 @@ struct PassParams {
   // scale applied on store (only when apply_scale != 0)
   double scale;
   int apply_scale;
+  // element-wise modifiers (Bluestein chirp / convolution kernel; wg_generic.cu and ew.cu only, zero elsewhere):
+  //   load : x_j  <- (j < valid_in  ? in[j] * lmod[j] : 0)
+  //   store: y_k  -> swap_post(swap_pre(y_k) * smod[k]), written only for k < valid_out
+  // lmod / smod == nullptr: no multiply; valid_* == 0: every element.  In the element-wise kernel (ew.cu, n == 1) the
+  // index j = k is the index along batch dimension 0.
+  int valid_in, valid_out;
+  const void* lmod;
+  const void* smod;
+  int mod_flags;  // ModFlags
+};
+
+enum ModFlags : int {
+  MOD_SWAP_PRE = 1,          // (re <-> im) before the smod multiply
+  MOD_SWAP_POST = 2,         // (re <-> im) after the smod multiply
+  MOD_NO_USER_SWAP_IN = 4,   // input is plan-internal data: the backward (re <-> im) swap does not apply on load
+  MOD_NO_USER_SWAP_OUT = 8   // output is plan-internal data: no backward swap on store
 };
 
 }  // namespace pfft

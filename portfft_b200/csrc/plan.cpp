@@ -1,6 +1,8 @@
 // Host planner. See plan.h for the reference counterparts.
 #include "plan.h"
 
+#include "tables.h"
+
 #include <algorithm>
 #include <cmath>
 #include <cstdlib>
@@ -529,6 +531,94 @@ bool split_factors(size_t n, int k, size_t fmax, std::vector<size_t>& out) {
   return false;
 }
 
+// One side (source or destination) of a multi-pass transform: buffer, element stride, offset and the distance of
+// every (merged) outer batch dimension.
+struct View {
+  int buf;
+  long long es, off;
+  std::vector<long long> dist;
+};
+
+// GLOBAL level for one smooth length L = N_1 * ... * N_k (k = 2..4): one pass per factor.  Pass p < k transforms the
+// stride-M_p columns (first pass: src -> work, then in place on `work`) and multiplies by the inter-factor twiddle
+// w_{M_{p-1}}^{c*k} on store; the last pass reads contiguous rows of `work` and writes the digit-reversed positions
+// of dst, so the transposition is folded into the store addresses.  `work` holds packed rows of L elements per outer
+// batch element (it may be the source buffer itself when that is packed: every pass before the last is in place).
+void emit_multipass(std::vector<PassHost>& passes, const DescHost& d, const DeviceLimits& lim, size_t L,
+                    const std::vector<long long>& outer_n, const View& src, int work, const View& dst) {
+  const bool dbl = d.is_double;
+  std::vector<size_t> factors;
+  for (int k = 2; k <= 4 && factors.empty(); ++k) {
+    std::vector<size_t> f;
+    const bool pow2 = (L & (L - 1)) == 0 && d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+    const size_t col_max = pow2 ? (dbl ? 256 : 512) : 1024;
+    if (split_factors(L, k, col_max, f)) factors = f;
+  }
+  if (factors.empty()) unsupported("FFT size ", L, " is too large");
+  std::sort(factors.begin(), factors.end(), std::greater<size_t>());
+  const size_t k = factors.size();
+  // work distance of every outer batch dimension (packed rows)
+  std::vector<long long> sdist(outer_n.size());
+  {
+    long long acc = (long long)L;
+    for (size_t i = 0; i < outer_n.size(); ++i) {
+      sdist[i] = acc;
+      acc *= outer_n[i];
+    }
+  }
+  long long M = (long long)L;  // M_{p-1}
+  long long done = 1;          // N_1 * ... * N_{p-1}
+  for (size_t pi = 0; pi < k; ++pi) {
+    const long long Np = (long long)factors[pi];
+    const long long Mp = M / Np;
+    const bool pfirst = pi == 0, plast = pi + 1 == k;
+    PassHost ps;
+    set_radices(ps.pp, (size_t)Np);
+    ps.level = LEVEL_GLOBAL;
+    std::vector<BDim> dims;
+    if (!plast) {
+      // columns c' (dim 0, carries the twiddle index), combined earlier digits K, outer batches
+      const long long in_unit = pfirst ? src.es : 1;
+      dims.push_back({Mp, in_unit, 1});
+      if (done > 1) dims.push_back({done, M, M});  // only for pi >= 1, work -> work
+      for (size_t i = 0; i < outer_n.size(); ++i) dims.push_back({outer_n[i], pfirst ? src.dist[i] : sdist[i], sdist[i]});
+      ps.pp.is = Mp * in_unit;
+      ps.pp.os = Mp;
+      ps.pp.ioff = pfirst ? src.off : 0;
+      ps.pp.ooff = 0;
+      ps.pp.gtw_dim = 0;
+      ps.pp.gtw_n = M;
+      ps.src = pfirst ? src.buf : work;
+      ps.dst = work;
+      set_batch_dims(ps.pp, merge_dims(dims, 1));
+    } else {
+      // last factor: contiguous rows of the work buffer, output digit-reversed into the destination layout
+      // rows are indexed by digits k_1..k_{k-1}: work distance M_q, output distance N_1..N_{q-1}
+      long long mq = (long long)L, prod = 1;
+      for (size_t q = 0; q + 1 < k; ++q) {
+        mq /= (long long)factors[q];
+        dims.push_back({(long long)factors[q], mq, prod * dst.es});
+        prod *= (long long)factors[q];
+      }
+      for (size_t i = 0; i < outer_n.size(); ++i) dims.push_back({outer_n[i], sdist[i], dst.dist[i]});
+      ps.pp.is = 1;
+      ps.pp.os = done * dst.es;
+      ps.pp.ioff = 0;
+      ps.pp.ooff = dst.off;
+      ps.pp.gtw_dim = -1;
+      ps.src = work;
+      ps.dst = dst.buf;
+      // dim 0 must be the unit-output-distance digit (k_1) so that the staged store coalesces along it
+      set_batch_dims(ps.pp, merge_dims(dims, 1));
+    }
+    configure_wg_generic(ps, dbl, lim, true);
+    select_col(ps, d, lim);
+    passes.push_back(ps);
+    M = Mp;
+    done *= Np;
+  }
+}
+
 struct Domain {
   std::vector<size_t> strides;
   size_t distance, offset;
@@ -542,8 +632,6 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   const Domain out{d.strides(odir), d.distance(odir), d.offset(odir)};
   const size_t D = d.lengths.size();
   const size_t wg_max = max_workgroup_length(dbl, lim);
-  // longest factor of a multi-pass (GLOBAL) transform; powers of two are cut into the column-tile kernel's lengths
-  const size_t col_max_any = 1024;
   std::vector<PassHost>& passes = plan.passes[dir];
   if (plan.dim_level.size() != D) plan.dim_level.assign(D, PFFT_LEVEL_WORKGROUP);
 
@@ -611,86 +699,134 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     }
 
     if (d.peer_last) unsupported("peer output buffers are supported for single-pass transform lengths only");
-    // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
-    if (!smooth31(L)) unsupported("FFT size ", L, " has a prime factor larger than 31, which is not supported");
-    std::vector<size_t> factors;
-    for (int k = 2; k <= 4 && factors.empty(); ++k) {
-      std::vector<size_t> f;
-      const bool pow2 = (L & (L - 1)) == 0 && d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
-      const size_t col_max = pow2 ? (dbl ? 256 : 512) : col_max_any;
-      if (split_factors(L, k, col_max, f)) factors = f;
-    }
-    if (factors.empty()) unsupported("FFT size ", L, " is too large");
-    std::sort(factors.begin(), factors.end(), std::greater<size_t>());
-    const size_t k = factors.size();
-    plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
-    // scratch: one packed length-L row per outer batch element
     std::vector<BDim> outer_m = merge_dims(outer, 0);
+    std::vector<long long> outer_n, outer_in, outer_out;
     long long outer_total = 1;
-    for (const BDim& b : outer_m) outer_total *= b.n;
-    plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * L);
-    // scratch distance of every outer batch dimension (packed in merge order)
+    for (const BDim& b : outer_m) {
+      outer_n.push_back(b.n);
+      outer_in.push_back(b.in);
+      outer_out.push_back(b.out);
+      outer_total *= b.n;
+    }
+    const View vin{src0, es_in, off_in, outer_in}, vout{BUF_OUT, es_out, off_out, outer_out};
+    if (smooth31(L)) {
+      // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
+      plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
+      plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * L);
+      emit_multipass(passes, d, lim, L, outer_n, vin, BUF_SCRATCH, vout);
+      continue;
+    }
+    // Bluestein: a length with a prime factor > 31 becomes a circular convolution of power-of-two length M >= 2L - 1
+    //   X_k = w_k * sum_j (x_j w_j) conj(w)_{k-j},  w_j = exp(-i pi j^2 / L)
+    // = two length-M transforms with the chirp multiplies, the zero padding, the product with FFT_M(conj w) and the
+    // truncation fused into their loads and stores.  (The reference rejects these lengths:
+    // committed_descriptor_impl.hpp:241, utils.hpp:102,126.)
+    size_t M = 1;
+    while (M < 2 * L - 1) M *= 2;
+    if (M > ((size_t)1 << 25)) unsupported("FFT size ", L, " (large prime factor) is too large");
+    if (outer_m.size() + 1 > (size_t)kMaxBatchDims) unsupported("too many independent batch dimensions");
     std::vector<long long> sdist(outer_m.size());
     {
-      long long acc = (long long)L;
+      long long acc = (long long)M;
       for (size_t i = 0; i < outer_m.size(); ++i) {
         sdist[i] = acc;
-        acc *= outer_m[i].n;
+        acc *= outer_n[i];
       }
     }
-    long long M = (long long)L;  // M_{p-1}
-    long long done = 1;          // N_1 * ... * N_{p-1}
-    for (size_t pi = 0; pi < k; ++pi) {
-      const long long Np = (long long)factors[pi];
-      const long long Mp = M / Np;
-      const bool pfirst = pi == 0, plast = pi + 1 == k;
+    plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * M);
+    auto bdims = [&](const std::vector<long long>& in_d, const std::vector<long long>& out_d) {
+      std::vector<BDim> v;
+      for (size_t i = 0; i < outer_m.size(); ++i) v.push_back({outer_n[i], in_d[i], out_d[i]});
+      return v;
+    };
+    auto mods = [&](PassHost& ps, int lkind, int skind, int valid_in, int valid_out, int flags) {
+      ps.lmod_kind = lkind;
+      ps.smod_kind = skind;
+      ps.mod_l = (long long)L;
+      ps.mod_m = (long long)M;
+      ps.pp.valid_in = valid_in;
+      ps.pp.valid_out = valid_out;
+      ps.pp.mod_flags = flags;
+    };
+    if (M <= wg_max) {
+      plan.dim_level[dim] = PFFT_LEVEL_WORKGROUP;
+      PassHost a;
+      set_radices(a.pp, M);
+      a.pp.is = es_in;
+      a.pp.os = 1;
+      a.pp.ioff = off_in;
+      a.pp.ooff = 0;
+      a.pp.gtw_dim = -1;
+      set_batch_dims(a.pp, merge_dims(bdims(outer_in, sdist), 0));
+      a.src = src0;
+      a.dst = BUF_SCRATCH;
+      configure_wg_generic(a, dbl, lim, false);
+      mods(a, MODT_CHIRP, MODT_CONV, (int)L, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_OUT);
+      passes.push_back(a);
+      PassHost b;
+      set_radices(b.pp, M);
+      b.pp.is = 1;
+      b.pp.os = es_out;
+      b.pp.ioff = 0;
+      b.pp.ooff = off_out;
+      b.pp.gtw_dim = -1;
+      set_batch_dims(b.pp, merge_dims(bdims(sdist, outer_out), 0));
+      b.src = BUF_SCRATCH;
+      b.dst = BUF_OUT;
+      configure_wg_generic(b, dbl, lim, false);
+      mods(b, MODT_NONE, MODT_CHIRP_OVER_M, 0, (int)L, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
+      passes.push_back(b);
+      continue;
+    }
+    // convolution length beyond one CTA: element-wise passes around two multi-pass transforms, ping-pong between two
+    // packed scratch buffers (rows of M elements)
+    plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
+    plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)outer_total * M);
+    auto ew = [&](int src, int dst, long long n0, long long e_in, long long o_in, const std::vector<long long>& d_in,
+                  long long e_out, long long o_out, const std::vector<long long>& d_out) {
       PassHost ps;
-      set_radices(ps.pp, (size_t)Np);
+      ps.pp.n = 1;
+      ps.pp.num_radices = 1;
+      ps.pp.radix[0] = 1;
+      ps.pp.threads_per_fft = 1;
+      ps.pp.ffts_per_block = 256;
+      ps.pp.is = ps.pp.os = 1;
+      ps.pp.ioff = o_in;
+      ps.pp.ooff = o_out;
+      ps.pp.gtw_dim = -1;
+      std::vector<BDim> dims{{n0, e_in, e_out}};
+      for (size_t i = 0; i < outer_m.size(); ++i) dims.push_back({outer_n[i], d_in[i], d_out[i]});
+      set_batch_dims(ps.pp, dims);  // dimension 0 (the element index) is never merged
+      ps.src = src;
+      ps.dst = dst;
+      ps.kernel = KERNEL_EW;
       ps.level = LEVEL_GLOBAL;
-      std::vector<BDim> dims;
-      if (!plast) {
-        // columns c' (dim 0, carries the twiddle index), combined earlier digits K, outer batches
-        const long long in_unit = pfirst ? es_in : 1;
-        dims.push_back({Mp, in_unit, 1});
-        if (done > 1) dims.push_back({done, M, M});  // only for pi >= 1, scratch -> scratch
-        for (size_t i = 0; i < outer_m.size(); ++i)
-          dims.push_back({outer_m[i].n, pfirst ? outer_m[i].in : sdist[i], sdist[i]});
-        ps.pp.is = Mp * in_unit;
-        ps.pp.os = Mp;
-        ps.pp.ioff = pfirst ? off_in : 0;
-        ps.pp.ooff = 0;
-        ps.pp.gtw_dim = 0;
-        ps.pp.gtw_n = M;
-        ps.src = pfirst ? src0 : BUF_SCRATCH;
-        ps.dst = BUF_SCRATCH;
-        std::vector<BDim> md = merge_dims(dims, 1);
-        set_batch_dims(ps.pp, md);
-      } else {
-        // last factor: contiguous rows of the scratch, output digit-reversed into the user layout
-        // rows are indexed by digits k_1..k_{k-1}: scratch distance M_q, output distance N_1..N_{q-1}
-        long long mq = (long long)L, prod = 1;
-        for (size_t q = 0; q + 1 < k; ++q) {
-          mq /= (long long)factors[q];
-          dims.push_back({(long long)factors[q], mq, prod * es_out});
-          prod *= (long long)factors[q];
-        }
-        for (size_t i = 0; i < outer_m.size(); ++i) dims.push_back({outer_m[i].n, sdist[i], outer_m[i].out});
-        ps.pp.is = 1;
-        ps.pp.os = done * es_out;
-        ps.pp.ioff = 0;
-        ps.pp.ooff = off_out;
-        ps.pp.gtw_dim = -1;
-        ps.src = BUF_SCRATCH;
-        ps.dst = BUF_OUT;
-        // dim 0 must be the unit-output-distance digit (k_1) so that the staged store coalesces along it
-        std::vector<BDim> md = merge_dims(dims, 1);
-        set_batch_dims(ps.pp, md);
-      }
-      configure_wg_generic(ps, dbl, lim, true);
-      select_col(ps, d, lim);
+      ps.block = 256;
+      ps.grid = (int)std::min<long long>((ps.pp.batch_total + 255) / 256, (long long)lim.num_sms * 16);
+      ps.tw_n = 0;
+      return ps;
+    };
+    const std::vector<long long> row_n{outer_total}, row_d{(long long)M};
+    const View s1{BUF_SCRATCH, 1, 0, row_d}, s2{BUF_SCRATCH2, 1, 0, row_d};
+    {
+      PassHost ps = ew(src0, BUF_SCRATCH, (long long)M, es_in, off_in, outer_in, 1, 0, sdist);
+      mods(ps, MODT_CHIRP, MODT_NONE, (int)L, 0, MOD_NO_USER_SWAP_OUT);
       passes.push_back(ps);
-      M = Mp;
-      done *= Np;
+    }
+    // the two length-M transforms work on plan-internal data: plain forward transforms in either direction
+    const size_t inner0 = passes.size();
+    emit_multipass(passes, d, lim, M, row_n, s1, BUF_SCRATCH, s2);
+    {
+      PassHost ps = ew(BUF_SCRATCH2, BUF_SCRATCH2, (long long)M, 1, 0, sdist, 1, 0, sdist);
+      mods(ps, MODT_NONE, MODT_CONV, 0, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT);
+      passes.push_back(ps);
+    }
+    emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
+    for (size_t i = inner0; i < passes.size(); ++i) passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
+    {
+      PassHost ps = ew(BUF_SCRATCH, BUF_OUT, (long long)L, 1, 0, sdist, es_out, off_out, outer_out);
+      mods(ps, MODT_NONE, MODT_CHIRP_OVER_M, 0, 0, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
+      passes.push_back(ps);
     }
   }
   // scale on the last pass executed (committed_descriptor_impl.hpp:473-474)
@@ -713,13 +849,16 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
-  static const char* buf_names[] = {"in", "out", "scratch"};
+  static const char* buf_names[] = {"in", "out", "scratch", "scratch2"};
+  static const char* mod_names[] = {"none", "chirp", "chirp/M", "conv"};
   std::stringstream ss;
   ss << "levels:";
   for (int l : plan.dim_level) ss << " " << level_names[l];
-  ss << "; scratch_elems=" << plan.scratch_elems << "\n";
+  ss << "; scratch_elems=" << plan.scratch_elems;
+  if (plan.scratch2_elems) ss << " scratch2_elems=" << plan.scratch2_elems;
+  ss << "\n";
   for (const PassHost& ps : plan.passes[direction]) {
     const PassParams& p = ps.pp;
     ss << "pass kernel=" << kernel_names[ps.kernel] << " level=" << level_names[ps.level] << " n=" << p.n << " radices=";
@@ -737,9 +876,44 @@ std::string describe_plan(const PlanHost& plan, int direction) {
          << " tile_grid=" << ps.alt_grid << " (generic geometry above is the fallback)";
     }
     if (p.gtw_dim >= 0) ss << " gtw_n=" << p.gtw_n;
+    if (ps.lmod_kind || ps.smod_kind || p.valid_in || p.valid_out || p.mod_flags)
+      ss << " lmod=" << mod_names[ps.lmod_kind] << " smod=" << mod_names[ps.smod_kind] << " valid_in=" << p.valid_in
+         << " valid_out=" << p.valid_out << " mod_flags=" << p.mod_flags << " mod_l=" << ps.mod_l << " mod_m=" << ps.mod_m;
     if (p.apply_scale) ss << " scale=" << p.scale;
     ss << "\n";
   }
+  return ss.str();
+}
+
+std::string export_plan_json(const PlanHost& plan, int direction) {
+  std::stringstream ss;
+  ss.precision(17);
+  auto arr = [&](const char* name, const long long* v, int n) {
+    ss << "\"" << name << "\": [";
+    for (int i = 0; i < n; ++i) ss << (i ? ", " : "") << v[i];
+    ss << "]";
+  };
+  ss << "{\"scratch_elems\": " << plan.scratch_elems << ", \"scratch2_elems\": " << plan.scratch2_elems
+     << ", \"is_double\": " << (plan.desc.is_double ? 1 : 0) << ", \"passes\": [";
+  bool firstp = true;
+  for (const PassHost& ps : plan.passes[direction]) {
+    const PassParams& p = ps.pp;
+    ss << (firstp ? "" : ", ") << "{\"kernel\": " << ps.kernel << ", \"level\": " << ps.level << ", \"src\": " << ps.src
+       << ", \"dst\": " << ps.dst << ", \"n\": " << p.n << ", \"is\": " << p.is << ", \"os\": " << p.os
+       << ", \"ioff\": " << p.ioff << ", \"ooff\": " << p.ooff << ", ";
+    arr("nb", p.nb, kMaxBatchDims);
+    ss << ", ";
+    arr("ibd", p.ibd, kMaxBatchDims);
+    ss << ", ";
+    arr("obd", p.obd, kMaxBatchDims);
+    ss << ", \"gtw_dim\": " << p.gtw_dim << ", \"gtw_n\": " << (p.gtw_dim >= 0 ? p.gtw_n : 0) << ", \"peer_dim\": " << p.peer_dim
+       << ", \"valid_in\": " << p.valid_in << ", \"valid_out\": " << p.valid_out << ", \"mod_flags\": " << p.mod_flags
+       << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
+       << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
+       << ", \"variant\": " << ps.variant << "}";
+    firstp = false;
+  }
+  ss << "]}";
   return ss.str();
 }
 

@@ -54,9 +54,9 @@ std::vector<size_t> default_strides(const std::vector<size_t>& lengths);
 int get_layout(const DescHost& d, int dir);
 void validate_descriptor(const DescHost& d);  // throws PlanError
 
-enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2 };
+enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2, BUF_SCRATCH2 = 3 };
 
-enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5 };
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5, KERNEL_EW = 6 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -70,6 +70,9 @@ struct PassHost {
   long long tw_n = 0;  // per-pass twiddle table w_n^k (0: none)
   int alt_grid = 0;    // launch geometry of the specialised kernel (the generic geometry stays valid as fallback)
   int variant = 0;
+  // element-wise modifier tables (tables.h ModTable) for transform length mod_l / convolution length mod_m
+  int lmod_kind = 0, smod_kind = 0;
+  long long mod_l = 0, mod_m = 0;
 };
 
 // geometry limits of the thread- and warp-level kernels (wi.cuh, sg.cuh); sg_supports_m lives in sg_f32.cu
@@ -89,6 +92,7 @@ struct PlanHost {
   std::vector<PassHost> passes[2];  // [direction]
   std::vector<int> dim_level;       // per dimension, PFFT_LEVEL_*
   size_t scratch_elems = 0;         // complex elements of plan-owned workspace
+  size_t scratch2_elems = 0;        // second workspace (Bluestein with a multi-pass convolution length)
 };
 
 struct DeviceLimits {
@@ -101,5 +105,6 @@ std::vector<int> choose_radices(size_t n);
 size_t max_workgroup_length(bool is_double, const DeviceLimits& lim);
 PlanHost build_plan(const DescHost& d, const DeviceLimits& lim);  // validates first; throws PlanError
 std::string describe_plan(const PlanHost& plan, int direction);
+std::string export_plan_json(const PlanHost& plan, int direction);
 
 }  // namespace pfft

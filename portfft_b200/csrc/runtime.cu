@@ -22,6 +22,7 @@
 #include "../../include/pfft.h"
 #include "kernels.h"
 #include "plan.h"
+#include "tables.h"
 
 namespace pfft {
 
@@ -34,37 +35,6 @@ static std::atomic<unsigned long long> g_total_launches{0};
     if (_e != cudaSuccess)                                                                            \
       throw PlanError(PFFT_CUDA_ERROR, std::string(#expr) + " failed: " + cudaGetErrorString(_e));    \
   } while (0)
-
-// cos(2*pi*p/q), sin(2*pi*p/q) in long double with exact octant reduction
-static long double sin2pi_ld(long long p, long long q);
-static long double cos2pi_ld(long long p, long long q) {
-  p %= q;
-  if (p < 0) p += q;
-  if (2 * p > q) p = q - p;
-  if (4 * p > q) return -cos2pi_ld(q - 2 * p, 2 * q);
-  if (8 * p > q) return sin2pi_ld(q - 4 * p, 4 * q);
-  return cosl(6.283185307179586476925286766559L * (long double)p / (long double)q);
-}
-static long double sin2pi_ld(long long p, long long q) {
-  p %= q;
-  if (p < 0) p += q;
-  if (2 * p > q) return -sin2pi_ld(q - p, q);
-  if (4 * p > q) return sin2pi_ld(q - 2 * p, 2 * q);
-  if (8 * p > q) return cos2pi_ld(q - 4 * p, 4 * q);
-  return sinl(6.283185307179586476925286766559L * (long double)p / (long double)q);
-}
-
-// table[i] = w_n^{i * mult} = exp(-2*pi*i * i*mult / n), i in [0, count)
-template <typename T>
-static std::vector<T> make_twiddles(long long n, long long count, long long mult) {
-  std::vector<T> t((size_t)count * 2);
-  for (long long i = 0; i < count; ++i) {
-    const long long k = (long long)(((__int128)i * mult) % n);
-    t[2 * i] = (T)cos2pi_ld(k, n);
-    t[2 * i + 1] = (T)(-sin2pi_ld(k, n));
-  }
-  return t;
-}
 
 struct GtwTable {
   void* lo = nullptr;
@@ -82,8 +52,10 @@ struct pfft_plan {
   cudaStream_t stream = nullptr;
   std::map<long long, void*> tw;
   std::map<long long, GtwTable> gtw;
+  std::map<std::pair<int, std::pair<long long, long long>>, void*> mod;  // (ModTable, (L, M)) -> device table
   void* scratch = nullptr;
-  size_t scratch_bytes = 0;
+  void* scratch2 = nullptr;
+  size_t scratch_bytes = 0, scratch2_bytes = 0;
   // device staging for pfft_compute_host
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
@@ -101,6 +73,7 @@ struct pfft_plan {
       if (s) cudaStreamDestroy(s);
     for (void* p : owned) cudaFree(p);
     if (scratch) cudaFree(scratch);
+    if (scratch2) cudaFree(scratch2);
     for (void* p : stage)
       if (p) cudaFree(p);
   }
@@ -139,6 +112,13 @@ static void build_tables(pfft_plan* plan) {
         g.hi = upload(plan, hi.data(), hi.size() * sizeof(T));
         plan->gtw[n] = g;
       }
+      for (int kind : {ps.lmod_kind, ps.smod_kind}) {
+        const auto key = std::make_pair(kind, std::make_pair(ps.mod_l, ps.mod_m));
+        if (kind != MODT_NONE && !plan->mod.count(key)) {
+          std::vector<T> t = make_mod_table<T>(kind, ps.mod_l, ps.mod_m);
+          plan->mod[key] = upload(plan, t.data(), t.size() * sizeof(T));
+        }
+      }
     }
   }
 }
@@ -152,6 +132,8 @@ static void commit_device(pfft_plan* plan) {
   const size_t scalar = plan->host.desc.is_double ? 8 : 4;
   plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
   if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
+  plan->scratch2_bytes = plan->host.scratch2_elems * 2 * scalar;
+  if (plan->scratch2_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch2, plan->scratch2_bytes));
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
       ps.pp.tw = ps.tw_n > 0 ? plan->tw[ps.tw_n] : nullptr;
@@ -161,6 +143,8 @@ static void commit_device(pfft_plan* plan) {
         ps.pp.gtw_hi = g.hi;
         ps.pp.gtw_bits = g.bits;
       }
+      if (ps.lmod_kind != MODT_NONE) ps.pp.lmod = plan->mod[std::make_pair(ps.lmod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
+      if (ps.smod_kind != MODT_NONE) ps.pp.smod = plan->mod[std::make_pair(ps.smod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
     }
   }
 }
@@ -196,17 +180,25 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   }
   void* s_re = plan->scratch;
   void* s_im = il ? nullptr : (void*)((char*)plan->scratch + plan->host.scratch_elems * scalar);
+  void* s2_re = plan->scratch2;
+  void* s2_im = il ? nullptr : (void*)((char*)plan->scratch2 + plan->host.scratch2_elems * scalar);
   for (const PassHost& ps : plan->host.passes[dir]) {
     PassParams p = ps.pp;
     switch (ps.src) {
       case BUF_IN: p.in_re = uin_re; p.in_im = uin_im; break;
       case BUF_OUT: p.in_re = uout_re; p.in_im = uout_im; break;
+      case BUF_SCRATCH2: p.in_re = s2_re; p.in_im = s2_im; break;
       default: p.in_re = s_re; p.in_im = s_im; break;
     }
     switch (ps.dst) {
       case BUF_OUT: p.out_re = uout_re; p.out_im = uout_im; break;
+      case BUF_SCRATCH2: p.out_re = s2_re; p.out_im = s2_im; break;
       default: p.out_re = s_re; p.out_im = s_im; break;
     }
+    // backward on interleaved data = (re <-> im) swap on load and store; passes between plan-internal buffers
+    // (Bluestein's inner transforms) always run the plain forward transform
+    const int internal = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
+    const bool swap = il && bwd && (p.mod_flags & internal) != internal;
     if (p.peer_dim >= 0) {
       if (peers == nullptr || peers->n != (size_t)p.nb[p.peer_dim])
         throw PlanError(PFFT_INVALID_CONFIGURATION,
@@ -223,29 +215,32 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     cudaError_t e = cudaSuccess;
     switch (ps.kernel) {
       case KERNEL_WG_GENERIC:
-        e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+        e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
         break;
       case KERNEL_WI:
-        e = d.is_double ? launch_wi_f64(p, il, il && bwd, ps.grid, stream) : launch_wi_f32(p, il, il && bwd, ps.grid, stream);
+        e = d.is_double ? launch_wi_f64(p, il, swap, ps.grid, stream) : launch_wi_f32(p, il, swap, ps.grid, stream);
         break;
       case KERNEL_SG:
-        e = d.is_double ? launch_sg_f64(p, il, il && bwd, ps.grid, stream) : launch_sg_f32(p, il, il && bwd, ps.grid, stream);
+        e = d.is_double ? launch_sg_f64(p, il, swap, ps.grid, stream) : launch_sg_f32(p, il, swap, ps.grid, stream);
         break;
       case KERNEL_WG_R3:
-        e = launch_wg_r3(p, d.is_double, il, il && bwd, ps.grid, stream);
+        e = launch_wg_r3(p, d.is_double, il, swap, ps.grid, stream);
         break;
       case KERNEL_WG_COL: {
         bool used = false;
-        e = launch_wg_col(p, d.is_double, il && bwd, ps.variant, ps.alt_grid, stream, &used);
-        if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+        e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used);
+        if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
         break;
       }
       case KERNEL_WG_CUBE:
         // cp.async.bulk needs 16-byte aligned global addresses; otherwise run the generic kernel
         if (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0)
-          e = launch_wg_cube(p, d.is_double, bwd, ps.variant, ps.alt_grid, stream);
+          e = launch_wg_cube(p, d.is_double, swap, ps.variant, ps.alt_grid, stream);
         else
-          e = launch_wg_generic(p, d.is_double, il, il && bwd, ps.grid, stream);
+          e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
+        break;
+      case KERNEL_EW:
+        e = launch_ew(p, d.is_double, il, swap, ps.grid, stream);
         break;
       default:
         throw PlanError(PFFT_INTERNAL_ERROR, "unknown kernel kind");
@@ -415,6 +410,33 @@ pfft_status pfft_plan_describe(const pfft_desc* desc, int direction, char* buf, 
       const size_t n = std::min(buf_len - 1, s.size());
       std::memcpy(buf, s.data(), n);
       buf[n] = 0;
+    }
+  });
+}
+
+pfft_status pfft_plan_export(const pfft_desc* desc, int direction, char* buf, size_t buf_len, size_t* needed) {
+  return guarded([&] {
+    PlanHost plan = build_plan(desc_from_c(desc), DeviceLimits{});
+    std::string s = export_plan_json(plan, direction);
+    if (needed) *needed = s.size() + 1;
+    if (buf && buf_len) {
+      const size_t n = std::min(buf_len - 1, s.size());
+      std::memcpy(buf, s.data(), n);
+      buf[n] = 0;
+    }
+  });
+}
+
+pfft_status pfft_table_host(int precision, int kind, size_t transform_length, size_t convolution_length, void* out) {
+  return guarded([&] {
+    if (out == nullptr || kind < MODT_CHIRP || kind > MODT_CONV || transform_length == 0)
+      throw PlanError(PFFT_INVALID_CONFIGURATION, "pfft_table_host: bad arguments");
+    if (precision == PFFT_DOUBLE) {
+      std::vector<double> t = make_mod_table<double>(kind, (long long)transform_length, (long long)convolution_length);
+      std::memcpy(out, t.data(), t.size() * sizeof(double));
+    } else {
+      std::vector<float> t = make_mod_table<float>(kind, (long long)transform_length, (long long)convolution_length);
+      std::memcpy(out, t.data(), t.size() * sizeof(float));
     }
   });
 }

@@ -32,12 +32,31 @@ __device__ __forceinline__ cx<T> finalize(const PassParams& p, cx<T> v, long lon
     const cx<T> w = cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & ((1LL << p.gtw_bits) - 1)));
     v = cmul(v, w);
   }
+  if (p.mod_flags & MOD_SWAP_PRE) v = cx<T>{v.y, v.x};
+  if (p.smod != nullptr) v = cmul(v, ldg_cx<T>(p.smod, k));
+  if (p.mod_flags & MOD_SWAP_POST) v = cx<T>{v.y, v.x};
   if (p.apply_scale) v = cscale(v, T(p.scale));
   return v;
 }
 
+// element j of the transform whose first element lives at `base`: zero beyond valid_in, times lmod[j] (both optional)
+template <typename T>
+__device__ __forceinline__ cx<T> load_in(const PassParams& p, IoFlags fl, long long base, int j) {
+  if (p.valid_in > 0 && j >= p.valid_in) return cx<T>{T(0), T(0)};
+  cx<T> v = gload<T>(p, fl, base + (long long)j * p.is);
+  if (p.lmod != nullptr) v = cmul(v, ldg_cx<T>(p.lmod, j));
+  return v;
+}
+
+template <typename T>
+__device__ __forceinline__ void store_out(const PassParams& p, IoFlags fl, long long base, int k, cx<T> v, long long c,
+                                          int peer) {
+  if (p.valid_out > 0 && k >= p.valid_out) return;
+  gstore<T>(p, fl, base + (long long)k * p.os, finalize<T>(p, v, c, k), peer);
+}
+
 template <typename T, int R>
-__device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, int ns, bool src_global,
+__device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, IoFlags flo, int ns, bool src_global,
                                               bool dst_global, const cx<T>* __restrict__ src, cx<T>* __restrict__ dst,
                                               long long ibase, long long obase, long long gtw_c, int peer, int tj) {
   const int n = p.n;
@@ -46,7 +65,7 @@ __device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, i
     cx<T> v[R];
     if (src_global) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = gload<T>(p, fl, ibase + (long long)(j + r * nbf) * p.is);
+      for (int r = 0; r < R; ++r) v[r] = load_in<T>(p, fl, ibase, j + r * nbf);
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = src[padidx<T>(j + r * nbf)];
@@ -61,10 +80,7 @@ __device__ __forceinline__ void stockham_pass(const PassParams& p, IoFlags fl, i
     const int ob = (j - k) * R + k;
     if (dst_global) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const int idx = ob + r * ns;
-        gstore<T>(p, fl, obase + (long long)idx * p.os, finalize<T>(p, v[r], gtw_c, idx), peer);
-      }
+      for (int r = 0; r < R; ++r) store_out<T>(p, flo, obase, ob + r * ns, v[r], gtw_c, peer);
     } else {
 #pragma unroll
       for (int r = 0; r < R; ++r) dst[padidx<T>(ob + r * ns)] = v[r];
@@ -84,7 +100,8 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
   long long* s_obase = s_ibase + F;
   long long* s_gtw = s_obase + F;
   int* s_peer = reinterpret_cast<int*>(s_gtw + F);
-  const IoFlags fl{il, swap};
+  const IoFlags fl{il, swap && !(p.mod_flags & MOD_NO_USER_SWAP_IN)};
+  const IoFlags flo{il, swap && !(p.mod_flags & MOD_NO_USER_SWAP_OUT)};
   const int tid = threadIdx.x;
   const int nthreads = blockDim.x;
   const int f = tid / T_;
@@ -120,7 +137,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
       for (unsigned e = tid; e < total; e += nthreads) {
         const unsigned ff = e / (unsigned)n;
         const int i = (int)(e - ff * (unsigned)n);
-        cur[ff * pitch + padidx<T>(i)] = gload<T>(p, fl, s_ibase[ff] + (long long)i * p.is);
+        cur[ff * pitch + padidx<T>(i)] = load_in<T>(p, fl, s_ibase[ff], i);
       }
       __syncthreads();
     } else if (p.in_mode == IO_STAGED_BATCH) {
@@ -128,7 +145,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
       for (unsigned e = tid; e < total; e += nthreads) {
         const int ff = (int)(e & (unsigned)(F - 1));
         const int i = (int)(e / (unsigned)F);
-        if (ff < nf) cur[ff * pitch + padidx<T>(i)] = gload<T>(p, fl, s_ibase[ff] + (long long)i * p.is);
+        if (ff < nf) cur[ff * pitch + padidx<T>(i)] = load_in<T>(p, fl, s_ibase[ff], i);
       }
       __syncthreads();
     }
@@ -148,7 +165,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
         switch (R) {
 #define PFFT_CASE(RR)                                                                                         \
   case RR:                                                                                                    \
-    stockham_pass<T, RR>(p, fl, ns, src_global, dst_global, s, d, ibase, obase, gtw_c, peer, tj);                  \
+    stockham_pass<T, RR>(p, fl, flo, ns, src_global, dst_global, s, d, ibase, obase, gtw_c, peer, tj);             \
     break;
           PFFT_CASE(1)
           PFFT_CASE(2)
@@ -187,17 +204,14 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
       for (unsigned e = tid; e < total; e += nthreads) {
         const unsigned ff = e / (unsigned)n;
         const int i = (int)(e - ff * (unsigned)n);
-        gstore<T>(p, fl, s_obase[ff] + (long long)i * p.os,
-                  finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i), s_peer[ff]);
+        store_out<T>(p, flo, s_obase[ff], i, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], s_peer[ff]);
       }
     } else if (p.out_mode == IO_STAGED_BATCH) {
       const unsigned total = (unsigned)F * (unsigned)n;
       for (unsigned e = tid; e < total; e += nthreads) {
         const int ff = (int)(e & (unsigned)(F - 1));
         const int i = (int)(e / (unsigned)F);
-        if (ff < nf)
-          gstore<T>(p, fl, s_obase[ff] + (long long)i * p.os,
-                    finalize<T>(p, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], i), s_peer[ff]);
+        if (ff < nf) store_out<T>(p, flo, s_obase[ff], i, cur[ff * pitch + padidx<T>(i)], s_gtw[ff], s_peer[ff]);
       }
     }
   }

@@ -98,6 +98,17 @@ SUITES = {
     "StridedStrideEqualsDistance": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [1], [(8, 2, 2, 2, 2), (8, 1, 1, 1, 1)]),
     "workItemStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [4], [(4, 4, 4, 3, 3)]),
     "SubgroupStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [13], [(85, 13, 13, 12, 12)]),
+    # not in the reference grid (it rejects these as unsupported): layouts beyond PACKED at the GLOBAL
+    # level and for N-D transforms
+    "GlobalLayoutsTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16384, 32768]),
+    "GlobalStridedTest": layouts(["OOP"], BOTH_DIR, STORAGES, [2],
+                                 [(16384, 2, 3, 40000, 50000), (9800, 3, 1, 30000, 9800)]),
+    # lengths with prime factors > 31 (Bluestein; the reference throws unsupported_configuration):
+    # one CTA per convolution (M <= 8192 fp32 / 4096 fp64) and the multi-pass form
+    "BluesteinTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 5], [37, 67, 1031, 2 * 1031]),
+    "BluesteinGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3], [4099, 65537]),
+    "BluesteinMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [2], [[6, 37], [37, 6], [41, 43]]),
+    "BluesteinOffsetsTest": offsets(OOP_ALL, BOTH_DIR, [3], [131], [(0, 7), (9, 0), (5, 11)]),
 }
 
 CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.items() for tp in tps]

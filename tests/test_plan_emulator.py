@@ -1,0 +1,56 @@
+"""CPU tests of the planner: the exported pass list (pfft_plan_export) replayed in numpy (tests/plan_emulator.py) must
+reproduce the oracle's expected output on the same seeded inputs -- pass geometry, offsets, inter-factor twiddles,
+digit reversal of the GLOBAL level, N-D passes, and the Bluestein passes with their chirp tables.  No GPU needed: the
+per-pass DFT is numpy's, so this checks WHAT the kernels are asked to do; tests/test_fft_gpu.py checks the kernels."""
+import numpy as np
+import pytest
+
+import portfft_oracle as oracle
+from fft_check import BI, P, U, CaseParams, make_descriptors
+from plan_emulator import run_plan
+
+CASES = [
+    # single pass, every layout family
+    CaseParams([64], 5, "OOP", P, P, "fwd"),
+    CaseParams([1000], 3, "IP", BI, BI, "bwd", backward_scale=1e-3),
+    CaseParams([96], 4, "OOP", U, U, "fwd", forward_strides=[3], backward_strides=[2], forward_distance=300,
+               backward_distance=200, forward_offset=7, backward_offset=3),
+    # GLOBAL level: two and three factors, both directions, offsets, batch-interleaved and strided layouts
+    CaseParams([16384], 2, "OOP", P, P, "fwd"),
+    CaseParams([32768], 2, "IP", P, P, "bwd", backward_scale=0.5),
+    CaseParams([9800], 3, "OOP", P, P, "fwd", forward_offset=5, backward_offset=9),
+    CaseParams([8192 * 4], 3, "OOP", BI, P, "fwd"),
+    CaseParams([8192 * 2], 3, "OOP", P, BI, "bwd"),
+    CaseParams([16384], 2, "OOP", U, U, "fwd", forward_strides=[2], backward_strides=[3], forward_distance=40000,
+               backward_distance=50000),
+    CaseParams([1 << 18], 1, "OOP", P, P, "fwd", scalar="double"),
+    # N-D
+    CaseParams([4, 6, 10], 2, "OOP", P, P, "fwd"),
+    CaseParams([16, 512], 2, "IP", P, P, "bwd"),
+    CaseParams([8, 16384], 1, "OOP", P, P, "fwd"),
+    # Bluestein: prime lengths, one CTA per convolution (M <= 8192 fp32 / 4096 fp64) and the multi-pass form
+    CaseParams([37], 3, "OOP", P, P, "fwd"),
+    CaseParams([1031], 2, "OOP", P, P, "bwd", backward_scale=1.0 / 1031),
+    CaseParams([2 * 1031], 2, "IP", P, P, "fwd", scalar="double"),
+    CaseParams([67], 5, "OOP", BI, BI, "fwd", storage="split"),
+    CaseParams([4099], 2, "OOP", P, P, "fwd"),
+    CaseParams([4099], 2, "OOP", P, P, "bwd", scalar="double"),
+    CaseParams([65537], 1, "OOP", P, P, "fwd"),
+    CaseParams([6, 37], 2, "OOP", P, P, "fwd"),
+    CaseParams([37, 6], 2, "OOP", P, P, "bwd"),
+]
+
+
+@pytest.mark.parametrize("tp", CASES, ids=[tp.ident() for tp in CASES])
+def test_exported_plan_matches_oracle(tp):
+    d, od = make_descriptors(tp)
+    dr = oracle.FORWARD if tp.dir == "fwd" else oracle.BACKWARD
+    host_in, host_ref = oracle.expected_io(od, dr)
+    if tp.placement == "IP":
+        out = host_in.copy()
+        run_plan(d, dr, out, out)
+    else:
+        pad = oracle.PADDING_VALUE
+        out = np.full(host_ref.shape, complex(pad, pad), dtype=host_ref.dtype)
+        run_plan(d, dr, host_in.copy(), out)
+    oracle.verify_dft(od, dr, host_ref, out)
