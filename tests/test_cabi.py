@@ -139,7 +139,15 @@ def test_planner_levels_for_baseline_configs():
     d = pf.descriptor([512, 512, 512])
     txt = d.describe_plan()
     assert len(_levels(txt)) == 3 and txt.count("pass ") == 3  # reference: 1 + 512 + 1 launches
-    d = pf.descriptor([2 * 3 * 5 * 7 * 37])
+    # a prime factor > 31: the reference throws unsupported_configuration (committed_descriptor_impl.hpp:241); here
+    # it becomes a Bluestein plan: two transforms of the padded power-of-two convolution length
+    d = pf.descriptor([2 * 7 * 37])
+    txt = d.describe_plan()
+    assert txt.count("pass ") == 2 and txt.count(" n=2048 ") == 2 and "smod=conv" in txt and "lmod=chirp" in txt
+    d = pf.descriptor([65537])
+    txt = d.describe_plan()
+    assert _levels(txt) == ["GLOBAL"] and txt.count("kernel=ew") == 3 and "scratch2_elems=262144" in txt
+    d = pf.descriptor([(1 << 24) + 1])
     with pytest.raises(pf.unsupported_configuration):
         d.describe_plan()
 
