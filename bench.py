@@ -52,6 +52,8 @@ CONFIGS = {
                 desc="1D C2C fp32 N=65536 batch=2048 out-of-place (reference bench_float large_1d)"),
     "S16": dict(lengths=[16], batch=8 * 1024 * 1024, scalar="float", inplace=False, split=False,
                 desc="1D C2C fp32 N=16 batch=8Mi out-of-place (reference bench_float small_1d)"),
+    "M512": dict(lengths=[512], batch=256 * 1024, scalar="float", inplace=False, split=False,
+                 desc="1D C2C fp32 N=512 batch=256Ki out-of-place (packed rows, N = 8^3 tile kernel)"),
     "M256": dict(lengths=[256], batch=512 * 1024, scalar="float", inplace=False, split=False,
                  desc="1D C2C fp32 N=256 batch=512Ki out-of-place (reference bench_float medium_small_1d)"),
 }

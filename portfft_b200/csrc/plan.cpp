@@ -427,12 +427,16 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
   bool single_batch_dim = true;
   for (int i = 1; i < kMaxBatchDims; ++i) single_batch_dim = single_batch_dim && p.nb[i] == 1;
-  if (!d.is_double && p.n == 4096 && il && p.is == 1 && p.os == 1 && single_batch_dim && p.gtw_dim < 0 &&
-      p.peer_dim < 0 &&
+  int tile = 0, per_sm = 0;
+  const char* env512 = std::getenv("PFFT_NO_CUBE512");
+  if (p.n == 512 && env512 && std::atoi(env512) != 0) return;
+  if (cube_supported(p.n, d.is_double, &tile, &per_sm) && il && p.is == 1 && p.os == 1 && single_batch_dim &&
+      p.gtw_dim < 0 && p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 &&
       p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0) {
     ps.kernel = KERNEL_WG_CUBE;
     ps.variant = variant;
-    ps.alt_grid = (int)std::min<long long>(p.batch_total, 2LL * lim.num_sms);
+    const long long tiles = (p.batch_total + tile - 1) / tile;
+    ps.alt_grid = (int)std::min<long long>(tiles, (long long)per_sm * lim.num_sms);
   }
 }
 

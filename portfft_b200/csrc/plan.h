@@ -84,6 +84,9 @@ bool col_supported(int n, bool is_double, int* n1, int* n2);
 size_t col_smem_bytes(int n, bool is_double, bool ring);
 int col_threads(int n, bool is_double);
 int col_tile_columns(int n, bool is_double);
+// N = R^3 kernel (wg_cube.cu): packed interleaved fp32 4096 (one transform per tile) and 512 (kCube512Tile per tile)
+constexpr int kCube512Tile = 4;
+bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm);
 // three-radix kernel (wg_r3.cu)
 bool r3_supported(int n, bool is_double, int* threads_per_fft, int* pitch);
 

@@ -90,7 +90,11 @@ enum : int {
   IN_ROWS_BULK = 2    // contiguous rows, 16-byte aligned: cp.async.bulk (TMA 1-D) into the ring, layout [row][j]
 };
 
-template <typename T, int N1, int N2, int N3, int IN>
+// INPLACE (strided columns in and out, two passes, one last-pass butterfly per thread): the exchange between the two
+// passes happens inside the stage buffer -- pass 1 writes its outputs back to the rows it read, pass 2 then finds its
+// N2 inputs in N2 consecutive rows -- so no exchange buffer exists and more CTAs fit one SM.  The [row][column]
+// stage layout is conflict free for both passes because lanes always run along the 128-byte row segment.
+template <typename T, int N1, int N2, int N3, int IN, bool INPLACE = false>
 struct ColCfg {
   static_assert(N3 == 1 || (N1 == N2 && N2 == N3), "three-pass variant: equal radices (one butterfly per thread)");
   static constexpr int N = N1 * N2 * N3;
@@ -104,17 +108,24 @@ struct ColCfg {
   static constexpr int NT = C * TPC;
   static constexpr int PITCH = col::pitch<T>(N);
   // ring depth (a one-stage ring with three CTAs per SM was measured for fp64: 2.45 ms on C4 against 2.39 ms)
-  static constexpr int RING = 2;
-  static constexpr int STAGES = IN == IN_ROWS_DIRECT ? 0 : RING;
   static constexpr size_t kStageBytes = (size_t)N * C * 2 * sizeof(T);
-  static constexpr size_t kSmem = STAGES * kStageBytes + (size_t)C * PITCH * 2 * sizeof(T) + 64;
+  // in place: one stage when a tile is 64 KiB (the refill then overlaps the last pass's arithmetic and stores and the
+  // other CTAs of the SM), two otherwise
+  static constexpr int RING = INPLACE && kStageBytes > 48 * 1024 ? 1 : 2;
+  static constexpr int STAGES = IN == IN_ROWS_DIRECT ? 0 : RING;
+  static constexpr size_t kSmem = STAGES * kStageBytes + (INPLACE ? 0 : (size_t)C * PITCH * 2 * sizeof(T)) + 64;
+  static_assert(!INPLACE || (IN == IN_COLS_TMA && N3 == 1 && N1 == TPC && (N / N1) % TPC == 0),
+                "in-place exchange: TMA column tiles, two passes, one last-pass butterfly per thread");
   static constexpr int kBoxRows = N < 256 ? N : 256;
+  // resident CTAs per SM the register allocation is bounded for (in place, fp32 N = 256: three 64 KiB rings per SM)
+  static constexpr int kMinBlocks = INPLACE && sizeof(T) == 4 && N == 256 ? 3 : 1;
 };
 
-template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS>
-__global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
+template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS, bool INPLACE = false>
+__global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg<T, N1, N2, N3, IN, INPLACE>::kMinBlocks)
     wg_col_kernel(const PassParams p, const __grid_constant__ CUtensorMap tmap, const bool swap) {
-  using Cfg = ColCfg<T, N1, N2, N3, IN>;
+  using Cfg = ColCfg<T, N1, N2, N3, IN, INPLACE>;
+  static_assert(!INPLACE || !OUT_ROWS, "in-place exchange: column output only");
   constexpr int N = Cfg::N, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH, NL = Cfg::NL, NS = Cfg::NS;
   constexpr int B1 = N / N1;  // butterflies of pass 1
   constexpr bool IN_ROWS = IN != IN_COLS_TMA;
@@ -192,7 +203,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
     // ---- pass 1: radix N1 over x[j + N2*r], result to E[transform][pad(j*N1 + r)] -------------------------------
     {
       const int st = it % Cfg::RING;
-      const cx<T>* S = reinterpret_cast<const cx<T>*>(stage0 + st * Cfg::kStageBytes);
+      cx<T>* S = reinterpret_cast<cx<T>*>(stage0 + st * Cfg::kStageBytes);
       const bool live = c0 + c1 < p.nb[0];
       const long long ib = p.ioff + (long long)(c0 + c1) * p.ibd[0] + (long long)b1 * p.ibd[1] +
                            (long long)b2 * p.ibd[2] + (long long)b3 * p.ibd[3];
@@ -220,12 +231,17 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
           }
         }
         DFT<N1, T>::run(v);
+        if (INPLACE) {
 #pragma unroll
-        for (int r = 0; r < N1; ++r) E[c1 * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+          for (int r = 0; r < N1; ++r) S[(j + B1 * r) * C + c1] = v[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < N1; ++r) E[c1 * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+        }
       }
     }
     __syncthreads();
-    if (RING && tid == 0) {
+    if (RING && !INPLACE && tid == 0) {
       // the stage just consumed is free: refill it with the tile RING iterations ahead
       const long long nxt = tile + (long long)Cfg::RING * gridDim.x;
       if (nxt < total_tiles) {
@@ -257,8 +273,24 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
 #pragma unroll 1
       for (int j = t2; j < NS; j += TPC) {
         cx<T> v[NL];
+        if (INPLACE) {
+          // element j + NS*r of the exchange is output j of pass-1 butterfly r: row r + (N/N1)*j of the stage
+          const int st = it % Cfg::RING;
+          const cx<T>* S = reinterpret_cast<const cx<T>*>(stage0 + st * Cfg::kStageBytes);
 #pragma unroll
-        for (int r = 0; r < NL; ++r) v[r] = E[c2 * PITCH + col::pad<T>(j + NS * r)];
+          for (int r = 0; r < NL; ++r) v[r] = S[(r + B1 * j) * C + c2];
+          __syncthreads();  // (one iteration per thread) every thread has taken its inputs: the stage is free
+          if (tid == 0) {
+            const long long nxt = tile + (long long)Cfg::RING * gridDim.x;
+            if (nxt < total_tiles) {
+              col::fence_proxy_async();
+              issue(nxt, st);
+            }
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < NL; ++r) v[r] = E[c2 * PITCH + col::pad<T>(j + NS * r)];
+        }
 #pragma unroll
         for (int r = 1; r < NL; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
         DFT<NL, T>::run(v);
@@ -291,7 +323,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN>::NT)
         }
       }
     }
-    __syncthreads();  // E is rewritten by the next tile's pass 1
+    if (!INPLACE) __syncthreads();  // E is rewritten by the next tile's pass 1
   }
 }
 
@@ -343,19 +375,39 @@ static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_
   return r == CUDA_SUCCESS;
 }
 
-template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS>
-static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, int grid, cudaStream_t stream) {
-  using Cfg = ColCfg<T, N1, N2, N3, IN>;
-  auto kern = wg_col_kernel<T, N1, N2, N3, IN, OUT_ROWS>;
+// Persistent grid: one CTA per resident slot (occupancy of this instantiation x SMs), never more than there are tiles.
+template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS, bool INPLACE>
+static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, cudaStream_t stream) {
+  using Cfg = ColCfg<T, N1, N2, N3, IN, INPLACE>;
+  auto kern = wg_col_kernel<T, N1, N2, N3, IN, OUT_ROWS, INPLACE>;
+  static const int slots = [&] {
+    int occ = 0, dev = 0, sms = 0;
+    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem) != cudaSuccess) return 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::kSmem) != cudaSuccess) return 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return occ * sms;
+  }();
+  if (slots <= 0) return cudaErrorLaunchOutOfResources;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
   if (e != cudaSuccess) return e;
+  const long long tiles = ((p.nb[0] + Cfg::C - 1) / Cfg::C) * p.nb[1] * p.nb[2] * p.nb[3];
+  const int grid = (int)(tiles < slots ? tiles : slots);
   kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
   return cudaGetLastError();
 }
 
+static bool inplace_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("PFFT_COL_INPLACE");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
 // variant: bits 0-1 = input mode, bit 2 = OUT_ROWS
 template <typename T, int N1, int N2, int N3>
-static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int grid, cudaStream_t stream, bool* used) {
+static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cudaStream_t stream, bool* used) {
   *used = false;
   int in = variant & 3;
   const bool out_rows = (variant & 4) != 0;
@@ -370,14 +422,21 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, int
     if (base % 16 != 0) in = IN_ROWS_DIRECT;
   }
   *used = true;
-  if (in == IN_COLS_TMA)
-    return out_rows ? launch_col_v<T, N1, N2, N3, IN_COLS_TMA, true>(p, swap, map, grid, stream)
-                    : launch_col_v<T, N1, N2, N3, IN_COLS_TMA, false>(p, swap, map, grid, stream);
+  if (in == IN_COLS_TMA) {
+    // columns in, columns out: exchange inside the stage buffer where the geometry allows (see ColCfg)
+    constexpr int kTpc = col::cmin(col::cmin(N1, N2), 16);
+    constexpr bool kCanInplace = N3 == 1 && N1 == kTpc && (N2 % kTpc) == 0;
+    if constexpr (kCanInplace) {
+      if (!out_rows && inplace_enabled()) return launch_col_v<T, N1, N2, N3, IN_COLS_TMA, false, true>(p, swap, map, stream);
+    }
+    return out_rows ? launch_col_v<T, N1, N2, N3, IN_COLS_TMA, true, false>(p, swap, map, stream)
+                    : launch_col_v<T, N1, N2, N3, IN_COLS_TMA, false, false>(p, swap, map, stream);
+  }
   if (in == IN_ROWS_BULK)
-    return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, true>(p, swap, map, grid, stream)
-                    : launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, false>(p, swap, map, grid, stream);
-  return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, true>(p, swap, map, grid, stream)
-                  : launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, false>(p, swap, map, grid, stream);
+    return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, true, false>(p, swap, map, stream)
+                    : launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, false, false>(p, swap, map, stream);
+  return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, true, false>(p, swap, map, stream)
+                  : launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, false, false>(p, swap, map, stream);
 }
 
 bool col_supported(int n, bool is_double, int* n1, int* n2) {
@@ -416,10 +475,11 @@ int col_threads(int n, bool is_double) {
 // *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
 cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
                           bool* used) {
+  (void)grid;  // the planner's estimate; the launch sizes the persistent grid from the kernel's actual occupancy
 #define PFFT_COL(NN, A, B, CC)                                                                   \
   case NN:                                                                                       \
-    return is_double ? launch_col_t<double, A, B, CC>(p, swap, variant, grid, stream, used)      \
-                     : launch_col_t<float, A, B, CC>(p, swap, variant, grid, stream, used);
+    return is_double ? launch_col_t<double, A, B, CC>(p, swap, variant, stream, used)      \
+                     : launch_col_t<float, A, B, CC>(p, swap, variant, stream, used);
   *used = false;
   switch (p.n) {
     PFFT_COL(64, 8, 8, 1)
@@ -432,9 +492,9 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
         const char* e = std::getenv("PFFT_COL512");
         return e ? std::atoi(e) == 3 : 0;
       }();
-      if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, grid, stream, used);
-      return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, grid, stream, used)
-                       : launch_col_t<float, 8, 8, 8>(p, swap, variant, grid, stream, used);
+      if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, stream, used);
+      return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, stream, used)
+                       : launch_col_t<float, 8, 8, 8>(p, swap, variant, stream, used);
     }
     default:
       return cudaErrorInvalidValue;

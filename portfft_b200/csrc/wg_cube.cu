@@ -1,5 +1,6 @@
-// WORKGROUP level, specialised: N = R^3 (4096 = 16^3, 512 = 8^3), packed interleaved data, one transform per CTA
-// iteration, persistent CTAs.  This is the hot kernel of BASELINE config C2 (fp32 N=4096, batch 65536, in place).
+// WORKGROUP level, specialised: N = R^3 (4096 = 16^3: one transform per CTA iteration; 512 = 8^3: a tile of F = 4
+// consecutive transforms per iteration), packed interleaved data, persistent CTAs.  This is the hot kernel of BASELINE
+// config C2 (fp32 N=4096, batch 65536, in place) and of the contiguous (z) pass of C5 (512^3).
 //
 // Reference counterpart: workgroup_impl + wg_dft (/root/reference/src/portfft/dispatcher/workgroup_dispatcher.hpp:
 // 94-281, /root/reference/src/portfft/common/workgroup.hpp:319-346): 64 work-items per 4096-point transform, 32
@@ -9,8 +10,9 @@
 //   * the whole 32 KiB transform is fetched by ONE cp.async.bulk (TMA 1-D) into a 2-stage shared-memory ring
 //     guarded by mbarriers, so the next transform streams from HBM while this one is computed;
 //   * exchange 1 goes through a padded buffer (2 complex per 16: conflict-free 128-bit stores and 64-bit loads),
-//     exchange 2 is written back into the consumed stage buffer (conflict-free unpadded) -> 2 block barriers per
-//     transform;
+//     exchange 2 is written back into the consumed stage buffer (R = 16: conflict-free as is; R = 8: bit 6 of the
+//     index is folded into bit 3 so that the two index groups of a half-warp use different banks) -> 2 block
+//     barriers per tile;
 //   * per-thread twiddles (w_256^{(t%16) r}, w_4096^{t r}) are loaded once per CTA and stay in registers;
 //   * results leave with coalesced 64-bit stores straight from registers; backward = re/im swap; scale fused.
 #include <cstdint>
@@ -61,21 +63,30 @@ struct CubeArgs {
   int apply_scale;
 };
 
-template <typename T, int R, bool SWAP, bool USE_TMA>
-__global__ void __launch_bounds__(R* R, 2) wg_cube_kernel(const CubeArgs a) {
-  constexpr int NT = R * R;
+// position of element e of the exchange-2 layout inside a stage buffer (a permutation within aligned 16-groups, so
+// that the pass-3 reads of 16 consecutive elements stay conflict free)
+template <int R>
+__device__ __forceinline__ constexpr int sw2(int e) {
+  return R == 8 ? (e ^ ((e >> 3) & 8)) : e;
+}
+
+template <typename T, int R, int F, bool SWAP, bool USE_TMA>
+__global__ void __launch_bounds__(R* R* F, F == 1 ? 2 : 4) wg_cube_kernel(const CubeArgs a) {
+  constexpr int NT = R * R;  // threads per transform
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);  // TMA: stage 0 ; non-TMA: exchange-2 buffer
-  cx<T>* S1 = S0 + N;                              // TMA: stage 1
-  cx<T>* E = USE_TMA ? (S1 + N) : (S0 + N);        // padded exchange-1 buffer
-  uint64_t* full = reinterpret_cast<uint64_t*>(E + EN);
-  const int t = threadIdx.x;
+  cx<T>* S1 = S0 + F * N;                          // TMA: stage 1
+  cx<T>* E = USE_TMA ? (S1 + F * N) : (S0 + F * N);  // padded exchange-1 buffer
+  uint64_t* full = reinterpret_cast<uint64_t*>(E + F * EN);
+  const int f = F == 1 ? 0 : threadIdx.x / NT;  // transform of the tile
+  const int t = F == 1 ? threadIdx.x : threadIdx.x % NT;
   const int k2 = t % R;
   const cx<T>* gin = reinterpret_cast<const cx<T>*>(a.in) + a.ioff;
   cx<T>* gout = reinterpret_cast<cx<T>*>(a.out) + a.ooff;
-  const long long stride = gridDim.x;
+  const long long stride = (long long)gridDim.x * F;
+  const bool contig = a.idist == N;  // the F transforms of a tile are one contiguous run
 
   // per-thread twiddles, resident in registers for the whole batch loop
   cx<T> tw2[R - 1], tw3[R - 1];
@@ -86,121 +97,147 @@ __global__ void __launch_bounds__(R* R, 2) wg_cube_kernel(const CubeArgs a) {
   }
   const T scale = T(a.scale);
 
+  // one thread: fetch the tile starting at transform k into stage buffer Sd
+  auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
+    const int rows = (int)min((long long)F, a.batch - k);
+    mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
+    if (F == 1 || contig) {
+      bulk_g2s(Sd, gin + k * a.idist, (uint32_t)(rows * N * sizeof(cx<T>)), bar);
+    } else {
+      for (int r = 0; r < rows; ++r) bulk_g2s(Sd + r * N, gin + (k + r) * a.idist, (uint32_t)(N * sizeof(cx<T>)), bar);
+    }
+  };
+
   if (USE_TMA) {
-    if (t == 0) {
+    if (threadIdx.x == 0) {
       mbar_init(&full[0], 1);
       mbar_init(&full[1], 1);
       fence_mbar_init();
       fence_proxy_async();
     }
     __syncthreads();
-    if (t == 0) {
-      long long k = blockIdx.x;
-      if (k < a.batch) {
-        mbar_expect_tx(&full[0], N * sizeof(cx<T>));
-        bulk_g2s(S0, gin + k * a.idist, N * sizeof(cx<T>), &full[0]);
-      }
+    if (threadIdx.x == 0) {
+      long long k = (long long)blockIdx.x * F;
+      if (k < a.batch) issue(k, S0, &full[0]);
       k += stride;
-      if (k < a.batch) {
-        mbar_expect_tx(&full[1], N * sizeof(cx<T>));
-        bulk_g2s(S1, gin + k * a.idist, N * sizeof(cx<T>), &full[1]);
-      }
+      if (k < a.batch) issue(k, S1, &full[1]);
     }
   }
 
   int it = 0;
-  for (long long k = blockIdx.x; k < a.batch; k += stride, ++it) {
-    cx<T>* S = USE_TMA ? ((it & 1) ? S1 : S0) : S0;
+  for (long long k0 = (long long)blockIdx.x * F; k0 < a.batch; k0 += stride, ++it) {
+    const long long k = k0 + f;
+    const bool live = F == 1 || k < a.batch;  // ragged last tile: idle threads still take part in the barriers
+    cx<T>* S = (USE_TMA ? ((it & 1) ? S1 : S0) : S0) + f * N;
+    cx<T>* Ef = E + f * EN;
     cx<T> v[R];
     // ---- pass 1: x[t + NT r] -> radix R -> E[R t + r'] -------------------------------------------------------
     if (USE_TMA) {
       mbar_wait(&full[it & 1], (it >> 1) & 1);
+      if (live) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
-    } else {
+        for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
+      }
+    } else if (live) {
       const cx<T>* src = gin + k * a.idist;
 #pragma unroll
       for (int r = 0; r < R; ++r) v[r] = src[t + NT * r];
     }
-    if (SWAP) {
+    if (live) {
+      if (SWAP) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        const T tmp = v[r].x;
-        v[r].x = v[r].y;
-        v[r].y = tmp;
+        for (int r = 0; r < R; ++r) {
+          const T tmp = v[r].x;
+          v[r].x = v[r].y;
+          v[r].y = tmp;
+        }
       }
-    }
-    DFT<R, T>::run(v);
-    {
-      cx<T>* dst = E + (R * t + 2 * ((R * t) / 16));  // R*t..R*t+R-1 lie in whole 16-groups when R == 16
-      if constexpr (R == 16 && sizeof(T) == 4) {
+      DFT<R, T>::run(v);
+      cx<T>* dst = Ef + (R * t + 2 * ((R * t) / 16));  // R*t..R*t+R-1 lie inside one 16-group (R divides 16)
+      if constexpr (sizeof(T) == 4) {
 #pragma unroll
         for (int r = 0; r < R; r += 2)
           *reinterpret_cast<float4*>(dst + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
       } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) E[epad<R>(R * t + r)] = v[r];
+        for (int r = 0; r < R; ++r) dst[r] = v[r];
       }
     }
     __syncthreads();
-    if (USE_TMA && t == 0 && it >= 1) {
+    if (USE_TMA && threadIdx.x == 0 && it >= 1) {
       // every thread has finished reading the stage used by iteration it-1 (its pass 3 precedes this barrier)
-      const long long kn = k + stride;
+      const long long kn = k0 + stride;
       if (kn < a.batch) {
-        cx<T>* Sn = (it & 1) ? S0 : S1;
         fence_proxy_async();
-        mbar_expect_tx(&full[(it + 1) & 1], N * sizeof(cx<T>));
-        bulk_g2s(Sn, gin + kn * a.idist, N * sizeof(cx<T>), &full[(it + 1) & 1]);
+        issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
       }
     }
-    // ---- pass 2: E[t + NT r] * w_{R^2}^{k2 r} -> radix R -> S[(t - k2) R + k2 + R r'] ---------------------------
+    if (live) {
+      // ---- pass 2: E[t + NT r] * w_{R^2}^{k2 r} -> radix R -> S[(t - k2) R + k2 + R r'] -------------------------
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = E[epad<R>(t + NT * r)];
+      for (int r = 0; r < R; ++r) v[r] = Ef[epad<R>(t + NT * r)];
 #pragma unroll
-    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r - 1]);
-    DFT<R, T>::run(v);
-    {
-      cx<T>* dst = S + (t - k2) * R + k2;
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r - 1]);
+      DFT<R, T>::run(v);
 #pragma unroll
-      for (int r = 0; r < R; ++r) dst[R * r] = v[r];
+      for (int r = 0; r < R; ++r) S[sw2<R>((t - k2) * R + k2 + R * r)] = v[r];
     }
     __syncthreads();
-    // ---- pass 3: S[t + NT r] * w_N^{t r} -> radix R -> out[t + NT r'] ------------------------------------------
+    if (live) {
+      // ---- pass 3: S[t + NT r] * w_N^{t r} -> radix R -> out[t + NT r'] ----------------------------------------
 #pragma unroll
-    for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
+      for (int r = 0; r < R; ++r) v[r] = S[sw2<R>(t + NT * r)];
 #pragma unroll
-    for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw3[r - 1]);
-    DFT<R, T>::run(v);
-    cx<T>* dst = gout + k * a.odist;
+      for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw3[r - 1]);
+      DFT<R, T>::run(v);
+      cx<T>* dst = gout + k * a.odist;
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      cx<T> o = v[r];
-      if (a.apply_scale) o = cscale(o, scale);
-      if (SWAP) {
-        const T tmp = o.x;
-        o.x = o.y;
-        o.y = tmp;
+      for (int r = 0; r < R; ++r) {
+        cx<T> o = v[r];
+        if (a.apply_scale) o = cscale(o, scale);
+        if (SWAP) {
+          const T tmp = o.x;
+          o.x = o.y;
+          o.y = tmp;
+        }
+        dst[t + NT * r] = o;
       }
-      dst[t + NT * r] = o;
     }
   }
 }
 
-template <typename T, int R>
-size_t cube_smem_bytes(bool use_tma) {
+template <typename T, int R, int F>
+size_t cube_smem_bytes_t(bool use_tma) {
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
-  return ((use_tma ? 2 : 1) * (size_t)N + EN) * sizeof(cx<T>) + 64;
+  return ((use_tma ? 2 : 1) * (size_t)N + EN) * F * sizeof(cx<T>) + 64;
 }
 
-template <typename T, int R, bool SWAP, bool USE_TMA>
+template <typename T, int R, int F, bool SWAP, bool USE_TMA>
 static cudaError_t launch_cube_t(const CubeArgs& a, int grid, cudaStream_t stream) {
-  const size_t smem = cube_smem_bytes<T, R>(USE_TMA);
-  auto kern = wg_cube_kernel<T, R, SWAP, USE_TMA>;
+  const size_t smem = cube_smem_bytes_t<T, R, F>(USE_TMA);
+  auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA>;
   cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, R * R, smem, stream>>>(a);
+  kern<<<grid, R * R * F, smem, stream>>>(a);
   return cudaGetLastError();
+}
+
+template <typename T, int R, int F>
+static cudaError_t launch_cube_v(const CubeArgs& a, bool swap, bool tma, int grid, cudaStream_t stream) {
+  if (tma) return swap ? launch_cube_t<T, R, F, true, true>(a, grid, stream) : launch_cube_t<T, R, F, false, true>(a, grid, stream);
+  return swap ? launch_cube_t<T, R, F, true, false>(a, grid, stream) : launch_cube_t<T, R, F, false, false>(a, grid, stream);
+}
+
+bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm) {
+  if (is_double) return false;
+  int f = 0, c = 0;
+  if (n == 4096) f = 1, c = 2;
+  if (n == 512) f = kCube512Tile, c = 4;
+  if (f == 0) return false;
+  if (transforms_per_tile) *transforms_per_tile = f;
+  if (ctas_per_sm) *ctas_per_sm = c;
+  return true;
 }
 
 // p: a single-pass plan entry with n == R^3, interleaved storage, unit strides, one batch dimension
@@ -217,10 +254,8 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   a.scale = p.scale;
   a.apply_scale = p.apply_scale;
   const bool tma = variant == 0;
-  if (!is_double && p.n == 4096) {
-    if (tma) return swap ? launch_cube_t<float, 16, true, true>(a, grid, stream) : launch_cube_t<float, 16, false, true>(a, grid, stream);
-    return swap ? launch_cube_t<float, 16, true, false>(a, grid, stream) : launch_cube_t<float, 16, false, false>(a, grid, stream);
-  }
+  if (!is_double && p.n == 4096) return launch_cube_v<float, 16, 1>(a, swap, tma, grid, stream);
+  if (!is_double && p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, grid, stream);
   return cudaErrorInvalidValue;
 }
 

@@ -1,0 +1,29 @@
+#!/bin/bash
+# A/B timing of kernel variants on one B200 (run under gpurun): each line = config, environment, ms per step.
+set -u
+O=gpurun_out/ab
+mkdir -p $O
+run() {  # name config env...
+  local name=$1 cfg=$2; shift 2
+  env "$@" python bench.py --config $cfg --steps 30 --warmup 4 --no-cpu-baseline --no-e2e > $O/$name.json 2> $O/$name.err
+  python - "$O/$name.json" "$name" <<'PY'
+import json, sys
+try:
+    d = json.load(open(sys.argv[1]))
+    print(f"{sys.argv[2]:28s} ms={d['ms_per_step']:.4f} frac={d['roofline']['frac']:.3f} rt={d.get('roundtrip_rel_l2')}")
+except Exception as e:
+    print(sys.argv[2], "FAILED", e)
+PY
+}
+run C5_new C5 X=1
+run C5_nocube512 C5 PFFT_NO_CUBE512=1
+run C5_noinplace C5 PFFT_COL_INPLACE=0
+run C5_old C5 PFFT_COL_INPLACE=0 PFFT_NO_CUBE512=1
+run C4_new C4 X=1
+run C4_noinplace C4 PFFT_COL_INPLACE=0
+run L1D_new L1D X=1
+run L1D_noinplace L1D PFFT_COL_INPLACE=0
+run M512_new M512 X=1
+run M512_nocube M512 PFFT_NO_CUBE512=1
+run M256 M256 X=1
+run C2 C2 X=1
