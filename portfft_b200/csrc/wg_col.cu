@@ -133,7 +133,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* stage0 = smem_raw;
   cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + Cfg::STAGES * Cfg::kStageBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(E + (size_t)C * PITCH);
+  uint64_t* full = reinterpret_cast<uint64_t*>(E + (INPLACE ? 0 : (size_t)C * PITCH));  // in place: no exchange buffer
   const IoFlags fl{true, swap};
   const int tid = threadIdx.x;
   // column mapping: lanes run along the transform index (used where memory is contiguous across transforms)
