@@ -69,7 +69,10 @@ class committed_descriptor {
     return compute_forward(inout_real, inout_imag, inout_real, inout_imag, dependencies);
   }
   event compute_backward(complex_type* inout, const std::vector<event>& dependencies = {}) {
-    return compute_backward(inout, inout, dependencies);
+    if constexpr (Domain == domain::REAL)
+      return compute_backward(inout, reinterpret_cast<scalar_type*>(inout), dependencies);
+    else
+      return compute_backward(inout, inout, dependencies);
   }
   event compute_backward(scalar_type* inout_real, scalar_type* inout_imag,
                          const std::vector<event>& dependencies = {}) {
@@ -92,12 +95,38 @@ class committed_descriptor {
     require_split();
     return run(direction::BACKWARD, in_real, in_imag, out_real, out_imag, dependencies);
   }
-  // ---- real-to-complex stubs, as in the reference (:201-206, :273-278) --------------------------------------------
-  event compute_forward(const scalar_type* /*in*/, complex_type* /*out*/, const std::vector<event>& = {}) {
-    throw unsupported_configuration("Real to complex FFTs not yet implemented.");
+  // ---- REAL domain: the overloads the reference reserves and leaves unimplemented (:134-137, :201-206, :273-278).
+  // Forward: real array -> half spectrum (lengths[last] / 2 + 1 complex elements along the last dimension);
+  // backward: half spectrum -> real array.
+  event compute_forward(const scalar_type* in, complex_type* out, const std::vector<event>& dependencies = {}) {
+    require_real();
+    return run(direction::FORWARD, in, nullptr, out, nullptr, dependencies);
+  }
+  event compute_forward(scalar_type* inout, const std::vector<event>& dependencies = {}) {
+    return compute_forward(inout, reinterpret_cast<complex_type*>(inout), dependencies);
+  }
+  event compute_forward(const scalar_type* in, scalar_type* out_real, scalar_type* out_imag,
+                        const std::vector<event>& dependencies = {}) {
+    require_real();
+    require_split();
+    return run(direction::FORWARD, in, nullptr, out_real, out_imag, dependencies);
+  }
+  event compute_backward(const complex_type* in, scalar_type* out, const std::vector<event>& dependencies = {}) {
+    require_real();
+    return run(direction::BACKWARD, in, nullptr, out, nullptr, dependencies);
+  }
+  event compute_backward(const scalar_type* in_real, const scalar_type* in_imag, scalar_type* out,
+                         const std::vector<event>& dependencies = {}) {
+    require_real();
+    require_split();
+    return run(direction::BACKWARD, in_real, in_imag, out, nullptr, dependencies);
   }
 
  private:
+  void require_real() const {
+    if (Domain != domain::REAL)
+      throw invalid_configuration("real-to-complex / complex-to-real overloads need a descriptor of domain::REAL");
+  }
   void require_split() const {
     if (params.complex_storage != complex_storage::SPLIT_COMPLEX)
       throw invalid_configuration(

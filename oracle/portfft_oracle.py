@@ -89,6 +89,7 @@ class OracleDescriptor:
     forward_offset: int = 0
     backward_offset: int = 0
     is_double: bool = False
+    is_real: bool = False  # Domain == domain::REAL (descriptor.hpp:43-57)
 
     def __post_init__(self):
         self.lengths = [int(x) for x in self.lengths]
@@ -118,10 +119,19 @@ class OracleDescriptor:
     def get_scale(self, d):
         return self.forward_scale if d == FORWARD else self.backward_scale
 
+    def domain_lengths(self, d) -> List[int]:
+        """Lengths of the data in one domain.  REAL descriptors hold lengths[-1] // 2 + 1 complex elements along the
+        last dimension of the backward domain -- the shape numpy.fft.rfftn returns, which is what the reference's
+        generator reads back (test/common/reference_data_wrangler.hpp:136-137,196)."""
+        l = list(self.lengths)
+        if self.is_real and d == BACKWARD:
+            l[-1] = l[-1] // 2 + 1
+        return l
+
     # descriptor.hpp:172-183
     def get_input_count(self, d) -> int:
-        return get_buffer_count(self.lengths, self.number_of_transforms, self.get_strides(d), self.get_distance(d),
-                                self.get_offset(d))
+        return get_buffer_count(self.domain_lengths(d), self.number_of_transforms, self.get_strides(d),
+                                self.get_distance(d), self.get_offset(d))
 
     def get_output_count(self, d) -> int:
         return self.get_input_count(inv(d))
@@ -293,19 +303,24 @@ def ref_fits_in_sg(n: int, sg: int, is_double: bool) -> bool:
 # data generation / expected results
 # ---------------------------------------------------------------------------------------------------------------------
 
-def gen_data(batch: int, dims: Sequence[int], is_double: bool, seed: int = 0) -> Tuple[np.ndarray, np.ndarray]:
-    """Restatement of the numpy script at test/common/reference_data_wrangler.hpp:117-145 (complex domain).
+def gen_data(batch: int, dims: Sequence[int], is_double: bool, seed: int = 0,
+             is_real: bool = False) -> Tuple[np.ndarray, np.ndarray]:
+    """Restatement of the numpy script at test/common/reference_data_wrangler.hpp:117-145.
 
-    Returns (inData, outData) with shape [batch] + dims; `outData = fftn(inData, axes=1..)`, unscaled.
+    Returns (inData, outData) with shape [batch] + dims; `outData = fftn(inData, axes=1..)`, unscaled.  REAL domain
+    (`is_complex` False in the script): inData is real and outData = rfftn(inData), last dimension dims[-1] // 2 + 1.
     """
     scalar_type = np.float64 if is_double else np.float32
     complex_type = np.complex128 if is_double else np.complex64
     shape = [int(batch)] + [int(d) for d in dims]
     rng = np.random.Generator(np.random.SFC64(seed))
     in_data = rng.uniform(-1, 1, shape).astype(scalar_type)
+    axes = tuple(range(1, len(dims) + 1))
+    if is_real:
+        out_data = np.fft.rfftn(in_data.astype(np.float64), axes=axes).astype(complex_type)
+        return in_data, out_data
     in_data = in_data + 1j * rng.uniform(-1, 1, shape).astype(scalar_type)
     in_data = in_data.astype(complex_type)
-    axes = tuple(range(1, len(dims) + 1))
     out_data = np.fft.fftn(in_data.astype(np.complex128), axes=axes).astype(complex_type)
     return in_data, out_data
 
@@ -327,7 +342,7 @@ def element_indices(desc: OracleDescriptor, direction: int) -> np.ndarray:
     """Flat index of every addressed element, shape [batch] + lengths (src/portfft/descriptor.hpp:91-92)."""
     idx = desc.get_offset(direction) + np.arange(desc.number_of_transforms, dtype=np.int64) * desc.get_distance(direction)
     idx = idx.reshape([desc.number_of_transforms] + [1] * len(desc.lengths))
-    for k, (n, s) in enumerate(zip(desc.lengths, desc.get_strides(direction))):
+    for k, (n, s) in enumerate(zip(desc.domain_lengths(direction), desc.get_strides(direction))):
         shape = [1] * (len(desc.lengths) + 1)
         shape[k + 1] = n
         idx = idx + (np.arange(n, dtype=np.int64) * s).reshape(shape)
@@ -343,7 +358,7 @@ def expected_io(desc: OracleDescriptor, direction: int, seed: int = 0,
     BACKWARD: input = fftn in the backward layout, expected = numpy input * backward_scale * N in the forward layout
     (:202-210)."""
     scalar = np.float64 if desc.is_double else np.float32
-    fwd, bwd = gen_data(desc.number_of_transforms, desc.lengths, desc.is_double, seed)
+    fwd, bwd = gen_data(desc.number_of_transforms, desc.lengths, desc.is_double, seed, desc.is_real)
     if direction == FORWARD:
         bwd = bwd * scalar(desc.forward_scale)
     else:

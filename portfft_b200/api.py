@@ -266,10 +266,23 @@ class committed_descriptor:
 
     def _dispatch(self, d: direction, args, queue):
         n = len(args)
-        if n == 1:      # in-place interleaved  (committed_descriptor.hpp:171-176)
+        split = self.params.complex_storage == complex_storage.SPLIT_COMPLEX
+        if self.params.domain == domain.REAL:
+            # REAL domain (committed_descriptor.hpp:201-206,273-278): the forward-domain side is one scalar array.
+            # forward: (inout) | (in, out) | split (in, out_re, out_im); backward: (inout) | (in, out) | split (in_re, in_im, out)
+            fwd = d == direction.FORWARD
+            if n == 1 and not split:
+                a = (args[0], None, args[0], None)
+            elif n == 2 and not split:
+                a = (args[0], None, args[1], None)
+            elif n == 3 and split:
+                a = (args[0], None, args[1], args[2]) if fwd else (args[0], args[1], args[2], None)
+            else:
+                raise TypeError("REAL-domain compute_* takes (inout), (in, out) or, for split storage, 3 data arguments")
+        elif n == 1:      # in-place interleaved  (committed_descriptor.hpp:171-176)
             a = (args[0], None, args[0], None)
         elif n == 2:
-            if self.params.complex_storage == complex_storage.SPLIT_COMPLEX:
+            if split:
                 a = (args[0], args[1], args[0], args[1])  # in-place split (:186-192)
             else:
                 a = (args[0], None, args[1], None)        # out-of-place interleaved (:242-246)

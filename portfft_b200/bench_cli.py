@@ -25,6 +25,12 @@ RUNS_TO_AVERAGE = 10  # bench_utils.hpp:39
 
 CANNED_FLOAT = [("small_1d", [16], 8 * 1024 * 1024), ("medium_small_1d", [256], 512 * 1024),
                 ("medium_large_1d", [4096], 32 * 1024), ("large_1d", [65536], 2048)]
+# register_complex_float_benchmark_set / register_real_float_benchmark_set (utils/reference_dft_set.hpp:87-112): the
+# sets the reference registers for the closed-source comparison benches.  "large_1d_prime" (65537) cannot run on the
+# reference (a prime factor beyond one work-item, committed_descriptor_impl.hpp:241); it runs here (Bluestein).
+CANNED_COMPLEX_SET = CANNED_FLOAT + [("large_1d_prime", [65537], 2048)]
+CANNED_REAL_SET = [("small_1d", [32], 8 * 1024 * 1024), ("medium_small_1d", [512], 512 * 1024),
+                   ("medium_large_1d", [8192], 32 * 1024), ("large_1d", [128 * 1024], 2048)]
 
 
 class bench_error(RuntimeError):
@@ -137,9 +143,11 @@ def ops_estimate(n: int, batch: int) -> float:
     return 5.0 * batch * n * math.log2(n)
 
 
-def mem_transactions(n: int, batch: int, scalar: str) -> float:
-    """global_mem_transactions, utils/ops_estimate.hpp:47-50 (one read + one write of complex<scalar>)"""
-    return 2.0 * batch * n * (16 if scalar == "double" else 8)
+def mem_transactions(n: int, batch: int, scalar: str, real: bool = False) -> float:
+    """global_mem_transactions<forward_t, complex_type>(batch, N, N), utils/ops_estimate.hpp:47-50 (one read of the
+    forward type + one write of complex<scalar>; launch_bench.hpp:138-141)"""
+    c = 16 if scalar == "double" else 8
+    return float(batch) * n * ((c // 2 if real else c) + c)
 
 
 def run_host_device_benchmark(desc, suffix: str, iterations: int = 10, device: int = 0) -> List[dict]:
@@ -154,15 +162,22 @@ def run_host_device_benchmark(desc, suffix: str, iterations: int = 10, device: i
     n = desc.get_flattened_length()
     batch = desc.number_of_transforms
     cdt = torch.complex128 if desc.scalar == "double" else torch.complex64
+    rdt = torch.float64 if desc.scalar == "double" else torch.float32
+    real = int(desc.domain) == int(pf.domain.REAL)
     n_in, n_out = desc.get_input_count(pf.direction.FORWARD), desc.get_output_count(pf.direction.FORWARD)
     in_place = desc.placement == pf.placement.IN_PLACE
+    if real and in_place:
+        raise bench_error("REAL-domain benchmarks run out of place")
     esz = 16 if desc.scalar == "double" else 8
+    isz = esz // 2 if real else esz
     total = torch.cuda.get_device_properties(dev).total_memory
-    num_inputs = RUNS_TO_AVERAGE if n_in * esz * RUNS_TO_AVERAGE + (0 if in_place else n_out * esz) <= 0.9 * total else 1
-    inputs = [torch.zeros(n_in, dtype=cdt, device=dev) for _ in range(num_inputs)]
+    num_inputs = RUNS_TO_AVERAGE if n_in * isz * RUNS_TO_AVERAGE + (0 if in_place else n_out * esz) <= 0.9 * total else 1
+    inputs = [torch.zeros(n_in, dtype=rdt if real else cdt, device=dev) for _ in range(num_inputs)]
     out = None if in_place else torch.zeros(n_out, dtype=cdt, device=dev)
-    host = torch.view_as_complex(torch.rand(n_in, 2, dtype=torch.float64 if desc.scalar == "double" else torch.float32)
-                                 * 2 - 1).pin_memory()
+    if real:
+        host = (torch.rand(n_in, dtype=rdt) * 2 - 1).pin_memory()
+    else:
+        host = torch.view_as_complex(torch.rand(n_in, 2, dtype=rdt) * 2 - 1).pin_memory()
     plan = desc.commit(stream, device)
 
     def compute(buf):
@@ -173,7 +188,7 @@ def run_host_device_benchmark(desc, suffix: str, iterations: int = 10, device: i
 
     compute(inputs[0])
     torch.cuda.synchronize(dev)
-    ops, byts = ops_estimate(n, batch), mem_transactions(n, batch, desc.scalar)
+    ops, byts = ops_estimate(n, batch), mem_transactions(n, batch, desc.scalar, real)
     host_name, dev_name = benchmark_names(desc, suffix)
     # ---- average_host_time ----------------------------------------------------------------------------------------
     t_host = []

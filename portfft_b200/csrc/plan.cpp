@@ -21,10 +21,17 @@ size_t DescHost::flattened_length() const {
   return t;
 }
 
+std::vector<size_t> DescHost::domain_lengths(int dir) const {
+  std::vector<size_t> l = lengths;
+  if (is_real() && dir == PFFT_BACKWARD && !l.empty()) l.back() = l.back() / 2 + 1;
+  return l;
+}
+
 size_t DescHost::buffer_count(int dir) const {
   const auto& s = strides(dir);
+  const std::vector<size_t> len = domain_lengths(dir);
   size_t last = (number_of_transforms - 1) * distance(dir);
-  for (size_t i = 0; i < lengths.size() && i < s.size(); ++i) last += (lengths[i] - 1) * s[i];
+  for (size_t i = 0; i < len.size() && i < s.size(); ++i) last += (len[i] - 1) * s[i];
   for (size_t i = 0; i < extra.size(); ++i) {
     if (peer_last && i + 1 == extra.size() && dir == PFFT_BACKWARD) continue;  // selects a buffer, not an address
     last += (extra[i].count - 1) * (dir == PFFT_FORWARD ? extra[i].forward_distance : extra[i].backward_distance);
@@ -148,13 +155,23 @@ void check_strides_distance(const std::vector<size_t>& lengths, size_t batch, co
 }  // namespace
 
 void validate_descriptor(const DescHost& d) {
-  // descriptor_validation.hpp:268-270
-  if (d.domain == PFFT_DOMAIN_REAL) unsupported("REAL domain is unsupported");
   if (d.number_of_transforms == 0) invalid("Invalid number of transform ", d.number_of_transforms, ", must be positive");
   // :38-47
   if (d.lengths.empty()) invalid("Invalid lengths, must have at least 1 dimension");
   for (size_t i = 0; i < d.lengths.size(); ++i)
     if (d.lengths[i] == 0) invalid("Invalid lengths[", i, "]=", d.lengths[i], ", must be positive");
+  if (d.is_real()) {
+    // The reference stops here (descriptor_validation.hpp:268-270: "REAL domain is unsupported").  Forward domain:
+    // real scalars of `lengths`; backward domain: lengths[last] / 2 + 1 complex elements along the last dimension.
+    // Every pass that reads the input finishes before the first pass writes the output, so IN_PLACE needs no
+    // relation between the two layouts beyond each being overlap-free.
+    if (d.lengths.size() != 1) unsupported("REAL domain: multi-dimensional transforms are not supported");
+    if (!d.extra.empty()) unsupported("REAL domain: extra batch dimensions are not supported");
+    check_strides_distance(d.lengths, d.number_of_transforms, d.forward_strides, d.forward_distance, "forward");
+    check_strides_distance(d.domain_lengths(PFFT_BACKWARD), d.number_of_transforms, d.backward_strides,
+                           d.backward_distance, "backward");
+    return;
+  }
   // :237-253
   if (d.placement == PFFT_IN_PLACE) {
     if (d.forward_strides != d.backward_strides)
@@ -535,6 +552,36 @@ bool split_factors(size_t n, int k, size_t fmax, std::vector<size_t>& out) {
   return false;
 }
 
+// One launch for a whole transform of length L <= max_workgroup_length: picks the level / kernel (thread, warp or
+// block level; specialised block-level kernels where the layout allows).
+PassHost single_pass(const DescHost& d, const DeviceLimits& lim, size_t L, long long es_in, long long es_out,
+                     long long off_in, long long off_out, const std::vector<BDim>& dims, int src, int dst) {
+  const bool dbl = d.is_double;
+  PassHost ps;
+  set_radices(ps.pp, L);
+  ps.pp.is = es_in;
+  ps.pp.os = es_out;
+  ps.pp.ioff = off_in;
+  ps.pp.ooff = off_out;
+  ps.pp.gtw_dim = -1;
+  set_batch_dims(ps.pp, dims);
+  ps.src = src;
+  ps.dst = dst;
+  ps.level = LEVEL_WORKGROUP;
+  const int force = force_level();
+  if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, lim)) return ps;
+  // block-level tile kernel first where it applies (it out-runs the warp-level kernel on B200: TMA-fed,
+  // persistent); the warp-level kernel takes the unit-stride sizes it does not cover
+  PassHost wg = ps;
+  configure_wg_generic(wg, dbl, lim, false);
+  select_specialised(wg, d, lim);
+  if (wg.kernel == KERNEL_WG_GENERIC) select_col(wg, d, lim);
+  if (wg.kernel == KERNEL_WG_GENERIC) select_r3(wg, d, lim);
+  if (force == LEVEL_WORKGROUP || (force < 0 && wg.kernel != KERNEL_WG_GENERIC)) return wg;
+  if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) return ps;
+  return wg;
+}
+
 // One side (source or destination) of a multi-pass transform: buffer, element stride, offset and the distance of
 // every (merged) outer batch dimension.
 struct View {
@@ -628,8 +675,121 @@ struct Domain {
   size_t distance, offset;
 };
 
+// REAL domain, 1-D (see real.cu for the scheme).  Forward: [pack] -> complex transform of length L (N/2 for even N,
+// N for odd N) -> r2c_post; backward: c2r_pre -> complex transform -> [unpack].  The pack / unpack passes disappear
+// when the real rows can be addressed as interleaved complex pairs (even N, unit stride, even offset and distance).
+// Plan-internal rows live packed and interleaved in the workspaces, whatever the descriptor's complex storage.
+void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
+  const DescHost& d = plan.desc;
+  DescHost dint = d;  // the descriptor as the inner complex passes see it
+  dint.complex_storage = PFFT_INTERLEAVED_COMPLEX;
+  const bool dbl = d.is_double;
+  const bool fwd = dir == PFFT_FORWARD;
+  const long long N = (long long)d.lengths[0], H = N / 2;
+  const bool even = N % 2 == 0;
+  const int variant = even ? 0 : 1;
+  const long long L = even ? H : N;
+  const long long batch = (long long)d.number_of_transforms;
+  const long long rs = (long long)d.forward_strides[0], roff = (long long)d.forward_offset, rdist = (long long)d.forward_distance;
+  const long long cs = (long long)d.backward_strides[0], coff = (long long)d.backward_offset, cdist = (long long)d.backward_distance;
+  const size_t wg_max = max_workgroup_length(dbl, lim);
+  std::vector<PassHost>& passes = plan.passes[dir];
+  if (!smooth31((size_t)L))
+    unsupported("REAL domain: length ", N, " needs a complex transform of length ", L,
+                " with a prime factor larger than 31, which is not supported");
+  const bool single = (size_t)L <= wg_max;
+  plan.dim_level.assign(1, single ? PFFT_LEVEL_WORKGROUP : PFFT_LEVEL_GLOBAL);
+  plan.scratch_elems = std::max(plan.scratch_elems, (size_t)(batch * L));
+  const bool pairs = even && rs == 1 && roff % 2 == 0 && (batch == 1 || rdist % 2 == 0);
+  const std::vector<long long> outer_n(1, batch), row_d(1, L), pair_d(1, rdist / 2);
+  const View s1{BUF_SCRATCH, 1, 0, row_d}, s2{BUF_SCRATCH2, 1, 0, row_d};
+  const View rview{fwd ? BUF_IN : BUF_OUT, 1, roff / 2, pair_d};  // the real rows as complex pairs
+
+  auto rows_pass = [&](int kernel, int src, int dst, long long es_in, long long o_in, long long d_in, long long es_out,
+                       long long o_out, long long d_out, long long work_per_row) {
+    PassHost ps;
+    ps.pp.n = (int)N;
+    ps.pp.num_radices = 1;
+    ps.pp.radix[0] = 1;
+    ps.pp.threads_per_fft = 1;
+    ps.pp.ffts_per_block = 256;
+    ps.pp.is = es_in;
+    ps.pp.os = es_out;
+    ps.pp.ioff = o_in;
+    ps.pp.ooff = o_out;
+    ps.pp.gtw_dim = -1;
+    set_batch_dims(ps.pp, {BDim{batch, d_in, d_out}});
+    ps.src = src;
+    ps.dst = dst;
+    ps.kernel = kernel;
+    ps.variant = variant;
+    ps.level = single ? LEVEL_WORKGROUP : LEVEL_GLOBAL;
+    ps.block = 256;
+    ps.grid = (int)std::min<long long>((batch * work_per_row + 255) / 256, (long long)lim.num_sms * 16);
+    ps.tw_n = (even && (kernel == KERNEL_R2C_POST || kernel == KERNEL_C2R_PRE)) ? N : 0;
+    return ps;
+  };
+  // complex transform of length L between two views; returns the buffer holding the result
+  auto transform = [&](const View& src, const View* final_dst) {
+    const size_t first = passes.size();
+    int result;
+    if (single) {
+      const View dst = final_dst ? *final_dst : View{src.buf == BUF_IN ? BUF_SCRATCH : src.buf, 1, 0, row_d};
+      passes.push_back(single_pass(dint, lim, (size_t)L, src.es, dst.es, src.off, dst.off,
+                                   merge_dims({BDim{batch, src.dist[0], dst.dist[0]}}, 0), src.buf, dst.buf));
+      result = dst.buf;
+    } else {
+      // multi-pass: in place on a packed workspace, the last pass moves to the other one (or to the final view)
+      const int work = src.buf == BUF_IN ? BUF_SCRATCH2 : src.buf;
+      const View other = work == BUF_SCRATCH ? s2 : s1;
+      const View dst = final_dst ? *final_dst : other;
+      if (!final_dst || src.buf == BUF_IN) plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)(batch * L));
+      emit_multipass(passes, dint, lim, (size_t)L, outer_n, src, work, dst);
+      result = dst.buf;
+    }
+    for (size_t i = first; i < passes.size(); ++i) {
+      passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;  // plain forward transforms
+      passes[i].internal_storage = 1;
+    }
+    return result;
+  };
+
+  if (fwd) {
+    int zbuf;
+    if (pairs) {
+      zbuf = transform(rview, nullptr);
+    } else {
+      passes.push_back(rows_pass(KERNEL_REAL_PACK, BUF_IN, BUF_SCRATCH, rs, roff, rdist, 1, 0, L, L));
+      zbuf = transform(s1, nullptr);
+    }
+    passes.push_back(rows_pass(KERNEL_R2C_POST, zbuf, BUF_OUT, 1, 0, L, cs, coff, cdist, H + 1));
+  } else {
+    passes.push_back(rows_pass(KERNEL_C2R_PRE, BUF_IN, BUF_SCRATCH, cs, coff, cdist, 1, 0, L, L));
+    if (pairs) {
+      transform(s1, &rview);
+    } else {
+      const int ybuf = transform(s1, nullptr);
+      passes.push_back(rows_pass(KERNEL_REAL_UNPACK, ybuf, BUF_OUT, 1, 0, L, rs, roff, rdist, L));
+    }
+  }
+  // passes that address the user's real buffer as complex pairs
+  for (PassHost& ps : passes) {
+    if (ps.kernel >= KERNEL_REAL_PACK) continue;
+    if (ps.src == BUF_IN) ps.real_view |= 1;
+    if (ps.dst == BUF_OUT) ps.real_view |= 2;
+  }
+  const double scale = d.scale(dir);
+  PassHost& last = passes.back();
+  last.pp.scale = d.is_double ? scale : (double)(float)scale;
+  last.pp.apply_scale = (d.is_double ? scale : (double)(float)scale) != 1.0;
+}
+
 void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   const DescHost& d = plan.desc;
+  if (d.is_real()) {
+    build_real_direction(plan, dir, lim);
+    return;
+  }
   const bool dbl = d.is_double;
   const Domain in{d.strides(dir), d.distance(dir), d.offset(dir)};
   const int odir = dir == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
@@ -669,34 +829,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     const int src0 = first ? BUF_IN : BUF_OUT;
 
     if (L <= wg_max && !choose_radices(L).empty()) {
-      PassHost ps;
-      set_radices(ps.pp, L);
-      ps.pp.is = es_in;
-      ps.pp.os = es_out;
-      ps.pp.ioff = off_in;
-      ps.pp.ooff = off_out;
-      ps.pp.gtw_dim = -1;
-      set_batch_dims(ps.pp, merge_dims(outer, 0));
-      ps.src = src0;
-      ps.dst = BUF_OUT;
-      ps.level = LEVEL_WORKGROUP;
-      const int force = force_level();
-      if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, lim)) {
-      } else {
-        // block-level tile kernel first where it applies (it out-runs the warp-level kernel on B200: TMA-fed,
-        // persistent); the warp-level kernel takes the unit-stride sizes it does not cover
-        PassHost wg = ps;
-        configure_wg_generic(wg, dbl, lim, false);
-        select_specialised(wg, d, lim);
-        if (wg.kernel == KERNEL_WG_GENERIC) select_col(wg, d, lim);
-        if (wg.kernel == KERNEL_WG_GENERIC) select_r3(wg, d, lim);
-        if (force == LEVEL_WORKGROUP || (force < 0 && wg.kernel != KERNEL_WG_GENERIC)) {
-          ps = wg;
-        } else if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) {
-        } else {
-          ps = wg;
-        }
-      }
+      PassHost ps = single_pass(d, lim, L, es_in, es_out, off_in, off_out, merge_dims(outer, 0), src0, BUF_OUT);
       passes.push_back(ps);
       plan.dim_level[dim] = ps.level;
       continue;
@@ -853,7 +986,7 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew", "real_pack", "r2c_post", "c2r_pre", "real_unpack"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
   static const char* buf_names[] = {"in", "out", "scratch", "scratch2"};
   static const char* mod_names[] = {"none", "chirp", "chirp/M", "conv"};
@@ -884,6 +1017,8 @@ std::string describe_plan(const PlanHost& plan, int direction) {
       ss << " lmod=" << mod_names[ps.lmod_kind] << " smod=" << mod_names[ps.smod_kind] << " valid_in=" << p.valid_in
          << " valid_out=" << p.valid_out << " mod_flags=" << p.mod_flags << " mod_l=" << ps.mod_l << " mod_m=" << ps.mod_m;
     if (p.apply_scale) ss << " scale=" << p.scale;
+    if (ps.real_view) ss << " real_view=" << ps.real_view;
+    if (ps.kernel >= KERNEL_REAL_PACK) ss << " variant=" << ps.variant;
     ss << "\n";
   }
   return ss.str();
@@ -898,7 +1033,8 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
     ss << "]";
   };
   ss << "{\"scratch_elems\": " << plan.scratch_elems << ", \"scratch2_elems\": " << plan.scratch2_elems
-     << ", \"is_double\": " << (plan.desc.is_double ? 1 : 0) << ", \"passes\": [";
+     << ", \"is_double\": " << (plan.desc.is_double ? 1 : 0) << ", \"is_real\": " << (plan.desc.is_real() ? 1 : 0)
+     << ", \"passes\": [";
   bool firstp = true;
   for (const PassHost& ps : plan.passes[direction]) {
     const PassParams& p = ps.pp;
@@ -914,7 +1050,7 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
        << ", \"valid_in\": " << p.valid_in << ", \"valid_out\": " << p.valid_out << ", \"mod_flags\": " << p.mod_flags
        << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
        << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
-       << ", \"variant\": " << ps.variant << "}";
+       << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view << "}";
     firstp = false;
   }
   ss << "]}";

@@ -47,6 +47,11 @@ struct DescHost {
   double scale(int dir) const { return dir == PFFT_FORWARD ? forward_scale : backward_scale; }
   size_t flattened_length() const;
   size_t buffer_count(int dir) const;
+  // lengths of the data in one domain: REAL descriptors hold lengths[last] / 2 + 1 complex elements along the last
+  // dimension of the backward domain (the half spectrum, as numpy.fft.rfftn:
+  // /root/reference/test/common/reference_data_wrangler.hpp:136-137,196), everything else equals `lengths`
+  std::vector<size_t> domain_lengths(int dir) const;
+  bool is_real() const { return domain == PFFT_DOMAIN_REAL; }
 };
 
 DescHost desc_from_c(const pfft_desc* d);
@@ -56,7 +61,8 @@ void validate_descriptor(const DescHost& d);  // throws PlanError
 
 enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2, BUF_SCRATCH2 = 3 };
 
-enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5, KERNEL_EW = 6 };
+enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5, KERNEL_EW = 6,
+                        KERNEL_REAL_PACK = 7, KERNEL_R2C_POST = 8, KERNEL_C2R_PRE = 9, KERNEL_REAL_UNPACK = 10 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -73,6 +79,11 @@ struct PassHost {
   // element-wise modifier tables (tables.h ModTable) for transform length mod_l / convolution length mod_m
   int lmod_kind = 0, smod_kind = 0;
   long long mod_l = 0, mod_m = 0;
+  // REAL-domain plans: plan-internal data is always interleaved complex; `user_side` tells which side of the pass
+  // (bit 0 input, bit 1 output) is user memory in the descriptor's complex storage.  `real_view`: the input (bit 0)
+  // or output (bit 1) is the user's REAL buffer read / written as interleaved complex pairs (x[2j], x[2j+1]).
+  int internal_storage = 0;  // 1: run this pass with interleaved storage whatever the descriptor says
+  int real_view = 0;
 };
 
 // geometry limits of the thread- and warp-level kernels (wi.cuh, sg.cuh); sg_supports_m lives in sg_f32.cu

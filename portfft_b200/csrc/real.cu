@@ -1,0 +1,171 @@
+// REAL domain (real-to-complex forward, complex-to-real backward), the pre- / post-processing passes around the
+// complex transform of half the length.
+//
+// The reference reserves this API and throws (`compute_forward(const Scalar*, complex_type*)`:
+// /root/reference/src/portfft/committed_descriptor.hpp:134-137,201-206,273-278; validate_descriptor:
+// /root/reference/src/portfft/descriptor_validation.hpp:268-270); its test generator already defines the expected
+// result as numpy.fft.rfftn (/root/reference/test/common/reference_data_wrangler.hpp:136-137,196).  Scheme (N even,
+// H = N/2, w = exp(-2 pi i / N)):
+//   forward : z_j = x_{2j} + i x_{2j+1}, Z = DFT_H(z),  X_k = E_k + w^k O_k,  k = 0..H,
+//             E_k = (Z_k + conj Z_{H-k}) / 2,  O_k = (Z_k - conj Z_{H-k}) / (2i)                      (r2c_post)
+//   backward: Z'_k = (X_k + conj X_{H-k}) + i conj(w^k) (X_k - conj X_{H-k}),  k = 0..H-1, stored in REVERSED index
+//             order so that the plain forward DFT_H of the scratch row is the unnormalised inverse,
+//             x_{2j} = Re z_j, x_{2j+1} = Im z_j                                                         (c2r_pre)
+// When the real buffer has unit stride and even offsets the complex passes read / write it directly as interleaved
+// pairs (no pack / unpack pass).  Odd N: the real row is widened to a complex row (real_pack), transformed at full
+// length and truncated to N/2 + 1 outputs (r2c_post, variant 1); backward mirrors it (c2r_pre / real_unpack variant 1).
+// Plan-internal rows are packed interleaved complex; the user's complex side follows the descriptor's storage.
+#include "device_utils.cuh"
+#include "io.cuh"
+#include "kernels.h"
+#include "pass.h"
+
+namespace pfft {
+
+namespace {
+
+// batch multi-index of row g -> input / output base offsets
+__device__ __forceinline__ void row_bases(const PassParams& p, long long g, long long& ib, long long& ob) {
+  ib = p.ioff;
+  ob = p.ooff;
+#pragma unroll
+  for (int d = 0; d < kMaxBatchDims; ++d) {
+    const long long q = g / p.nb[d];
+    const long long b = g - q * p.nb[d];
+    g = q;
+    ib += b * p.ibd[d];
+    ob += b * p.obd[d];
+  }
+}
+
+// variant 0: out[m] = (x[2m], x[2m+1]), m < n/2;  variant 1: out[m] = (x[m], 0), m < n.  Input: REAL scalars.
+template <typename T>
+__global__ void __launch_bounds__(256) real_pack_kernel(const PassParams p, const int variant) {
+  const long long count = variant == 0 ? p.n / 2 : p.n;
+  const long long total = p.batch_total * count;
+  const T* x = reinterpret_cast<const T*>(p.in_re);
+  cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / count, m = e - g * count;
+    long long ib, ob;
+    row_bases(p, g, ib, ob);
+    cx<T> v;
+    if (variant == 0) {
+      v.x = x[ib + (2 * m) * p.is];
+      v.y = x[ib + (2 * m + 1) * p.is];
+    } else {
+      v.x = x[ib + m * p.is];
+      v.y = T(0);
+    }
+    out[ob + m] = v;
+  }
+}
+
+// variant 0: out[2m] = Re z[m], out[2m+1] = Im z[m], m < n/2;  variant 1: out[m] = Re y[m], m < n.  Output: REAL scalars.
+template <typename T>
+__global__ void __launch_bounds__(256) real_unpack_kernel(const PassParams p, const int variant) {
+  const long long count = variant == 0 ? p.n / 2 : p.n;
+  const long long total = p.batch_total * count;
+  const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
+  T* x = reinterpret_cast<T*>(p.out_re);
+  const T scale = p.apply_scale ? T(p.scale) : T(1);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / count, m = e - g * count;
+    long long ib, ob;
+    row_bases(p, g, ib, ob);
+    const cx<T> v = in[ib + m];
+    if (variant == 0) {
+      x[ob + (2 * m) * p.os] = v.x * scale;
+      x[ob + (2 * m + 1) * p.os] = v.y * scale;
+    } else {
+      x[ob + m * p.os] = v.x * scale;
+    }
+  }
+}
+
+// Input: packed interleaved rows (variant 0: Z of length n/2; variant 1: the full-length transform Y).  Output: the
+// half spectrum X_k, k = 0..n/2, in the user's layout (element stride os, descriptor's storage).
+template <typename T>
+__global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const int variant, const bool il) {
+  const long long h = p.n / 2, count = h + 1;
+  const long long total = p.batch_total * count;
+  const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
+  const IoFlags fl{il, false};
+  const T scale = p.apply_scale ? T(p.scale) : T(1);
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / count, k = e - g * count;
+    long long ib, ob;
+    row_bases(p, g, ib, ob);
+    cx<T> o;
+    if (variant == 0) {
+      const cx<T> a = in[ib + (k == h ? 0 : k)];
+      cx<T> b = in[ib + (k == 0 ? 0 : h - k)];
+      b.y = -b.y;  // conj Z_{H-k}
+      const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
+      const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
+      o = ev + cmul(ldg_cx<T>(p.tw, k), od);
+    } else {
+      o = in[ib + k];
+    }
+    gstore<T>(p, fl, ob + k * p.os, cscale(o, scale));
+  }
+}
+
+// Input: the half spectrum in the user's layout (element stride is, descriptor's storage).  Output: packed
+// interleaved rows, index-reversed (see the header): variant 0 length n/2, variant 1 the Hermitian extension, length n.
+template <typename T>
+__global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const int variant, const bool il) {
+  const long long n = p.n, h = n / 2;
+  const long long count = variant == 0 ? h : (n + 1) / 2;
+  const long long total = p.batch_total * count;
+  cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
+  const IoFlags fl{il, false};
+  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const long long g = e / count, k = e - g * count;
+    long long ib, ob;
+    row_bases(p, g, ib, ob);
+    cx<T> a = gload<T>(p, fl, ib + k * p.is);
+    if (k == 0) a.y = T(0);  // the imaginary parts of X_0 (and X_{N/2}) do not enter a real inverse (numpy.fft.irfft)
+    if (variant == 0) {
+      cx<T> b = gload<T>(p, fl, ib + (h - k) * p.is);
+      if (k == 0) b.y = T(0);
+      b.y = -b.y;  // conj X_{H-k}
+      const cx<T> s = a + b, d = a - b;
+      cx<T> w = ldg_cx<T>(p.tw, k);
+      w.y = -w.y;  // conj(w^k)
+      const cx<T> t = cmul(w, d);
+      out[ob + (k == 0 ? 0 : h - k)] = cx<T>{s.x - t.y, s.y + t.x};  // s + i t
+    } else {
+      // reversed Hermitian extension: row[k] = conj X_k, row[n - k] = X_k
+      out[ob + k] = cx<T>{a.x, -a.y};
+      if (k > 0) out[ob + n - k] = a;
+    }
+  }
+}
+
+template <typename K, typename... Args>
+cudaError_t launch_rows(K kern, int grid, cudaStream_t stream, Args... args) {
+  kern<<<grid, 256, 0, stream>>>(args...);
+  return cudaGetLastError();
+}
+
+}  // namespace
+
+cudaError_t launch_real_pack(const PassParams& p, bool is_double, int variant, int grid, cudaStream_t stream) {
+  return is_double ? launch_rows(real_pack_kernel<double>, grid, stream, p, variant)
+                   : launch_rows(real_pack_kernel<float>, grid, stream, p, variant);
+}
+cudaError_t launch_real_unpack(const PassParams& p, bool is_double, int variant, int grid, cudaStream_t stream) {
+  return is_double ? launch_rows(real_unpack_kernel<double>, grid, stream, p, variant)
+                   : launch_rows(real_unpack_kernel<float>, grid, stream, p, variant);
+}
+cudaError_t launch_r2c_post(const PassParams& p, bool is_double, bool il, int variant, int grid, cudaStream_t stream) {
+  return is_double ? launch_rows(r2c_post_kernel<double>, grid, stream, p, variant, il)
+                   : launch_rows(r2c_post_kernel<float>, grid, stream, p, variant, il);
+}
+cudaError_t launch_c2r_pre(const PassParams& p, bool is_double, bool il, int variant, int grid, cudaStream_t stream) {
+  return is_double ? launch_rows(c2r_pre_kernel<double>, grid, stream, p, variant, il)
+                   : launch_rows(c2r_pre_kernel<float>, grid, stream, p, variant, il);
+}
+
+}  // namespace pfft

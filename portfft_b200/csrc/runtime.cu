@@ -159,22 +159,28 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
                     cudaStream_t stream, const PeerTable* peers = nullptr) {
   const DescHost& d = plan->host.desc;
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
-  // committed_descriptor_impl.hpp:862-871
-  if (il && (in_imag != nullptr || out_imag != nullptr))
+  const bool real = d.is_real();
+  const bool bwd = dir == PFFT_BACKWARD;
+  // committed_descriptor_impl.hpp:862-871 (for REAL descriptors the check applies to the complex side of the call;
+  // the real side is one scalar array: committed_descriptor.hpp:201-206,273-278)
+  const bool in_cplx = !real || bwd, out_cplx = !real || !bwd;
+  if ((in_cplx && il && in_imag != nullptr) || (out_cplx && il && out_imag != nullptr))
     throw PlanError(PFFT_INVALID_CONFIGURATION,
                     "To use interleaved data layout, please set the storage in the descriptor to INTERLEAVED_COMPLEX");
-  if (!il && (in_imag == nullptr || out_imag == nullptr))
+  if ((in_cplx && !il && in_imag == nullptr) || (out_cplx && !il && out_imag == nullptr))
     throw PlanError(PFFT_INVALID_CONFIGURATION,
                     "To use split data layout, please set the storage in the descriptor to SPLIT_COMPLEX");
+  if ((!in_cplx && in_imag != nullptr) || (!out_cplx && out_imag != nullptr))
+    throw PlanError(PFFT_INVALID_CONFIGURATION, "the real side of a REAL-domain transform is a single scalar array");
   if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
-  const bool bwd = dir == PFFT_BACKWARD;
   const size_t scalar = d.is_double ? 8 : 4;
   // backward = forward transform of the (re <-> im)-swapped data, swapped back: free for split storage
+  // (REAL plans never swap: c2r_pre writes its rows index-reversed instead, real.cu)
   const void* uin_re = in;
   const void* uin_im = in_imag;
   void* uout_re = out;
   void* uout_im = out_imag;
-  if (!il && bwd) {
+  if (!il && bwd && !real) {
     std::swap(uin_re, uin_im);
     std::swap(uout_re, uout_im);
   }
@@ -198,7 +204,15 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     // backward on interleaved data = (re <-> im) swap on load and store; passes between plan-internal buffers
     // (Bluestein's inner transforms) always run the plain forward transform
     const int internal = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
-    const bool swap = il && bwd && (p.mod_flags & internal) != internal;
+    const bool pil = il || ps.internal_storage != 0;  // storage this pass runs with
+    const bool swap = pil && bwd && !real && (p.mod_flags & internal) != internal;
+    if (ps.real_view) {
+      // the user's real rows addressed as interleaved complex pairs: needs complex alignment of the first element
+      const uintptr_t a = (ps.real_view & 1) ? (uintptr_t)p.in_re + (size_t)p.ioff * 2 * scalar
+                                            : (uintptr_t)p.out_re + (size_t)p.ooff * 2 * scalar;
+      if (a % (2 * scalar) != 0)
+        throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION, "REAL domain: the real buffer must be aligned to a complex element");
+    }
     if (p.peer_dim >= 0) {
       if (peers == nullptr || peers->n != (size_t)p.nb[p.peer_dim])
         throw PlanError(PFFT_INVALID_CONFIGURATION,
@@ -215,21 +229,21 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     cudaError_t e = cudaSuccess;
     switch (ps.kernel) {
       case KERNEL_WG_GENERIC:
-        e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
+        e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_WI:
-        e = d.is_double ? launch_wi_f64(p, il, swap, ps.grid, stream) : launch_wi_f32(p, il, swap, ps.grid, stream);
+        e = d.is_double ? launch_wi_f64(p, pil, swap, ps.grid, stream) : launch_wi_f32(p, pil, swap, ps.grid, stream);
         break;
       case KERNEL_SG:
-        e = d.is_double ? launch_sg_f64(p, il, swap, ps.grid, stream) : launch_sg_f32(p, il, swap, ps.grid, stream);
+        e = d.is_double ? launch_sg_f64(p, pil, swap, ps.grid, stream) : launch_sg_f32(p, pil, swap, ps.grid, stream);
         break;
       case KERNEL_WG_R3:
-        e = launch_wg_r3(p, d.is_double, il, swap, ps.grid, stream);
+        e = launch_wg_r3(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_WG_COL: {
         bool used = false;
         e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used);
-        if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
+        if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       }
       case KERNEL_WG_CUBE:
@@ -237,10 +251,22 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         if (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0)
           e = launch_wg_cube(p, d.is_double, swap, ps.variant, ps.alt_grid, stream);
         else
-          e = launch_wg_generic(p, d.is_double, il, swap, ps.grid, stream);
+          e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_EW:
-        e = launch_ew(p, d.is_double, il, swap, ps.grid, stream);
+        e = launch_ew(p, d.is_double, pil, swap, ps.grid, stream);
+        break;
+      case KERNEL_REAL_PACK:
+        e = launch_real_pack(p, d.is_double, ps.variant, ps.grid, stream);
+        break;
+      case KERNEL_REAL_UNPACK:
+        e = launch_real_unpack(p, d.is_double, ps.variant, ps.grid, stream);
+        break;
+      case KERNEL_R2C_POST:
+        e = launch_r2c_post(p, d.is_double, il, ps.variant, ps.grid, stream);
+        break;
+      case KERNEL_C2R_PRE:
+        e = launch_c2r_pre(p, d.is_double, il, ps.variant, ps.grid, stream);
         break;
       default:
         throw PlanError(PFFT_INTERNAL_ERROR, "unknown kernel kind");
@@ -290,18 +316,21 @@ static void compute_host_monolithic(pfft_plan* plan, int direction, const void* 
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
   const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
   const bool inplace = in == out;
+  // REAL descriptors: the real side of the call is a single plane of scalars
+  const bool in2 = !il && !(d.is_real() && direction == PFFT_FORWARD);
+  const bool out2 = !il && !(d.is_real() && direction == PFFT_BACKWARD);
   cudaStream_t s = plan->stream;
   PFFT_CUDA_CHECK(cudaMemcpyAsync(din, in, plane_in, cudaMemcpyHostToDevice, s));
-  if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
+  if (in2) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
   // elements of the output buffer that the descriptor does not address must survive the round trip
-  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
+  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0 && !d.is_real();
   if (!inplace && !out_dense) {
     PFFT_CUDA_CHECK(cudaMemcpyAsync(dout, out, plane_out, cudaMemcpyHostToDevice, s));
-    if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
+    if (out2) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
   }
-  execute(plan, direction, din, il ? nullptr : din + plane_in, dout, il ? nullptr : dout + plane_out, s);
+  execute(plan, direction, din, in2 ? din + plane_in : nullptr, dout, out2 ? dout + plane_out : nullptr, s);
   PFFT_CUDA_CHECK(cudaMemcpyAsync(out, dout, plane_out, cudaMemcpyDeviceToHost, s));
-  if (!il) PFFT_CUDA_CHECK(cudaMemcpyAsync(out_imag, dout + plane_out, plane_out, cudaMemcpyDeviceToHost, s));
+  if (out2) PFFT_CUDA_CHECK(cudaMemcpyAsync(out_imag, dout + plane_out, plane_out, cudaMemcpyDeviceToHost, s));
   PFFT_CUDA_CHECK(cudaStreamSynchronize(s));
 }
 
@@ -502,11 +531,17 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
     const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
     const size_t scalar = d.is_double ? 8 : 4;
     const size_t in_elems = d.buffer_count(direction), out_elems = d.buffer_count(odir);
-    const size_t plane_in = in_elems * scalar * (il ? 2 : 1), plane_out = out_elems * scalar * (il ? 2 : 1);
-    const size_t planes = il ? 1 : 2;
+    // bytes of one plane per side; REAL descriptors: the real side is one plane of scalars
+    const bool real = d.is_real();
+    const bool in_real = real && direction == PFFT_FORWARD, out_real = real && direction == PFFT_BACKWARD;
+    const size_t plane_in = in_elems * scalar * (in_real ? 1 : (il ? 2 : 1));
+    const size_t plane_out = out_elems * scalar * (out_real ? 1 : (il ? 2 : 1));
+    const size_t planes_in = (il || in_real) ? 1 : 2, planes_out = (il || out_real) ? 1 : 2;
+    if (real && in == out)
+      throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION, "pfft_compute_host: REAL-domain transforms take distinct host buffers");
     const bool inplace = in == out;
     PFFT_CUDA_CHECK(cudaSetDevice(plan->device));
-    const size_t need[2] = {plane_in * planes, inplace ? 0 : plane_out * planes};
+    const size_t need[2] = {plane_in * planes_in, inplace ? 0 : plane_out * planes_out};
     for (int i = 0; i < 2; ++i) {
       if (need[i] > plan->stage_bytes[i]) {
         if (plan->stage[i]) PFFT_CUDA_CHECK(cudaFree(plan->stage[i]));
@@ -522,10 +557,10 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
     const HostDomain hi = host_domain(d, direction), ho = host_domain(d, odir);
     const size_t batch = d.number_of_transforms;
     size_t chunks = 1;
-    if (batch >= 2 && hi.extent <= hi.dist && ho.extent <= ho.dist) {
+    if (batch >= 2 && hi.extent <= hi.dist && ho.extent <= ho.dist && !real) {
       const char* env = std::getenv("PFFT_HOST_CHUNK_BYTES");
       const size_t target = env ? (size_t)std::atoll(env) : ((size_t)32 << 20);
-      chunks = std::min<size_t>(std::min<size_t>(batch, 64), std::max<size_t>(1, (plane_in * planes) / std::max<size_t>(1, target)));
+      chunks = std::min<size_t>(std::min<size_t>(batch, 64), std::max<size_t>(1, (plane_in * planes_in) / std::max<size_t>(1, target)));
     }
     if (chunks <= 1)
       compute_host_monolithic(plan, direction, in, in_imag, out, out_imag, din, dout, plane_in, plane_out);

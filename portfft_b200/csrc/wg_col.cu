@@ -425,7 +425,10 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cud
   if (in == IN_COLS_TMA) {
     // columns in, columns out: exchange inside the stage buffer where the geometry allows (see ColCfg)
     constexpr int kTpc = col::cmin(col::cmin(N1, N2), 16);
-    constexpr bool kCanInplace = N3 == 1 && N1 == kTpc && (N2 % kTpc) == 0;
+    // measured on B200 (tools/ab_run.sh): fp32 N = 256 (L1D) 0.946 -> 0.823 ms with three in-place CTAs per SM, fp64
+    // N = 256 (C4) 2.337 -> 2.316 ms; fp32 N = 512 (one 64 KiB stage, two CTAs per SM, no prefetch inside the CTA)
+    // 1.178 -> 1.312 ms on 512^3, so that size keeps the exchange buffer and the two-stage ring
+    constexpr bool kCanInplace = N3 == 1 && N1 == kTpc && (N2 % kTpc) == 0 && (size_t)N1 * N2 * 128 <= 48 * 1024;
     if constexpr (kCanInplace) {
       if (!out_rows && inplace_enabled()) return launch_col_v<T, N1, N2, N3, IN_COLS_TMA, false, true>(p, swap, map, stream);
     }

@@ -39,9 +39,10 @@ class CaseParams:
     backward_strides: Optional[List[int]] = None
     forward_distance: Optional[int] = None
     backward_distance: Optional[int] = None
+    domain: str = "complex"         # "complex" / "real" (REAL: forward domain real, backward domain half spectrum)
 
     def ident(self) -> str:
-        s = f"{self.scalar}-{self.placement}-{self.input_layout[:2]}to{self.output_layout[:2]}-{self.dir}-{self.storage[:5]}"
+        s = f"{'re-' if self.domain == 'real' else ''}{self.scalar}-{self.placement}-{self.input_layout[:2]}to{self.output_layout[:2]}-{self.dir}-{self.storage[:5]}"
         s += f"-b{self.batch}-n" + "x".join(str(x) for x in self.lengths)
         if self.forward_strides is not None:
             s += "-fs" + "_".join(map(str, self.forward_strides)) + "-bs" + "_".join(map(str, self.backward_strides))
@@ -55,7 +56,7 @@ class CaseParams:
 
 def make_descriptors(tp: CaseParams):
     """-> (portfft_b200.descriptor, oracle.OracleDescriptor), fields set as `get_descriptor` does."""
-    d = pf.descriptor(list(tp.lengths), tp.scalar)
+    d = pf.descriptor(list(tp.lengths), tp.scalar, pf.domain.REAL if tp.domain == "real" else pf.domain.COMPLEX)
     d.number_of_transforms = tp.batch
     d.placement = pf.placement.IN_PLACE if tp.placement == "IP" else pf.placement.OUT_OF_PLACE
     d.complex_storage = (pf.complex_storage.INTERLEAVED_COMPLEX if tp.storage == "interleaved"
@@ -95,7 +96,7 @@ def make_descriptors(tp: CaseParams):
         placement=int(d.placement), forward_strides=list(d.forward_strides),
         backward_strides=list(d.backward_strides), forward_distance=d.forward_distance,
         backward_distance=d.backward_distance, forward_offset=d.forward_offset, backward_offset=d.backward_offset,
-        is_double=(tp.scalar == "double"))
+        is_double=(tp.scalar == "double"), is_real=(tp.domain == "real"))
     return d, od
 
 
@@ -112,9 +113,34 @@ def run_case(tp: CaseParams, device: int = 0, rel_l2_tol: Optional[float] = None
     split = tp.storage == "split"
     committed = d.commit(torch.cuda.current_stream(dev), device)
     fn = committed.compute_forward if tp.dir == "fwd" else committed.compute_backward
+    pad = oracle.PADDING_VALUE
+    if tp.domain == "real":
+        # forward: real array -> half spectrum; backward: half spectrum -> real array (out of place)
+        assert not in_place
+        fwd = tp.dir == "fwd"
+        if fwd or not split:
+            args_in = [torch.from_numpy(host_in).to(dev)]
+        else:
+            args_in = [torch.from_numpy(np.ascontiguousarray(host_in.real)).to(dev),
+                       torch.from_numpy(np.ascontiguousarray(host_in.imag)).to(dev)]
+        n_out = host_ref.shape[0]
+        rdt = torch.float64 if tp.scalar == "double" else torch.float32
+        if not fwd:
+            outs = [torch.full((n_out,), pad, dtype=rdt, device=dev)]
+        elif split:
+            outs = [torch.full((n_out,), pad, dtype=rdt, device=dev), torch.full((n_out,), pad, dtype=rdt, device=dev)]
+        else:
+            outs = [torch.full((n_out,), complex(pad, pad), dtype=cdt, device=dev)]
+        fn(*args_in, *outs)
+        torch.cuda.synchronize(dev)
+        if fwd and split:
+            actual = (outs[0].cpu().numpy() + 1j * outs[1].cpu().numpy()).astype(host_ref.dtype)
+        else:
+            actual = outs[0].cpu().numpy()
+        committed.destroy()
+        return oracle.verify_dft(od, dr, host_ref, actual, rel_l2_tol)
     if in_place:
         assert host_in.shape == host_ref.shape
-    pad = oracle.PADDING_VALUE
     if not split:
         t_in = torch.from_numpy(host_in).to(dev)
         if in_place:

@@ -14,12 +14,78 @@ import portfft_b200 as pf
 from portfft_b200 import api
 
 BUF_IN, BUF_OUT, BUF_SCRATCH, BUF_SCRATCH2 = 0, 1, 2, 3
-KERNEL_EW = 6
+KERNEL_EW, KERNEL_REAL_PACK, KERNEL_R2C_POST, KERNEL_C2R_PRE, KERNEL_REAL_UNPACK = 6, 7, 8, 9, 10
 MOD_SWAP_PRE, MOD_SWAP_POST, MOD_NO_USER_SWAP_IN, MOD_NO_USER_SWAP_OUT = 1, 2, 4, 8
 
 
 def _swap(a):
     return a.imag + 1j * a.real
+
+
+class _PairView:
+    """A REAL user buffer addressed as interleaved complex pairs (x[2j], x[2j+1]) -- what the complex passes of a
+    REAL-domain plan see when the real rows have unit stride (csrc/real.cu)."""
+
+    def __init__(self, real: np.ndarray):
+        self.real = real
+
+    def __getitem__(self, idx):
+        return self.real[2 * idx] + 1j * self.real[2 * idx + 1]
+
+    def __setitem__(self, idx, v):
+        self.real[2 * idx] = v.real
+        self.real[2 * idx + 1] = v.imag
+
+
+def _real_rows(ps, src, dst, grids, ib, ob, cdt):
+    """The four REAL-domain row kernels of csrc/real.cu, restated with the same index arithmetic."""
+    n, variant, k = ps["n"], ps["variant"], ps["kernel"]
+    h = n // 2
+    w = np.exp(-2j * np.pi * np.arange(h + 1) / n)
+    ibx, obx = ib[..., None], ob[..., None]
+    if k == KERNEL_REAL_PACK:
+        if variant == 0:
+            m = np.arange(h)
+            dst[obx + m] = (src[ibx + 2 * m * ps["is"]] + 1j * src[ibx + (2 * m + 1) * ps["is"]]).astype(cdt)
+        else:
+            m = np.arange(n)
+            dst[obx + m] = src[ibx + m * ps["is"]].astype(cdt)
+    elif k == KERNEL_REAL_UNPACK:
+        s = ps["scale"] if ps["apply_scale"] else 1.0
+        if variant == 0:
+            m = np.arange(h)
+            z = src[ibx + m]
+            dst[obx + 2 * m * ps["os"]] = z.real * s
+            dst[obx + (2 * m + 1) * ps["os"]] = z.imag * s
+        else:
+            m = np.arange(n)
+            dst[obx + m * ps["os"]] = src[ibx + m].real * s
+    elif k == KERNEL_R2C_POST:
+        s = ps["scale"] if ps["apply_scale"] else 1.0
+        kk = np.arange(h + 1)
+        if variant == 0:
+            a = src[ibx + np.where(kk == h, 0, kk)].astype(np.complex128)
+            b = np.conj(src[ibx + np.where(kk == 0, 0, h - kk)].astype(np.complex128))
+            x = (a + b) / 2 + w * (a - b) / 2j
+        else:
+            x = src[ibx + kk]
+        dst[obx + kk * ps["os"]] = (x * s).astype(dst.dtype)
+    elif k == KERNEL_C2R_PRE:
+        if variant == 0:
+            kk = np.arange(h)
+            a = src[ibx + kk * ps["is"]].astype(np.complex128)
+            b = src[ibx + (h - kk) * ps["is"]].astype(np.complex128)
+            a[..., 0] = a[..., 0].real
+            b[..., 0] = b[..., 0].real
+            b = np.conj(b)
+            z = (a + b) + 1j * np.conj(w[:h]) * (a - b)
+            dst[obx + np.where(kk == 0, 0, h - kk)] = z.astype(cdt)
+        else:
+            kk = np.arange((n + 1) // 2)
+            a = src[ibx + kk * ps["is"]].astype(np.complex128)
+            a[..., 0] = a[..., 0].real
+            dst[obx + kk] = np.conj(a).astype(cdt)
+            dst[obx + (n - kk[1:])] = a[..., 1:].astype(cdt)
 
 
 def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.ndarray) -> np.ndarray:
@@ -34,8 +100,14 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
     bufs = {BUF_IN: in_buf, BUF_OUT: out_buf,
             BUF_SCRATCH: np.full(max(1, plan["scratch_elems"]), np.nan + 0j, dtype=cdt),
             BUF_SCRATCH2: np.full(max(1, plan["scratch2_elems"]), np.nan + 0j, dtype=cdt)}
+    if plan["is_real"]:
+        bwd = False  # REAL plans never use the (re <-> im) swap
     for ps in plan["passes"]:
         src, dst = bufs[ps["src"]], bufs[ps["dst"]]
+        if ps["real_view"] & 1:
+            src = _PairView(src)
+        if ps["real_view"] & 2:
+            dst = _PairView(dst)
         nb, ibd, obd = ps["nb"], ps["ibd"], ps["obd"]
         grids = np.meshgrid(*[np.arange(c, dtype=np.int64) for c in nb], indexing="ij")
         ib = ps["ioff"] + sum(g * d for g, d in zip(grids, ibd))
@@ -48,6 +120,9 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
         smod = api.mod_table(scalar, ps["smod"], ps["mod_l"], ps["mod_m"]) if ps["smod"] else None
         n = ps["n"]
         assert ps["peer_dim"] < 0
+        if ps["kernel"] >= KERNEL_REAL_PACK:
+            _real_rows(ps, src, dst, grids, ib, ob, cdt)
+            continue
         if ps["kernel"] == KERNEL_EW:
             assert n == 1
             j = grids[0]

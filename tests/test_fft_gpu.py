@@ -44,6 +44,27 @@ def offsets(layouts_, dirs, batches, lengths, offs):
     return out
 
 
+def real(dirs, storages, batches, lengths):
+    """REAL domain, out of place, packed rows: forward real -> half spectrum, backward half spectrum -> real.
+    The backward distance is the packed half-spectrum length n // 2 + 1."""
+    out = []
+    for dr, st, b, n, sc in itertools.product(dirs, storages, batches, lengths, SCALARS):
+        out.append(CaseParams([n], b, "OOP", U, U, dr, st, sc, forward_strides=[1], backward_strides=[1],
+                              forward_distance=n, backward_distance=n // 2 + 1, domain="real",
+                              backward_scale=(1.0 / n if dr == "bwd" else None)))
+    return out
+
+
+def real_layouts(dirs, storages, batches, lps):
+    """REAL domain with explicit layouts: (n, fwd_stride, bwd_stride, fwd_dist, bwd_dist, fwd_off, bwd_off)"""
+    out = []
+    for dr, st, b, lp, sc in itertools.product(dirs, storages, batches, lps, SCALARS):
+        out.append(CaseParams([lp[0]], b, "OOP", U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
+                              forward_distance=lp[3], backward_distance=lp[4], forward_offset=lp[5],
+                              backward_offset=lp[6], domain="real"))
+    return out
+
+
 def scaled(dr, lengths, fs, bs):
     out = []
     for n, sc in itertools.product(lengths, SCALARS):
@@ -109,6 +130,16 @@ SUITES = {
     "BluesteinGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3], [4099, 65537]),
     "BluesteinMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [2], [[6, 37], [37, 6], [41, 43]]),
     "BluesteinOffsetsTest": offsets(OOP_ALL, BOTH_DIR, [3], [131], [(0, 7), (9, 0), (5, 11)]),
+    # REAL domain (the reference reserves the API and throws; expected values = numpy rfft as in its generator,
+    # reference_data_wrangler.hpp:136-137): even lengths on the pair view, odd lengths, every level of the
+    # half-length complex transform, strided / offset layouts through the pack and unpack passes
+    "RealTest": real(BOTH_DIR, STORAGES, [1, 3, 131], [1, 2, 4, 8, 9, 15, 16, 30, 64, 100, 256, 512, 1000, 1024, 4096,
+                                                        8192]),
+    "RealGlobalTest": real(BOTH_DIR, STORAGES, [1, 3], [16384, 65536, 3 * 16384, 1 << 20]),
+    "RealLayoutsTest": real_layouts(BOTH_DIR, STORAGES, [1, 5],
+                                    [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
+                                     (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
+                                     (8, 5, 5, 1, 1, 0, 0)]),
 }
 
 CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.items() for tp in tps]

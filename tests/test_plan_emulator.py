@@ -38,6 +38,26 @@ CASES = [
     CaseParams([65537], 1, "OOP", P, P, "fwd"),
     CaseParams([6, 37], 2, "OOP", P, P, "fwd"),
     CaseParams([37, 6], 2, "OOP", P, P, "bwd"),
+    # REAL domain: even lengths on the pair view and through pack / unpack (strided, odd offsets), odd lengths,
+    # multi-pass half-length transforms, split complex storage
+    CaseParams([8], 3, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([8], 3, "OOP", P, P, "bwd", domain="real"),
+    CaseParams([2], 3, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([1], 3, "OOP", P, P, "bwd", domain="real"),
+    CaseParams([9], 3, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([15], 2, "OOP", P, P, "bwd", domain="real", backward_scale=1.0 / 15),
+    CaseParams([4096], 2, "OOP", P, P, "fwd", domain="real", storage="split"),
+    CaseParams([1000], 3, "OOP", P, P, "bwd", domain="real", scalar="double", backward_scale=1e-3),
+    CaseParams([96], 4, "OOP", U, U, "fwd", domain="real", forward_strides=[3], backward_strides=[2],
+               forward_distance=300, backward_distance=100, forward_offset=7, backward_offset=3),
+    CaseParams([96], 4, "OOP", U, U, "bwd", domain="real", forward_strides=[1], backward_strides=[2],
+               forward_distance=97, backward_distance=100, forward_offset=1, backward_offset=3),
+    CaseParams([65536], 2, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([65536], 2, "OOP", P, P, "bwd", domain="real", storage="split"),
+    CaseParams([32768], 2, "OOP", U, U, "fwd", domain="real", forward_strides=[2], backward_strides=[1],
+               forward_distance=70000, backward_distance=16385),
+    CaseParams([3 * 16384], 1, "OOP", U, U, "bwd", domain="real", forward_strides=[2], backward_strides=[1],
+               forward_distance=100000, backward_distance=30000),
 ]
 
 

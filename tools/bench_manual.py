@@ -3,6 +3,7 @@
 
     python tools/bench_manual.py [--double] "d=cpx,n=64,b=1024" "d=cpx,n=512x512,p=ip" ...
     python tools/bench_manual.py --canned            # the four bench_float configurations
+    python tools/bench_manual.py --reference-set     # reference_dft_set.hpp: complex (incl. 65537) and real float sets
 
 Prints one JSON object per benchmark with the reference's names and counters (portfft_b200/bench_cli.py)."""
 import json
@@ -31,6 +32,16 @@ def main():
         args.remove("--canned")
         for name, lengths, batch in bench_cli.CANNED_FLOAT:
             d = pf.descriptor(lengths, "float")
+            d.number_of_transforms = batch
+            configs.append((d, name))
+    if "--reference-set" in args:
+        args.remove("--reference-set")
+        for name, lengths, batch in bench_cli.CANNED_COMPLEX_SET:
+            d = pf.descriptor(lengths, "float")
+            d.number_of_transforms = batch
+            configs.append((d, name))
+        for name, lengths, batch in bench_cli.CANNED_REAL_SET:
+            d = pf.descriptor(lengths, "float", pf.domain.REAL)
             d.number_of_transforms = batch
             configs.append((d, name))
     for a in args:
