@@ -20,17 +20,30 @@ __global__ void __launch_bounds__(256) ew_kernel(const PassParams p, const bool 
   const IoFlags flo{il, swap && !(p.mod_flags & MOD_NO_USER_SWAP_OUT)};
   const long long n0 = p.nb[0];
   const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < p.batch_total; g += stride) {
-    long long q = g / n0;
-    const long long j = g - q * n0;
+  // (row q, element j) of the flat index advance incrementally: one 64-bit division per thread, not per element
+  const long long sq = stride / n0, sr = stride - sq * n0;
+  const bool one_outer = p.nb[2] == 1 && p.nb[3] == 1;
+  long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  long long q = g / n0, j = g - q * n0;
+  for (; g < p.batch_total; g += stride, j += sr, q += sq) {
+    if (j >= n0) {
+      j -= n0;
+      ++q;
+    }
     long long ib = p.ioff + j * p.ibd[0], ob = p.ooff + j * p.obd[0];
+    if (one_outer) {
+      ib += q * p.ibd[1];
+      ob += q * p.obd[1];
+    } else {
+      long long r = q;
 #pragma unroll
-    for (int d = 1; d < kMaxBatchDims; ++d) {
-      const long long q2 = q / p.nb[d];
-      const long long b = q - q2 * p.nb[d];
-      q = q2;
-      ib += b * p.ibd[d];
-      ob += b * p.obd[d];
+      for (int d = 1; d < kMaxBatchDims; ++d) {
+        const long long q2 = r / p.nb[d];
+        const long long b = r - q2 * p.nb[d];
+        r = q2;
+        ib += b * p.ibd[d];
+        ob += b * p.obd[d];
+      }
     }
     if (p.valid_out > 0 && j >= p.valid_out) continue;
     cx<T> v{T(0), T(0)};

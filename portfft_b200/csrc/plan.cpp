@@ -725,7 +725,13 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     ps.variant = variant;
     ps.level = single ? LEVEL_WORKGROUP : LEVEL_GLOBAL;
     ps.block = 256;
-    ps.grid = (int)std::min<long long>((batch * work_per_row + 255) / 256, (long long)lim.num_sms * 16);
+    {
+      // real.cu RowLoop: a CTA covers 256 / lanes rows, lanes = power of two >= the row's element count (<= 256)
+      long long lanes = 1;
+      while (lanes < work_per_row && lanes < 256) lanes *= 2;
+      const long long rows_per_cta = 256 / lanes;
+      ps.grid = (int)std::min<long long>((batch + rows_per_cta - 1) / rows_per_cta, (long long)lim.num_sms * 32);
+    }
     ps.tw_n = (even && (kernel == KERNEL_R2C_POST || kernel == KERNEL_C2R_PRE)) ? N : 0;
     return ps;
   };

@@ -38,47 +38,66 @@ __device__ __forceinline__ void row_bases(const PassParams& p, long long g, long
   }
 }
 
+// Work distribution shared by the four kernels: a CTA of 256 threads is a (rows x lanes) rectangle, lanes running
+// along the element index of a row (coalesced on the packed side), `lanes` = the power of two >= the row's element
+// count, at most 256.  The row bases are computed once per thread and row, not per element.
+struct RowLoop {
+  int lanes, rows_per_cta, lane, row_in_cta;
+  __device__ RowLoop(long long count) {
+    lanes = 1;
+    while (lanes < count && lanes < 256) lanes <<= 1;
+    rows_per_cta = 256 / lanes;
+    lane = threadIdx.x % lanes;
+    row_in_cta = threadIdx.x / lanes;
+  }
+};
+#define PFFT_FOR_ROWS(p, loop, g)                                                                           \
+  for (long long g = (long long)blockIdx.x * loop.rows_per_cta + loop.row_in_cta; g < p.batch_total;         \
+       g += (long long)gridDim.x * loop.rows_per_cta)
+
 // variant 0: out[m] = (x[2m], x[2m+1]), m < n/2;  variant 1: out[m] = (x[m], 0), m < n.  Input: REAL scalars.
 template <typename T>
 __global__ void __launch_bounds__(256) real_pack_kernel(const PassParams p, const int variant) {
-  const long long count = variant == 0 ? p.n / 2 : p.n;
-  const long long total = p.batch_total * count;
+  const int count = variant == 0 ? p.n / 2 : p.n;
   const T* x = reinterpret_cast<const T*>(p.in_re);
   cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long g = e / count, m = e - g * count;
+  const RowLoop loop(count);
+  PFFT_FOR_ROWS(p, loop, g) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    cx<T> v;
-    if (variant == 0) {
-      v.x = x[ib + (2 * m) * p.is];
-      v.y = x[ib + (2 * m + 1) * p.is];
-    } else {
-      v.x = x[ib + m * p.is];
-      v.y = T(0);
+    for (int m = loop.lane; m < count; m += loop.lanes) {
+      cx<T> v;
+      if (variant == 0) {
+        v.x = x[ib + (2LL * m) * p.is];
+        v.y = x[ib + (2LL * m + 1) * p.is];
+      } else {
+        v.x = x[ib + (long long)m * p.is];
+        v.y = T(0);
+      }
+      out[ob + m] = v;
     }
-    out[ob + m] = v;
   }
 }
 
 // variant 0: out[2m] = Re z[m], out[2m+1] = Im z[m], m < n/2;  variant 1: out[m] = Re y[m], m < n.  Output: REAL scalars.
 template <typename T>
 __global__ void __launch_bounds__(256) real_unpack_kernel(const PassParams p, const int variant) {
-  const long long count = variant == 0 ? p.n / 2 : p.n;
-  const long long total = p.batch_total * count;
+  const int count = variant == 0 ? p.n / 2 : p.n;
   const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
   T* x = reinterpret_cast<T*>(p.out_re);
   const T scale = p.apply_scale ? T(p.scale) : T(1);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long g = e / count, m = e - g * count;
+  const RowLoop loop(count);
+  PFFT_FOR_ROWS(p, loop, g) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    const cx<T> v = in[ib + m];
-    if (variant == 0) {
-      x[ob + (2 * m) * p.os] = v.x * scale;
-      x[ob + (2 * m + 1) * p.os] = v.y * scale;
-    } else {
-      x[ob + m * p.os] = v.x * scale;
+    for (int m = loop.lane; m < count; m += loop.lanes) {
+      const cx<T> v = in[ib + m];
+      if (variant == 0) {
+        x[ob + (2LL * m) * p.os] = v.x * scale;
+        x[ob + (2LL * m + 1) * p.os] = v.y * scale;
+      } else {
+        x[ob + (long long)m * p.os] = v.x * scale;
+      }
     }
   }
 }
@@ -87,27 +106,28 @@ __global__ void __launch_bounds__(256) real_unpack_kernel(const PassParams p, co
 // half spectrum X_k, k = 0..n/2, in the user's layout (element stride os, descriptor's storage).
 template <typename T>
 __global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const int variant, const bool il) {
-  const long long h = p.n / 2, count = h + 1;
-  const long long total = p.batch_total * count;
+  const int h = p.n / 2, count = h + 1;
   const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
   const IoFlags fl{il, false};
   const T scale = p.apply_scale ? T(p.scale) : T(1);
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long g = e / count, k = e - g * count;
+  const RowLoop loop(count);
+  PFFT_FOR_ROWS(p, loop, g) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    cx<T> o;
-    if (variant == 0) {
-      const cx<T> a = in[ib + (k == h ? 0 : k)];
-      cx<T> b = in[ib + (k == 0 ? 0 : h - k)];
-      b.y = -b.y;  // conj Z_{H-k}
-      const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
-      const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
-      o = ev + cmul(ldg_cx<T>(p.tw, k), od);
-    } else {
-      o = in[ib + k];
+    for (int k = loop.lane; k < count; k += loop.lanes) {
+      cx<T> o;
+      if (variant == 0) {
+        const cx<T> a = in[ib + (k == h ? 0 : k)];
+        cx<T> b = in[ib + (k == 0 ? 0 : h - k)];
+        b.y = -b.y;  // conj Z_{H-k}
+        const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
+        const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
+        o = ev + cmul(ldg_cx<T>(p.tw, k), od);
+      } else {
+        o = in[ib + k];
+      }
+      gstore<T>(p, fl, ob + (long long)k * p.os, cscale(o, scale));
     }
-    gstore<T>(p, fl, ob + k * p.os, cscale(o, scale));
   }
 }
 
@@ -115,33 +135,35 @@ __global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const
 // interleaved rows, index-reversed (see the header): variant 0 length n/2, variant 1 the Hermitian extension, length n.
 template <typename T>
 __global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const int variant, const bool il) {
-  const long long n = p.n, h = n / 2;
-  const long long count = variant == 0 ? h : (n + 1) / 2;
-  const long long total = p.batch_total * count;
+  const int n = p.n, h = n / 2;
+  const int count = variant == 0 ? h : (n + 1) / 2;
   cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
   const IoFlags fl{il, false};
-  for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const long long g = e / count, k = e - g * count;
+  const RowLoop loop(count);
+  PFFT_FOR_ROWS(p, loop, g) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    cx<T> a = gload<T>(p, fl, ib + k * p.is);
-    if (k == 0) a.y = T(0);  // the imaginary parts of X_0 (and X_{N/2}) do not enter a real inverse (numpy.fft.irfft)
-    if (variant == 0) {
-      cx<T> b = gload<T>(p, fl, ib + (h - k) * p.is);
-      if (k == 0) b.y = T(0);
-      b.y = -b.y;  // conj X_{H-k}
-      const cx<T> s = a + b, d = a - b;
-      cx<T> w = ldg_cx<T>(p.tw, k);
-      w.y = -w.y;  // conj(w^k)
-      const cx<T> t = cmul(w, d);
-      out[ob + (k == 0 ? 0 : h - k)] = cx<T>{s.x - t.y, s.y + t.x};  // s + i t
-    } else {
-      // reversed Hermitian extension: row[k] = conj X_k, row[n - k] = X_k
-      out[ob + k] = cx<T>{a.x, -a.y};
-      if (k > 0) out[ob + n - k] = a;
+    for (int k = loop.lane; k < count; k += loop.lanes) {
+      cx<T> a = gload<T>(p, fl, ib + (long long)k * p.is);
+      if (k == 0) a.y = T(0);  // the imaginary parts of X_0 (and X_{N/2}) do not enter a real inverse (numpy.fft.irfft)
+      if (variant == 0) {
+        cx<T> b = gload<T>(p, fl, ib + (long long)(h - k) * p.is);
+        if (k == 0) b.y = T(0);
+        b.y = -b.y;  // conj X_{H-k}
+        const cx<T> s = a + b, d = a - b;
+        cx<T> w = ldg_cx<T>(p.tw, k);
+        w.y = -w.y;  // conj(w^k)
+        const cx<T> t = cmul(w, d);
+        out[ob + (k == 0 ? 0 : h - k)] = cx<T>{s.x - t.y, s.y + t.x};  // s + i t
+      } else {
+        // reversed Hermitian extension: row[k] = conj X_k, row[n - k] = X_k
+        out[ob + k] = cx<T>{a.x, -a.y};
+        if (k > 0) out[ob + n - k] = a;
+      }
     }
   }
 }
+#undef PFFT_FOR_ROWS
 
 template <typename K, typename... Args>
 cudaError_t launch_rows(K kern, int grid, cudaStream_t stream, Args... args) {

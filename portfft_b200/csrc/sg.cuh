@@ -16,6 +16,7 @@
 //   * backward = (re <-> im) swap on load and store, scale fused on store.
 #pragma once
 #include "io.cuh"
+#include "launch_utils.h"
 #include "kernels.h"
 
 namespace pfft {
@@ -122,7 +123,7 @@ template <int M, typename T>
 cudaError_t launch_sg_m(const PassParams& p, bool il, bool swap, int grid, cudaStream_t stream) {
   const size_t smem = sg_smem_bytes(M, sizeof(T));
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(sg_kernel<M, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(sg_kernel<M, T>, smem);
     if (e != cudaSuccess) return e;
   }
   sg_kernel<M, T><<<grid, kSgBlock, smem, stream>>>(p, il, swap);

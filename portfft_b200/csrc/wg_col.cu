@@ -29,6 +29,7 @@
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
+#include "launch_utils.h"
 
 namespace pfft {
 
@@ -328,6 +329,145 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// fp32 N = 512, columns in and out: two consumer groups over a three-stage ring.
+//
+// One tile (512 rows x 16 columns) is 64 KiB, so the generic variant above fits one CTA of 8 warps per SM and its
+// arithmetic phases (4 issue slots, 2 warps each) cannot cover each other.  Here one CTA of 16 warps is two groups of
+// 256 threads that work on alternate tiles, half a tile apart in time; each group runs the in-place two-pass scheme
+// (radix 16, then radix 32 on 32 consecutive rows) on its stage with its own named barrier, and the third stage
+// always holds the tile in flight: the thread that finishes reading a stage refills it with the tile three ahead.
+// ---------------------------------------------------------------------------------------------------------------
+namespace col {
+__device__ __forceinline__ void group_sync(int group) {
+  asm volatile("bar.sync %0, 256;" ::"r"(group + 1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+}  // namespace col
+
+struct Col512 {
+  static constexpr int N = 512, N1 = 16, N2 = 32, C = 16, B1 = N / N1, RING = 3, GROUP = 256, NT = 2 * GROUP;
+  static constexpr size_t kStageBytes = (size_t)N * C * sizeof(cx<float>);
+  static constexpr size_t kSmem = RING * kStageBytes + 64;
+};
+
+// Stage s is used in turn by tiles s, s + 3, s + 6, ... of the CTA, alternately by the two groups.  `full[s]` completes
+// one phase per load; `freed[s]` completes one phase per use, when the using group has taken its inputs and posted the
+// next load.  A group waits for freed (previous use, by the other group) before it waits for full: it completed the
+// use before that itself, so both one-bit phase parities are unambiguous however far the groups drift apart.
+__global__ void __launch_bounds__(Col512::NT, 1)
+    wg_col512_kernel(const PassParams p, const __grid_constant__ CUtensorMap tmap, const bool swap) {
+  using T = float;
+  constexpr int N = Col512::N, N1 = Col512::N1, N2 = Col512::N2, C = Col512::C, B1 = Col512::B1, RING = Col512::RING;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + RING * Col512::kStageBytes);
+  uint64_t* freed = full + RING;
+  const IoFlags fl{true, swap};
+  const int group = threadIdx.x / Col512::GROUP, gt = threadIdx.x % Col512::GROUP;
+  const int cc = gt % C, tc = gt / C;  // column of the tile, butterfly index (16 per column)
+  const long long tiles_c = (p.nb[0] + C - 1) / C;
+  const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
+  const T scale = T(p.scale);
+  const long long gmask = (1LL << p.gtw_bits) - 1;
+
+  auto decode = [&](long long tile, int& c0, int& b1, int& b2, int& b3) {
+    long long q = tile / tiles_c;
+    c0 = (int)(tile - q * tiles_c) * C;
+    long long q2 = q / p.nb[1];
+    b1 = (int)(q - q2 * p.nb[1]);
+    long long q3 = q2 / p.nb[2];
+    b2 = (int)(q2 - q3 * p.nb[2]);
+    b3 = (int)q3;
+  };
+  auto issue = [&](long long tile, int s) {
+    int c0, b1, b2, b3;
+    decode(tile, c0, b1, b2, b3);
+    unsigned char* dst = smem_raw + s * Col512::kStageBytes;
+    col::mbar_expect_tx(&full[s], (uint32_t)Col512::kStageBytes);
+#pragma unroll
+    for (int r0 = 0; r0 < N; r0 += 256)
+      col::tma_load_5d(dst + (size_t)r0 * C * sizeof(cx<T>), &tmap, 2 * c0, r0, b1, b2, b3, &full[s]);
+  };
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < RING; ++s) {
+      col::mbar_init(&full[s], 1);
+      col::mbar_init(&freed[s], 1);
+    }
+    col::fence_mbar_init();
+    col::fence_proxy_async();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long t0 = blockIdx.x;
+    for (int s = 0; s < RING; ++s, t0 += gridDim.x)
+      if (t0 < total_tiles) issue(t0, s);
+  }
+
+  // k-th tile of this CTA: blockIdx.x + k * gridDim.x, in stage k % 3, mbarrier phase (k / 3) & 1; group g takes k = g, g + 2, ...
+  for (long long k = group;; k += 2) {
+    const long long tile = blockIdx.x + k * gridDim.x;
+    if (tile >= total_tiles) break;
+    const int st = (int)(k % RING);
+    cx<T>* S = reinterpret_cast<cx<T>*>(smem_raw + st * Col512::kStageBytes);
+    int c0, b1, b2, b3;
+    decode(tile, c0, b1, b2, b3);
+    const long long use = k / RING;
+    if (use > 0) col::mbar_wait(&freed[st], (uint32_t)((use - 1) & 1));
+    col::mbar_wait(&full[st], (uint32_t)(use & 1));
+    // ---- pass 1: radix 16 over rows j + 32 r, written back to the rows it read --------------------------------
+#pragma unroll 1
+    for (int j = tc; j < B1; j += 16) {
+      cx<T> v[N1];
+#pragma unroll
+      for (int r = 0; r < N1; ++r) v[r] = S[(j + B1 * r) * C + cc];
+      if (swap) {
+#pragma unroll
+        for (int r = 0; r < N1; ++r) v[r] = cx<T>{v[r].y, v[r].x};
+      }
+      DFT<N1, T>::run(v);
+#pragma unroll
+      for (int r = 0; r < N1; ++r) S[(j + B1 * r) * C + cc] = v[r];
+    }
+    col::group_sync(group);
+    // ---- pass 2: butterfly tc takes rows 32 tc .. 32 tc + 31 (element tc + 16 r of the exchange), radix 32 -------
+    cx<T> v[N2];
+#pragma unroll
+    for (int r = 0; r < N2; ++r) v[r] = S[(r + B1 * tc) * C + cc];
+    col::group_sync(group);  // every thread of the group holds its inputs: the stage is free
+    if (gt == 0) {
+      const long long nxt = blockIdx.x + (k + RING) * gridDim.x;
+      if (nxt < total_tiles) {
+        col::fence_proxy_async();
+        issue(nxt, st);
+      }
+      col::mbar_arrive(&freed[st]);
+    }
+#pragma unroll
+    for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, tc * r));
+    DFT<N2, T>::run(v);
+    if (c0 + cc < p.nb[0]) {
+      const long long ob = p.ooff + (long long)(c0 + cc) * p.obd[0] + (long long)b1 * p.obd[1] +
+                           (long long)b2 * p.obd[2] + (long long)b3 * p.obd[3];
+      long long gidx = 0;
+      if (p.gtw_dim >= 0) gidx = p.gtw_dim == 0 ? c0 + cc : (p.gtw_dim == 1 ? b1 : (p.gtw_dim == 2 ? b2 : b3));
+#pragma unroll
+      for (int r = 0; r < N2; ++r) {
+        const int kk = tc + N1 * r;
+        cx<T> o = v[r];
+        if (p.gtw_dim >= 0) {
+          const long long m = gidx * kk;
+          o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & gmask)));
+        }
+        if (p.apply_scale) o = cscale(o, scale);
+        gstore<T>(p, fl, ob + (long long)kk * p.os, o);
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -389,7 +529,7 @@ static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMa
     return occ * sms;
   }();
   if (slots <= 0) return cudaErrorLaunchOutOfResources;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem);
+  cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem);
   if (e != cudaSuccess) return e;
   const long long tiles = ((p.nb[0] + Cfg::C - 1) / Cfg::C) * p.nb[1] * p.nb[2] * p.nb[3];
   const int grid = (int)(tiles < slots ? tiles : slots);
@@ -440,6 +580,35 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cud
                     : launch_col_v<T, N1, N2, N3, IN_ROWS_BULK, false, false>(p, swap, map, stream);
   return out_rows ? launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, true, false>(p, swap, map, stream)
                   : launch_col_v<T, N1, N2, N3, IN_ROWS_DIRECT, false, false>(p, swap, map, stream);
+}
+
+static bool col512_groups_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("PFFT_COL512_GROUPS");
+    return e ? std::atoi(e) != 0 : true;
+  }();
+  return on;
+}
+
+static cudaError_t launch_col512(const PassParams& p, bool swap, cudaStream_t stream, bool* used) {
+  *used = false;
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (!make_tensor_map(p, false, Col512::C, 256, &map)) return cudaSuccess;  // caller falls back
+  *used = true;
+  static const int sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+  }();
+  if (sms <= 0) return cudaErrorLaunchOutOfResources;
+  cudaError_t e = ensure_dynamic_smem(wg_col512_kernel, Col512::kSmem);
+  if (e != cudaSuccess) return e;
+  const long long tiles = ((p.nb[0] + Col512::C - 1) / Col512::C) * p.nb[1] * p.nb[2] * p.nb[3];
+  const int grid = (int)(tiles < sms ? tiles : sms);
+  wg_col512_kernel<<<grid, Col512::NT, Col512::kSmem, stream>>>(p, map, swap);
+  return cudaGetLastError();
 }
 
 bool col_supported(int n, bool is_double, int* n1, int* n2) {
@@ -495,6 +664,8 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
         const char* e = std::getenv("PFFT_COL512");
         return e ? std::atoi(e) == 3 : 0;
       }();
+      if (!three_pass && !is_double && (variant & 3) == IN_COLS_TMA && (variant & 4) == 0 && col512_groups_enabled())
+        return launch_col512(p, swap, stream, used);
       if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, stream, used);
       return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, stream, used)
                        : launch_col_t<float, 8, 8, 8>(p, swap, variant, stream, used);

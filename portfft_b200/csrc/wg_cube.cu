@@ -19,6 +19,7 @@
 
 #include "device_utils.cuh"
 #include "kernels.h"
+#include "launch_utils.h"
 
 namespace pfft {
 
@@ -217,7 +218,7 @@ template <typename T, int R, int F, bool SWAP, bool USE_TMA>
 static cudaError_t launch_cube_t(const CubeArgs& a, int grid, cudaStream_t stream) {
   const size_t smem = cube_smem_bytes_t<T, R, F>(USE_TMA);
   auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, R * R * F, smem, stream>>>(a);
   return cudaGetLastError();

@@ -15,6 +15,7 @@
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
+#include "launch_utils.h"
 #include "pass.h"
 
 namespace pfft {
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(sizeof(T) == 4 ? 512 : 256) wg_generic_kernel(
 template <typename T>
 static cudaError_t launch_wg_generic_t(const PassParams& p, bool il, bool swap, int grid, cudaStream_t stream) {
   const size_t smem = wg_generic_smem_bytes(p.ffts_per_block, p.pitch, sizeof(T));
-  cudaError_t e = cudaFuncSetAttribute(wg_generic_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(wg_generic_kernel<T>, smem);
   if (e != cudaSuccess) return e;
   wg_generic_kernel<T><<<grid, p.ffts_per_block * p.threads_per_fft, smem, stream>>>(p, il, swap);
   return cudaGetLastError();

@@ -17,6 +17,7 @@
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
+#include "launch_utils.h"
 
 namespace pfft {
 
@@ -122,7 +123,7 @@ static cudaError_t launch_r3_t(const PassParams& p, bool il, bool swap, int grid
   using Cfg = R3Cfg<R0, R1, R2>;
   const size_t smem = (size_t)2 * p.ffts_per_block * Cfg::PITCH * sizeof(cx<T>);
   auto kern = wg_r3_kernel<T, R0, R1, R2>;
-  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, p.ffts_per_block * Cfg::TPF, smem, stream>>>(p, il, swap);
   return cudaGetLastError();

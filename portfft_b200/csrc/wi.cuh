@@ -16,6 +16,7 @@
 #include <cstdint>
 
 #include "io.cuh"
+#include "launch_utils.h"
 #include "kernels.h"
 
 namespace pfft {
@@ -155,7 +156,7 @@ cudaError_t launch_wi_n(const PassParams& p, bool il, bool swap, int grid, cudaS
   const bool staged = p.in_mode == IO_STAGED_ELEM || p.out_mode == IO_STAGED_ELEM;
   const size_t smem = staged ? wi_smem_bytes(N, sizeof(T)) : 0;
   if (smem > 48 * 1024) {
-    cudaError_t e = cudaFuncSetAttribute(wi_kernel<N, T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_dynamic_smem(wi_kernel<N, T>, smem);
     if (e != cudaSuccess) return e;
   }
   // cp.async needs the source aligned to the copy size: element alignment of the user's pointers

@@ -16,13 +16,9 @@ except Exception as e:
 PY
 }
 run C5_new C5 X=1
-run C5_nocube512 C5 PFFT_NO_CUBE512=1
-run C5_noinplace C5 PFFT_COL_INPLACE=0
-run C5_old C5 PFFT_COL_INPLACE=0 PFFT_NO_CUBE512=1
+run C5_nogroups C5 PFFT_COL512_GROUPS=0
 run C4_new C4 X=1
-run C4_noinplace C4 PFFT_COL_INPLACE=0
 run L1D_new L1D X=1
-run L1D_noinplace L1D PFFT_COL_INPLACE=0
 run M512_new M512 X=1
 run M512_nocube M512 PFFT_NO_CUBE512=1
 run M256 M256 X=1
