@@ -15,9 +15,9 @@
 namespace pfft {
 
 template <typename T>
-__global__ void __launch_bounds__(256) ew_kernel(const PassParams p, const bool il, const bool swap) {
-  const IoFlags fl{il, swap && !(p.mod_flags & MOD_NO_USER_SWAP_IN)};
-  const IoFlags flo{il, swap && !(p.mod_flags & MOD_NO_USER_SWAP_OUT)};
+__global__ void __launch_bounds__(256) ew_kernel(const PassParams p, const bool il_in, const bool il_out, const bool swap) {
+  const IoFlags fl{il_in, swap && !(p.mod_flags & MOD_NO_USER_SWAP_IN)};
+  const IoFlags flo{il_out, swap && !(p.mod_flags & MOD_NO_USER_SWAP_OUT)};
   const long long n0 = p.nb[0];
   const long long stride = (long long)gridDim.x * blockDim.x;
   // (row q, element j) of the flat index advance incrementally: one 64-bit division per thread, not per element
@@ -59,11 +59,12 @@ __global__ void __launch_bounds__(256) ew_kernel(const PassParams p, const bool 
   }
 }
 
-cudaError_t launch_ew(const PassParams& p, bool is_double, bool il, bool swap, int grid, cudaStream_t stream) {
+cudaError_t launch_ew(const PassParams& p, bool is_double, bool il_in, bool il_out, bool swap, int grid,
+                      cudaStream_t stream) {
   if (is_double)
-    ew_kernel<double><<<grid, 256, 0, stream>>>(p, il, swap);
+    ew_kernel<double><<<grid, 256, 0, stream>>>(p, il_in, il_out, swap);
   else
-    ew_kernel<float><<<grid, 256, 0, stream>>>(p, il, swap);
+    ew_kernel<float><<<grid, 256, 0, stream>>>(p, il_in, il_out, swap);
   return cudaGetLastError();
 }
 

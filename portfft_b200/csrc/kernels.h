@@ -45,7 +45,8 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
 cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
 // element-wise pass with modifiers (ew.cu): n == 1, modifier index = index along batch dimension 0
-cudaError_t launch_ew(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
+cudaError_t launch_ew(const PassParams& p, bool is_double, bool interleaved_in, bool interleaved_out, bool swap, int grid,
+                      cudaStream_t stream);
 
 // REAL domain pre / post passes (real.cu).  variant 0: even length (half-length complex transform), 1: odd length
 cudaError_t launch_real_pack(const PassParams& p, bool is_double, int variant, int grid, cudaStream_t stream);

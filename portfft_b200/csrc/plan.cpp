@@ -165,7 +165,6 @@ void validate_descriptor(const DescHost& d) {
     // real scalars of `lengths`; backward domain: lengths[last] / 2 + 1 complex elements along the last dimension.
     // Every pass that reads the input finishes before the first pass writes the output, so IN_PLACE needs no
     // relation between the two layouts beyond each being overlap-free.
-    if (d.lengths.size() != 1) unsupported("REAL domain: multi-dimensional transforms are not supported");
     if (!d.extra.empty()) unsupported("REAL domain: extra batch dimensions are not supported");
     check_strides_distance(d.lengths, d.number_of_transforms, d.forward_strides, d.forward_distance, "forward");
     check_strides_distance(d.domain_lengths(PFFT_BACKWARD), d.number_of_transforms, d.backward_strides,
@@ -675,38 +674,220 @@ struct Domain {
   size_t distance, offset;
 };
 
-// REAL domain, 1-D (see real.cu for the scheme).  Forward: [pack] -> complex transform of length L (N/2 for even N,
-// N for odd N) -> r2c_post; backward: c2r_pre -> complex transform -> [unpack].  The pack / unpack passes disappear
-// when the real rows can be addressed as interleaved complex pairs (even N, unit stride, even offset and distance).
-// Plan-internal rows live packed and interleaved in the workspaces, whatever the descriptor's complex storage.
+// All passes of ONE dimension of a complex transform: length L along element strides (es_in, es_out), `outer` = the
+// batch dimensions this dimension sees (fastest first), reading src0 and writing dst_buf.  Single pass when L fits
+// one CTA, one pass per factor (GLOBAL level) when it is smooth, Bluestein otherwise.  Returns the level.
+int emit_dim(PlanHost& plan, std::vector<PassHost>& passes, const DescHost& d, const DeviceLimits& lim, size_t L,
+             const std::vector<BDim>& outer, long long es_in, long long es_out, long long off_in, long long off_out,
+             int src0, int dst_buf) {
+  const bool dbl = d.is_double;
+  const size_t wg_max = max_workgroup_length(dbl, lim);
+  if (L <= wg_max && !choose_radices(L).empty()) {
+    PassHost ps = single_pass(d, lim, L, es_in, es_out, off_in, off_out, merge_dims(outer, 0), src0, dst_buf);
+    passes.push_back(ps);
+    return ps.level;
+  }
+
+  if (d.peer_last) unsupported("peer output buffers are supported for single-pass transform lengths only");
+  std::vector<BDim> outer_m = merge_dims(outer, 0);
+  std::vector<long long> outer_n, outer_in, outer_out;
+  long long outer_total = 1;
+  for (const BDim& b : outer_m) {
+    outer_n.push_back(b.n);
+    outer_in.push_back(b.in);
+    outer_out.push_back(b.out);
+    outer_total *= b.n;
+  }
+  const View vin{src0, es_in, off_in, outer_in}, vout{dst_buf, es_out, off_out, outer_out};
+  if (smooth31(L)) {
+    // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
+    plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * L);
+    emit_multipass(passes, d, lim, L, outer_n, vin, BUF_SCRATCH, vout);
+    return PFFT_LEVEL_GLOBAL;
+  }
+  // Bluestein: a length with a prime factor > 31 becomes a circular convolution of power-of-two length M >= 2L - 1
+  //   X_k = w_k * sum_j (x_j w_j) conj(w)_{k-j},  w_j = exp(-i pi j^2 / L)
+  // = two length-M transforms with the chirp multiplies, the zero padding, the product with FFT_M(conj w) and the
+  // truncation fused into their loads and stores.  (The reference rejects these lengths:
+  // committed_descriptor_impl.hpp:241, utils.hpp:102,126.)
+  size_t M = 1;
+  while (M < 2 * L - 1) M *= 2;
+  if (M > ((size_t)1 << 25)) unsupported("FFT size ", L, " (large prime factor) is too large");
+  if (outer_m.size() + 1 > (size_t)kMaxBatchDims) unsupported("too many independent batch dimensions");
+  std::vector<long long> sdist(outer_m.size());
+  {
+    long long acc = (long long)M;
+    for (size_t i = 0; i < outer_m.size(); ++i) {
+      sdist[i] = acc;
+      acc *= outer_n[i];
+    }
+  }
+  plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * M);
+  auto bdims = [&](const std::vector<long long>& in_d, const std::vector<long long>& out_d) {
+    std::vector<BDim> v;
+    for (size_t i = 0; i < outer_m.size(); ++i) v.push_back({outer_n[i], in_d[i], out_d[i]});
+    return v;
+  };
+  auto mods = [&](PassHost& ps, int lkind, int skind, int valid_in, int valid_out, int flags) {
+    ps.lmod_kind = lkind;
+    ps.smod_kind = skind;
+    ps.mod_l = (long long)L;
+    ps.mod_m = (long long)M;
+    ps.pp.valid_in = valid_in;
+    ps.pp.valid_out = valid_out;
+    ps.pp.mod_flags = flags;
+  };
+  if (M <= wg_max) {
+    PassHost a;
+    set_radices(a.pp, M);
+    a.pp.is = es_in;
+    a.pp.os = 1;
+    a.pp.ioff = off_in;
+    a.pp.ooff = 0;
+    a.pp.gtw_dim = -1;
+    set_batch_dims(a.pp, merge_dims(bdims(outer_in, sdist), 0));
+    a.src = src0;
+    a.dst = BUF_SCRATCH;
+    configure_wg_generic(a, dbl, lim, false);
+    mods(a, MODT_CHIRP, MODT_CONV, (int)L, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_OUT);
+    passes.push_back(a);
+    PassHost b;
+    set_radices(b.pp, M);
+    b.pp.is = 1;
+    b.pp.os = es_out;
+    b.pp.ioff = 0;
+    b.pp.ooff = off_out;
+    b.pp.gtw_dim = -1;
+    set_batch_dims(b.pp, merge_dims(bdims(sdist, outer_out), 0));
+    b.src = BUF_SCRATCH;
+    b.dst = dst_buf;
+    configure_wg_generic(b, dbl, lim, false);
+    mods(b, MODT_NONE, MODT_CHIRP_OVER_M, 0, (int)L, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
+    passes.push_back(b);
+    return PFFT_LEVEL_WORKGROUP;
+  }
+  // convolution length beyond one CTA: element-wise passes around two multi-pass transforms, ping-pong between two
+  // packed scratch buffers (rows of M elements)
+  plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)outer_total * M);
+  auto ew = [&](int src, int dst, long long n0, long long e_in, long long o_in, const std::vector<long long>& d_in,
+                long long e_out, long long o_out, const std::vector<long long>& d_out) {
+    PassHost ps;
+    ps.pp.n = 1;
+    ps.pp.num_radices = 1;
+    ps.pp.radix[0] = 1;
+    ps.pp.threads_per_fft = 1;
+    ps.pp.ffts_per_block = 256;
+    ps.pp.is = ps.pp.os = 1;
+    ps.pp.ioff = o_in;
+    ps.pp.ooff = o_out;
+    ps.pp.gtw_dim = -1;
+    std::vector<BDim> dims{{n0, e_in, e_out}};
+    for (size_t i = 0; i < outer_m.size(); ++i) dims.push_back({outer_n[i], d_in[i], d_out[i]});
+    set_batch_dims(ps.pp, dims);  // dimension 0 (the element index) is never merged
+    ps.src = src;
+    ps.dst = dst;
+    ps.kernel = KERNEL_EW;
+    ps.level = LEVEL_GLOBAL;
+    ps.block = 256;
+    ps.grid = (int)std::min<long long>((ps.pp.batch_total + 255) / 256, (long long)lim.num_sms * 16);
+    ps.tw_n = 0;
+    return ps;
+  };
+  const std::vector<long long> row_n{outer_total}, row_d{(long long)M};
+  const View s1{BUF_SCRATCH, 1, 0, row_d}, s2{BUF_SCRATCH2, 1, 0, row_d};
+  {
+    PassHost ps = ew(src0, BUF_SCRATCH, (long long)M, es_in, off_in, outer_in, 1, 0, sdist);
+    mods(ps, MODT_CHIRP, MODT_NONE, (int)L, 0, MOD_NO_USER_SWAP_OUT);
+    passes.push_back(ps);
+  }
+  // the two length-M transforms work on plan-internal data: plain forward transforms in either direction
+  const size_t inner0 = passes.size();
+  emit_multipass(passes, d, lim, M, row_n, s1, BUF_SCRATCH, s2);
+  {
+    PassHost ps = ew(BUF_SCRATCH2, BUF_SCRATCH2, (long long)M, 1, 0, sdist, 1, 0, sdist);
+    mods(ps, MODT_NONE, MODT_CONV, 0, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT);
+    passes.push_back(ps);
+  }
+  emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
+  for (size_t i = inner0; i < passes.size(); ++i) passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
+  {
+    PassHost ps = ew(BUF_SCRATCH, dst_buf, (long long)L, 1, 0, sdist, es_out, off_out, outer_out);
+    mods(ps, MODT_NONE, MODT_CHIRP_OVER_M, 0, 0, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
+    passes.push_back(ps);
+  }
+  return PFFT_LEVEL_GLOBAL;
+}
+
+// REAL domain (see real.cu for the scheme).  Along the last dimension, forward: [pack] -> complex transform of length
+// L (N/2 for even N, N for odd N) -> r2c_post; backward: c2r_pre -> complex transform -> [unpack].  The pack / unpack
+// passes disappear when the real rows can be addressed as interleaved complex pairs (even N, unit stride, even offset
+// and distances).  Plan-internal rows live packed and interleaved in the workspaces, whatever the descriptor's
+// complex storage.  N-D: forward = the real-to-complex rows first, then complex passes along the other dimensions in
+// place on the half-spectrum output; backward = the half spectrum copied to a packed workspace, inverse complex
+// passes along the other dimensions there, the complex-to-real rows last (the Hermitian symmetry that c2r_pre relies
+// on holds along the last dimension only after the other dimensions are transformed).
 void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   const DescHost& d = plan.desc;
   DescHost dint = d;  // the descriptor as the inner complex passes see it
   dint.complex_storage = PFFT_INTERLEAVED_COMPLEX;
   const bool dbl = d.is_double;
   const bool fwd = dir == PFFT_FORWARD;
-  const long long N = (long long)d.lengths[0], H = N / 2;
+  const size_t D = d.lengths.size();
+  const std::vector<size_t> clen = d.domain_lengths(PFFT_BACKWARD);
+  const long long N = (long long)d.lengths[D - 1], H = N / 2;
   const bool even = N % 2 == 0;
   const int variant = even ? 0 : 1;
   const long long L = even ? H : N;
-  const long long batch = (long long)d.number_of_transforms;
-  const long long rs = (long long)d.forward_strides[0], roff = (long long)d.forward_offset, rdist = (long long)d.forward_distance;
-  const long long cs = (long long)d.backward_strides[0], coff = (long long)d.backward_offset, cdist = (long long)d.backward_distance;
+  const long long rs = (long long)d.forward_strides[D - 1], roff = (long long)d.forward_offset;
+  const long long cs = (long long)d.backward_strides[D - 1], coff = (long long)d.backward_offset;
   const size_t wg_max = max_workgroup_length(dbl, lim);
   std::vector<PassHost>& passes = plan.passes[dir];
   if (!smooth31((size_t)L))
     unsupported("REAL domain: length ", N, " needs a complex transform of length ", L,
                 " with a prime factor larger than 31, which is not supported");
   const bool single = (size_t)L <= wg_max;
-  plan.dim_level.assign(1, single ? PFFT_LEVEL_WORKGROUP : PFFT_LEVEL_GLOBAL);
-  plan.scratch_elems = std::max(plan.scratch_elems, (size_t)(batch * L));
-  const bool pairs = even && rs == 1 && roff % 2 == 0 && (batch == 1 || rdist % 2 == 0);
-  const std::vector<long long> outer_n(1, batch), row_d(1, L), pair_d(1, rdist / 2);
-  const View s1{BUF_SCRATCH, 1, 0, row_d}, s2{BUF_SCRATCH2, 1, 0, row_d};
+  plan.dim_level.assign(D, single ? PFFT_LEVEL_WORKGROUP : PFFT_LEVEL_GLOBAL);
+  // rows of the last dimension: (i_{D-2}, ..., i_0, batch), fastest first; real / complex / workspace distances.
+  // The workspace W (backward, N-D) holds the half spectrum packed: [batch][d_0]..[d_{D-2}][H + 1].
+  std::vector<long long> row_n, row_r, row_c, row_w, row_s;
+  {
+    long long wacc = H + 1;
+    for (size_t e = D - 1; e > 0; --e) {
+      row_n.push_back((long long)d.lengths[e - 1]);
+      row_r.push_back((long long)d.forward_strides[e - 1]);
+      row_c.push_back((long long)d.backward_strides[e - 1]);
+      row_w.push_back(wacc);
+      wacc *= (long long)d.lengths[e - 1];
+    }
+    row_n.push_back((long long)d.number_of_transforms);
+    row_r.push_back((long long)d.forward_distance);
+    row_c.push_back((long long)d.backward_distance);
+    row_w.push_back(wacc);
+    long long sacc = L;
+    for (size_t i = 0; i < row_n.size(); ++i) {
+      row_s.push_back(sacc);  // packed rows of L elements in the scratch buffers
+      sacc *= row_n[i];
+    }
+  }
+  long long rows = 1;
+  for (long long n : row_n) rows *= n;
+  plan.scratch_elems = std::max(plan.scratch_elems, (size_t)(rows * L));
+  bool pairs = even && rs == 1 && roff % 2 == 0;
+  std::vector<long long> pair_d;
+  for (size_t i = 0; i < row_n.size(); ++i) {
+    if (row_n[i] > 1 && row_r[i] % 2 != 0) pairs = false;
+    pair_d.push_back(row_r[i] / 2);
+  }
+  const View s1{BUF_SCRATCH, 1, 0, row_s}, s2{BUF_SCRATCH2, 1, 0, row_s};
   const View rview{fwd ? BUF_IN : BUF_OUT, 1, roff / 2, pair_d};  // the real rows as complex pairs
 
-  auto rows_pass = [&](int kernel, int src, int dst, long long es_in, long long o_in, long long d_in, long long es_out,
-                       long long o_out, long long d_out, long long work_per_row) {
+  auto row_dims = [&](const std::vector<long long>& d_in, const std::vector<long long>& d_out) {
+    std::vector<BDim> v;
+    for (size_t i = 0; i < row_n.size(); ++i) v.push_back({row_n[i], d_in[i], d_out[i]});
+    return merge_dims(v, 0);
+  };
+  auto rows_pass = [&](int kernel, int src, int dst, long long es_in, long long o_in, const std::vector<long long>& d_in,
+                       long long es_out, long long o_out, const std::vector<long long>& d_out, long long work_per_row) {
     PassHost ps;
     ps.pp.n = (int)N;
     ps.pp.num_radices = 1;
@@ -718,7 +899,7 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     ps.pp.ioff = o_in;
     ps.pp.ooff = o_out;
     ps.pp.gtw_dim = -1;
-    set_batch_dims(ps.pp, {BDim{batch, d_in, d_out}});
+    set_batch_dims(ps.pp, row_dims(d_in, d_out));
     ps.src = src;
     ps.dst = dst;
     ps.kernel = kernel;
@@ -730,9 +911,11 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       long long lanes = 1;
       while (lanes < work_per_row && lanes < 256) lanes *= 2;
       const long long rows_per_cta = 256 / lanes;
-      ps.grid = (int)std::min<long long>((batch + rows_per_cta - 1) / rows_per_cta, (long long)lim.num_sms * 32);
+      ps.grid = (int)std::min<long long>((rows + rows_per_cta - 1) / rows_per_cta, (long long)lim.num_sms * 32);
     }
     ps.tw_n = (even && (kernel == KERNEL_R2C_POST || kernel == KERNEL_C2R_PRE)) ? N : 0;
+    // the scratch side of these passes is interleaved whatever the descriptor says
+    ps.internal_storage = (src != BUF_IN ? 1 : 0) | (dst != BUF_OUT ? 2 : 0);
     return ps;
   };
   // complex transform of length L between two views; returns the buffer holding the result
@@ -740,24 +923,32 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     const size_t first = passes.size();
     int result;
     if (single) {
-      const View dst = final_dst ? *final_dst : View{src.buf == BUF_IN ? BUF_SCRATCH : src.buf, 1, 0, row_d};
-      passes.push_back(single_pass(dint, lim, (size_t)L, src.es, dst.es, src.off, dst.off,
-                                   merge_dims({BDim{batch, src.dist[0], dst.dist[0]}}, 0), src.buf, dst.buf));
+      const View dst = final_dst ? *final_dst : View{src.buf == BUF_IN ? BUF_SCRATCH : src.buf, 1, 0, row_s};
+      passes.push_back(single_pass(dint, lim, (size_t)L, src.es, dst.es, src.off, dst.off, row_dims(src.dist, dst.dist),
+                                   src.buf, dst.buf));
       result = dst.buf;
     } else {
       // multi-pass: in place on a packed workspace, the last pass moves to the other one (or to the final view)
       const int work = src.buf == BUF_IN ? BUF_SCRATCH2 : src.buf;
       const View other = work == BUF_SCRATCH ? s2 : s1;
       const View dst = final_dst ? *final_dst : other;
-      if (!final_dst || src.buf == BUF_IN) plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)(batch * L));
-      emit_multipass(passes, dint, lim, (size_t)L, outer_n, src, work, dst);
+      if (!final_dst || src.buf == BUF_IN) plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)(rows * L));
+      emit_multipass(passes, dint, lim, (size_t)L, row_n, src, work, dst);
       result = dst.buf;
     }
     for (size_t i = first; i < passes.size(); ++i) {
       passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;  // plain forward transforms
-      passes[i].internal_storage = 1;
+      passes[i].internal_storage = 3;
     }
     return result;
+  };
+  // batch dimensions seen by a complex transform along dimension `dim` of the half-spectrum array (fastest first)
+  auto outer_of = [&](size_t dim, const std::vector<long long>& strides, long long distance) {
+    std::vector<BDim> outer;
+    for (size_t e = D; e > 0; --e)
+      if (e - 1 != dim) outer.push_back({(long long)clen[e - 1], strides[e - 1], strides[e - 1]});
+    outer.push_back({(long long)d.number_of_transforms, distance, distance});
+    return outer;
   };
 
   if (fwd) {
@@ -765,24 +956,88 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     if (pairs) {
       zbuf = transform(rview, nullptr);
     } else {
-      passes.push_back(rows_pass(KERNEL_REAL_PACK, BUF_IN, BUF_SCRATCH, rs, roff, rdist, 1, 0, L, L));
+      passes.push_back(rows_pass(KERNEL_REAL_PACK, BUF_IN, BUF_SCRATCH, rs, roff, row_r, 1, 0, row_s, L));
       zbuf = transform(s1, nullptr);
     }
-    passes.push_back(rows_pass(KERNEL_R2C_POST, zbuf, BUF_OUT, 1, 0, L, cs, coff, cdist, H + 1));
+    passes.push_back(rows_pass(KERNEL_R2C_POST, zbuf, BUF_OUT, 1, 0, row_s, cs, coff, row_c, H + 1));
+    // the other dimensions: complex passes in place on the half-spectrum output
+    std::vector<long long> bst(d.backward_strides.begin(), d.backward_strides.end());
+    for (size_t e = D - 1; e > 0; --e) {
+      const size_t dim = e - 1;
+      plan.dim_level[dim] = emit_dim(plan, passes, d, lim, d.lengths[dim], outer_of(dim, bst, (long long)d.backward_distance),
+                                     bst[dim], bst[dim], coff, coff, BUF_OUT, BUF_OUT);
+    }
   } else {
-    passes.push_back(rows_pass(KERNEL_C2R_PRE, BUF_IN, BUF_SCRATCH, cs, coff, cdist, 1, 0, L, L));
+    int xbuf = BUF_IN;
+    long long xs = cs, xoff = coff;
+    std::vector<long long> xd = row_c;
+    if (D > 1) {
+      // half spectrum -> packed interleaved workspace W, then inverse complex passes along the other dimensions on W
+      std::vector<long long> wst(D);
+      {
+        long long acc = 1;
+        for (size_t e = D; e > 0; --e) {
+          wst[e - 1] = acc;
+          acc *= (long long)clen[e - 1];
+        }
+        plan.scratch3_elems = std::max(plan.scratch3_elems, (size_t)(acc * (long long)d.number_of_transforms));
+      }
+      const long long wdist = wst[0] * (long long)clen[0];
+      {
+        PassHost ps;
+        ps.pp.n = 1;
+        ps.pp.num_radices = 1;
+        ps.pp.radix[0] = 1;
+        ps.pp.threads_per_fft = 1;
+        ps.pp.ffts_per_block = 256;
+        ps.pp.is = ps.pp.os = 1;
+        ps.pp.ioff = coff;
+        ps.pp.ooff = 0;
+        ps.pp.gtw_dim = -1;
+        std::vector<BDim> dims{{H + 1, cs, 1}};
+        std::vector<BDim> rest;
+        for (size_t i = 0; i < row_n.size(); ++i) rest.push_back({row_n[i], row_c[i], row_w[i]});
+        rest = merge_dims(rest, 0);
+        dims.insert(dims.end(), rest.begin(), rest.end());
+        set_batch_dims(ps.pp, dims);  // dimension 0 (the element index) is never merged
+        ps.src = BUF_IN;
+        ps.dst = BUF_SCRATCH3;
+        ps.kernel = KERNEL_EW;
+        ps.level = LEVEL_WORKGROUP;
+        ps.block = 256;
+        ps.grid = (int)std::min<long long>((ps.pp.batch_total + 255) / 256, (long long)lim.num_sms * 16);
+        ps.internal_storage = 2;
+        ps.pp.mod_flags = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
+        passes.push_back(ps);
+      }
+      for (size_t e = D - 1; e > 0; --e) {
+        const size_t dim = e - 1;
+        const size_t first = passes.size();
+        plan.dim_level[dim] = emit_dim(plan, passes, dint, lim, d.lengths[dim], outer_of(dim, wst, wdist), wst[dim], wst[dim],
+                                       0, 0, BUF_SCRATCH3, BUF_SCRATCH3);
+        for (size_t i = first; i < passes.size(); ++i) {
+          passes[i].internal_storage = 3;
+          passes[i].force_swap = 1;  // unnormalised inverse = forward transform of the (re <-> im)-swapped data
+        }
+      }
+      xbuf = BUF_SCRATCH3;
+      xs = 1;
+      xoff = 0;
+      xd = row_w;
+    }
+    passes.push_back(rows_pass(KERNEL_C2R_PRE, xbuf, BUF_SCRATCH, xs, xoff, xd, 1, 0, row_s, L));
     if (pairs) {
       transform(s1, &rview);
     } else {
       const int ybuf = transform(s1, nullptr);
-      passes.push_back(rows_pass(KERNEL_REAL_UNPACK, ybuf, BUF_OUT, 1, 0, L, rs, roff, rdist, L));
+      passes.push_back(rows_pass(KERNEL_REAL_UNPACK, ybuf, BUF_OUT, 1, 0, row_s, rs, roff, row_r, L));
     }
   }
   // passes that address the user's real buffer as complex pairs
   for (PassHost& ps : passes) {
-    if (ps.kernel >= KERNEL_REAL_PACK) continue;
-    if (ps.src == BUF_IN) ps.real_view |= 1;
-    if (ps.dst == BUF_OUT) ps.real_view |= 2;
+    if (ps.kernel >= KERNEL_EW) continue;
+    if (fwd && ps.src == BUF_IN) ps.real_view |= 1;
+    if (!fwd && ps.dst == BUF_OUT) ps.real_view |= 2;
   }
   const double scale = d.scale(dir);
   PassHost& last = passes.back();
@@ -796,12 +1051,10 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     build_real_direction(plan, dir, lim);
     return;
   }
-  const bool dbl = d.is_double;
   const Domain in{d.strides(dir), d.distance(dir), d.offset(dir)};
   const int odir = dir == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
   const Domain out{d.strides(odir), d.distance(odir), d.offset(odir)};
   const size_t D = d.lengths.size();
-  const size_t wg_max = max_workgroup_length(dbl, lim);
   std::vector<PassHost>& passes = plan.passes[dir];
   if (plan.dim_level.size() != D) plan.dim_level.assign(D, PFFT_LEVEL_WORKGROUP);
 
@@ -834,143 +1087,7 @@ void build_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     const long long off_out = (long long)out.offset;
     const int src0 = first ? BUF_IN : BUF_OUT;
 
-    if (L <= wg_max && !choose_radices(L).empty()) {
-      PassHost ps = single_pass(d, lim, L, es_in, es_out, off_in, off_out, merge_dims(outer, 0), src0, BUF_OUT);
-      passes.push_back(ps);
-      plan.dim_level[dim] = ps.level;
-      continue;
-    }
-
-    if (d.peer_last) unsupported("peer output buffers are supported for single-pass transform lengths only");
-    std::vector<BDim> outer_m = merge_dims(outer, 0);
-    std::vector<long long> outer_n, outer_in, outer_out;
-    long long outer_total = 1;
-    for (const BDim& b : outer_m) {
-      outer_n.push_back(b.n);
-      outer_in.push_back(b.in);
-      outer_out.push_back(b.out);
-      outer_total *= b.n;
-    }
-    const View vin{src0, es_in, off_in, outer_in}, vout{BUF_OUT, es_out, off_out, outer_out};
-    if (smooth31(L)) {
-      // GLOBAL level: L = N_1 * ... * N_k, one pass per factor, twiddle + transposition fused into the stores
-      plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
-      plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * L);
-      emit_multipass(passes, d, lim, L, outer_n, vin, BUF_SCRATCH, vout);
-      continue;
-    }
-    // Bluestein: a length with a prime factor > 31 becomes a circular convolution of power-of-two length M >= 2L - 1
-    //   X_k = w_k * sum_j (x_j w_j) conj(w)_{k-j},  w_j = exp(-i pi j^2 / L)
-    // = two length-M transforms with the chirp multiplies, the zero padding, the product with FFT_M(conj w) and the
-    // truncation fused into their loads and stores.  (The reference rejects these lengths:
-    // committed_descriptor_impl.hpp:241, utils.hpp:102,126.)
-    size_t M = 1;
-    while (M < 2 * L - 1) M *= 2;
-    if (M > ((size_t)1 << 25)) unsupported("FFT size ", L, " (large prime factor) is too large");
-    if (outer_m.size() + 1 > (size_t)kMaxBatchDims) unsupported("too many independent batch dimensions");
-    std::vector<long long> sdist(outer_m.size());
-    {
-      long long acc = (long long)M;
-      for (size_t i = 0; i < outer_m.size(); ++i) {
-        sdist[i] = acc;
-        acc *= outer_n[i];
-      }
-    }
-    plan.scratch_elems = std::max(plan.scratch_elems, (size_t)outer_total * M);
-    auto bdims = [&](const std::vector<long long>& in_d, const std::vector<long long>& out_d) {
-      std::vector<BDim> v;
-      for (size_t i = 0; i < outer_m.size(); ++i) v.push_back({outer_n[i], in_d[i], out_d[i]});
-      return v;
-    };
-    auto mods = [&](PassHost& ps, int lkind, int skind, int valid_in, int valid_out, int flags) {
-      ps.lmod_kind = lkind;
-      ps.smod_kind = skind;
-      ps.mod_l = (long long)L;
-      ps.mod_m = (long long)M;
-      ps.pp.valid_in = valid_in;
-      ps.pp.valid_out = valid_out;
-      ps.pp.mod_flags = flags;
-    };
-    if (M <= wg_max) {
-      plan.dim_level[dim] = PFFT_LEVEL_WORKGROUP;
-      PassHost a;
-      set_radices(a.pp, M);
-      a.pp.is = es_in;
-      a.pp.os = 1;
-      a.pp.ioff = off_in;
-      a.pp.ooff = 0;
-      a.pp.gtw_dim = -1;
-      set_batch_dims(a.pp, merge_dims(bdims(outer_in, sdist), 0));
-      a.src = src0;
-      a.dst = BUF_SCRATCH;
-      configure_wg_generic(a, dbl, lim, false);
-      mods(a, MODT_CHIRP, MODT_CONV, (int)L, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_OUT);
-      passes.push_back(a);
-      PassHost b;
-      set_radices(b.pp, M);
-      b.pp.is = 1;
-      b.pp.os = es_out;
-      b.pp.ioff = 0;
-      b.pp.ooff = off_out;
-      b.pp.gtw_dim = -1;
-      set_batch_dims(b.pp, merge_dims(bdims(sdist, outer_out), 0));
-      b.src = BUF_SCRATCH;
-      b.dst = BUF_OUT;
-      configure_wg_generic(b, dbl, lim, false);
-      mods(b, MODT_NONE, MODT_CHIRP_OVER_M, 0, (int)L, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
-      passes.push_back(b);
-      continue;
-    }
-    // convolution length beyond one CTA: element-wise passes around two multi-pass transforms, ping-pong between two
-    // packed scratch buffers (rows of M elements)
-    plan.dim_level[dim] = PFFT_LEVEL_GLOBAL;
-    plan.scratch2_elems = std::max(plan.scratch2_elems, (size_t)outer_total * M);
-    auto ew = [&](int src, int dst, long long n0, long long e_in, long long o_in, const std::vector<long long>& d_in,
-                  long long e_out, long long o_out, const std::vector<long long>& d_out) {
-      PassHost ps;
-      ps.pp.n = 1;
-      ps.pp.num_radices = 1;
-      ps.pp.radix[0] = 1;
-      ps.pp.threads_per_fft = 1;
-      ps.pp.ffts_per_block = 256;
-      ps.pp.is = ps.pp.os = 1;
-      ps.pp.ioff = o_in;
-      ps.pp.ooff = o_out;
-      ps.pp.gtw_dim = -1;
-      std::vector<BDim> dims{{n0, e_in, e_out}};
-      for (size_t i = 0; i < outer_m.size(); ++i) dims.push_back({outer_n[i], d_in[i], d_out[i]});
-      set_batch_dims(ps.pp, dims);  // dimension 0 (the element index) is never merged
-      ps.src = src;
-      ps.dst = dst;
-      ps.kernel = KERNEL_EW;
-      ps.level = LEVEL_GLOBAL;
-      ps.block = 256;
-      ps.grid = (int)std::min<long long>((ps.pp.batch_total + 255) / 256, (long long)lim.num_sms * 16);
-      ps.tw_n = 0;
-      return ps;
-    };
-    const std::vector<long long> row_n{outer_total}, row_d{(long long)M};
-    const View s1{BUF_SCRATCH, 1, 0, row_d}, s2{BUF_SCRATCH2, 1, 0, row_d};
-    {
-      PassHost ps = ew(src0, BUF_SCRATCH, (long long)M, es_in, off_in, outer_in, 1, 0, sdist);
-      mods(ps, MODT_CHIRP, MODT_NONE, (int)L, 0, MOD_NO_USER_SWAP_OUT);
-      passes.push_back(ps);
-    }
-    // the two length-M transforms work on plan-internal data: plain forward transforms in either direction
-    const size_t inner0 = passes.size();
-    emit_multipass(passes, d, lim, M, row_n, s1, BUF_SCRATCH, s2);
-    {
-      PassHost ps = ew(BUF_SCRATCH2, BUF_SCRATCH2, (long long)M, 1, 0, sdist, 1, 0, sdist);
-      mods(ps, MODT_NONE, MODT_CONV, 0, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT);
-      passes.push_back(ps);
-    }
-    emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
-    for (size_t i = inner0; i < passes.size(); ++i) passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
-    {
-      PassHost ps = ew(BUF_SCRATCH, BUF_OUT, (long long)L, 1, 0, sdist, es_out, off_out, outer_out);
-      mods(ps, MODT_NONE, MODT_CHIRP_OVER_M, 0, 0, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
-      passes.push_back(ps);
-    }
+    plan.dim_level[dim] = emit_dim(plan, passes, d, lim, L, outer, es_in, es_out, off_in, off_out, src0, BUF_OUT);
   }
   // scale on the last pass executed (committed_descriptor_impl.hpp:473-474)
   const double scale = d.scale(dir);
@@ -994,13 +1111,14 @@ std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
   static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew", "real_pack", "r2c_post", "c2r_pre", "real_unpack"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
-  static const char* buf_names[] = {"in", "out", "scratch", "scratch2"};
+  static const char* buf_names[] = {"in", "out", "scratch", "scratch2", "scratch3"};
   static const char* mod_names[] = {"none", "chirp", "chirp/M", "conv"};
   std::stringstream ss;
   ss << "levels:";
   for (int l : plan.dim_level) ss << " " << level_names[l];
   ss << "; scratch_elems=" << plan.scratch_elems;
   if (plan.scratch2_elems) ss << " scratch2_elems=" << plan.scratch2_elems;
+  if (plan.scratch3_elems) ss << " scratch3_elems=" << plan.scratch3_elems;
   ss << "\n";
   for (const PassHost& ps : plan.passes[direction]) {
     const PassParams& p = ps.pp;
@@ -1024,6 +1142,7 @@ std::string describe_plan(const PlanHost& plan, int direction) {
          << " valid_out=" << p.valid_out << " mod_flags=" << p.mod_flags << " mod_l=" << ps.mod_l << " mod_m=" << ps.mod_m;
     if (p.apply_scale) ss << " scale=" << p.scale;
     if (ps.real_view) ss << " real_view=" << ps.real_view;
+    if (ps.force_swap) ss << " force_swap";
     if (ps.kernel >= KERNEL_REAL_PACK) ss << " variant=" << ps.variant;
     ss << "\n";
   }
@@ -1039,6 +1158,7 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
     ss << "]";
   };
   ss << "{\"scratch_elems\": " << plan.scratch_elems << ", \"scratch2_elems\": " << plan.scratch2_elems
+     << ", \"scratch3_elems\": " << plan.scratch3_elems
      << ", \"is_double\": " << (plan.desc.is_double ? 1 : 0) << ", \"is_real\": " << (plan.desc.is_real() ? 1 : 0)
      << ", \"passes\": [";
   bool firstp = true;
@@ -1056,7 +1176,8 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
        << ", \"valid_in\": " << p.valid_in << ", \"valid_out\": " << p.valid_out << ", \"mod_flags\": " << p.mod_flags
        << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
        << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
-       << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view << "}";
+       << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view
+       << ", \"force_swap\": " << ps.force_swap << "}";
     firstp = false;
   }
   ss << "]}";

@@ -59,7 +59,7 @@ std::vector<size_t> default_strides(const std::vector<size_t>& lengths);
 int get_layout(const DescHost& d, int dir);
 void validate_descriptor(const DescHost& d);  // throws PlanError
 
-enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2, BUF_SCRATCH2 = 3 };
+enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2, BUF_SCRATCH2 = 3, BUF_SCRATCH3 = 4 };
 
 enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5, KERNEL_EW = 6,
                         KERNEL_REAL_PACK = 7, KERNEL_R2C_POST = 8, KERNEL_C2R_PRE = 9, KERNEL_REAL_UNPACK = 10 };
@@ -82,8 +82,9 @@ struct PassHost {
   // REAL-domain plans: plan-internal data is always interleaved complex; `user_side` tells which side of the pass
   // (bit 0 input, bit 1 output) is user memory in the descriptor's complex storage.  `real_view`: the input (bit 0)
   // or output (bit 1) is the user's REAL buffer read / written as interleaved complex pairs (x[2j], x[2j+1]).
-  int internal_storage = 0;  // 1: run this pass with interleaved storage whatever the descriptor says
+  int internal_storage = 0;  // bit 0 / bit 1: the input / output side is plan-internal, interleaved complex
   int real_view = 0;
+  int force_swap = 0;        // REAL N-D backward: inverse complex pass on the (interleaved) workspace
 };
 
 // geometry limits of the thread- and warp-level kernels (wi.cuh, sg.cuh); sg_supports_m lives in sg_f32.cu
@@ -107,6 +108,7 @@ struct PlanHost {
   std::vector<int> dim_level;       // per dimension, PFFT_LEVEL_*
   size_t scratch_elems = 0;         // complex elements of plan-owned workspace
   size_t scratch2_elems = 0;        // second workspace (Bluestein with a multi-pass convolution length)
+  size_t scratch3_elems = 0;        // REAL N-D backward: the half spectrum, packed
 };
 
 struct DeviceLimits {

@@ -26,6 +26,11 @@ namespace {
 
 // batch multi-index of row g -> input / output base offsets
 __device__ __forceinline__ void row_bases(const PassParams& p, long long g, long long& ib, long long& ob) {
+  if (single_batch_dim(p)) {  // the common case costs no 64-bit division
+    ib = p.ioff + g * p.ibd[0];
+    ob = p.ooff + g * p.obd[0];
+    return;
+  }
   ib = p.ioff;
   ob = p.ooff;
 #pragma unroll

@@ -55,7 +55,8 @@ struct pfft_plan {
   std::map<std::pair<int, std::pair<long long, long long>>, void*> mod;  // (ModTable, (L, M)) -> device table
   void* scratch = nullptr;
   void* scratch2 = nullptr;
-  size_t scratch_bytes = 0, scratch2_bytes = 0;
+  void* scratch3 = nullptr;
+  size_t scratch_bytes = 0, scratch2_bytes = 0, scratch3_bytes = 0;
   // device staging for pfft_compute_host
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
@@ -74,6 +75,7 @@ struct pfft_plan {
     for (void* p : owned) cudaFree(p);
     if (scratch) cudaFree(scratch);
     if (scratch2) cudaFree(scratch2);
+    if (scratch3) cudaFree(scratch3);
     for (void* p : stage)
       if (p) cudaFree(p);
   }
@@ -134,6 +136,8 @@ static void commit_device(pfft_plan* plan) {
   if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
   plan->scratch2_bytes = plan->host.scratch2_elems * 2 * scalar;
   if (plan->scratch2_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch2, plan->scratch2_bytes));
+  plan->scratch3_bytes = plan->host.scratch3_elems * 2 * scalar;
+  if (plan->scratch3_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch3, plan->scratch3_bytes));
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
       ps.pp.tw = ps.tw_n > 0 ? plan->tw[ps.tw_n] : nullptr;
@@ -194,18 +198,22 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
       case BUF_IN: p.in_re = uin_re; p.in_im = uin_im; break;
       case BUF_OUT: p.in_re = uout_re; p.in_im = uout_im; break;
       case BUF_SCRATCH2: p.in_re = s2_re; p.in_im = s2_im; break;
+      case BUF_SCRATCH3: p.in_re = plan->scratch3; p.in_im = nullptr; break;  // always interleaved
       default: p.in_re = s_re; p.in_im = s_im; break;
     }
     switch (ps.dst) {
       case BUF_OUT: p.out_re = uout_re; p.out_im = uout_im; break;
       case BUF_SCRATCH2: p.out_re = s2_re; p.out_im = s2_im; break;
+      case BUF_SCRATCH3: p.out_re = plan->scratch3; p.out_im = nullptr; break;
       default: p.out_re = s_re; p.out_im = s_im; break;
     }
     // backward on interleaved data = (re <-> im) swap on load and store; passes between plan-internal buffers
     // (Bluestein's inner transforms) always run the plain forward transform
     const int internal = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
-    const bool pil = il || ps.internal_storage != 0;  // storage this pass runs with
-    const bool swap = pil && bwd && !real && (p.mod_flags & internal) != internal;
+    // storage of each side of this pass: the descriptor's, or interleaved for plan-internal rows of a REAL plan
+    const bool il_in = il || (ps.internal_storage & 1), il_out = il || (ps.internal_storage & 2);
+    const bool pil = il_in && il_out;  // the transform kernels take one storage for both sides (the planner pairs them)
+    const bool swap = ps.force_swap ? true : (pil && bwd && !real && (p.mod_flags & internal) != internal);
     if (ps.real_view) {
       // the user's real rows addressed as interleaved complex pairs: needs complex alignment of the first element
       const uintptr_t a = (ps.real_view & 1) ? (uintptr_t)p.in_re + (size_t)p.ioff * 2 * scalar
@@ -254,7 +262,7 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
           e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_EW:
-        e = launch_ew(p, d.is_double, pil, swap, ps.grid, stream);
+        e = launch_ew(p, d.is_double, il_in, il_out, swap, ps.grid, stream);
         break;
       case KERNEL_REAL_PACK:
         e = launch_real_pack(p, d.is_double, ps.variant, ps.grid, stream);
@@ -263,10 +271,10 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         e = launch_real_unpack(p, d.is_double, ps.variant, ps.grid, stream);
         break;
       case KERNEL_R2C_POST:
-        e = launch_r2c_post(p, d.is_double, il, ps.variant, ps.grid, stream);
+        e = launch_r2c_post(p, d.is_double, il_out, ps.variant, ps.grid, stream);
         break;
       case KERNEL_C2R_PRE:
-        e = launch_c2r_pre(p, d.is_double, il, ps.variant, ps.grid, stream);
+        e = launch_c2r_pre(p, d.is_double, il_in, ps.variant, ps.grid, stream);
         break;
       default:
         throw PlanError(PFFT_INTERNAL_ERROR, "unknown kernel kind");

@@ -13,7 +13,7 @@ import numpy as np
 import portfft_b200 as pf
 from portfft_b200 import api
 
-BUF_IN, BUF_OUT, BUF_SCRATCH, BUF_SCRATCH2 = 0, 1, 2, 3
+BUF_IN, BUF_OUT, BUF_SCRATCH, BUF_SCRATCH2, BUF_SCRATCH3 = 0, 1, 2, 3, 4
 KERNEL_EW, KERNEL_REAL_PACK, KERNEL_R2C_POST, KERNEL_C2R_PRE, KERNEL_REAL_UNPACK = 6, 7, 8, 9, 10
 MOD_SWAP_PRE, MOD_SWAP_POST, MOD_NO_USER_SWAP_IN, MOD_NO_USER_SWAP_OUT = 1, 2, 4, 8
 
@@ -99,7 +99,8 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
     bwd = int(direction) == 1
     bufs = {BUF_IN: in_buf, BUF_OUT: out_buf,
             BUF_SCRATCH: np.full(max(1, plan["scratch_elems"]), np.nan + 0j, dtype=cdt),
-            BUF_SCRATCH2: np.full(max(1, plan["scratch2_elems"]), np.nan + 0j, dtype=cdt)}
+            BUF_SCRATCH2: np.full(max(1, plan["scratch2_elems"]), np.nan + 0j, dtype=cdt),
+            BUF_SCRATCH3: np.full(max(1, plan["scratch3_elems"]), np.nan + 0j, dtype=cdt)}
     if plan["is_real"]:
         bwd = False  # REAL plans never use the (re <-> im) swap
     for ps in plan["passes"]:
@@ -114,8 +115,9 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
         ob = ps["ooff"] + sum(g * d for g, d in zip(grids, obd))
         internal = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT
         flags = ps["mod_flags"]
-        swap_in = bwd and not (flags & MOD_NO_USER_SWAP_IN)
-        swap_out = bwd and not (flags & MOD_NO_USER_SWAP_OUT)
+        swapped = bwd or bool(ps["force_swap"])
+        swap_in = swapped and not (flags & MOD_NO_USER_SWAP_IN)
+        swap_out = swapped and not (flags & MOD_NO_USER_SWAP_OUT)
         lmod = api.mod_table(scalar, ps["lmod"], ps["mod_l"], ps["mod_m"]) if ps["lmod"] else None
         smod = api.mod_table(scalar, ps["smod"], ps["mod_l"], ps["mod_m"]) if ps["smod"] else None
         n = ps["n"]

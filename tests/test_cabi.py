@@ -63,13 +63,13 @@ def test_mismatching_strides_length_and_real_domain():
     with pytest.raises(pf.invalid_configuration):
         d.validate()
     # REAL domain: the reference throws unsupported_configuration for every REAL descriptor
-    # (descriptor_validation.hpp:268-270); here 1-D is implemented, N-D still reports unsupported
+    # (descriptor_validation.hpp:268-270); here it is implemented (half spectrum along the last dimension)
     d = pf.descriptor([8], dom=pf.domain.REAL)
     d.validate()
     assert d.get_input_count(pf.direction.FORWARD) == 8 and d.get_input_count(pf.direction.BACKWARD) == 5
     d = pf.descriptor([4, 8], dom=pf.domain.REAL)
-    with pytest.raises(pf.unsupported_configuration):
-        d.validate()
+    d.validate()
+    assert d.get_input_count(pf.direction.FORWARD) == 32 and d.get_input_count(pf.direction.BACKWARD) == 3 * 8 + 5
     d = pf.descriptor([])
     with pytest.raises(pf.invalid_configuration):
         d.validate()

@@ -65,6 +65,26 @@ def real_layouts(dirs, storages, batches, lps):
     return out
 
 
+def real_md(dirs, storages, batches, lengths_list, packed):
+    """REAL domain, N-D, out of place.  packed=False: the descriptor's default strides (row-major over `lengths` in
+    both domains, as the reference's constructor sets them: descriptor.hpp:137-144); packed=True: the half spectrum
+    stored densely ([.., n_last // 2 + 1])."""
+    out = []
+    for dr, st, b, lens, sc in itertools.product(dirs, storages, batches, lengths_list, SCALARS):
+        lens = list(lens)
+        if not packed:
+            out.append(CaseParams(lens, b, "OOP", P, P, dr, st, sc, domain="real"))
+            continue
+        cl = lens[:-1] + [lens[-1] // 2 + 1]
+        fs, bs, fa, ba = [0] * len(lens), [0] * len(lens), 1, 1
+        for i in range(len(lens) - 1, -1, -1):
+            fs[i], bs[i] = fa, ba
+            fa, ba = fa * lens[i], ba * cl[i]
+        out.append(CaseParams(lens, b, "OOP", U, U, dr, st, sc, forward_strides=fs, backward_strides=bs,
+                              forward_distance=fa, backward_distance=ba, domain="real"))
+    return out
+
+
 def scaled(dr, lengths, fs, bs):
     out = []
     for n, sc in itertools.product(lengths, SCALARS):
@@ -140,6 +160,10 @@ SUITES = {
                                     [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
                                      (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
                                      (8, 5, 5, 1, 1, 0, 0)]),
+    "RealMultidimensionalTest": real_md(BOTH_DIR, STORAGES, [1, 3],
+                                        [[4, 8], [3, 5], [6, 9], [2, 3, 4], [16, 512], [64, 64, 64], [37, 8]], False),
+    "RealMultidimensionalPackedTest": real_md(BOTH_DIR, STORAGES, [1, 3],
+                                              [[4, 8], [6, 9], [2, 3, 4], [16, 512], [8, 16384], [128, 128, 128]], True),
 }
 
 CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.items() for tp in tps]

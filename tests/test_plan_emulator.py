@@ -58,6 +58,16 @@ CASES = [
                forward_distance=70000, backward_distance=16385),
     CaseParams([3 * 16384], 1, "OOP", U, U, "bwd", domain="real", forward_strides=[2], backward_strides=[1],
                forward_distance=100000, backward_distance=30000),
+    # REAL N-D: real-to-complex rows, then complex passes on the half spectrum (forward); workspace + inverse passes,
+    # then complex-to-real rows (backward)
+    CaseParams([4, 8], 3, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([4, 8], 3, "OOP", P, P, "bwd", domain="real", storage="split"),
+    CaseParams([6, 9], 2, "OOP", P, P, "bwd", domain="real", backward_scale=1.0 / 54),
+    CaseParams([2, 3, 4], 2, "OOP", P, P, "fwd", domain="real", storage="split"),
+    CaseParams([5, 4, 6], 1, "OOP", P, P, "bwd", domain="real", scalar="double"),
+    CaseParams([37, 8], 2, "OOP", P, P, "bwd", domain="real"),
+    CaseParams([8, 16384], 1, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([8, 16384], 1, "OOP", P, P, "bwd", domain="real"),
 ]
 
 
