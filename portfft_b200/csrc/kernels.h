@@ -24,6 +24,9 @@ inline size_t wi_smem_bytes(int n, size_t scalar_bytes) {
 cudaError_t launch_wi_f32(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
 cudaError_t launch_wi_f64(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
+// WORKITEM level, TMA tiles in and out (wi_tma.cu): packed interleaved rows of exactly 128 bytes (fp32 N = 16, fp64 N = 8)
+cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaStream_t stream, bool* used);
+
 // SUBGROUP level (sg.cuh, sg_f32.cu, sg_f64.cu): n = lanes * m, `lanes` (power of two <= 32) threads per transform,
 // m <= kSgMaxM points per lane, cross-lane stages through __shfl_xor_sync
 inline size_t sg_smem_bytes(int m, size_t scalar_bytes) { return (size_t)kSgBlock * (m | 1) * 2 * scalar_bytes; }

@@ -372,7 +372,7 @@ void set_radices(PassParams& p, size_t n) {
 
 // WORKITEM level (wi.cuh): one thread per transform.  Staged (coalesced tile copy through shared memory) on a side
 // whose elements lie closer together than its batches, direct (lanes along the batch) otherwise.
-bool configure_wi(PassHost& ps, bool dbl, const DeviceLimits& lim) {
+bool configure_wi(PassHost& ps, bool dbl, bool interleaved, const DeviceLimits& lim) {
   PassParams& p = ps.pp;
   if (p.n > (dbl ? kWiMaxNDouble : kWiMaxNFloat) || p.gtw_dim >= 0) return false;
   p.threads_per_fft = 1;
@@ -393,6 +393,16 @@ bool configure_wi(PassHost& ps, bool dbl, const DeviceLimits& lim) {
   ps.kernel = KERNEL_WI;
   ps.level = LEVEL_WORKITEM;
   ps.tw_n = 0;
+  // packed rows of exactly one 128-byte line, large batches: TMA tiles in and out (wi_tma.cu); the geometry above
+  // stays valid as the fallback for pointers a tensor map cannot describe
+  ps.variant = 0;
+  const char* env = std::getenv("PFFT_NO_WI_TMA");
+  bool one_dim = true;
+  for (int i = 1; i < kMaxBatchDims; ++i) one_dim = one_dim && p.nb[i] == 1;
+  if (!(env && std::atoi(env) != 0) && wi_tma_supported(p.n, dbl) && interleaved && one_dim && p.is == 1 && p.os == 1 &&
+      p.ibd[0] >= p.n && p.obd[0] >= p.n && (p.ibd[0] * (dbl ? 16 : 8)) % 16 == 0 && (p.obd[0] * (dbl ? 16 : 8)) % 16 == 0 &&
+      (p.ioff * (dbl ? 16 : 8)) % 16 == 0 && (p.ooff * (dbl ? 16 : 8)) % 16 == 0 && p.peer_dim < 0 && p.batch_total >= 4096)
+    ps.variant = 1;
   return true;
 }
 
@@ -568,7 +578,7 @@ PassHost single_pass(const DescHost& d, const DeviceLimits& lim, size_t L, long 
   ps.dst = dst;
   ps.level = LEVEL_WORKGROUP;
   const int force = force_level();
-  if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, lim)) return ps;
+  if ((force < 0 || force == LEVEL_WORKITEM) && configure_wi(ps, dbl, d.complex_storage == PFFT_INTERLEAVED_COMPLEX, lim)) return ps;
   // block-level tile kernel first where it applies (it out-runs the warp-level kernel on B200: TMA-fed,
   // persistent); the warp-level kernel takes the unit-stride sizes it does not cover
   PassHost wg = ps;

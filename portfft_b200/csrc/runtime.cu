@@ -239,9 +239,13 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
       case KERNEL_WG_GENERIC:
         e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
-      case KERNEL_WI:
-        e = d.is_double ? launch_wi_f64(p, pil, swap, ps.grid, stream) : launch_wi_f32(p, pil, swap, ps.grid, stream);
+      case KERNEL_WI: {
+        bool used = false;
+        if (ps.variant == 1) e = launch_wi_tma(p, d.is_double, swap, stream, &used);
+        if (e == cudaSuccess && !used)
+          e = d.is_double ? launch_wi_f64(p, pil, swap, ps.grid, stream) : launch_wi_f32(p, pil, swap, ps.grid, stream);
         break;
+      }
       case KERNEL_SG:
         e = d.is_double ? launch_sg_f64(p, pil, swap, ps.grid, stream) : launch_sg_f32(p, pil, swap, ps.grid, stream);
         break;

@@ -1,0 +1,225 @@
+// WORKITEM level, TMA in and out: packed interleaved transforms whose row is exactly one 128-byte line
+// (fp32 N = 16 -- the reference's `small_1d` benchmark, /root/reference/test/bench/utils/reference_dft_set.hpp:91 --
+// and fp64 N = 8).
+//
+// The general thread-per-transform kernel (wi.cuh) stages its tile with 8-byte cp.async copies and per-thread
+// global stores through a padded buffer; this variant lets the TMA engine move whole tiles in both directions:
+//   * a tile of 128 rows (16 KiB) arrives by ONE cp.async.bulk.tensor.2d load with the 128-byte swizzle, so that
+//     thread t finds 16-byte chunk c of its row at chunk position c ^ (t & 7): the 8 LDS.128 of a quarter-warp hit
+//     8 different bank groups although every thread reads its own row (no padding, static register indices);
+//   * the transform runs in registers (dft.cuh) and is written back over the row it came from;
+//   * the tile leaves by ONE cp.async.bulk.tensor.2d store from the same stage (rows beyond the batch are clipped by
+//     the tensor map), three stages per CTA: load(i+2) / compute(i) / store(i-1) overlap without any per-thread
+//     global access.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstring>
+
+#include "device_utils.cuh"
+#include "kernels.h"
+#include "launch_utils.h"
+
+namespace pfft {
+
+namespace wt {
+constexpr int kRows = 128, kStages = 3, kStageBytes = kRows * 128;
+constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 + 64;  // + alignment slack + mbarriers
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  do {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, int c0, int r0, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+          smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int r0, const void* src) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(
+                   reinterpret_cast<uint64_t>(map)),
+               "r"(c0), "r"(r0), "r"(smem_u32(src))
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int Pending>
+__device__ __forceinline__ void bulk_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(Pending) : "memory");
+}
+}  // namespace wt
+
+template <typename T, int N>
+__global__ void __launch_bounds__(wt::kRows) wi_tma_kernel(const __grid_constant__ CUtensorMap in_map,
+                                                           const __grid_constant__ CUtensorMap out_map,
+                                                           const long long batch, const bool swap, const int apply_scale,
+                                                           const T scale) {
+  static_assert(N * 2 * sizeof(T) == 128, "one transform = one 128-byte line");
+  constexpr int kChunk = 16 / sizeof(T);  // scalars per 16-byte chunk
+  extern __shared__ unsigned char smem_dyn[];
+  // the 128-byte swizzle pattern repeats every 1024 bytes: stages start on 1024-byte boundaries
+  unsigned char* base = smem_dyn + ((1024 - (wt::smem_u32(smem_dyn) & 1023)) & 1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + wt::kStages * wt::kStageBytes);
+  const int t = threadIdx.x;
+  const long long tiles = (batch + wt::kRows - 1) / wt::kRows;
+
+  if (t == 0) {
+    for (int s = 0; s < wt::kStages; ++s) wt::mbar_init(&full[s], 1);
+    wt::fence_mbar_init();
+    wt::fence_proxy_async();
+  }
+  __syncthreads();
+  if (t == 0) {
+    long long tile = blockIdx.x;
+    for (int s = 0; s < 2; ++s, tile += gridDim.x)
+      if (tile < tiles) {
+        wt::mbar_expect_tx(&full[s], wt::kStageBytes);
+        wt::tma_load_2d(base + s * wt::kStageBytes, &in_map, 0, (int)(tile * wt::kRows), &full[s]);
+      }
+  }
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int st = it % wt::kStages;
+    unsigned char* row = base + st * wt::kStageBytes + t * 128;
+    wt::mbar_wait(&full[st], (uint32_t)((it / wt::kStages) & 1));
+    cx<T> v[N];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const T* src = reinterpret_cast<const T*>(row + ((c ^ (t & 7)) << 4));
+      if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(src);
+        v[2 * c] = cx<T>{q.x, q.y};
+        v[2 * c + 1] = cx<T>{q.z, q.w};
+      } else {
+        const double2 q = *reinterpret_cast<const double2*>(src);
+        v[c] = cx<T>{q.x, q.y};
+      }
+    }
+    (void)kChunk;
+    if (swap) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = cx<T>{v[j].y, v[j].x};
+    }
+    DFT<N, T>::run(v);
+    if (apply_scale) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = cscale(v[j], scale);
+    }
+    if (swap) {
+#pragma unroll
+      for (int j = 0; j < N; ++j) v[j] = cx<T>{v[j].y, v[j].x};
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      T* dst = reinterpret_cast<T*>(row + ((c ^ (t & 7)) << 4));
+      if constexpr (sizeof(T) == 4)
+        *reinterpret_cast<float4*>(dst) = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+      else
+        *reinterpret_cast<double2*>(dst) = make_double2(v[c].x, v[c].y);
+    }
+    wt::fence_proxy_async();  // the rows written above must be visible to the TMA store
+    __syncthreads();
+    if (t == 0) {
+      wt::tma_store_2d(&out_map, 0, (int)(tile * wt::kRows), base + st * wt::kStageBytes);
+      wt::bulk_commit();
+      // the store issued one iteration ago has finished reading its stage: refill it with the tile two ahead
+      wt::bulk_wait_read<1>();
+      const long long nxt = tile + 2LL * gridDim.x;
+      if (nxt < tiles) {
+        const int sn = (it + 2) % wt::kStages;
+        wt::mbar_expect_tx(&full[sn], wt::kStageBytes);
+        wt::tma_load_2d(base + sn * wt::kStageBytes, &in_map, 0, (int)(nxt * wt::kRows), &full[sn]);
+      }
+    }
+  }
+  if (t == 0) wt::bulk_wait_read<0>();  // shared memory must outlive the last store's reads
+}
+
+typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFnW encode_fn_w() {
+  static EncodeTiledFnW fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+      f = nullptr;
+    return reinterpret_cast<EncodeTiledFnW>(f);
+  }();
+  return fn;
+}
+
+// rows of 128 bytes, `rows` of them `pitch_bytes` apart; box = 128 bytes x kRows, 128-byte swizzle
+static bool make_row_map(const void* base, bool is_double, long long rows, long long pitch_bytes, CUtensorMap* map) {
+  EncodeTiledFnW enc = encode_fn_w();
+  if (enc == nullptr || reinterpret_cast<uintptr_t>(base) % 16 != 0 || pitch_bytes % 16 != 0 || rows <= 0 ||
+      rows > (1LL << 31) - wt::kRows)
+    return false;
+  const cuuint32_t inner = is_double ? 16 : 32;
+  cuuint64_t dims[2] = {inner, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)pitch_bytes};
+  cuuint32_t box[2] = {inner, (cuuint32_t)wt::kRows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base),
+             dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+             CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool wi_tma_supported(int n, bool is_double) { return is_double ? n == 8 : n == 16; }
+
+// p: single batch dimension, unit element strides, interleaved storage (the planner checks); *used == false with
+// cudaSuccess when the pointers cannot be described by a tensor map -> the caller runs the general kernel
+cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaStream_t stream, bool* used) {
+  *used = false;
+  const size_t esz = is_double ? 16 : 8;
+  CUtensorMap in_map, out_map;
+  memset(&in_map, 0, sizeof(in_map));
+  memset(&out_map, 0, sizeof(out_map));
+  const char* in = reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz;
+  char* out = reinterpret_cast<char*>(p.out_re) + (size_t)p.ooff * esz;
+  if (!make_row_map(in, is_double, p.batch_total, p.ibd[0] * (long long)esz, &in_map)) return cudaSuccess;
+  if (!make_row_map(out, is_double, p.batch_total, p.obd[0] * (long long)esz, &out_map)) return cudaSuccess;
+  *used = true;
+  static const int sms = [] {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+    return n;
+  }();
+  if (sms <= 0) return cudaErrorLaunchOutOfResources;
+  const long long tiles = (p.batch_total + wt::kRows - 1) / wt::kRows;
+  const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);
+  cudaError_t e;
+  if (is_double) {
+    e = ensure_dynamic_smem(wi_tma_kernel<double, 8>, wt::kSmem);
+    if (e != cudaSuccess) return e;
+    wi_tma_kernel<double, 8><<<grid, wt::kRows, wt::kSmem, stream>>>(in_map, out_map, p.batch_total, swap, p.apply_scale,
+                                                                       p.scale);
+  } else {
+    e = ensure_dynamic_smem(wi_tma_kernel<float, 16>, wt::kSmem);
+    if (e != cudaSuccess) return e;
+    wi_tma_kernel<float, 16><<<grid, wt::kRows, wt::kSmem, stream>>>(in_map, out_map, p.batch_total, swap, p.apply_scale,
+                                                                       (float)p.scale);
+  }
+  return cudaGetLastError();
+}
+
+}  // namespace pfft
