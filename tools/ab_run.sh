@@ -15,11 +15,8 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run C5_new C5 X=1
-run C5_nogroups C5 PFFT_COL512_GROUPS=0
-run C4_new C4 X=1
-run L1D_new L1D X=1
-run M512_new M512 X=1
-run M512_nocube M512 PFFT_NO_CUBE512=1
-run M256 M256 X=1
-run C2 C2 X=1
+run S16_tma S16 X=1
+run S16_notma S16 PFFT_NO_WI_TMA=1
+run C5 C5 X=1
+run C3 C3 X=1
+run C1 C1 X=1
