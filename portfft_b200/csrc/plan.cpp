@@ -917,11 +917,9 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     ps.level = single ? LEVEL_WORKGROUP : LEVEL_GLOBAL;
     ps.block = 256;
     {
-      // real.cu RowLoop: a CTA covers 256 / lanes rows, lanes = power of two >= the row's element count (<= 256)
-      long long lanes = 1;
-      while (lanes < work_per_row && lanes < 256) lanes *= 2;
-      const long long rows_per_cta = 256 / lanes;
-      ps.grid = (int)std::min<long long>((rows + rows_per_cta - 1) / rows_per_cta, (long long)lim.num_sms * 32);
+      // real.cu: a CTA takes chunks of about 2048 elements = 2048 / (elements per row) consecutive rows
+      const long long chunk = work_per_row >= 2048 ? 1 : 2048 / std::max<long long>(1, work_per_row);
+      ps.grid = (int)std::min<long long>((rows + chunk - 1) / chunk, (long long)lim.num_sms * 16);
     }
     ps.tw_n = (even && (kernel == KERNEL_R2C_POST || kernel == KERNEL_C2R_PRE)) ? N : 0;
     // the scratch side of these passes is interleaved whatever the descriptor says

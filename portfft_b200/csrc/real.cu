@@ -43,22 +43,19 @@ __device__ __forceinline__ void row_bases(const PassParams& p, long long g, long
   }
 }
 
-// Work distribution shared by the four kernels: a CTA of 256 threads is a (rows x lanes) rectangle, lanes running
-// along the element index of a row (coalesced on the packed side), `lanes` = the power of two >= the row's element
-// count, at most 256.  The row bases are computed once per thread and row, not per element.
-struct RowLoop {
-  int lanes, rows_per_cta, lane, row_in_cta;
-  __device__ RowLoop(long long count) {
-    lanes = 1;
-    while (lanes < count && lanes < 256) lanes <<= 1;
-    rows_per_cta = 256 / lanes;
-    lane = threadIdx.x % lanes;
-    row_in_cta = threadIdx.x / lanes;
-  }
-};
-#define PFFT_FOR_ROWS(p, loop, g)                                                                           \
-  for (long long g = (long long)blockIdx.x * loop.rows_per_cta + loop.row_in_cta; g < p.batch_total;         \
-       g += (long long)gridDim.x * loop.rows_per_cta)
+// Work distribution shared by the four kernels: a CTA takes a chunk of consecutive rows (about 2048 elements) and
+// spreads the chunk's (row, element) pairs over its 256 threads, lanes running along the element index -- full lanes
+// for every row length (17 elements of an N = 32 row as well as 257 of an N = 512 row), 32-bit index arithmetic, and
+// no 64-bit division when the pass has a single batch dimension (row_bases).
+__device__ __forceinline__ int chunk_rows(int count) { return count >= 2048 ? 1 : 2048 / count; }
+#define PFFT_FOR_ROW_ELEMS(p, count, g, k)                                                                          \
+  for (long long g0_ = (long long)blockIdx.x * chunk_rows(count); g0_ < p.batch_total;                                \
+       g0_ += (long long)gridDim.x * chunk_rows(count))                                                               \
+    for (unsigned idx_ = threadIdx.x,                                                                                 \
+                  items_ = (unsigned)min((long long)chunk_rows(count), p.batch_total - g0_) * (unsigned)(count),      \
+                  row_ = 0, k = 0;                                                                                    \
+         idx_ < items_ && (row_ = idx_ / (unsigned)(count), k = idx_ - row_ * (unsigned)(count), true); idx_ += 256)  \
+      for (long long g = g0_ + row_, once_ = 1; once_; once_ = 0)
 
 // variant 0: out[m] = (x[2m], x[2m+1]), m < n/2;  variant 1: out[m] = (x[m], 0), m < n.  Input: REAL scalars.
 template <typename T>
@@ -66,11 +63,10 @@ __global__ void __launch_bounds__(256) real_pack_kernel(const PassParams p, cons
   const int count = variant == 0 ? p.n / 2 : p.n;
   const T* x = reinterpret_cast<const T*>(p.in_re);
   cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
-  const RowLoop loop(count);
-  PFFT_FOR_ROWS(p, loop, g) {
+  PFFT_FOR_ROW_ELEMS(p, count, g, m) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    for (int m = loop.lane; m < count; m += loop.lanes) {
+    {
       cx<T> v;
       if (variant == 0) {
         v.x = x[ib + (2LL * m) * p.is];
@@ -91,11 +87,10 @@ __global__ void __launch_bounds__(256) real_unpack_kernel(const PassParams p, co
   const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
   T* x = reinterpret_cast<T*>(p.out_re);
   const T scale = p.apply_scale ? T(p.scale) : T(1);
-  const RowLoop loop(count);
-  PFFT_FOR_ROWS(p, loop, g) {
+  PFFT_FOR_ROW_ELEMS(p, count, g, m) {
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    for (int m = loop.lane; m < count; m += loop.lanes) {
+    {
       const cx<T> v = in[ib + m];
       if (variant == 0) {
         x[ob + (2LL * m) * p.os] = v.x * scale;
@@ -115,11 +110,11 @@ __global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const
   const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
   const IoFlags fl{il, false};
   const T scale = p.apply_scale ? T(p.scale) : T(1);
-  const RowLoop loop(count);
-  PFFT_FOR_ROWS(p, loop, g) {
+  PFFT_FOR_ROW_ELEMS(p, count, g, ku) {
+    const int k = (int)ku;
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    for (int k = loop.lane; k < count; k += loop.lanes) {
+    {
       cx<T> o;
       if (variant == 0) {
         const cx<T> a = in[ib + (k == h ? 0 : k)];
@@ -144,11 +139,11 @@ __global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const 
   const int count = variant == 0 ? h : (n + 1) / 2;
   cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
   const IoFlags fl{il, false};
-  const RowLoop loop(count);
-  PFFT_FOR_ROWS(p, loop, g) {
+  PFFT_FOR_ROW_ELEMS(p, count, g, ku) {
+    const int k = (int)ku;
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    for (int k = loop.lane; k < count; k += loop.lanes) {
+    {
       cx<T> a = gload<T>(p, fl, ib + (long long)k * p.is);
       if (k == 0) a.y = T(0);  // the imaginary parts of X_0 (and X_{N/2}) do not enter a real inverse (numpy.fft.irfft)
       if (variant == 0) {
@@ -168,7 +163,7 @@ __global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const 
     }
   }
 }
-#undef PFFT_FOR_ROWS
+#undef PFFT_FOR_ROW_ELEMS
 
 template <typename K, typename... Args>
 cudaError_t launch_rows(K kern, int grid, cudaStream_t stream, Args... args) {
