@@ -393,15 +393,18 @@ bool configure_wi(PassHost& ps, bool dbl, bool interleaved, const DeviceLimits& 
   ps.kernel = KERNEL_WI;
   ps.level = LEVEL_WORKITEM;
   ps.tw_n = 0;
-  // packed rows of exactly one 128-byte line, large batches: TMA tiles in and out (wi_tma.cu); the geometry above
-  // stays valid as the fallback for pointers a tensor map cannot describe
+  // packed contiguous power-of-two rows of at most one 128-byte line, large batches: TMA tiles in and out (wi_tma.cu);
+  // the geometry above stays valid as the fallback for buffers a tensor map of whole lines cannot describe
   ps.variant = 0;
   const char* env = std::getenv("PFFT_NO_WI_TMA");
   bool one_dim = true;
   for (int i = 1; i < kMaxBatchDims; ++i) one_dim = one_dim && p.nb[i] == 1;
   if (!(env && std::atoi(env) != 0) && wi_tma_supported(p.n, dbl) && interleaved && one_dim && p.is == 1 && p.os == 1 &&
-      p.ibd[0] >= p.n && p.obd[0] >= p.n && (p.ibd[0] * (dbl ? 16 : 8)) % 16 == 0 && (p.obd[0] * (dbl ? 16 : 8)) % 16 == 0 &&
-      (p.ioff * (dbl ? 16 : 8)) % 16 == 0 && (p.ooff * (dbl ? 16 : 8)) % 16 == 0 && p.peer_dim < 0 && p.batch_total >= 4096)
+      ((p.ibd[0] == p.n && p.obd[0] == p.n) ||
+       (p.n * (dbl ? 16 : 8) == 128 && p.ibd[0] >= p.n && p.obd[0] >= p.n && (p.ibd[0] * (dbl ? 16 : 8)) % 16 == 0 &&
+        (p.obd[0] * (dbl ? 16 : 8)) % 16 == 0)) &&
+      (p.ioff * (dbl ? 16 : 8)) % 16 == 0 && (p.ooff * (dbl ? 16 : 8)) % 16 == 0 && p.peer_dim < 0 &&
+      p.batch_total * p.n >= 65536)
     ps.variant = 1;
   return true;
 }

@@ -1,13 +1,14 @@
-// WORKITEM level, TMA in and out: packed interleaved transforms whose row is exactly one 128-byte line
-// (fp32 N = 16 -- the reference's `small_1d` benchmark, /root/reference/test/bench/utils/reference_dft_set.hpp:91 --
-// and fp64 N = 8).
+// WORKITEM level, TMA in and out: packed, contiguous, interleaved power-of-two transforms of at most one 128-byte line
+// (fp32 N = 2, 4, 8, 16 -- N = 16 is the reference's `small_1d` benchmark,
+// /root/reference/test/bench/utils/reference_dft_set.hpp:91 -- and fp64 N = 2, 4, 8).  One thread owns one 128-byte
+// line = 128 / (N * sizeof(complex)) whole transforms.
 //
 // The general thread-per-transform kernel (wi.cuh) stages its tile with 8-byte cp.async copies and per-thread
 // global stores through a padded buffer; this variant lets the TMA engine move whole tiles in both directions:
-//   * a tile of 128 rows (16 KiB) arrives by ONE cp.async.bulk.tensor.2d load with the 128-byte swizzle, so that
-//     thread t finds 16-byte chunk c of its row at chunk position c ^ (t & 7): the 8 LDS.128 of a quarter-warp hit
-//     8 different bank groups although every thread reads its own row (no padding, static register indices);
-//   * the transform runs in registers (dft.cuh) and is written back over the row it came from;
+//   * a tile of 128 lines (16 KiB) arrives by ONE cp.async.bulk.tensor.2d load with the 128-byte swizzle, so that
+//     thread t finds 16-byte chunk c of its line at chunk position c ^ (t & 7): the 8 LDS.128 of a quarter-warp hit
+//     8 different bank groups although every thread reads its own line (no padding, static register indices);
+//   * the transforms run in registers (dft.cuh) and are written back over the line they came from;
 //   * the tile leaves by ONE cp.async.bulk.tensor.2d store from the same stage (rows beyond the batch are clipped by
 //     the tensor map), three stages per CTA: load(i+2) / compute(i) / store(i-1) overlap without any per-thread
 //     global access.
@@ -70,8 +71,9 @@ __global__ void __launch_bounds__(wt::kRows) wi_tma_kernel(const __grid_constant
                                                            const __grid_constant__ CUtensorMap out_map,
                                                            const long long batch, const bool swap, const int apply_scale,
                                                            const T scale) {
-  static_assert(N * 2 * sizeof(T) == 128, "one transform = one 128-byte line");
-  constexpr int kChunk = 16 / sizeof(T);  // scalars per 16-byte chunk
+  // `batch` counts 128-byte lines; every line holds PER whole transforms
+  constexpr int PER = 128 / (N * 2 * (int)sizeof(T)), NV = 128 / (2 * (int)sizeof(T));
+  static_assert(PER >= 1 && PER * N * 2 * sizeof(T) == 128, "whole transforms per 128-byte line");
   extern __shared__ unsigned char smem_dyn[];
   // the 128-byte swizzle pattern repeats every 1024 bytes: stages start on 1024-byte boundaries
   unsigned char* base = smem_dyn + ((1024 - (wt::smem_u32(smem_dyn) & 1023)) & 1023);
@@ -98,7 +100,7 @@ __global__ void __launch_bounds__(wt::kRows) wi_tma_kernel(const __grid_constant
     const int st = it % wt::kStages;
     unsigned char* row = base + st * wt::kStageBytes + t * 128;
     wt::mbar_wait(&full[st], (uint32_t)((it / wt::kStages) & 1));
-    cx<T> v[N];
+    cx<T> v[NV];
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
       const T* src = reinterpret_cast<const T*>(row + ((c ^ (t & 7)) << 4));
@@ -111,19 +113,19 @@ __global__ void __launch_bounds__(wt::kRows) wi_tma_kernel(const __grid_constant
         v[c] = cx<T>{q.x, q.y};
       }
     }
-    (void)kChunk;
     if (swap) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = cx<T>{v[j].y, v[j].x};
+      for (int j = 0; j < NV; ++j) v[j] = cx<T>{v[j].y, v[j].x};
     }
-    DFT<N, T>::run(v);
+#pragma unroll
+    for (int i = 0; i < PER; ++i) DFT<N, T>::run(v + i * N);
     if (apply_scale) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = cscale(v[j], scale);
+      for (int j = 0; j < NV; ++j) v[j] = cscale(v[j], scale);
     }
     if (swap) {
 #pragma unroll
-      for (int j = 0; j < N; ++j) v[j] = cx<T>{v[j].y, v[j].x};
+      for (int j = 0; j < NV; ++j) v[j] = cx<T>{v[j].y, v[j].x};
     }
 #pragma unroll
     for (int c = 0; c < 8; ++c) {
@@ -183,20 +185,37 @@ static bool make_row_map(const void* base, bool is_double, long long rows, long 
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-bool wi_tma_supported(int n, bool is_double) { return is_double ? n == 8 : n == 16; }
+bool wi_tma_supported(int n, bool is_double) {
+  return is_double ? (n == 2 || n == 4 || n == 8) : (n == 2 || n == 4 || n == 8 || n == 16);
+}
 
-// p: single batch dimension, unit element strides, interleaved storage (the planner checks); *used == false with
-// cudaSuccess when the pointers cannot be described by a tensor map -> the caller runs the general kernel
+template <typename T, int N>
+static cudaError_t launch_wi_tma_n(const CUtensorMap& in_map, const CUtensorMap& out_map, long long lines, bool swap,
+                                   const PassParams& p, int grid, cudaStream_t stream) {
+  cudaError_t e = ensure_dynamic_smem(wi_tma_kernel<T, N>, wt::kSmem);
+  if (e != cudaSuccess) return e;
+  wi_tma_kernel<T, N><<<grid, wt::kRows, wt::kSmem, stream>>>(in_map, out_map, lines, swap, p.apply_scale, (T)p.scale);
+  return cudaGetLastError();
+}
+
+// p: single batch dimension, contiguous transforms (distance == n), unit element strides, interleaved storage (the
+// planner checks); *used == false with cudaSuccess when the buffers cannot be described as whole 128-byte lines ->
+// the caller runs the general kernel
 cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaStream_t stream, bool* used) {
   *used = false;
   const size_t esz = is_double ? 16 : 8;
+  // one transform per line: rows may be padded (any 16-byte multiple pitch); several per line: contiguous buffers only
+  const bool one_per_line = p.n * (long long)esz == 128;
+  if (!one_per_line && (p.ibd[0] != p.n || p.obd[0] != p.n || (p.batch_total * p.n * (long long)esz) % 128 != 0))
+    return cudaSuccess;
+  const long long lines = one_per_line ? p.batch_total : p.batch_total * p.n * (long long)esz / 128;
   CUtensorMap in_map, out_map;
   memset(&in_map, 0, sizeof(in_map));
   memset(&out_map, 0, sizeof(out_map));
   const char* in = reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz;
   char* out = reinterpret_cast<char*>(p.out_re) + (size_t)p.ooff * esz;
-  if (!make_row_map(in, is_double, p.batch_total, p.ibd[0] * (long long)esz, &in_map)) return cudaSuccess;
-  if (!make_row_map(out, is_double, p.batch_total, p.obd[0] * (long long)esz, &out_map)) return cudaSuccess;
+  if (!make_row_map(in, is_double, lines, one_per_line ? p.ibd[0] * (long long)esz : 128, &in_map)) return cudaSuccess;
+  if (!make_row_map(out, is_double, lines, one_per_line ? p.obd[0] * (long long)esz : 128, &out_map)) return cudaSuccess;
   *used = true;
   static const int sms = [] {
     int dev = 0, n = 0;
@@ -205,21 +224,23 @@ cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaSt
     return n;
   }();
   if (sms <= 0) return cudaErrorLaunchOutOfResources;
-  const long long tiles = (p.batch_total + wt::kRows - 1) / wt::kRows;
+  const long long tiles = (lines + wt::kRows - 1) / wt::kRows;
   const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);
-  cudaError_t e;
   if (is_double) {
-    e = ensure_dynamic_smem(wi_tma_kernel<double, 8>, wt::kSmem);
-    if (e != cudaSuccess) return e;
-    wi_tma_kernel<double, 8><<<grid, wt::kRows, wt::kSmem, stream>>>(in_map, out_map, p.batch_total, swap, p.apply_scale,
-                                                                       p.scale);
+    switch (p.n) {
+      case 2: return launch_wi_tma_n<double, 2>(in_map, out_map, lines, swap, p, grid, stream);
+      case 4: return launch_wi_tma_n<double, 4>(in_map, out_map, lines, swap, p, grid, stream);
+      case 8: return launch_wi_tma_n<double, 8>(in_map, out_map, lines, swap, p, grid, stream);
+    }
   } else {
-    e = ensure_dynamic_smem(wi_tma_kernel<float, 16>, wt::kSmem);
-    if (e != cudaSuccess) return e;
-    wi_tma_kernel<float, 16><<<grid, wt::kRows, wt::kSmem, stream>>>(in_map, out_map, p.batch_total, swap, p.apply_scale,
-                                                                       (float)p.scale);
+    switch (p.n) {
+      case 2: return launch_wi_tma_n<float, 2>(in_map, out_map, lines, swap, p, grid, stream);
+      case 4: return launch_wi_tma_n<float, 4>(in_map, out_map, lines, swap, p, grid, stream);
+      case 8: return launch_wi_tma_n<float, 8>(in_map, out_map, lines, swap, p, grid, stream);
+      case 16: return launch_wi_tma_n<float, 16>(in_map, out_map, lines, swap, p, grid, stream);
+    }
   }
-  return cudaGetLastError();
+  return cudaErrorInvalidValue;
 }
 
 }  // namespace pfft

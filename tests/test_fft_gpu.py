@@ -161,7 +161,9 @@ SUITES = {
                                      (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
                                      (8, 5, 5, 1, 1, 0, 0)]),
     # thread-level kernel with TMA tiles in and out (rows of exactly 128 bytes: fp32 N = 16, fp64 N = 8; large batches)
-    "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000], [8, 16]),
+    "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000, 65536],
+                             [2, 4, 8, 16]),
+    "workItemTmaPaddedRowsTest": layouts(["OOP"], BOTH_DIR, ["interleaved"], [5000], [(16, 1, 1, 20, 18), (8, 1, 1, 8, 10)]),
     "workItemTmaOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [5000], [16], [(0, 2), (6, 0), (3, 5)]),
     "RealMultidimensionalTest": real_md(BOTH_DIR, STORAGES, [1, 3],
                                         [[4, 8], [3, 5], [6, 9], [2, 3, 4], [16, 512], [64, 64, 64], [37, 8]], False),
