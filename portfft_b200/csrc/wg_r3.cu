@@ -13,6 +13,10 @@
 //   * two exchanges through ping-pong shared-memory buffers padded by one element per R0 (index i -> i + i/R0): with
 //     the radix-R0 scatter of pass 0 this makes every access pattern of all three passes (nearly) conflict free for
 //     radix 10 as well as for radix 16 -- the generic kernel's power-of-two padding gives 57% conflicts at N = 1000;
+//   * the inputs of the CTA's NEXT group of transforms are loaded into registers before the current group is
+//     transformed (one butterfly per thread in pass 0), so the global-load latency -- strided 4-byte loads for C3 --
+//     is covered by three passes of arithmetic instead of stalling pass 0 (ncu: long_scoreboard was the top stall);
+//   * storage (interleaved / split) and the backward swap are template parameters: no per-element branches;
 //   * backward = (re <-> im) swap, scale fused into the store; two block barriers per transform.
 #include "device_utils.cuh"
 #include "io.cuh"
@@ -35,15 +39,16 @@ struct R3Cfg {
   __host__ __device__ static constexpr int pad(int i) { return i + i / R0; }
 };
 
-template <typename T, int R0, int R1, int R2>
-__global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p, const bool il, const bool swap) {
+template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
+__global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
   using Cfg = R3Cfg<R0, R1, R2>;
   constexpr int N = Cfg::N, TPF = Cfg::TPF, PITCH = Cfg::PITCH;
+  constexpr bool PREFETCH = N / R0 == TPF;  // one pass-0 butterfly per thread: its inputs can be fetched a group ahead
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int F = p.ffts_per_block;
   cx<T>* buf0 = reinterpret_cast<cx<T>*>(smem_raw);
   cx<T>* buf1 = buf0 + (size_t)F * PITCH;
-  const IoFlags fl{il, swap};
+  const IoFlags fl{IL, SWAP};
   const int f = threadIdx.x / TPF, t = threadIdx.x - f * TPF;
   const bool one_dim = single_batch_dim(p);
   const T scale = T(p.scale);
@@ -60,13 +65,39 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p, const bo
     for (int r = 1; r < R2; ++r) tw2[r] = ldg_cx<T>(p.tw, (long long)(t % (R0 * R1)) * r);
   }
 
-  for (long long g0 = (long long)blockIdx.x * F; g0 < p.batch_total; g0 += (long long)gridDim.x * F) {
-    const bool active = g0 + f < p.batch_total;
-    long long ib = 0, ob = 0;
-    int peer = -1;
-    if (active) batch_bases(p, one_dim, g0 + f, ib, ob, peer);
+  const long long gstride = (long long)gridDim.x * F;
+  long long g0 = (long long)blockIdx.x * F;
+  bool active = g0 + f < p.batch_total;
+  long long ib = 0, ob = 0;
+  int peer = -1;
+  if (active) batch_bases(p, one_dim, g0 + f, ib, ob, peer);
+  cx<T> nxt[PREFETCH ? R0 : 1];
+  if (PREFETCH && active) {
+#pragma unroll
+    for (int r = 0; r < R0; ++r) nxt[r] = gload<T>(p, fl, ib + (long long)(t + r * (N / R0)) * p.is);
+  }
+  for (; g0 < p.batch_total; g0 += gstride) {
+    const bool cur_active = active;
+    const long long cur_ob = ob;
+    const int cur_peer = peer;
     // ---- pass 0: radix R0, global -> buf0 ---------------------------------------------------------------------
-    if (active) {
+    if (PREFETCH) {
+      cx<T> v[R0];
+#pragma unroll
+      for (int r = 0; r < R0; ++r) v[r] = nxt[r];
+      // inputs of the next group: in flight while this group runs its three passes
+      active = g0 + gstride + f < p.batch_total;
+      if (active) {
+        batch_bases(p, one_dim, g0 + gstride + f, ib, ob, peer);
+#pragma unroll
+        for (int r = 0; r < R0; ++r) nxt[r] = gload<T>(p, fl, ib + (long long)(t + r * (N / R0)) * p.is);
+      }
+      if (cur_active) {
+        DFT<R0, T>::run(v);
+#pragma unroll
+        for (int r = 0; r < R0; ++r) b0[Cfg::pad(t * R0 + r)] = v[r];
+      }
+    } else if (cur_active) {
 #pragma unroll 1
       for (int j = t; j < N / R0; j += TPF) {
         cx<T> v[R0];
@@ -79,7 +110,7 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p, const bo
     }
     __syncthreads();
     // ---- pass 1: radix R1, buf0 -> buf1 -----------------------------------------------------------------------
-    if (active) {
+    if (cur_active) {
 #pragma unroll 1
       for (int j = t; j < N / R1; j += TPF) {
         const int k = j % R0;
@@ -96,7 +127,7 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p, const bo
     }
     __syncthreads();
     // ---- pass 2: radix R2, buf1 -> global ---------------------------------------------------------------------
-    if (active) {
+    if (cur_active) {
 #pragma unroll 1
       for (int j = t; j < N / R2; j += TPF) {
         const int k = j % (R0 * R1);
@@ -111,22 +142,33 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p, const bo
         for (int r = 0; r < R2; ++r) {
           cx<T> o = v[r];
           if (p.apply_scale) o = cscale(o, scale);
-          gstore<T>(p, fl, ob + (long long)(ob2 + r * (R0 * R1)) * p.os, o, peer);
+          gstore<T>(p, fl, cur_ob + (long long)(ob2 + r * (R0 * R1)) * p.os, o, cur_peer);
         }
       }
+    }
+    if (!PREFETCH) {
+      active = g0 + gstride + f < p.batch_total;
+      if (active) batch_bases(p, one_dim, g0 + gstride + f, ib, ob, peer);
     }
   }
 }
 
-template <typename T, int R0, int R1, int R2>
-static cudaError_t launch_r3_t(const PassParams& p, bool il, bool swap, int grid, cudaStream_t stream) {
+template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
+static cudaError_t launch_r3_v(const PassParams& p, int grid, cudaStream_t stream) {
   using Cfg = R3Cfg<R0, R1, R2>;
   const size_t smem = (size_t)2 * p.ffts_per_block * Cfg::PITCH * sizeof(cx<T>);
-  auto kern = wg_r3_kernel<T, R0, R1, R2>;
+  auto kern = wg_r3_kernel<T, R0, R1, R2, IL, SWAP>;
   cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
-  kern<<<grid, p.ffts_per_block * Cfg::TPF, smem, stream>>>(p, il, swap);
+  kern<<<grid, p.ffts_per_block * Cfg::TPF, smem, stream>>>(p);
   return cudaGetLastError();
+}
+
+template <typename T, int R0, int R1, int R2>
+static cudaError_t launch_r3_t(const PassParams& p, bool il, bool swap, int grid, cudaStream_t stream) {
+  if (!il) return launch_r3_v<T, R0, R1, R2, false, false>(p, grid, stream);
+  return swap ? launch_r3_v<T, R0, R1, R2, true, true>(p, grid, stream)
+              : launch_r3_v<T, R0, R1, R2, true, false>(p, grid, stream);
 }
 
 #define PFFT_R3_LIST(X) \

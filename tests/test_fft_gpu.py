@@ -160,6 +160,12 @@ SUITES = {
                                     [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
                                      (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
                                      (8, 5, 5, 1, 1, 0, 0)]),
+    # BASELINE config C3's kernel (three compile-time radices, N = 1000) on every layout family and C3's own layout
+    "ThreeRadixTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3, 1031], [1000]),
+    "ThreeRadixC3LayoutTest": [CaseParams([1000], b, "OOP", U, U, dr, "split", sc, forward_strides=[2],
+                                          backward_strides=[1], forward_distance=2048, backward_distance=1024,
+                                          forward_offset=7, backward_offset=3, backward_scale=1e-3)
+                               for b in (5, 1500) for dr in BOTH_DIR for sc in SCALARS],
     # thread-level kernel with TMA tiles in and out (rows of exactly 128 bytes: fp32 N = 16, fp64 N = 8; large batches)
     "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000, 65536],
                              [2, 4, 8, 16]),
