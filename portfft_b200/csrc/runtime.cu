@@ -65,6 +65,10 @@ struct pfft_plan {
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_up, chunk_done;
   std::map<size_t, pfft_plan*> child;
+  // L2-resident execution of multi-pass plans: the batch is processed in chunks of `l2_chunk` transforms (0: off),
+  // each chunk by a sub-batch plan whose small workspace stays in the 126 MB L2 between its passes
+  size_t l2_chunk = 0;
+  bool allow_l2_chunk = true;
 
   ~pfft_plan() {
     for (auto& kv : child) delete kv.second;
@@ -132,12 +136,14 @@ static void commit_device(pfft_plan* plan) {
   else
     build_tables<float>(plan);
   const size_t scalar = plan->host.desc.is_double ? 8 : 4;
-  plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
-  if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
-  plan->scratch2_bytes = plan->host.scratch2_elems * 2 * scalar;
-  if (plan->scratch2_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch2, plan->scratch2_bytes));
-  plan->scratch3_bytes = plan->host.scratch3_elems * 2 * scalar;
-  if (plan->scratch3_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch3, plan->scratch3_bytes));
+  if (plan->l2_chunk == 0) {  // (chunked plans run through their sub-batch plans and own no workspace themselves)
+    plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
+    if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
+    plan->scratch2_bytes = plan->host.scratch2_elems * 2 * scalar;
+    if (plan->scratch2_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch2, plan->scratch2_bytes));
+    plan->scratch3_bytes = plan->host.scratch3_elems * 2 * scalar;
+    if (plan->scratch3_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch3, plan->scratch3_bytes));
+  }
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
       ps.pp.tw = ps.tw_n > 0 ? plan->tw[ps.tw_n] : nullptr;
@@ -159,8 +165,40 @@ struct PeerTable {
   void* const* im = nullptr;
 };
 
+static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, bool allow_l2_chunk = true);
 static void execute(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
-                    cudaStream_t stream, const PeerTable* peers = nullptr) {
+                    cudaStream_t stream, const PeerTable* peers = nullptr);
+
+// L2-resident execution (see choose_l2_chunk): sub-batch plans over consecutive batch ranges
+static void execute_chunked(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
+                            cudaStream_t stream) {
+  const DescHost& d = plan->host.desc;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  const int odir = dir == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
+  const size_t scalar = d.is_double ? 8 : 4;
+  // bytes between consecutive transforms, per plane, on each side (REAL: the forward domain counts real scalars)
+  const size_t unit_in = (d.is_real() && dir == PFFT_FORWARD) ? scalar : (il ? 2 * scalar : scalar);
+  const size_t unit_out = (d.is_real() && dir == PFFT_BACKWARD) ? scalar : (il ? 2 * scalar : scalar);
+  const size_t step_in = d.distance(dir) * unit_in, step_out = d.distance(odir) * unit_out;
+  const size_t batch = d.number_of_transforms;
+  for (size_t b0 = 0; b0 < batch; b0 += plan->l2_chunk) {
+    const size_t nb = std::min(plan->l2_chunk, batch - b0);
+    pfft_plan*& sub = plan->child[nb];
+    if (sub == nullptr) {
+      DescHost dc = d;
+      dc.number_of_transforms = nb;
+      sub = make_plan(dc, plan->device, plan->stream, false);
+    }
+    const char* i0 = (const char*)in + b0 * step_in;
+    const char* i1 = in_imag ? (const char*)in_imag + b0 * step_in : nullptr;
+    char* o0 = (char*)out + b0 * step_out;
+    char* o1 = out_imag ? (char*)out_imag + b0 * step_out : nullptr;
+    execute(sub, dir, i0, i1, o0, o1, stream, nullptr);
+  }
+}
+
+static void execute(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
+                    cudaStream_t stream, const PeerTable* peers) {
   const DescHost& d = plan->host.desc;
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
   const bool real = d.is_real();
@@ -177,6 +215,10 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   if ((!in_cplx && in_imag != nullptr) || (!out_cplx && out_imag != nullptr))
     throw PlanError(PFFT_INVALID_CONFIGURATION, "the real side of a REAL-domain transform is a single scalar array");
   if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
+  if (plan->l2_chunk != 0 && peers == nullptr) {
+    execute_chunked(plan, dir, in, in_imag, out, out_imag, stream);
+    return;
+  }
   const size_t scalar = d.is_double ? 8 : 4;
   // backward = forward transform of the (re <-> im)-swapped data, swapped back: free for split storage
   // (REAL plans never swap: c2r_pre writes its rows index-reversed instead, real.cu)
@@ -288,7 +330,33 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   }
 }
 
-static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream) {
+// ---------------------------------------------------------------------------------------------------------------
+// L2-resident chunking.  A plan with k > 1 passes moves its intermediate results through a workspace; run over the
+// whole batch at once, every pass streams the full data set through HBM (k round trips).  When the per-transform
+// workspace is small against the 126 MB L2, the batch is instead cut into chunks whose workspace (a few tens of MB,
+// the SAME addresses for every chunk) stays L2 resident: each chunk runs all its passes back to back, the
+// intermediate writes are absorbed and re-read by L2, and HBM sees one read of the input and one write of the output.
+// Chunks are sub-batch plans on the base pointers advanced by b0 * distance (the descriptor's own addressing:
+// /root/reference/src/portfft/descriptor.hpp:91-92), exactly like the host pipeline below.
+// ---------------------------------------------------------------------------------------------------------------
+static void choose_l2_chunk(pfft_plan* plan) {
+  const PlanHost& h = plan->host;
+  const DescHost& d = h.desc;
+  plan->l2_chunk = 0;
+  if (!plan->allow_l2_chunk || !d.extra.empty() || d.number_of_transforms < 2) return;
+  const size_t ws = h.scratch_elems + h.scratch2_elems + h.scratch3_elems;
+  if (ws == 0) return;
+  const char* env = std::getenv("PFFT_L2_CHUNK_BYTES");
+  const size_t budget = env ? (size_t)std::atoll(env) : ((size_t)32 << 20);
+  if (budget == 0) return;
+  const size_t per = ws * 2 * (d.is_double ? 8 : 4) / d.number_of_transforms;  // workspace bytes per transform
+  if (per == 0 || per > budget) return;                                        // one transform alone outgrows L2
+  const size_t chunk = budget / per;
+  if (chunk >= d.number_of_transforms) return;  // the whole batch fits: nothing to cut
+  plan->l2_chunk = chunk;
+}
+
+static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, bool allow_l2_chunk) {
   PFFT_CUDA_CHECK(cudaSetDevice(device));
   cudaDeviceProp prop;
   PFFT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
@@ -299,6 +367,8 @@ static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream) 
   plan->host = build_plan(d, lim);
   plan->device = device;
   plan->stream = stream;
+  plan->allow_l2_chunk = allow_l2_chunk;
+  choose_l2_chunk(plan.get());
   commit_device(plan.get());
   return plan.release();
 }
@@ -590,7 +660,14 @@ pfft_status pfft_destroy(pfft_plan* plan) {
   });
 }
 
-size_t pfft_workspace_bytes(const pfft_plan* plan) { return plan ? plan->scratch_bytes : 0; }
+size_t pfft_workspace_bytes(const pfft_plan* plan) {
+  if (!plan) return 0;
+  size_t total = plan->scratch_bytes + plan->scratch2_bytes + plan->scratch3_bytes;
+  for (const auto& kv : plan->child) total += pfft_workspace_bytes(kv.second);
+  return total;
+}
+
+size_t pfft_plan_l2_chunk(const pfft_plan* plan) { return plan ? plan->l2_chunk : 0; }
 
 int pfft_plan_level(const pfft_plan* plan, size_t dimension) {
   if (!plan || dimension >= plan->host.dim_level.size()) return -1;
