@@ -143,7 +143,7 @@ pfft_status pfft_destroy(pfft_plan* plan);
 size_t pfft_workspace_bytes(const pfft_plan* plan);
 /* Multi-pass plans whose per-transform workspace is small against the L2 run the batch in chunks of this many
  * transforms, so that the intermediate results stay L2 resident between the passes (0: the plan runs in one piece). */
-size_t pfft_plan_l2_chunk(const pfft_plan* plan);
+size_t pfft_plan_chunk_transforms(const pfft_plan* plan);
 int pfft_plan_level(const pfft_plan* plan, size_t dimension); /* PFFT_LEVEL_* of one dimension, -1 if out of range */
 size_t pfft_plan_num_launches(const pfft_plan* plan, int direction); /* kernel launches per compute call */
 unsigned long long pfft_total_launches(void);                        /* kernels launched by this process so far */

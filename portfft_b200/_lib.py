@@ -57,7 +57,7 @@ SYMBOLS = {
     "pfft_compute_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfft_destroy": (c_int, [c_void_p]),
     "pfft_workspace_bytes": (c_size_t, [c_void_p]),
-    "pfft_plan_l2_chunk": (c_size_t, [c_void_p]),
+    "pfft_plan_chunk_transforms": (c_size_t, [c_void_p]),
     "pfft_plan_level": (c_int, [c_void_p, c_size_t]),
     "pfft_plan_num_launches": (c_size_t, [c_void_p, c_int]),
     "pfft_total_launches": (c_ulonglong, []),

@@ -322,7 +322,7 @@ class committed_descriptor:
 
     def l2_chunk(self) -> int:
         """Transforms per L2-resident chunk (0: the plan runs over the whole batch in one piece)."""
-        return int(_lib.load().pfft_plan_l2_chunk(self._handle))
+        return int(_lib.load().pfft_plan_chunk_transforms(self._handle))
 
     def num_launches(self, d=direction.FORWARD) -> int:
         return int(_lib.load().pfft_plan_num_launches(self._handle, int(d)))

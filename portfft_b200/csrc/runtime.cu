@@ -69,8 +69,16 @@ struct pfft_plan {
   // each chunk by a sub-batch plan whose small workspace stays in the 126 MB L2 between its passes
   size_t l2_chunk = 0;
   bool allow_l2_chunk = true;
+  // N-D variant (packed layouts): the passes along dimensions 1..D-1 run L2 resident on chunks of `nd_chunk`
+  // dimension-0 planes (sub-plans `child`), then ONE pass along dimension 0 over everything (`nd_outer`)
+  size_t nd_chunk = 0;
+  std::map<size_t, pfft_plan*> nd_child;     // planes per chunk -> sub-plan over dimensions 1..D-1
+  pfft_plan* nd_outer[2] = {nullptr, nullptr};  // [direction]: the pass along dimension 0, in place on the output
 
   ~pfft_plan() {
+    delete nd_outer[0];
+    delete nd_outer[1];
+    for (auto& kv : nd_child) delete kv.second;
     for (auto& kv : child) delete kv.second;
     for (cudaEvent_t e : chunk_up) cudaEventDestroy(e);
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
@@ -136,7 +144,7 @@ static void commit_device(pfft_plan* plan) {
   else
     build_tables<float>(plan);
   const size_t scalar = plan->host.desc.is_double ? 8 : 4;
-  if (plan->l2_chunk == 0) {  // (chunked plans run through their sub-batch plans and own no workspace themselves)
+  if (plan->l2_chunk == 0 && plan->nd_chunk == 0) {  // (chunked plans run through their sub-plans and own no workspace)
     plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
     if (plan->scratch_bytes) PFFT_CUDA_CHECK(cudaMalloc(&plan->scratch, plan->scratch_bytes));
     plan->scratch2_bytes = plan->host.scratch2_elems * 2 * scalar;
@@ -197,6 +205,56 @@ static void execute_chunked(pfft_plan* plan, int dir, const void* in, const void
   }
 }
 
+// N-D, packed layouts: planes of dimension 0 (and of the batch) are independent for every pass except the one along
+// dimension 0.  Chunks of planes run those passes back to back (the first reads the user's input, the others work in
+// place on the output planes, which stay in L2 meanwhile); one strided pass along dimension 0 finishes in place.
+// 512^3: HBM sees 2 round trips instead of 3.
+static void execute_nd_chunked(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
+                               cudaStream_t stream) {
+  const DescHost& d = plan->host.desc;
+  const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  const size_t scalar = d.is_double ? 8 : 4;
+  const size_t unit = il ? 2 * scalar : scalar;
+  size_t plane = 1;
+  for (size_t i = 1; i < d.lengths.size(); ++i) plane *= d.lengths[i];
+  const size_t planes = d.number_of_transforms * d.lengths[0];
+  // (the sub-plans carry the descriptor's offsets themselves)
+  for (size_t p0 = 0; p0 < planes; p0 += plan->nd_chunk) {
+    const size_t np = std::min(plan->nd_chunk, planes - p0);
+    pfft_plan*& sub = plan->nd_child[np];
+    if (sub == nullptr) {
+      DescHost dc = d;
+      dc.lengths.assign(d.lengths.begin() + 1, d.lengths.end());
+      dc.forward_strides.assign(d.forward_strides.begin() + 1, d.forward_strides.end());
+      dc.backward_strides.assign(d.backward_strides.begin() + 1, d.backward_strides.end());
+      dc.number_of_transforms = np;
+      dc.forward_distance = dc.backward_distance = plane;
+      dc.forward_scale = dc.backward_scale = 1.0;  // the scale belongs to the last pass (nd_outer)
+      sub = make_plan(dc, plan->device, plan->stream, false);
+    }
+    const size_t step = p0 * plane * unit;
+    execute(sub, dir, (const char*)in + step, in_imag ? (const char*)in_imag + step : nullptr, (char*)out + step,
+            out_imag ? (char*)out_imag + step : nullptr, stream, nullptr);
+  }
+  pfft_plan*& outer = plan->nd_outer[dir == PFFT_FORWARD ? 0 : 1];
+  if (outer == nullptr) {
+    DescHost dc = d;
+    dc.lengths.assign(1, d.lengths[0]);
+    dc.forward_strides.assign(1, plane);
+    dc.backward_strides.assign(1, plane);
+    dc.number_of_transforms = plane;
+    dc.forward_distance = dc.backward_distance = 1;
+    dc.placement = PFFT_IN_PLACE;
+    // in place on the OUTPUT buffer in either direction: both domains of this sub-plan carry the output's offset
+    dc.forward_offset = dc.backward_offset = d.offset(dir == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD);
+    outer = make_plan(dc, plan->device, plan->stream, false);
+  }
+  const size_t total = d.lengths[0] * plane * unit;
+  for (size_t b = 0; b < d.number_of_transforms; ++b)
+    execute(outer, dir, (const char*)out + b * total, out_imag ? (const char*)out_imag + b * total : nullptr,
+            (char*)out + b * total, out_imag ? (char*)out_imag + b * total : nullptr, stream, nullptr);
+}
+
 static void execute(pfft_plan* plan, int dir, const void* in, const void* in_imag, void* out, void* out_imag,
                     cudaStream_t stream, const PeerTable* peers) {
   const DescHost& d = plan->host.desc;
@@ -217,6 +275,10 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
   if (plan->l2_chunk != 0 && peers == nullptr) {
     execute_chunked(plan, dir, in, in_imag, out, out_imag, stream);
+    return;
+  }
+  if (plan->nd_chunk != 0 && peers == nullptr) {
+    execute_nd_chunked(plan, dir, in, in_imag, out, out_imag, stream);
     return;
   }
   const size_t scalar = d.is_double ? 8 : 4;
@@ -356,6 +418,27 @@ static void choose_l2_chunk(pfft_plan* plan) {
   plan->l2_chunk = chunk;
 }
 
+static void choose_nd_chunk(pfft_plan* plan) {
+  const DescHost& d = plan->host.desc;
+  plan->nd_chunk = 0;
+  if (!plan->allow_l2_chunk || plan->l2_chunk != 0 || !d.extra.empty() || d.is_real() || d.lengths.size() < 2 ||
+      d.lengths[0] < 2)
+    return;
+  if (get_layout(d, PFFT_FORWARD) != PFFT_LAYOUT_PACKED || get_layout(d, PFFT_BACKWARD) != PFFT_LAYOUT_PACKED) return;
+  if (d.forward_offset != d.backward_offset && d.placement == PFFT_IN_PLACE) return;
+  const char* env = std::getenv("PFFT_L2_CHUNK_BYTES");
+  const size_t budget = env ? (size_t)std::atoll(env) : ((size_t)32 << 20);
+  if (budget == 0) return;
+  size_t plane = 1;
+  for (size_t i = 1; i < d.lengths.size(); ++i) plane *= d.lengths[i];
+  const size_t plane_bytes = plane * 2 * (d.is_double ? 8 : 4);
+  const size_t planes = d.number_of_transforms * d.lengths[0];
+  const size_t chunk = budget / plane_bytes;
+  // worth it only when the whole array does not fit L2 anyway and a chunk holds at least two planes
+  if (chunk < 2 || chunk >= planes || planes * plane_bytes <= ((size_t)96 << 20)) return;
+  plan->nd_chunk = chunk;
+}
+
 static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, bool allow_l2_chunk) {
   PFFT_CUDA_CHECK(cudaSetDevice(device));
   cudaDeviceProp prop;
@@ -369,6 +452,7 @@ static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, 
   plan->stream = stream;
   plan->allow_l2_chunk = allow_l2_chunk;
   choose_l2_chunk(plan.get());
+  choose_nd_chunk(plan.get());
   commit_device(plan.get());
   return plan.release();
 }
@@ -664,10 +748,13 @@ size_t pfft_workspace_bytes(const pfft_plan* plan) {
   if (!plan) return 0;
   size_t total = plan->scratch_bytes + plan->scratch2_bytes + plan->scratch3_bytes;
   for (const auto& kv : plan->child) total += pfft_workspace_bytes(kv.second);
+  for (const auto& kv : plan->nd_child) total += pfft_workspace_bytes(kv.second);
+  for (const pfft_plan* o : plan->nd_outer)
+    if (o) total += pfft_workspace_bytes(o);
   return total;
 }
 
-size_t pfft_plan_l2_chunk(const pfft_plan* plan) { return plan ? plan->l2_chunk : 0; }
+size_t pfft_plan_chunk_transforms(const pfft_plan* plan) { return plan ? (plan->l2_chunk ? plan->l2_chunk : plan->nd_chunk) : 0; }
 
 int pfft_plan_level(const pfft_plan* plan, size_t dimension) {
   if (!plan || dimension >= plan->host.dim_level.size()) return -1;

@@ -15,8 +15,12 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run S16_tma S16 X=1
-run S16_notma S16 PFFT_NO_WI_TMA=1
-run C5 C5 X=1
-run C3 C3 X=1
-run C1 C1 X=1
+run C3_new C3 X=1
+run L1D_chunk32M L1D X=1
+run L1D_nochunk L1D PFFT_L2_CHUNK_BYTES=0
+run L1D_chunk8M L1D PFFT_L2_CHUNK_BYTES=8388608
+run L1D_chunk16M L1D PFFT_L2_CHUNK_BYTES=16777216
+run L1D_chunk48M L1D PFFT_L2_CHUNK_BYTES=50331648
+run L1D_chunk64M L1D PFFT_L2_CHUNK_BYTES=67108864
+run S16 S16 X=1
+run C2 C2 X=1
