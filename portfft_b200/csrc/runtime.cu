@@ -435,7 +435,7 @@ static void choose_nd_chunk(pfft_plan* plan) {
   const size_t planes = d.number_of_transforms * d.lengths[0];
   const size_t chunk = budget / plane_bytes;
   // worth it only when the whole array does not fit L2 anyway and a chunk holds at least two planes
-  if (chunk < 2 || chunk >= planes || planes * plane_bytes <= ((size_t)96 << 20)) return;
+  if (chunk < 2 || chunk >= planes || planes * plane_bytes <= 3 * budget) return;
   plan->nd_chunk = chunk;
 }
 

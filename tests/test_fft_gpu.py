@@ -194,6 +194,16 @@ FORCED = {
                           basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16, 64, 100, 512, 1000, 4096]) +
                           basic(GLOBAL_LAYOUTS, ["fwd"], ["interleaved"], [3], [32768, 65536]) +
                           basic(MD_LAYOUTS, ["fwd"], ["interleaved"], [3], [[16, 512], [64, 64, 64]])),
+    # L2-resident execution (batch chunks of multi-pass plans, plane chunks of N-D transforms): forced on small
+    # problems by shrinking the L2 budget
+    "l2_chunked": ({"PFFT_L2_CHUNK_BYTES": "300000"},
+                   basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [5], [16384]) +
+                   basic(GLOBAL_LAYOUTS, BOTH_DIR, ["interleaved"], [7], [4099, 9800]) +
+                   basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3], [[64, 64, 64], [40, 16, 512], [300, 256], [37, 8, 64]]) +
+                   offsets(MD_LAYOUTS, BOTH_DIR, [2], [[64, 64, 64]], [(3, 3), (16, 16)]) +
+                   offsets([("OOP", P, P)], BOTH_DIR, [2], [[64, 64, 64]], [(0, 5), (7, 2)]) +
+                   scaled("fwd", [[64, 64, 64], 16384], -1.0, 2.0) + scaled("bwd", [[64, 64, 64], 16384], -1.0, 2.0) +
+                   real(BOTH_DIR, STORAGES, [5], [65536])),
     "cube_direct_loads": ({"PFFT_CUBE_VARIANT": "1"}, basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"],
                                                             [5], [4096])),
 }
