@@ -47,6 +47,11 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
 // 3072, 4096}; geometry = p.ffts_per_block transforms per CTA, r3_supported's threads per transform
 cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
+// WORKGROUP level, column tiles of any 31-smooth length, in place in shared memory (wg_colg.cu): p.ffts_per_block =
+// columns per tile, p.threads_per_fft = butterfly threads per column; needs ibd[0] == obd[0] == 1
+size_t colg_smem_bytes(int n, int columns, bool is_double);
+cudaError_t launch_wg_colg(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
+
 // element-wise pass with modifiers (ew.cu): n == 1, modifier index = index along batch dimension 0
 cudaError_t launch_ew(const PassParams& p, bool is_double, bool interleaved_in, bool interleaved_out, bool swap, int grid,
                       cudaStream_t stream);

@@ -495,6 +495,33 @@ void select_r3(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   ps.kernel = KERNEL_WG_R3;
 }
 
+// Generic column-tile kernel (wg_colg.cu): any 31-smooth length, any storage, transforms whose batch neighbours are
+// adjacent in both domains (batch-interleaved layouts, outer dimensions of N-D transforms), in place in shared memory.
+// Rewrites the pass geometry (no fallback needed).
+void select_colg(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
+  PassParams& p = ps.pp;
+  const char* env = std::getenv("PFFT_NO_COLG");
+  if (env && std::atoi(env) != 0) return;
+  if (p.gtw_dim >= 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
+  if (p.ibd[0] != 1 || p.obd[0] != 1 || p.nb[0] < 2) return;
+  int c = d.is_double ? 8 : 16;
+  while (c > 1 && c / 2 >= p.nb[0]) c /= 2;
+  while (c > 1 && colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) c /= 2;
+  if (c * (d.is_double ? 16 : 8) < 32 || colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) return;
+  int rmax = 1;
+  for (int i = 0; i < p.num_radices; ++i) rmax = std::max(rmax, p.radix[i]);
+  const int tb = std::max(1, std::min(512 / c, p.n / rmax));
+  p.ffts_per_block = c;
+  p.threads_per_fft = tb;
+  p.in_mode = p.out_mode = IO_DIRECT;
+  ps.block = c * tb;
+  ps.smem = colg_smem_bytes(p.n, c, d.is_double);
+  const long long tiles = ((p.nb[0] + c - 1) / c) * p.nb[1] * p.nb[2] * p.nb[3];
+  const int per_sm = std::max<int>(1, std::min<size_t>(2048 / ps.block, (lim.max_smem_per_block + 1024) / (ps.smem + 1024)));
+  ps.grid = (int)std::min<long long>(tiles, (long long)lim.num_sms * per_sm);
+  ps.kernel = KERNEL_WG_COLG;
+}
+
 // Tile kernel (wg_col.cu): 16 (fp32) / 8 (fp64) transforms per CTA iteration, fed by TMA.  Input side: strided columns
 // whose fastest batch dimension is contiguous (TMA tensor tiles) or contiguous rows (cp.async.bulk / direct loads);
 // output side: columns (fastest batch dimension contiguous) or contiguous rows.  Covers the packed 1-D sizes
@@ -589,6 +616,7 @@ PassHost single_pass(const DescHost& d, const DeviceLimits& lim, size_t L, long 
   select_specialised(wg, d, lim);
   if (wg.kernel == KERNEL_WG_GENERIC) select_col(wg, d, lim);
   if (wg.kernel == KERNEL_WG_GENERIC) select_r3(wg, d, lim);
+  if (wg.kernel == KERNEL_WG_GENERIC) select_colg(wg, d, lim);
   if (force == LEVEL_WORKGROUP || (force < 0 && wg.kernel != KERNEL_WG_GENERIC)) return wg;
   if ((force < 0 || force == LEVEL_SUBGROUP) && configure_sg(ps, dbl, lim)) return ps;
   return wg;
@@ -1046,7 +1074,7 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   }
   // passes that address the user's real buffer as complex pairs
   for (PassHost& ps : passes) {
-    if (ps.kernel >= KERNEL_EW) continue;
+    if (ps.kernel >= KERNEL_EW && ps.kernel <= KERNEL_REAL_UNPACK) continue;
     if (fwd && ps.src == BUF_IN) ps.real_view |= 1;
     if (!fwd && ps.dst == BUF_OUT) ps.real_view |= 2;
   }
@@ -1120,7 +1148,7 @@ PlanHost build_plan(const DescHost& d, const DeviceLimits& lim) {
 
 std::string describe_plan(const PlanHost& plan, int direction) {
   static const char* level_names[] = {"WORKITEM", "SUBGROUP", "WORKGROUP", "GLOBAL"};
-  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew", "real_pack", "r2c_post", "c2r_pre", "real_unpack"};
+  static const char* kernel_names[] = {"wg_generic", "wi", "sg", "wg_cube", "wg_col", "wg_r3", "ew", "real_pack", "r2c_post", "c2r_pre", "real_unpack", "wg_colg"};
   static const char* mode_names[] = {"direct", "staged_elem", "staged_batch"};
   static const char* buf_names[] = {"in", "out", "scratch", "scratch2", "scratch3"};
   static const char* mod_names[] = {"none", "chirp", "chirp/M", "conv"};
@@ -1154,7 +1182,7 @@ std::string describe_plan(const PlanHost& plan, int direction) {
     if (p.apply_scale) ss << " scale=" << p.scale;
     if (ps.real_view) ss << " real_view=" << ps.real_view;
     if (ps.force_swap) ss << " force_swap";
-    if (ps.kernel >= KERNEL_REAL_PACK) ss << " variant=" << ps.variant;
+    if (ps.kernel >= KERNEL_REAL_PACK && ps.kernel <= KERNEL_REAL_UNPACK) ss << " variant=" << ps.variant;
     ss << "\n";
   }
   return ss.str();

@@ -62,7 +62,8 @@ void validate_descriptor(const DescHost& d);  // throws PlanError
 enum BufSel : int { BUF_IN = 0, BUF_OUT = 1, BUF_SCRATCH = 2, BUF_SCRATCH2 = 3, BUF_SCRATCH3 = 4 };
 
 enum KernelKind : int { KERNEL_WG_GENERIC = 0, KERNEL_WI = 1, KERNEL_SG = 2, KERNEL_WG_CUBE = 3, KERNEL_WG_COL = 4, KERNEL_WG_R3 = 5, KERNEL_EW = 6,
-                        KERNEL_REAL_PACK = 7, KERNEL_R2C_POST = 8, KERNEL_C2R_PRE = 9, KERNEL_REAL_UNPACK = 10 };
+                        KERNEL_REAL_PACK = 7, KERNEL_R2C_POST = 8, KERNEL_C2R_PRE = 9, KERNEL_REAL_UNPACK = 10,
+                        KERNEL_WG_COLG = 11 };
 
 // One launch. `pp` holds everything except pointers / table addresses, which the runtime patches in.
 struct PassHost {
@@ -100,6 +101,8 @@ int col_tile_columns(int n, bool is_double);
 // N = R^3 kernel (wg_cube.cu): packed interleaved fp32 4096 (one transform per tile) and 512 (kCube512Tile per tile)
 constexpr int kCube512Tile = 4;
 bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm);
+// generic in-place column-tile kernel (wg_colg.cu)
+size_t colg_smem_bytes(int n, int columns, bool is_double);
 // three-radix kernel (wg_r3.cu)
 bool r3_supported(int n, bool is_double, int* threads_per_fft, int* pitch);
 

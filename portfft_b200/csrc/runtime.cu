@@ -369,6 +369,9 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         else
           e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
+      case KERNEL_WG_COLG:
+        e = launch_wg_colg(p, d.is_double, pil, swap, ps.grid, stream);
+        break;
       case KERNEL_EW:
         e = launch_ew(p, d.is_double, il_in, il_out, swap, ps.grid, stream);
         break;

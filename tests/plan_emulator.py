@@ -122,7 +122,7 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
         smod = api.mod_table(scalar, ps["smod"], ps["mod_l"], ps["mod_m"]) if ps["smod"] else None
         n = ps["n"]
         assert ps["peer_dim"] < 0
-        if ps["kernel"] >= KERNEL_REAL_PACK:
+        if KERNEL_REAL_PACK <= ps["kernel"] <= KERNEL_REAL_UNPACK:
             _real_rows(ps, src, dst, grids, ib, ob, cdt)
             continue
         if ps["kernel"] == KERNEL_EW:

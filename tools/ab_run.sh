@@ -15,11 +15,7 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run C5_nochunk C5 X=1
-run C5_chunk32M C5 PFFT_L2_CHUNK_BYTES=33554432
-run C5_chunk8M C5 PFFT_L2_CHUNK_BYTES=8388608
-run C5_chunk16M C5 PFFT_L2_CHUNK_BYTES=16777216
-run C5_chunk48M C5 PFFT_L2_CHUNK_BYTES=50331648
-run C5_chunk64M C5 PFFT_L2_CHUNK_BYTES=67108864
-run C5_chunk128M C5 PFFT_L2_CHUNK_BYTES=134217728
-run L1D L1D X=1
+run C3B_colg C3B X=1
+run C3B_generic C3B PFFT_NO_COLG=1
+run C3 C3 X=1
+run C5 C5 X=1
