@@ -502,7 +502,7 @@ void select_colg(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   PassParams& p = ps.pp;
   const char* env = std::getenv("PFFT_NO_COLG");
   if (env && std::atoi(env) != 0) return;
-  if (p.gtw_dim >= 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
+  if (p.gtw_dim > 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
   if (p.ibd[0] != 1 || p.obd[0] != 1 || p.nb[0] < 2) return;
   int c = d.is_double ? 8 : 16;
   while (c > 1 && c / 2 >= p.nb[0]) c /= 2;
@@ -704,6 +704,7 @@ void emit_multipass(std::vector<PassHost>& passes, const DescHost& d, const Devi
     }
     configure_wg_generic(ps, dbl, lim, true);
     select_col(ps, d, lim);
+    if (ps.kernel == KERNEL_WG_GENERIC) select_colg(ps, d, lim);
     passes.push_back(ps);
     M = Mp;
     done *= Np;

@@ -13,7 +13,8 @@
 //     from, twiddle w_{N'}^{j r} applied to the outputs), so one tile buffer suffices -- no ping-pong -- and lengths
 //     up to 1792 (fp32, C = 16) fit one CTA; the digit-reversed order this leaves in the tile costs nothing because
 //     the store picks the rows in output order while its lanes still run along the columns;
-//   * backward = (re <-> im) swap on load and store, scale fused into the store.
+//   * backward = (re <-> im) swap on load and store, scale and the GLOBAL level's inter-factor twiddle fused into the
+//     store (the column passes of non-power-of-two multi-pass lengths such as 68640 run here too).
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
@@ -122,6 +123,10 @@ __global__ void __launch_bounds__(512) wg_colg_kernel(const PassParams p, const 
       }
       if (live) {
         cx<T> o = S[(size_t)row * C + c];
+        if (p.gtw_dim == 0) {  // GLOBAL level: inter-factor twiddle w_M^{column * k} (two-level table)
+          const long long m = (c0 + c) * (long long)k;
+          o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & ((1LL << p.gtw_bits) - 1))));
+        }
         if (p.apply_scale) o = cscale(o, scale);
         gstore<T>(p, fl, ob + (long long)c * p.obd[0] + (long long)k * p.os, o);
       }

@@ -166,6 +166,13 @@ SUITES = {
                                           backward_strides=[1], forward_distance=2048, backward_distance=1024,
                                           forward_offset=7, backward_offset=3, backward_scale=1e-3)
                                for b in (5, 1500) for dr in BOTH_DIR for sc in SCALARS],
+    # generic in-place column-tile kernel: batch-interleaved layouts of lengths the TMA tile kernel does not take,
+    # N-D outer dimensions that are not powers of two, non-power-of-two multi-pass lengths (column passes with the
+    # inter-factor twiddle)
+    "ColumnGenericTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [5, 131], [96, 100, 1000, 1536, 1792]),
+    "ColumnGenericMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                                               [[96, 40], [100, 100], [1000, 24], [60, 50, 40]]),
+    "ColumnGenericGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [3], [68640, 9800, 3 * 16384, 1 << 17]),
     # thread-level kernel with TMA tiles in and out (rows of exactly 128 bytes: fp32 N = 16, fp64 N = 8; large batches)
     "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000, 65536],
                              [2, 4, 8, 16]),
@@ -190,7 +197,8 @@ def test_reference_grid(tp):
 FORCED = {
     "subgroup": ({"PFFT_FORCE_LEVEL": "1"},
                  basic(ALL_LAYOUTS[:3], BOTH_DIR, STORAGES, [1, 131], [64, 96, 128, 256, 512, 1024])),
-    "workgroup_generic": ({"PFFT_FORCE_LEVEL": "2", "PFFT_NO_COL": "1", "PFFT_NO_R3": "1", "PFFT_CUBE_VARIANT": "-1"},
+    "workgroup_generic": ({"PFFT_FORCE_LEVEL": "2", "PFFT_NO_COL": "1", "PFFT_NO_R3": "1", "PFFT_CUBE_VARIANT": "-1",
+                           "PFFT_NO_COLG": "1"},
                           basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16, 64, 100, 512, 1000, 4096]) +
                           basic(GLOBAL_LAYOUTS, ["fwd"], ["interleaved"], [3], [32768, 65536]) +
                           basic(MD_LAYOUTS, ["fwd"], ["interleaved"], [3], [[16, 512], [64, 64, 64]])),
