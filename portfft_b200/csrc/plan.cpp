@@ -504,13 +504,17 @@ void select_colg(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   if (env && std::atoi(env) != 0) return;
   if (p.gtw_dim > 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
   if (p.ibd[0] != 1 || p.obd[0] != 1 || p.nb[0] < 2) return;
+  // columns per tile: full 128-byte row segments when two tiles fit one SM, else narrower tiles down to one 32-byte
+  // sector per plane (the tile is single buffered: a second resident CTA is what overlaps load, passes and store)
+  const int plane_bytes = (d.is_double ? 8 : 4) * (d.complex_storage == PFFT_INTERLEAVED_COMPLEX ? 2 : 1);
   int c = d.is_double ? 8 : 16;
   while (c > 1 && c / 2 >= p.nb[0]) c /= 2;
+  while (c > 1 && (c / 2) * plane_bytes >= 32 && colg_smem_bytes(p.n, c, d.is_double) > 100 * 1024) c /= 2;
   while (c > 1 && colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) c /= 2;
   if (c * (d.is_double ? 16 : 8) < 32 || colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) return;
   int rmax = 1;
   for (int i = 0; i < p.num_radices; ++i) rmax = std::max(rmax, p.radix[i]);
-  const int tb = std::max(1, std::min(512 / c, p.n / rmax));
+  const int tb = std::max(1, std::min(std::min(512 / c, 32), p.n / rmax));
   p.ffts_per_block = c;
   p.threads_per_fft = tb;
   p.in_mode = p.out_mode = IO_DIRECT;

@@ -74,8 +74,21 @@ __global__ void __launch_bounds__(512) wg_colg_kernel(const PassParams p, const 
     }
     const bool live = c0 + c < p.nb[0];
     // ---- load: row by row, lanes along the columns -------------------------------------------------------------
-    for (int row = tb; row < n; row += TB)
-      S[(size_t)row * C + c] = live ? gload<T>(p, fl, ib + (long long)c * p.ibd[0] + (long long)row * p.is) : cx<T>{T(0), T(0)};
+    // (eight independent loads per thread in flight before the first shared-memory store: the tile is single
+    // buffered, so memory-level parallelism inside the load phase is what hides the HBM latency)
+    for (int row0 = tb; row0 < n; row0 += 8 * TB) {
+      cx<T> v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = row0 + u * TB;
+        v[u] = (live && row < n) ? gload<T>(p, fl, ib + (long long)c * p.ibd[0] + (long long)row * p.is) : cx<T>{T(0), T(0)};
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int row = row0 + u * TB;
+        if (row < n) S[(size_t)row * C + c] = v[u];
+      }
+    }
     __syncthreads();
     // ---- in-place DIF passes ------------------------------------------------------------------------------------
     int np = n;
