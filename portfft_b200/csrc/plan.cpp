@@ -504,17 +504,16 @@ void select_colg(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   if (env && std::atoi(env) != 0) return;
   if (p.gtw_dim > 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
   if (p.ibd[0] != 1 || p.obd[0] != 1 || p.nb[0] < 2) return;
-  // columns per tile: full 128-byte row segments when two tiles fit one SM, else narrower tiles down to one 32-byte
-  // sector per plane (the tile is single buffered: a second resident CTA is what overlaps load, passes and store)
-  const int plane_bytes = (d.is_double ? 8 : 4) * (d.complex_storage == PFFT_INTERLEAVED_COMPLEX ? 2 : 1);
+  // columns per tile: as wide as shared memory allows, up to one 128-byte row segment.  Measured on C3b (N = 1000,
+  // split fp32): 16 columns (128 KB tile, one CTA per SM) 1.61 ms, 8 columns (three CTAs per SM) 1.73 ms -- the
+  // kernel is bound by the number of distinct lines per memory instruction, which narrower tiles make worse.
   int c = d.is_double ? 8 : 16;
   while (c > 1 && c / 2 >= p.nb[0]) c /= 2;
-  while (c > 1 && (c / 2) * plane_bytes >= 32 && colg_smem_bytes(p.n, c, d.is_double) > 100 * 1024) c /= 2;
   while (c > 1 && colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) c /= 2;
   if (c * (d.is_double ? 16 : 8) < 32 || colg_smem_bytes(p.n, c, d.is_double) > lim.max_smem_per_block) return;
   int rmax = 1;
   for (int i = 0; i < p.num_radices; ++i) rmax = std::max(rmax, p.radix[i]);
-  const int tb = std::max(1, std::min(std::min(512 / c, 32), p.n / rmax));
+  const int tb = std::max(1, std::min(512 / c, p.n / rmax));
   p.ffts_per_block = c;
   p.threads_per_fft = tb;
   p.in_mode = p.out_mode = IO_DIRECT;
