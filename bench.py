@@ -203,6 +203,9 @@ def cpu_sample_batch(cfg) -> int:
 
 
 def run_reference_arm(args, cfg, name):
+    # NCCL_DEBUG=VERSION makes NCCL print a banner on stdout, in front of the one JSON line this program owes
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
