@@ -48,7 +48,6 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
   const int F = p.ffts_per_block;
   cx<T>* buf0 = reinterpret_cast<cx<T>*>(smem_raw);
   cx<T>* buf1 = buf0 + (size_t)F * PITCH;
-  const IoFlags fl{IL, SWAP};
   const int f = threadIdx.x / TPF, t = threadIdx.x - f * TPF;
   const bool one_dim = single_batch_dim(p);
   const T scale = T(p.scale);
@@ -65,6 +64,24 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
     for (int r = 1; r < R2; ++r) tw2[r] = ldg_cx<T>(p.tw, (long long)(t % (R0 * R1)) * r);
   }
 
+  // Address arithmetic is kept out of the element loops: every shared-memory index of a pass is (per-butterfly base)
+  // + r * (compile-time stride) -- the padding i + i/R0 is affine in r because every stride is a multiple of R0 or
+  // smaller than R0 -- and every global address is (per-transform pointer) + r * (one 64-bit step).
+  constexpr int S1 = N / R1 + N / (R1 * R0);  // pad(j + r N/R1) = pad(j) + r S1
+  constexpr int S2 = N / R2 + N / (R2 * R0);  // pad(j + r N/R2) = pad(j) + r S2
+  const long long in_step = (long long)(N / R0) * p.is, out_step = (long long)(R0 * R1) * p.os;
+  auto load_elem = [&](long long idx) -> cx<T> {
+    cx<T> v;
+    if (IL) {
+      v = reinterpret_cast<const cx<T>*>(p.in_re)[idx];
+      if (SWAP) v = cx<T>{v.y, v.x};
+    } else {
+      v.x = reinterpret_cast<const T*>(p.in_re)[idx];
+      v.y = reinterpret_cast<const T*>(p.in_im)[idx];
+    }
+    return v;
+  };
+
   const long long gstride = (long long)gridDim.x * F;
   long long g0 = (long long)blockIdx.x * F;
   bool active = g0 + f < p.batch_total;
@@ -73,8 +90,9 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
   if (active) batch_bases(p, one_dim, g0 + f, ib, ob, peer);
   cx<T> nxt[PREFETCH ? R0 : 1];
   if (PREFETCH && active) {
+    const long long i0 = ib + (long long)t * p.is;
 #pragma unroll
-    for (int r = 0; r < R0; ++r) nxt[r] = gload<T>(p, fl, ib + (long long)(t + r * (N / R0)) * p.is);
+    for (int r = 0; r < R0; ++r) nxt[r] = load_elem(i0 + r * in_step);
   }
   for (; g0 < p.batch_total; g0 += gstride) {
     const bool cur_active = active;
@@ -89,23 +107,27 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
       active = g0 + gstride + f < p.batch_total;
       if (active) {
         batch_bases(p, one_dim, g0 + gstride + f, ib, ob, peer);
+        const long long i0 = ib + (long long)t * p.is;
 #pragma unroll
-        for (int r = 0; r < R0; ++r) nxt[r] = gload<T>(p, fl, ib + (long long)(t + r * (N / R0)) * p.is);
+        for (int r = 0; r < R0; ++r) nxt[r] = load_elem(i0 + r * in_step);
       }
       if (cur_active) {
         DFT<R0, T>::run(v);
+        cx<T>* dst = b0 + t * (R0 + 1);  // pad(t R0 + r) = t (R0 + 1) + r
 #pragma unroll
-        for (int r = 0; r < R0; ++r) b0[Cfg::pad(t * R0 + r)] = v[r];
+        for (int r = 0; r < R0; ++r) dst[r] = v[r];
       }
     } else if (cur_active) {
 #pragma unroll 1
       for (int j = t; j < N / R0; j += TPF) {
         cx<T> v[R0];
+        const long long i0 = ib + (long long)j * p.is;
 #pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = gload<T>(p, fl, ib + (long long)(j + r * (N / R0)) * p.is);
+        for (int r = 0; r < R0; ++r) v[r] = load_elem(i0 + r * in_step);
         DFT<R0, T>::run(v);
+        cx<T>* dst = b0 + j * (R0 + 1);
 #pragma unroll
-        for (int r = 0; r < R0; ++r) b0[Cfg::pad(j * R0 + r)] = v[r];
+        for (int r = 0; r < R0; ++r) dst[r] = v[r];
       }
     }
     __syncthreads();
@@ -115,34 +137,46 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
       for (int j = t; j < N / R1; j += TPF) {
         const int k = j % R0;
         cx<T> v[R1];
+        const cx<T>* src = b0 + Cfg::pad(j);
 #pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = b0[Cfg::pad(j + r * (N / R1))];
+        for (int r = 0; r < R1; ++r) v[r] = src[r * S1];
 #pragma unroll
         for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], TWREG ? tw1[r] : ldg_cx<T>(p.tw, (long long)k * r * R2));
         DFT<R1, T>::run(v);
-        const int ob1 = (j - k) * R1 + k;
+        cx<T>* dst = b1 + Cfg::pad((j - k) * R1 + k);  // (j - k) R1 is a multiple of R0: pad(. + r R0) = pad(.) + r (R0 + 1)
 #pragma unroll
-        for (int r = 0; r < R1; ++r) b1[Cfg::pad(ob1 + r * R0)] = v[r];
+        for (int r = 0; r < R1; ++r) dst[r * (R0 + 1)] = v[r];
       }
     }
     __syncthreads();
     // ---- pass 2: radix R2, buf1 -> global ---------------------------------------------------------------------
     if (cur_active) {
+      // output pointers of this transform (peer table: memory of another GPU)
+      T* ore = reinterpret_cast<T*>(cur_peer >= 0 ? p.out_tab_re[cur_peer] : p.out_re);
+      T* oim = reinterpret_cast<T*>(cur_peer >= 0 ? p.out_tab_im[cur_peer] : p.out_im);
 #pragma unroll 1
       for (int j = t; j < N / R2; j += TPF) {
         const int k = j % (R0 * R1);
         cx<T> v[R2];
+        const cx<T>* src = b1 + Cfg::pad(j);
 #pragma unroll
-        for (int r = 0; r < R2; ++r) v[r] = b1[Cfg::pad(j + r * (N / R2))];
+        for (int r = 0; r < R2; ++r) v[r] = src[r * S2];
 #pragma unroll
         for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], TWREG ? tw2[r] : ldg_cx<T>(p.tw, (long long)k * r));
         DFT<R2, T>::run(v);
-        const int ob2 = (j - k) * R2 + k;
+        const long long o0 = cur_ob + (long long)((j - k) * R2 + k) * p.os;
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
           cx<T> o = v[r];
           if (p.apply_scale) o = cscale(o, scale);
-          gstore<T>(p, fl, cur_ob + (long long)(ob2 + r * (R0 * R1)) * p.os, o, cur_peer);
+          const long long idx = o0 + r * out_step;
+          if (IL) {
+            if (SWAP) o = cx<T>{o.y, o.x};
+            reinterpret_cast<cx<T>*>(ore)[idx] = o;
+          } else {
+            ore[idx] = o.x;
+            oim[idx] = o.y;
+          }
         }
       }
     }
