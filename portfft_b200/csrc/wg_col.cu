@@ -508,10 +508,17 @@ static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_
     if (dims[i] == 0 || dims[i] > (1ULL << 32)) return false;
   cuuint32_t box[5] = {(cuuint32_t)(2 * C), (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  // L2 promotion of the strided 128-byte row segments (PFFT_COL_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B)
+  static const CUtensorMapL2promotion promo = [] {
+    const char* e = std::getenv("PFFT_COL_L2PROMO");
+    const int v = e ? std::atoi(e) : 2;
+    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                  : (v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                            : (v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  }();
   const CUresult r = enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
                          const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

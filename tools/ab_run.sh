@@ -15,7 +15,10 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run C3B_colg C3B X=1
-run C3B_generic C3B PFFT_NO_COLG=1
-run C3 C3 X=1
-run C5 C5 X=1
+run C5_promo128 C5 X=1
+run C5_promo256 C5 PFFT_COL_L2PROMO=3
+run C5_promo0 C5 PFFT_COL_L2PROMO=0
+run C4_promo128 C4 X=1
+run C4_promo256 C4 PFFT_COL_L2PROMO=3
+run L1D_promo128 L1D X=1
+run L1D_promo256 L1D PFFT_COL_L2PROMO=3
