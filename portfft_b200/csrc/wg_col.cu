@@ -511,7 +511,7 @@ static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_
   // L2 promotion of the strided 128-byte row segments (PFFT_COL_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B)
   static const CUtensorMapL2promotion promo = [] {
     const char* e = std::getenv("PFFT_COL_L2PROMO");
-    const int v = e ? std::atoi(e) : 2;
+    const int v = e ? std::atoi(e) : 3;  // measured: 256 B is never slower, C4 1.7 % faster (profiles/r1_ab_variants.txt)
     return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
                   : (v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
                             : (v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
