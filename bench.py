@@ -54,6 +54,10 @@ CONFIGS = {
                 desc="1D C2C fp32 N=16 batch=8Mi out-of-place (reference bench_float small_1d)"),
     "M512": dict(lengths=[512], batch=256 * 1024, scalar="float", inplace=False, split=False,
                  desc="1D C2C fp32 N=512 batch=256Ki out-of-place (packed rows, N = 8^3 tile kernel)"),
+    "M1024": dict(lengths=[1024], batch=128 * 1024, scalar="float", inplace=False, split=False,
+                  desc="1D C2C fp32 N=1024 batch=128Ki out-of-place (packed rows, three-radix kernel 16x8x8)"),
+    "M2048": dict(lengths=[2048], batch=64 * 1024, scalar="float", inplace=False, split=False,
+                  desc="1D C2C fp32 N=2048 batch=64Ki out-of-place (packed rows, three-radix kernel 16x16x8)"),
     "M256": dict(lengths=[256], batch=512 * 1024, scalar="float", inplace=False, split=False,
                  desc="1D C2C fp32 N=256 batch=512Ki out-of-place (reference bench_float medium_small_1d)"),
 }
