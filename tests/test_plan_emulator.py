@@ -84,3 +84,25 @@ def test_exported_plan_matches_oracle(tp):
         out = np.full(host_ref.shape, complex(pad, pad) if np.iscomplexobj(host_ref) else pad, dtype=host_ref.dtype)
         run_plan(d, dr, host_in.copy(), out)
     oracle.verify_dft(od, dr, host_ref, out)
+
+
+@pytest.mark.parametrize("scalar,L", [("float", 37), ("double", 1031), ("float", 4099)])
+def test_bluestein_tables_match_numpy(scalar, L):
+    """pfft_table_host: the chirp w_j = exp(-i pi j^2 / L) and the transformed convolution kernel FFT_M(conj w) the
+    plan uploads (csrc/tables.cpp, long double on the host) against a float64 numpy evaluation."""
+    from portfft_b200 import api
+
+    M = 1
+    while M < 2 * L - 1:
+        M *= 2
+    j = np.arange(L, dtype=np.int64)
+    w = np.exp(-1j * np.pi * ((j * j) % (2 * L)) / L)
+    eps = 1e-6 if scalar == "float" else 1e-14
+    np.testing.assert_allclose(api.mod_table(scalar, 1, L, M), w, atol=eps)
+    np.testing.assert_allclose(api.mod_table(scalar, 2, L, M), w / M, atol=eps / M)
+    b = np.zeros(M, dtype=np.complex128)
+    b[:L] = np.conj(w)
+    b[M - L + 1:] = np.conj(w[1:])[::-1]
+    ref = np.fft.fft(b)
+    got = api.mod_table(scalar, 3, L, M)
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < (1e-6 if scalar == "float" else 1e-13)
