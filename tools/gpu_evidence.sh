@@ -20,6 +20,9 @@ cap() {  # name kernel-regex skip count bench-args...
   local name=$1 rx=$2 skip=$3 cnt=$4; shift 4
   ncu --set full --clock-control none --import-source on -k regex:$rx -s $skip -c $cnt -o $O/full_$name \
       python bench.py "$@" --steps 2 --warmup 3 --no-cpu-baseline --no-e2e > /dev/null 2>&1
+  # only the text summary travels back (gpurun merges at most 64 MiB; the reports are 5-15 MB each)
+  python tools/ncu_summary.py $O/full_$name.ncu-rep > $O/full_${name}_ncu_summary.txt 2>/dev/null
+  if [ "${KEEP_NCU_REP:-0}" != "1" ]; then rm -f $O/full_$name.ncu-rep; fi
 }
 cap c2_wg_cube wg_cube 3 2
 cap m512_wg_cube wg_cube 3 2 --config M512
