@@ -459,6 +459,8 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   int tile = 0, per_sm = 0;
   const char* env512 = std::getenv("PFFT_NO_CUBE512");
   if (p.n == 512 && env512 && std::atoi(env512) != 0) return;
+  const char* envr3 = std::getenv("PFFT_NO_ROWS3");
+  if ((p.n == 1024 || p.n == 2048 || p.n == 8192) && ((envr3 && std::atoi(envr3) != 0) || variant != 0)) return;
   if (cube_supported(p.n, d.is_double, &tile, &per_sm) && il && p.is == 1 && p.os == 1 && single_batch_dim &&
       p.gtw_dim < 0 && p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 &&
       p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0) {

@@ -207,6 +207,148 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? 2 : 4) wg_cube_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Same scheme for the packed powers of two that are not cubes: N = R0 * R1 * R2 with R0 = 16 (1024 = 16*8*8, four
+// transforms per tile; 2048 = 16*16*8, two per tile; 8192 = 16*16*32, one per tile).  N / 16 threads per transform:
+// one radix-16 butterfly per thread in pass 1, N / (R1 NT) and N / (R2 NT) butterflies per thread in passes 2 and 3
+// (twiddles from the L1-resident table instead of registers).  TMA ring, padded exchange 1, exchange 2 written back
+// into the consumed stage, coalesced stores from registers -- as above.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int R0, int R1, int R2, int F, bool SWAP>
+__global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg_rows3_kernel(const CubeArgs a) {
+  static_assert(R0 == 16, "pass 1 writes whole padded 16-groups");
+  constexpr int N = R0 * R1 * R2;
+  constexpr int NT = N / R0;  // threads per transform
+  constexpr int EN = N + 2 * (N / 16);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);
+  cx<T>* S1 = S0 + F * N;
+  cx<T>* E = S1 + F * N;
+  uint64_t* full = reinterpret_cast<uint64_t*>(E + F * EN);
+  const int f = F == 1 ? 0 : threadIdx.x / NT;
+  const int t = F == 1 ? threadIdx.x : threadIdx.x % NT;
+  const cx<T>* gin = reinterpret_cast<const cx<T>*>(a.in) + a.ioff;
+  cx<T>* gout = reinterpret_cast<cx<T>*>(a.out) + a.ooff;
+  const long long stride = (long long)gridDim.x * F;
+  const bool contig = a.idist == N;
+  const T scale = T(a.scale);
+
+  auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
+    const int rows = (int)min((long long)F, a.batch - k);
+    mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
+    if (F == 1 || contig) {
+      bulk_g2s(Sd, gin + k * a.idist, (uint32_t)(rows * N * sizeof(cx<T>)), bar);
+    } else {
+      for (int r = 0; r < rows; ++r) bulk_g2s(Sd + r * N, gin + (k + r) * a.idist, (uint32_t)(N * sizeof(cx<T>)), bar);
+    }
+  };
+
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_mbar_init();
+    fence_proxy_async();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    long long k = (long long)blockIdx.x * F;
+    if (k < a.batch) issue(k, S0, &full[0]);
+    k += stride;
+    if (k < a.batch) issue(k, S1, &full[1]);
+  }
+
+  int it = 0;
+  for (long long k0 = (long long)blockIdx.x * F; k0 < a.batch; k0 += stride, ++it) {
+    const long long k = k0 + f;
+    const bool live = F == 1 || k < a.batch;
+    cx<T>* S = ((it & 1) ? S1 : S0) + f * N;
+    cx<T>* Ef = E + f * EN;
+    // ---- pass 1: x[t + NT r] -> radix 16 -> E[16 t + r'] -------------------------------------------------------
+    mbar_wait(&full[it & 1], (it >> 1) & 1);
+    if (live) {
+      cx<T> v[R0];
+#pragma unroll
+      for (int r = 0; r < R0; ++r) v[r] = S[t + NT * r];
+      if (SWAP) {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) v[r] = cx<T>{v[r].y, v[r].x};
+      }
+      DFT<R0, T>::run(v);
+      cx<T>* dst = Ef + 18 * t;  // epad(16 t + r) = 18 t + r
+      if constexpr (sizeof(T) == 4) {
+#pragma unroll
+        for (int r = 0; r < R0; r += 2)
+          *reinterpret_cast<float4*>(dst + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
+      } else {
+#pragma unroll
+        for (int r = 0; r < R0; ++r) dst[r] = v[r];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0 && it >= 1) {
+      const long long kn = k0 + stride;
+      if (kn < a.batch) {
+        fence_proxy_async();
+        issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
+      }
+    }
+    if (live) {
+      // ---- pass 2: E[j + (N/R1) r] * w_{R0 R1}^{k1 r} -> radix R1 -> S[(j - k1) R1 + k1 + R0 r'] ------------------
+#pragma unroll
+      for (int j = t; j < N / R1; j += NT) {
+        const int k1 = j % R0;
+        cx<T> v[R1];
+#pragma unroll
+        for (int r = 0; r < R1; ++r) v[r] = Ef[epad<R0>(j + (N / R1) * r)];
+#pragma unroll
+        for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], ldg_cx<T>(a.tw, k1 * r * R2));
+        DFT<R1, T>::run(v);
+        cx<T>* dst = S + (j - k1) * R1 + k1;
+#pragma unroll
+        for (int r = 0; r < R1; ++r) dst[R0 * r] = v[r];
+      }
+    }
+    __syncthreads();
+    if (live) {
+      // ---- pass 3: S[j + (N/R2) r] * w_N^{j r} -> radix R2 -> out[j + (N/R2) r'] -----------------------------------
+      cx<T>* dst = gout + k * a.odist;
+#pragma unroll
+      for (int j = t; j < N / R2; j += NT) {
+        cx<T> v[R2];
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = S[j + (N / R2) * r];
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ldg_cx<T>(a.tw, j * r));
+        DFT<R2, T>::run(v);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          cx<T> o = v[r];
+          if (a.apply_scale) o = cscale(o, scale);
+          if (SWAP) o = cx<T>{o.y, o.x};
+          dst[j + (N / R2) * r] = o;
+        }
+      }
+    }
+  }
+}
+
+template <typename T, int R0, int R1, int R2, int F>
+static cudaError_t launch_rows3(const CubeArgs& a, bool swap, int grid, cudaStream_t stream) {
+  constexpr int N = R0 * R1 * R2;
+  constexpr size_t smem = (2 * (size_t)N + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
+  cudaError_t e;
+  if (swap) {
+    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, true>, smem);
+    if (e != cudaSuccess) return e;
+    wg_rows3_kernel<T, R0, R1, R2, F, true><<<grid, (N / R0) * F, smem, stream>>>(a);
+  } else {
+    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, false>, smem);
+    if (e != cudaSuccess) return e;
+    wg_rows3_kernel<T, R0, R1, R2, F, false><<<grid, (N / R0) * F, smem, stream>>>(a);
+  }
+  return cudaGetLastError();
+}
+
 template <typename T, int R, int F>
 size_t cube_smem_bytes_t(bool use_tma) {
   constexpr int N = R * R * R;
@@ -235,6 +377,9 @@ bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_p
   int f = 0, c = 0;
   if (n == 4096) f = 1, c = 2;
   if (n == 512) f = kCube512Tile, c = 4;
+  if (n == 1024) f = 4, c = 2;  // wg_rows3_kernel 16 x 8 x 8
+  if (n == 2048) f = 2, c = 2;  // wg_rows3_kernel 16 x 16 x 8
+  if (n == 8192) f = 1, c = 1;  // wg_rows3_kernel 16 x 16 x 32
   if (f == 0) return false;
   if (transforms_per_tile) *transforms_per_tile = f;
   if (ctas_per_sm) *ctas_per_sm = c;
@@ -257,6 +402,9 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   const bool tma = variant == 0;
   if (!is_double && p.n == 4096) return launch_cube_v<float, 16, 1>(a, swap, tma, grid, stream);
   if (!is_double && p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, grid, stream);
+  if (!is_double && tma && p.n == 1024) return launch_rows3<float, 16, 8, 8, 4>(a, swap, grid, stream);
+  if (!is_double && tma && p.n == 2048) return launch_rows3<float, 16, 16, 8, 2>(a, swap, grid, stream);
+  if (!is_double && tma && p.n == 8192) return launch_rows3<float, 16, 16, 32, 1>(a, swap, grid, stream);
   return cudaErrorInvalidValue;
 }
 
