@@ -15,10 +15,9 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
-run C5_promo128 C5 X=1
-run C5_promo256 C5 PFFT_COL_L2PROMO=3
-run C5_promo0 C5 PFFT_COL_L2PROMO=0
-run C4_promo128 C4 X=1
-run C4_promo256 C4 PFFT_COL_L2PROMO=3
-run L1D_promo128 L1D X=1
-run L1D_promo256 L1D PFFT_COL_L2PROMO=3
+run M1024_rows3 M1024 X=1
+run M1024_r3 M1024 PFFT_NO_ROWS3=1
+run M2048_rows3 M2048 X=1
+run M2048_r3 M2048 PFFT_NO_ROWS3=1
+run M8192_rows3 M8192 X=1
+run M8192_generic M8192 PFFT_NO_ROWS3=1
