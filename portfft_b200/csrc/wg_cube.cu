@@ -232,6 +232,23 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
   const long long stride = (long long)gridDim.x * F;
   const bool contig = a.idist == N;
   const T scale = T(a.scale);
+  // twiddles of the thread's own butterflies, resident in registers for the whole batch loop when they are few
+  // (measured: table look-ups inside the passes cost 2048-point rows a third of their bandwidth)
+  constexpr int B2 = (N / R1 + NT - 1) / NT, B3 = (N / R2 + NT - 1) / NT;  // butterflies per thread in passes 2, 3
+  constexpr bool TW2REG = B2 * (R1 - 1) <= 16, TW3REG = B3 * (R2 - 1) <= 16;
+  cx<T> tw2[TW2REG ? B2 * (R1 - 1) : 1], tw3[TW3REG ? B3 * (R2 - 1) : 1];
+  if (TW2REG) {
+#pragma unroll
+    for (int i = 0; i < B2; ++i)
+#pragma unroll
+      for (int r = 1; r < R1; ++r) tw2[i * (R1 - 1) + r - 1] = ldg_cx<T>(a.tw, ((t + i * NT) % R0) * r * R2);
+  }
+  if (TW3REG) {
+#pragma unroll
+    for (int i = 0; i < B3; ++i)
+#pragma unroll
+      for (int r = 1; r < R2; ++r) tw3[i * (R2 - 1) + r - 1] = ldg_cx<T>(a.tw, ((t + i * NT) % (N / R2)) * r);
+  }
 
   auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
     const int rows = (int)min((long long)F, a.batch - k);
@@ -295,13 +312,16 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
     if (live) {
       // ---- pass 2: E[j + (N/R1) r] * w_{R0 R1}^{k1 r} -> radix R1 -> S[(j - k1) R1 + k1 + R0 r'] ------------------
 #pragma unroll
-      for (int j = t; j < N / R1; j += NT) {
+      for (int i = 0; i < B2; ++i) {
+        const int j = t + i * NT;
+        if (j >= N / R1) break;
         const int k1 = j % R0;
         cx<T> v[R1];
 #pragma unroll
         for (int r = 0; r < R1; ++r) v[r] = Ef[epad<R0>(j + (N / R1) * r)];
 #pragma unroll
-        for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], ldg_cx<T>(a.tw, k1 * r * R2));
+        for (int r = 1; r < R1; ++r)
+          v[r] = cmul(v[r], TW2REG ? tw2[TW2REG ? i * (R1 - 1) + r - 1 : 0] : ldg_cx<T>(a.tw, k1 * r * R2));
         DFT<R1, T>::run(v);
         cx<T>* dst = S + (j - k1) * R1 + k1;
 #pragma unroll
@@ -313,12 +333,15 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
       // ---- pass 3: S[j + (N/R2) r] * w_N^{j r} -> radix R2 -> out[j + (N/R2) r'] -----------------------------------
       cx<T>* dst = gout + k * a.odist;
 #pragma unroll
-      for (int j = t; j < N / R2; j += NT) {
+      for (int i = 0; i < B3; ++i) {
+        const int j = t + i * NT;
+        if (j >= N / R2) break;
         cx<T> v[R2];
 #pragma unroll
         for (int r = 0; r < R2; ++r) v[r] = S[j + (N / R2) * r];
 #pragma unroll
-        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], ldg_cx<T>(a.tw, j * r));
+        for (int r = 1; r < R2; ++r)
+          v[r] = cmul(v[r], TW3REG ? tw3[TW3REG ? i * (R2 - 1) + r - 1 : 0] : ldg_cx<T>(a.tw, j * r));
         DFT<R2, T>::run(v);
 #pragma unroll
         for (int r = 0; r < R2; ++r) {
