@@ -173,3 +173,47 @@ def test_planner_pass_factors_multiply_to_length():
             for r in rad:
                 pr *= int(r)
             assert pr == pn
+
+
+def _kernels(d, direction=None):
+    txt = d.describe_plan(direction if direction is not None else pf.direction.FORWARD)
+    return re.findall(r"pass kernel=(\w+)", txt)
+
+
+def test_planner_kernel_choices():
+    """Which kernel the planner picks for the BASELINE configs and the packed sizes (host only).  Guards the
+    selection logic: the measured numbers in DESIGN.md section 5 belong to exactly these choices."""
+    def packed(n, batch, scalar="float"):
+        d = pf.descriptor([n], scalar)
+        d.number_of_transforms = batch
+        return d
+
+    assert _kernels(packed(4096, 65536)) == ["wg_cube"]                      # C2
+    for n in (512, 1024, 2048, 8192):
+        assert _kernels(packed(n, 4096)) == ["wg_cube"], n                   # cube / rows3 family
+    for n in (64, 128, 256):
+        assert _kernels(packed(n, 4096)) == ["wg_col"], n                    # TMA tile kernel, rows in and out
+    assert _kernels(packed(16, 1 << 20)) == ["wi"] and _kernels(packed(96, 4096)) == ["sg"]
+    assert _kernels(packed(4096, 64, "double")) != ["wg_cube"]               # fp32 only
+    assert _kernels(pf.descriptor([512, 512, 512])) == ["wg_cube", "wg_col", "wg_col"]   # C5: z, y, x
+    assert _kernels(packed(1 << 24, 8, "double")) == ["wg_col"] * 3          # C4: 256^3
+    c3 = pf.descriptor([1000])                                               # C3: split, stride 2, offsets
+    c3.number_of_transforms = 100000
+    c3.complex_storage = pf.complex_storage.SPLIT_COMPLEX
+    c3.forward_strides, c3.forward_distance, c3.forward_offset = [2], 2048, 7
+    c3.backward_strides, c3.backward_distance, c3.backward_offset = [1], 1024, 3
+    assert _kernels(c3) == ["wg_r3"] and _kernels(c3, pf.direction.BACKWARD) == ["wg_r3"]
+    c3b = pf.descriptor([1000])                                              # C3b: batch-interleaved both domains
+    c3b.number_of_transforms = 100000
+    c3b.complex_storage = pf.complex_storage.SPLIT_COMPLEX
+    c3b.forward_strides = c3b.backward_strides = [100000]
+    c3b.forward_distance = c3b.backward_distance = 1
+    assert _kernels(c3b) == ["wg_colg"]
+    r = pf.descriptor([8192], "float", pf.domain.REAL)                       # real: half-length cube + post pass
+    r.number_of_transforms = 1024
+    assert _kernels(r) == ["wg_cube", "r2c_post"]
+    assert _kernels(r, pf.direction.BACKWARD) == ["c2r_pre", "wg_cube"]
+    r = pf.descriptor([8192], "float", pf.domain.REAL)                       # strided real rows: pack pass first
+    r.number_of_transforms = 4
+    r.forward_strides, r.forward_distance = [3], 3 * 8192
+    assert _kernels(r) == ["real_pack", "wg_cube", "r2c_post"]

@@ -25,6 +25,12 @@ CASES = [
     CaseParams([65536], 5, "OOP", P, P, "fwd", "interleaved", "float"),      # GLOBAL level sub-plans own scratch
     CaseParams([2048], 33, "OOP", P, P, "bwd", "interleaved", "float", forward_offset=2047, backward_offset=2049),
     CaseParams([8], 1, "OOP", P, P, "fwd", "interleaved", "float"),
+    # lengths with a large prime factor and the REAL domain through the host entry point
+    CaseParams([1031], 9, "OOP", P, P, "fwd", "interleaved", "float"),
+    CaseParams([4096], 21, "OOP", P, P, "fwd", "interleaved", "float", domain="real"),
+    CaseParams([4096], 21, "OOP", P, P, "bwd", "split", "float", domain="real", backward_scale=1.0 / 4096),
+    CaseParams([30], 77, "OOP", P, P, "fwd", "split", "double", domain="real"),
+    CaseParams([6, 16], 5, "OOP", P, P, "bwd", "interleaved", "double", domain="real"),
 ]
 
 
