@@ -15,9 +15,21 @@ except Exception as e:
     print(sys.argv[2], "FAILED", e)
 PY
 }
+# the variants behind the numbers of DESIGN.md section 5 (each pair: default / previous kernel)
+run C2 C2 X=1
+run M512_cube M512 X=1
+run M512_tile M512 PFFT_NO_CUBE512=1
 run M1024_rows3 M1024 X=1
 run M1024_r3 M1024 PFFT_NO_ROWS3=1
 run M2048_rows3 M2048 X=1
 run M2048_r3 M2048 PFFT_NO_ROWS3=1
 run M8192_rows3 M8192 X=1
 run M8192_generic M8192 PFFT_NO_ROWS3=1
+run S16_tma S16 X=1
+run S16_cpasync S16 PFFT_NO_WI_TMA=1
+run C5_groups C5 X=1
+run C5_nogroups C5 PFFT_COL512_GROUPS=0
+run L1D_inplace L1D X=1
+run L1D_exchange_buffer L1D PFFT_COL_INPLACE=0
+run C3B_colg C3B X=1
+run C3B_generic C3B PFFT_NO_COLG=1
