@@ -167,6 +167,19 @@ static void commit_device(pfft_plan* plan) {
   }
 }
 
+// The kernels of a plan must be launched with the plan's device current (its streams, tables and workspaces live
+// there); a caller that drives several GPUs from one thread gets its own current device back afterwards.
+struct DeviceGuard {
+  int prev = -1;
+  bool switched = false;
+  explicit DeviceGuard(int device) {
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+  }
+  ~DeviceGuard() {
+    if (switched) cudaSetDevice(prev);
+  }
+};
+
 struct PeerTable {
   size_t n = 0;
   void* const* re = nullptr;
@@ -659,6 +672,7 @@ pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const v
     if (direction != PFFT_FORWARD && direction != PFFT_BACKWARD)
       throw PlanError(PFFT_INVALID_CONFIGURATION, "invalid direction");
     cudaStream_t s = stream ? (cudaStream_t)stream : plan->stream;
+    DeviceGuard guard(plan->device);
     execute(plan, direction, in, in_imag, out, out_imag, s);
   });
 }
@@ -689,6 +703,7 @@ pfft_status pfft_compute_peer(pfft_plan* plan, int direction, const void* in, co
     if (!il && out_imag == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null imaginary peer table");
     PeerTable t{n_peers, out, out_imag};
     cudaStream_t s = stream ? (cudaStream_t)stream : plan->stream;
+    DeviceGuard guard(plan->device);
     // the "out" argument of execute only feeds its null checks and passes that do not write the final output
     execute(plan, direction, in, in_imag, out[0], il ? nullptr : out_imag[0], s, &t);
   });
