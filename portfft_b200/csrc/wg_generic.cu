@@ -11,7 +11,8 @@
 //     (lanes -> consecutive complex elements), otherwise the tile is staged with lanes along the batch index;
 //   * padding of one complex per 16 (fp32) / 8 (fp64) keeps the strided Stockham writes bank-conflict free;
 //   * backward = swap(re, im) on load and store (no conjugation pass), scale fused on store.
-// Hot sizes have fully specialised kernels (wg_pow2.cu); this one guarantees coverage.
+// Hot sizes and layouts have specialised kernels (wg_cube.cu, wg_col.cu, wg_colg.cu, wg_r3.cu); this one guarantees
+// coverage and carries the element-wise modifiers of the Bluestein passes.
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
