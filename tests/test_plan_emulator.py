@@ -106,3 +106,27 @@ def test_bluestein_tables_match_numpy(scalar, L):
     ref = np.fft.fft(b)
     got = api.mod_table(scalar, 3, L, M)
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < (1e-6 if scalar == "float" else 1e-13)
+
+
+def _grid_sample():
+    """Every 3rd case of the GPU parity grid (tests/test_fft_gpu.py) whose buffers stay small: the planner's pass lists
+    for the reference's own test matrix -- layouts, offsets, scales, storages, N-D, GLOBAL, Bluestein, REAL -- are
+    replayed on the CPU, so a planner regression shows up without a GPU."""
+    import test_fft_gpu as grid
+
+    out = []
+    i = 0
+    for suite, tps in grid.SUITES.items():
+        for tp in tps:
+            i += 1
+            n = 1
+            for l in tp.lengths:
+                n *= l
+            if i % 3 == 0 and n * tp.batch <= (1 << 18) and n <= (1 << 17):
+                out.append(pytest.param(tp, id=f"{suite}-{tp.ident()}"))
+    return out
+
+
+@pytest.mark.parametrize("tp", _grid_sample())
+def test_gpu_grid_sample_on_the_emulator(tp):
+    test_exported_plan_matches_oracle(tp)
