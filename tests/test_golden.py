@@ -17,8 +17,12 @@ def _numpy_fixtures():
     return sorted(glob.glob(os.path.join(GOLD, "numpy_*.npz")))
 
 
+def _real_fixtures():
+    return sorted(glob.glob(os.path.join(GOLD, "numpyre_*.npz")))
+
+
 def test_fixtures_present():
-    assert len(_numpy_fixtures()) == 12
+    assert len(_numpy_fixtures()) == 14 and len(_real_fixtures()) == 8
     assert os.path.exists(os.path.join(GOLD, "refcode_f32.npz")) and os.path.exists(os.path.join(GOLD, "refcode_f64.npz"))
 
 
@@ -31,6 +35,16 @@ def test_oracle_reproduces_numpy_fixture(path):
     x2, y2 = o.gen_data(x.shape[0], list(x.shape[1:]), dbl)
     assert np.array_equal(x, x2)
     assert np.linalg.norm(y - y2) <= 4 * np.finfo(x.real.dtype).eps * np.linalg.norm(y)
+
+
+@pytest.mark.parametrize("path", _real_fixtures(), ids=os.path.basename)
+def test_oracle_reproduces_real_fixture(path):
+    f = np.load(path)
+    x, y = f["input"], f["output"]
+    dbl = x.dtype == np.float64
+    x2, y2 = o.gen_data(x.shape[0], list(x.shape[1:]), dbl, is_real=True)
+    assert np.array_equal(x, x2) and y.shape == y2.shape and y.shape[-1] == x.shape[-1] // 2 + 1
+    assert np.linalg.norm(y - y2) <= 4 * np.finfo(x.dtype).eps * np.linalg.norm(y)
 
 
 @pytest.mark.parametrize("tag", ["f32", "f64"])
@@ -97,4 +111,40 @@ def test_cuda_matches_numpy_fixture(path):
     yy = y.reshape(x.shape[0], -1)
     err = np.max(np.linalg.norm(got - yy, axis=1) / np.linalg.norm(yy, axis=1))
     assert err <= o.rel_l2_bound(n, dbl)
+    c.destroy()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("path", _real_fixtures(), ids=os.path.basename)
+def test_cuda_matches_real_fixture(path):
+    """REAL domain: real input -> half spectrum (dense rows), then back with backward_scale = 1 / N."""
+    import torch
+
+    import portfft_b200 as pf
+
+    f = np.load(path)
+    x, y = f["input"], f["output"]
+    dbl = x.dtype == np.float64
+    dims = list(x.shape[1:])
+    n = int(np.prod(dims))
+    cdims = dims[:-1] + [dims[-1] // 2 + 1]
+    d = pf.descriptor(dims, "double" if dbl else "float", pf.domain.REAL)
+    d.number_of_transforms = x.shape[0]
+    d.backward_strides = pf.get_default_strides(cdims)
+    d.backward_distance = int(np.prod(cdims))
+    d.backward_scale = 1.0 / n
+    c = d.commit(torch.cuda.current_stream(), 0)
+    tin = torch.from_numpy(x.reshape(-1).copy()).cuda()
+    tout = torch.empty(y.size, dtype=torch.complex128 if dbl else torch.complex64, device="cuda")
+    c.compute_forward(tin, tout)
+    torch.cuda.synchronize()
+    got = tout.cpu().numpy().reshape(x.shape[0], -1)
+    yy = y.reshape(x.shape[0], -1)
+    assert np.max(np.linalg.norm(got - yy, axis=1) / np.linalg.norm(yy, axis=1)) <= o.rel_l2_bound(n, dbl)
+    back = torch.zeros_like(tin)
+    c.compute_backward(tout, back)
+    torch.cuda.synchronize()
+    xx = x.reshape(x.shape[0], -1)
+    bb = back.cpu().numpy().reshape(x.shape[0], -1)
+    assert np.max(np.linalg.norm(bb - xx, axis=1) / np.linalg.norm(xx, axis=1)) <= o.rel_l2_bound(n, dbl)
     c.destroy()

@@ -3,6 +3,7 @@ oracle/_ref's sources do not exist.
 
   numpy_*.npz  -- the reference test generator's input/expected pairs (reference_data_wrangler.hpp:117-145): protects
                   the oracle against numpy version drift between this container and the GPU box.
+  numpyre_*.npz -- the same for the generator's REAL-domain branch (real input, rfftn output).
   refcode_*.npz -- outputs of the REFERENCE's own wi_dft / sg_dft (compiled from /root/reference through
                   oracle/ref_shim into oracle/_ref) on the same SFC64(0) inputs.
 
@@ -23,9 +24,14 @@ os.makedirs(OUT, exist_ok=True)
 
 for dbl in (False, True):
     tag = "f64" if dbl else "f32"
-    for batch, dims in [(3, [8]), (2, [64]), (1, [1000]), (2, [4096]), (1, [2, 3, 6]), (1, [16, 32])]:
+    for batch, dims in [(3, [8]), (2, [64]), (1, [1000]), (2, [4096]), (1, [2, 3, 6]), (1, [16, 32]), (1, [1031])]:
         x, y = o.gen_data(batch, dims, dbl)
         name = f"numpy_{tag}_b{batch}_n" + "x".join(map(str, dims)) + ".npz"
+        np.savez_compressed(os.path.join(OUT, name), input=x, output=y)
+    # REAL domain: the generator's `is_complex = False` branch (real input, rfftn output; :130-137)
+    for batch, dims in [(2, [64]), (1, [30]), (1, [81]), (1, [4, 6])]:
+        x, y = o.gen_data(batch, dims, dbl, is_real=True)
+        name = f"numpyre_{tag}_b{batch}_n" + "x".join(map(str, dims)) + ".npz"
         np.savez_compressed(os.path.join(OUT, name), input=x, output=y)
 
 ref = ctypes.CDLL(os.path.join(ROOT, "oracle", "_ref", "libportfft_ref.so"))
