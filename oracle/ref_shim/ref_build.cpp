@@ -3,6 +3,8 @@
 //   wi_dft                 /root/reference/src/portfft/common/workitem.hpp:200-219
 //   sg_dft                 /root/reference/src/portfft/common/subgroup.hpp:271-291 (32 lock-step host threads)
 //   factorize, wi_temps, fits_in_wi, factorize_sg, fits_in_sg   workitem.hpp:135-185, subgroup.hpp:226-253
+//   validate_descriptor    /root/reference/src/portfft/descriptor_validation.hpp:264-281 (whole file)
+//   get_layout             /root/reference/src/portfft/utils.hpp:210-246
 // The SYCL runtime is replaced by oracle/ref_shim/sycl/sycl.hpp; the build defines are the reference's CMake
 // defaults (CMakeLists.txt:38-59).  TEST INFRASTRUCTURE ONLY.
 #define PORTFFT_REGISTERS_PER_WI 128
@@ -15,6 +17,8 @@
 
 #include <portfft/common/subgroup.hpp>
 #include <portfft/common/workitem.hpp>
+#include <portfft/descriptor_validation.hpp>
+#include <portfft/utils.hpp>
 
 #include <thread>
 #include <vector>
@@ -58,9 +62,71 @@ void run_sg(const T* in, T* out, int factor_wi, int factor_sg) {
     }
 }
 
+// The public fields and getters validate_descriptor / get_layout read from a portfft::descriptor
+// (descriptor.hpp:59-129,161-251); portfft::descriptor itself would drag the SYCL kernels in through
+// committed_descriptor.hpp.
+template <typename S, portfft::domain D>
+struct plain_descriptor {
+  using Scalar = S;
+  static constexpr portfft::domain Domain = D;
+  std::vector<std::size_t> lengths, forward_strides, backward_strides;
+  std::size_t number_of_transforms = 1, forward_distance = 1, backward_distance = 1;
+  portfft::placement placement = portfft::placement::OUT_OF_PLACE;
+  const std::vector<std::size_t>& get_strides(portfft::direction d) const {
+    return d == portfft::direction::FORWARD ? forward_strides : backward_strides;
+  }
+  std::size_t get_distance(portfft::direction d) const {
+    return d == portfft::direction::FORWARD ? forward_distance : backward_distance;
+  }
+  std::size_t get_flattened_length() const {
+    std::size_t t = 1;
+    for (std::size_t l : lengths) t *= l;
+    return t;
+  }
+};
+
+template <typename S>
+plain_descriptor<S, portfft::domain::COMPLEX> make_desc(int placement, std::size_t rank, const std::size_t* lengths,
+                                                        std::size_t nfs, const std::size_t* fs, std::size_t nbs,
+                                                        const std::size_t* bs, std::size_t fd, std::size_t bd,
+                                                        std::size_t batch) {
+  plain_descriptor<S, portfft::domain::COMPLEX> d;
+  d.lengths.assign(lengths, lengths + rank);
+  d.forward_strides.assign(fs, fs + nfs);
+  d.backward_strides.assign(bs, bs + nbs);
+  d.forward_distance = fd;
+  d.backward_distance = bd;
+  d.number_of_transforms = batch;
+  d.placement = placement == 0 ? portfft::placement::IN_PLACE : portfft::placement::OUT_OF_PLACE;
+  return d;
+}
+
 }  // namespace
 
 extern "C" {
+// the reference's validate_descriptor: 0 accepted, 1 invalid_configuration, 2 unsupported_configuration
+int refshim_validate(int is_double, int placement, std::size_t rank, const std::size_t* lengths, std::size_t nfs,
+                     const std::size_t* fs, std::size_t nbs, const std::size_t* bs, std::size_t fd, std::size_t bd,
+                     std::size_t batch) {
+  try {
+    if (is_double)
+      portfft::detail::validate::validate_descriptor(make_desc<double>(placement, rank, lengths, nfs, fs, nbs, bs, fd, bd, batch));
+    else
+      portfft::detail::validate::validate_descriptor(make_desc<float>(placement, rank, lengths, nfs, fs, nbs, bs, fd, bd, batch));
+  } catch (const portfft::invalid_configuration&) {
+    return 1;
+  } catch (const portfft::unsupported_configuration&) {
+    return 2;
+  }
+  return 0;
+}
+// the reference's get_layout: 0 PACKED, 1 UNPACKED, 2 BATCH_INTERLEAVED (enums.hpp:46)
+int refshim_get_layout(int direction, std::size_t rank, const std::size_t* lengths, const std::size_t* fs,
+                       const std::size_t* bs, std::size_t fd, std::size_t bd, std::size_t batch) {
+  auto d = make_desc<float>(1, rank, lengths, rank, fs, rank, bs, fd, bd, batch);
+  return static_cast<int>(portfft::detail::get_layout(
+      d, direction == 0 ? portfft::direction::FORWARD : portfft::direction::BACKWARD));
+}
 void ref_wi_dft_f32(const float* in, float* out, int n) { run_wi<float>(in, out, n); }
 void ref_wi_dft_f64(const double* in, double* out, int n) { run_wi<double>(in, out, n); }
 void ref_sg_dft_f32(const float* in, float* out, int factor_wi, int factor_sg) { run_sg<float>(in, out, factor_wi, factor_sg); }

@@ -4,6 +4,8 @@
 // repository; it contains no reference code.  A sub-group is emulated by 32 host threads that run in lock step:
 // every cross-lane operation publishes the lane's value, waits on a barrier, reads the peer's value, waits again.
 #pragma once
+#include <algorithm>
+#include <numeric>
 #include <cmath>
 #include <condition_variable>
 #include <cstddef>

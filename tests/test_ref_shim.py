@@ -88,3 +88,81 @@ def test_reference_sg_dft_matches_numpy_and_port(n, dbl):
     out_port = np.empty_like(x)
     (port.pfft_oracle_fft_f64 if dbl else port.pfft_oracle_fft_f32)(x.ctypes.data, out_port.ctypes.data, n, 1, 0, 1.0, 1)
     assert np.linalg.norm(out_port - out_ref) <= bound * np.linalg.norm(y)
+
+
+def _arr(v):
+    return (ctypes.c_size_t * max(1, len(v)))(*[int(x) for x in v])
+
+
+def _ref_validate(lib, lengths, fs, bs, fd, bd, batch, placement, dbl=False):
+    return lib.refshim_validate(int(dbl), placement, len(lengths), _arr(lengths), len(fs), _arr(fs), len(bs), _arr(bs),
+                                fd, bd, batch)
+
+
+def test_validation_matches_reference_code():
+    """descriptor_validation.hpp + utils.hpp::get_layout run AS THEY ARE (compiled from /root/reference through the
+    shim) against the numpy oracle and against the library's pfft_validate / pfft_get_layout:
+      * invalid_configuration: the same verdict from all three, on the reference's own invalid list
+        (instantiate_fft_tests.hpp:322-373) and on 4000 random descriptors;
+      * unsupported_configuration (validate_layout, :57-81): the oracle's `reference_layout_limits` switch reproduces
+        it; the library accepts those (it lifts the restriction) but never accepts an invalid one;
+      * layout classification identical."""
+    import random
+
+    import portfft_b200 as pf
+    from test_oracle import INVALID
+
+    lib = _ref()
+    szp = ctypes.POINTER(ctypes.c_size_t)
+    lib.refshim_validate.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_size_t, szp, ctypes.c_size_t, szp,
+                                     ctypes.c_size_t, szp, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_size_t]
+    lib.refshim_get_layout.argtypes = [ctypes.c_int, ctypes.c_size_t, szp, szp, szp, ctypes.c_size_t, ctypes.c_size_t,
+                                       ctypes.c_size_t]
+    for lengths, fs, bs, fd, bd, batch, pl in [c[:7] for c in INVALID]:
+        assert _ref_validate(lib, lengths, fs, bs, fd, bd, batch, pl) == 1, (lengths, fs, bs, fd, bd, batch, pl)
+
+    rng = random.Random(11)
+    lay = {o.PACKED: 0, o.UNPACKED: 1, o.BATCH_INTERLEAVED: 2}
+    counts = {0: 0, 1: 0, 2: 0}
+    for _ in range(4000):
+        rank = rng.choice([1, 1, 1, 2, 3])
+        lengths = [rng.choice([1, 2, 3, 4, 5, 8, 16, 75, 100]) for _ in range(rank)]
+        batch = rng.choice([1, 2, 3, 7, 33])
+        pl = rng.choice([0, 1])
+
+        def dom():
+            kind = rng.random()
+            if kind < 0.35:
+                st = o.get_default_strides(lengths)
+                return st, int(np.prod(lengths))
+            if kind < 0.5 and rank == 1:
+                return [batch], 1
+            return [rng.choice([1, 2, 3, 4, 6, 8, 16, 33, 64]) for _ in range(rank)], rng.choice(
+                [0, 1, 2, 3, 5, 8, 16, 40, 64, 300, 2000])
+
+        fs, fd = dom()
+        bs, bd = (fs, fd) if (pl == 0 and rng.random() < 0.7) else dom()
+        verdict = _ref_validate(lib, lengths, fs, bs, fd, bd, batch, pl)
+        counts[verdict] += 1
+        od = o.OracleDescriptor(lengths, number_of_transforms=batch, placement=pl, forward_strides=fs,
+                                backward_strides=bs, forward_distance=fd, backward_distance=bd)
+        try:
+            o.validate_descriptor(od, reference_layout_limits=True)
+            oracle_verdict = 0
+        except o.InvalidConfiguration:
+            oracle_verdict = 1
+        except o.UnsupportedConfiguration:
+            oracle_verdict = 2
+        assert oracle_verdict == verdict, (lengths, fs, bs, fd, bd, batch, pl, verdict, oracle_verdict)
+        d = pf.descriptor(lengths)
+        d.number_of_transforms, d.placement = batch, pf.placement(pl)
+        d.forward_strides, d.backward_strides, d.forward_distance, d.backward_distance = list(fs), list(bs), fd, bd
+        if verdict == 1:
+            with pytest.raises(pf.invalid_configuration):
+                d.validate()
+        else:
+            d.validate()  # accepted, including what the reference calls unsupported
+            for dr in (0, 1):
+                ref_layout = lib.refshim_get_layout(dr, rank, _arr(lengths), _arr(fs), _arr(bs), fd, bd, batch)
+                assert ref_layout == lay[o.get_layout(od, dr)] == int(d.get_layout(pf.direction(dr)))
+    assert counts[0] > 500 and counts[1] > 500 and counts[2] > 50, counts
