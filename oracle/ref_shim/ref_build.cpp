@@ -3,6 +3,9 @@
 //   wi_dft                 /root/reference/src/portfft/common/workitem.hpp:200-219
 //   sg_dft                 /root/reference/src/portfft/common/subgroup.hpp:271-291 (32 lock-step host threads)
 //   factorize, wi_temps, fits_in_wi, factorize_sg, fits_in_sg   workitem.hpp:135-185, subgroup.hpp:226-253
+//   wg_dft                 /root/reference/src/portfft/common/workgroup.hpp:319-346 (dimension_dft :85-286) on an
+//                          emulated work-group of 2 sub-groups x 32 lock-step host threads, twiddles laid out as
+//                          dispatcher/workgroup_dispatcher.hpp:382-443 does
 //   validate_descriptor    /root/reference/src/portfft/descriptor_validation.hpp:264-281 (whole file)
 //   get_layout             /root/reference/src/portfft/utils.hpp:210-246
 // The SYCL runtime is replaced by oracle/ref_shim/sycl/sycl.hpp; the build defines are the reference's CMake
@@ -17,6 +20,9 @@
 
 #include <portfft/common/subgroup.hpp>
 #include <portfft/common/workitem.hpp>
+#include <portfft/common/memory_views.hpp>
+#include <portfft/common/transfers.hpp>
+#include <portfft/common/workgroup.hpp>
 #include <portfft/descriptor_validation.hpp>
 #include <portfft/utils.hpp>
 
@@ -59,6 +65,60 @@ void run_sg(const T* in, T* out, int factor_wi, int factor_sg) {
     for (int j = 0; j < factor_wi; ++j) {
       out[2 * (j * factor_sg + l)] = priv[l][2 * j];
       out[2 * (j * factor_sg + l) + 1] = priv[l][2 * j + 1];
+    }
+}
+
+// One transform of the WORKGROUP level: what workgroup_impl does for a PACKED interleaved transform
+// (dispatcher/workgroup_dispatcher.hpp:232-251) -- input to padded local memory, wg_dft, transposing copy out.
+template <typename T>
+void run_wg(const T* in, T* out, int fft_size) {
+  using namespace portfft;
+  using namespace portfft::detail;
+  const Idx n = factorize(static_cast<Idx>(fft_size)), m = fft_size / n;
+  const Idx fsg_n = factorize_sg(n, 32), fwi_n = n / fsg_n, fsg_m = factorize_sg(m, 32), fwi_m = m / fsg_m;
+  std::vector<T> tw(static_cast<std::size_t>(2 * (m + n + fft_size)));
+  for (Idx a = 0; a < fsg_n; ++a)
+    for (Idx k = 0; k < fwi_n; ++k) sg_calc_twiddles<T>(fsg_n, fwi_n, a, k, tw.data() + 2 * m);
+  for (Idx a = 0; a < fsg_m; ++a)
+    for (Idx k = 0; k < fwi_m; ++k) sg_calc_twiddles<T>(fsg_m, fwi_m, a, k, tw.data());
+  for (Idx i = 0; i < n; ++i)
+    for (Idx j_wi = 0; j_wi < fwi_m; ++j_wi)
+      for (Idx j_sg = 0; j_sg < fsg_m; ++j_sg) {
+        const Idx j = j_wi + j_sg * fwi_m, j_loc = j_wi * fsg_m + j_sg;
+        const std::complex<T> w = calculate_twiddle<T>(i * j, static_cast<Idx>(fft_size));
+        tw[static_cast<std::size_t>(2 * (n + m + i * m + j_loc))] = w.real();
+        tw[static_cast<std::size_t>(2 * (n + m + i * m + j_loc) + 1)] = w.imag();
+      }
+  const Idx blp = bank_lines_per_pad_wg(2 * static_cast<Idx>(sizeof(T)) * m);
+  std::vector<T> loc(static_cast<std::size_t>(pad_local(2 * fft_size, blp)) + 64, T(0));
+  auto loc_view = padded_view(loc.data(), blp);
+  for (Idx i = 0; i < 2 * fft_size; ++i) loc_view[i] = in[i];
+  std::vector<T> loc_tw(tw.begin(), tw.begin() + 2 * (m + n));
+  const T* wg_tw = tw.data() + 2 * (m + n);
+  constexpr int kWg = 32 * PORTFFT_SGS_IN_WG;
+  sycl::wg_shared_state wg;
+  wg.size = kWg;
+  std::vector<sycl::sg_shared_state> sgs(PORTFFT_SGS_IN_WG);
+  std::vector<std::thread> items;
+  for (int lid = 0; lid < kWg; ++lid)
+    items.emplace_back([&, lid] {
+      sycl::sub_group sg(&sgs[lid / 32], static_cast<sycl::sub_group::linear_id_type>(lid % 32),
+                         static_cast<sycl::sub_group::linear_id_type>(lid / 32));
+      sycl::nd_item<1> it(&wg, sg, static_cast<std::size_t>(lid), kWg);
+      global_data_struct<1> gd(it);
+      std::vector<T> wi_scratch(2 * 4 * 64 + 16 * 64), priv(2 * 64 + 64);
+      wg_dft<32>(loc_view, loc_tw.data(), wg_tw, T(1), 1, 0, IdxGlobal(0), static_cast<const T*>(nullptr),
+                 static_cast<const T*>(nullptr), static_cast<Idx>(fft_size), n, m, complex_storage::INTERLEAVED_COMPLEX,
+                 layout::PACKED, elementwise_multiply::NOT_APPLIED, elementwise_multiply::NOT_APPLIED,
+                 apply_scale_factor::NOT_APPLIED, complex_conjugate::NOT_APPLIED, complex_conjugate::NOT_APPLIED, gd,
+                 wi_scratch.data(), priv.data());
+    });
+  for (auto& t : items) t.join();
+  // local (c, b) of the n x m matrix -> output (b, c): workgroup_dispatcher.hpp:247-251
+  for (Idx c = 0; c < n; ++c)
+    for (Idx b = 0; b < m; ++b) {
+      out[2 * (b * n + c)] = loc_view[2 * (c * m + b)];
+      out[2 * (b * n + c) + 1] = loc_view[2 * (c * m + b) + 1];
     }
 }
 
@@ -131,6 +191,8 @@ void ref_wi_dft_f32(const float* in, float* out, int n) { run_wi<float>(in, out,
 void ref_wi_dft_f64(const double* in, double* out, int n) { run_wi<double>(in, out, n); }
 void ref_sg_dft_f32(const float* in, float* out, int factor_wi, int factor_sg) { run_sg<float>(in, out, factor_wi, factor_sg); }
 void ref_sg_dft_f64(const double* in, double* out, int factor_wi, int factor_sg) { run_sg<double>(in, out, factor_wi, factor_sg); }
+void ref_wg_dft_f32(const float* in, float* out, int n) { run_wg<float>(in, out, n); }
+void ref_wg_dft_f64(const double* in, double* out, int n) { run_wg<double>(in, out, n); }
 long long refshim_factorize(long long n) { return portfft::detail::factorize<long long>(n); }
 long long refshim_wi_temps(long long n) { return portfft::detail::wi_temps<long long>(n); }
 int refshim_fits_in_wi(long long n, int is_double) {

@@ -5,6 +5,7 @@
 // every cross-lane operation publishes the lane's value, waits on a barrier, reads the peer's value, waits again.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <numeric>
 #include <cmath>
 #include <condition_variable>
@@ -77,6 +78,8 @@ struct id {
 template <typename T, int N>
 struct vec {
   T s[N];
+  T& operator[](int i) { return s[i]; }
+  const T& operator[](int i) const { return s[i]; }
 };
 
 inline float cospi(float x) { return static_cast<float>(std::cos(M_PI * static_cast<double>(x))); }
@@ -109,12 +112,51 @@ class sub_group {
  public:
   using linear_id_type = std::uint32_t;
   sub_group() = default;
-  sub_group(sg_shared_state* s, linear_id_type lane) : state(s), lane_id(lane) {}
+  sub_group(sg_shared_state* s, linear_id_type lane, linear_id_type group = 0) : state(s), lane_id(lane), group_id(group) {}
   linear_id_type get_local_linear_id() const { return lane_id; }
   linear_id_type get_local_range_size() const { return sg_shared_state::lanes; }
+  linear_id_type get_group_id() const { return group_id; }  // index of the sub-group inside its work-group
+  linear_id_type get_group_linear_range() const { return 1; }
+  // Intel block loads / stores (transfers.hpp:217-314, compiled out by PORTFFT_USE_SG_TRANSFERS = off): declared only
+  template <typename P>
+  auto load(P p) const { return *p; }
+  template <int N, typename P>
+  auto load(P p) const { return *p; }
+  template <typename P, typename V>
+  void store(P, const V&) const {}
+  template <int N, typename P, typename V>
+  void store(P, const V&) const {}
   sg_shared_state* state = nullptr;
   linear_id_type lane_id = 0;
+  linear_id_type group_id = 0;
 };
+
+// ---- work-group emulation: every work-item is a host thread; one barrier object per work-group ---------------------
+struct wg_shared_state {
+  std::mutex m;
+  std::condition_variable cv;
+  int size = 1, waiting = 0;
+  unsigned long generation = 0;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(m);
+    unsigned long gen = generation;
+    if (++waiting == size) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return gen != generation; });
+    }
+  }
+};
+template <int D>
+struct group {
+  wg_shared_state* state = nullptr;
+};
+template <int D>
+inline void group_barrier(group<D> g) {
+  if (g.state) g.state->barrier();
+}
 
 template <typename T>
 T select_from_group(sub_group sg, T value, std::size_t source_lane) {
@@ -133,12 +175,24 @@ inline void group_barrier(sub_group sg) { sg.state->barrier(); }
 template <int D>
 class nd_item {
  public:
-  sub_group get_sub_group() const { return {}; }
-  std::size_t get_local_linear_id() const { return 0; }
-  std::size_t get_global_linear_id() const { return 0; }
-  std::size_t get_local_range(int) const { return 1; }
-  std::size_t get_global_range(int) const { return 1; }
+  nd_item() = default;
+  nd_item(wg_shared_state* wg, sub_group sg, std::size_t local_id, std::size_t local_range)
+      : wg_(wg), sg_(sg), local_id_(local_id), local_range_(local_range) {}
+  sub_group get_sub_group() const { return sg_; }
+  group<D> get_group() const { return {wg_}; }
+  std::size_t get_group(int) const { return 0; }
+  std::size_t get_group_range(int) const { return 1; }
+  std::size_t get_local_linear_id() const { return local_id_; }
+  std::size_t get_local_id(int) const { return local_id_; }
+  std::size_t get_global_linear_id() const { return local_id_; }
+  std::size_t get_local_range(int) const { return local_range_; }
+  std::size_t get_global_range(int) const { return local_range_; }
   std::size_t get_group_linear_id() const { return 0; }
+
+ private:
+  wg_shared_state* wg_ = nullptr;
+  sub_group sg_;
+  std::size_t local_id_ = 0, local_range_ = 1;
 };
 class stream {
  public:

@@ -23,7 +23,8 @@ def _real_fixtures():
 
 def test_fixtures_present():
     assert len(_numpy_fixtures()) == 14 and len(_real_fixtures()) == 8
-    assert os.path.exists(os.path.join(GOLD, "refcode_f32.npz")) and os.path.exists(os.path.join(GOLD, "refcode_f64.npz"))
+    for name in ("refcode_f32.npz", "refcode_f64.npz", "refcode_wg_f32.npz", "refcode_wg_f64.npz"):
+        assert os.path.exists(os.path.join(GOLD, name)), name
 
 
 @pytest.mark.parametrize("path", _numpy_fixtures(), ids=os.path.basename)
@@ -60,6 +61,49 @@ def test_refcode_fixture_agrees_with_oracle(tag):
         x2, y2 = o.gen_data(1, [n], dbl)
         assert np.array_equal(x, x2.reshape(-1))
         assert np.linalg.norm(out - y2.reshape(-1)) <= o.rel_l2_bound(n, dbl) * np.linalg.norm(y2)
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_refcode_wg_fixture_agrees_with_oracle(tag):
+    """The reference's WORKGROUP-level code (wg_dft, workgroup.hpp:319-346) on N = 1000 ... 4096 against numpy."""
+    f = np.load(os.path.join(GOLD, f"refcode_wg_{tag}.npz"))
+    dbl = tag == "f64"
+    pos = 0
+    for n in f["sizes"]:
+        n = int(n)
+        x, out = f["inputs"][pos:pos + n], f["outputs"][pos:pos + n]
+        pos += n
+        x2, y2 = o.gen_data(1, [n], dbl)
+        assert np.array_equal(x, x2.reshape(-1))
+        assert np.linalg.norm(out - y2.reshape(-1)) <= o.rel_l2_bound(n, dbl) * np.linalg.norm(y2)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_cuda_matches_reference_wg_code_outputs(tag):
+    """CUDA path vs what the reference's own WORKGROUP-level code produced on the same inputs -- the lengths of
+    BASELINE configs C2 (4096) and C3 (1000) among them: north_star's 'match the reference's own implementation on
+    identical inputs' with the relative-L2 bound 1e-5 log2 N (fp32) / 1e-13 log2 N (fp64)."""
+    import torch
+
+    import portfft_b200 as pf
+
+    f = np.load(os.path.join(GOLD, f"refcode_wg_{tag}.npz"))
+    dbl = tag == "f64"
+    pos = 0
+    for n in f["sizes"]:
+        n = int(n)
+        x, ref = f["inputs"][pos:pos + n], f["outputs"][pos:pos + n]
+        pos += n
+        d = pf.descriptor([n], "double" if dbl else "float")
+        c = d.commit(torch.cuda.current_stream(), 0)
+        tin = torch.from_numpy(x.copy()).cuda()
+        tout = torch.empty_like(tin)
+        c.compute_forward(tin, tout)
+        torch.cuda.synchronize()
+        got = tout.cpu().numpy()
+        assert np.linalg.norm(got - ref) <= o.rel_l2_bound(n, dbl) * np.linalg.norm(ref), n
+        c.destroy()
 
 
 @pytest.mark.gpu

@@ -90,6 +90,24 @@ def test_reference_sg_dft_matches_numpy_and_port(n, dbl):
     assert np.linalg.norm(out_port - out_ref) <= bound * np.linalg.norm(y)
 
 
+@pytest.mark.parametrize("dbl", [False, True], ids=["float", "double"])
+@pytest.mark.parametrize("n", [1000, 1024, 2048, 3072, 4096, 8192])
+def test_reference_wg_dft_matches_numpy_and_port(n, dbl):
+    """workgroup.hpp:319-346 (wg_dft / dimension_dft) run as it is on an emulated work-group of 2 x 32 lock-step host
+    threads, with the twiddle layout of workgroup_dispatcher.hpp:382-443: agrees with numpy and with the C port."""
+    ref, port = _ref(), _port()
+    f = ref.ref_wg_dft_f64 if dbl else ref.ref_wg_dft_f32
+    f.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    x, y = o.gen_data(1, [n], dbl)
+    out_ref = np.empty_like(x)
+    f(x.ctypes.data, out_ref.ctypes.data, n)
+    bound = o.rel_l2_bound(n, dbl)
+    assert np.linalg.norm(out_ref - y) <= bound * np.linalg.norm(y)
+    out_port = np.empty_like(x)
+    (port.pfft_oracle_fft_f64 if dbl else port.pfft_oracle_fft_f32)(x.ctypes.data, out_port.ctypes.data, n, 1, 0, 1.0, 1)
+    assert np.linalg.norm(out_port - out_ref) <= bound * np.linalg.norm(y)
+
+
 def _arr(v):
     return (ctypes.c_size_t * max(1, len(v)))(*[int(x) for x in v])
 

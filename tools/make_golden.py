@@ -4,7 +4,7 @@ oracle/_ref's sources do not exist.
   numpy_*.npz  -- the reference test generator's input/expected pairs (reference_data_wrangler.hpp:117-145): protects
                   the oracle against numpy version drift between this container and the GPU box.
   numpyre_*.npz -- the same for the generator's REAL-domain branch (real input, rfftn output).
-  refcode_*.npz -- outputs of the REFERENCE's own wi_dft / sg_dft (compiled from /root/reference through
+  refcode_*.npz -- outputs of the REFERENCE's own wi_dft / sg_dft / wg_dft (compiled from /root/reference through
                   oracle/ref_shim into oracle/_ref) on the same SFC64(0) inputs.
 
 Run in the authoring container:  make -C oracle ref && python tools/make_golden.py
@@ -60,4 +60,19 @@ for dbl in (False, True):
         levels.append(lvl)
     np.savez_compressed(os.path.join(OUT, f"refcode_{tag}.npz"), sizes=np.array(sizes), levels=np.array(levels),
                         inputs=np.concatenate(ins), outputs=np.concatenate(outs))
+# the reference's WORKGROUP level (wg_dft on an emulated work-group): the lengths of BASELINE configs C2 and C3 among them
+for dbl in (False, True):
+    tag = "f64" if dbl else "f32"
+    wg = ref.ref_wg_dft_f64 if dbl else ref.ref_wg_dft_f32
+    wg.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+    ins, outs, sizes = [], [], []
+    for n in [1000, 1024, 2048, 3072, 4096]:
+        x, _ = o.gen_data(1, [n], dbl)
+        out = np.empty_like(x)
+        wg(x.ctypes.data, out.ctypes.data, n)
+        ins.append(x.reshape(-1))
+        outs.append(out.reshape(-1))
+        sizes.append(n)
+    np.savez_compressed(os.path.join(OUT, f"refcode_wg_{tag}.npz"), sizes=np.array(sizes), inputs=np.concatenate(ins),
+                        outputs=np.concatenate(outs))
 print(sorted(os.listdir(OUT)), sum(os.path.getsize(os.path.join(OUT, f)) for f in os.listdir(OUT)), "bytes")
