@@ -18,8 +18,12 @@ It restates, in numpy, what the reference's own test-suite uses to decide whethe
 Parity pinning: the reference stores no golden vectors; its expected outputs ARE numpy (`np.fft.fftn` on the
 SFC64(0) stream).  This module is therefore pinned by (a) the literal known answers the reference tests hold
 (buffer counts 33 / 17, flattened length 6, the invalid-configuration list, padding value -5, first element of the
-SFC64(0) stream) -- see tests/test_oracle.py -- and (b) the reference's own device arithmetic compiled from
-/root/reference through `oracle/ref_shim` into `oracle/_ref/` (tests/test_ref_shim.py).
+SFC64(0) stream) -- see tests/test_oracle.py -- and (b) the reference's own code compiled from /root/reference
+through `oracle/ref_shim` into `oracle/_ref/` (tests/test_ref_shim.py): its device arithmetic at the WORKITEM,
+SUBGROUP and WORKGROUP levels (wi_dft, sg_dft, wg_dft on emulated sub-groups / work-groups), its planner predicates,
+and its whole validate_descriptor / get_layout host code (4000 random descriptors, identical verdicts).  The REAL
+domain follows the generator's `is_complex = False` branch (rfftn), which the reference's tests never reach because
+its validation rejects REAL descriptors.
 
 numpy >= 2 computes `np.fft.fftn(complex64)` in single precision; the reference's script was written for numpy 1.x
 ("outData is always double precision at this point", reference_data_wrangler.hpp:139), so the transform is
