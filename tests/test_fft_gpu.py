@@ -1,6 +1,7 @@
 """GPU parity tests: the reference's FFT test grid (/root/reference/test/unit_test/instantiate_fft_tests.hpp:95-319,
 SURVEY.md App. B) re-expressed in pytest, run through the C ABI against the numpy oracle, for float and double."""
 import itertools
+import os
 
 import pytest
 
@@ -266,3 +267,15 @@ def test_real_in_place(n, scalar):
     err = np.max(np.linalg.norm(back - x, axis=1) / np.linalg.norm(x, axis=1))
     assert err <= bound, (err, bound)
     c.destroy()
+
+
+def _fuzz():
+    from test_plan_emulator import _fuzz_cases
+    return _fuzz_cases(400, 17)
+
+
+@pytest.mark.skipif(not os.environ.get("PFFT_GPU_FUZZ"), reason="opt-in (PFFT_GPU_FUZZ=1): the planner fuzz of "
+                    "tests/test_plan_emulator.py through the CUDA kernels; not yet part of the default GPU suite")
+@pytest.mark.parametrize("tp", _fuzz(), ids=lambda tp: tp.ident())
+def test_random_layouts(tp):
+    run_case(tp)
