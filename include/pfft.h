@@ -114,6 +114,11 @@ pfft_status pfft_table_host(int precision, int kind, size_t transform_length, si
  * queue the plan is committed to; it is used for the one-off table uploads and as default stream of pfft_compute. */
 pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_plan** plan_out);
 
+/* Copy of a committed plan (copy constructor of committed_descriptor_impl,
+ * src/portfft/committed_descriptor_impl.hpp:774-803): shares the immutable device tables (twiddles) with `plan` and
+ * owns fresh workspaces, so that the two can compute concurrently on different streams. */
+pfft_status pfft_clone(const pfft_plan* plan, pfft_plan** plan_out);
+
 /* pfft_commit with `n_extra` additional batch dimensions (1-D descriptors only; at most 2). */
 pfft_status pfft_commit_guru(const pfft_desc* desc, size_t n_extra, const pfft_batch_dim* extra, int flags, int device,
                              void* stream, pfft_plan** plan_out);

@@ -1,11 +1,14 @@
 // portfft::committed_descriptor<Scalar, Domain>: compute_forward / compute_backward on device (USM) pointers, the same
 // overload set as /root/reference/src/portfft/committed_descriptor.hpp:171-310.  The SYCL buffer overloads (:58-162)
-// have no CUDA meaning and are not provided.  A committed descriptor is copyable: copies share the plan.
+// have no CUDA meaning and are not provided.  A committed descriptor is copyable with the reference's semantics
+// (committed_descriptor_impl.hpp:774-803): a copy shares the immutable device tables and owns its own workspaces
+// (pfft_clone), so copies may compute concurrently on different queues.
 #ifndef PFFT_B200_PORTFFT_COMMITTED_DESCRIPTOR_HPP
 #define PFFT_B200_PORTFFT_COMMITTED_DESCRIPTOR_HPP
 
 #include <complex>
 #include <memory>
+#include <utility>
 #include <vector>
 
 #include "descriptor.hpp"
@@ -16,39 +19,55 @@ template <typename Scalar, domain Domain>
 class committed_descriptor {
   friend struct descriptor<Scalar, Domain>;
 
-  struct state {
-    pfft_plan* plan = nullptr;
-    cudaEvent_t ring[16] = {};
-    unsigned next = 0;
-    ~state() {
-      if (plan) pfft_destroy(plan);
-      for (cudaEvent_t e : ring)
-        if (e) cudaEventDestroy(e);
-    }
-  };
-
   descriptor<Scalar, Domain> params;
   queue queue_;
-  std::shared_ptr<state> st_;
+  pfft_plan* plan_ = nullptr;
 
-  committed_descriptor(const descriptor<Scalar, Domain>& d, queue& q) : params(d), queue_(q), st_(new state) {
+  committed_descriptor(const descriptor<Scalar, Domain>& d, queue& q) : params(d), queue_(q) {
     pfft_desc c = params.to_c();
-    detail::throw_on_status(pfft_commit(&c, q.device(), q.stream(), &st_->plan));
+    detail::throw_on_status(pfft_commit(&c, q.device(), q.stream(), &plan_));
   }
 
   event run(direction dir, const void* in, const void* in_imag, void* out, void* out_imag,
             const std::vector<event>& dependencies) {
     for (const event& e : dependencies)
       if (e.native()) cudaStreamWaitEvent(queue_.stream(), e.native(), 0);
-    detail::throw_on_status(
-        pfft_compute(st_->plan, static_cast<int>(dir), in, in_imag, out, out_imag, queue_.stream()));
-    cudaEvent_t& ev = st_->ring[st_->next++ % 16];
-    if (!ev) cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
-    cudaEventRecord(ev, queue_.stream());
-    return event(ev, queue_.stream());
+    detail::throw_on_status(pfft_compute(plan_, static_cast<int>(dir), in, in_imag, out, out_imag, queue_.stream()));
+    return event::record(queue_.stream(), queue_.device());  // one event per call, owned by the returned object and its copies
   }
 
  public:
+  committed_descriptor(const committed_descriptor& other) : params(other.params), queue_(other.queue_) {
+    detail::throw_on_status(pfft_clone(other.plan_, &plan_));
+  }
+  committed_descriptor(committed_descriptor&& other) noexcept
+      : params(std::move(other.params)), queue_(other.queue_), plan_(other.plan_) {
+    other.plan_ = nullptr;
+  }
+  committed_descriptor& operator=(const committed_descriptor& other) {
+    if (this != &other) {
+      committed_descriptor tmp(other);
+      swap(tmp);
+    }
+    return *this;
+  }
+  committed_descriptor& operator=(committed_descriptor&& other) noexcept {
+    if (this != &other) {
+      committed_descriptor tmp(std::move(other));
+      swap(tmp);
+    }
+    return *this;
+  }
+  /// Waits for the queue's outstanding work before releasing the plan (committed_descriptor_impl.hpp:825-828).
+  ~committed_descriptor() {
+    if (plan_) pfft_destroy(plan_);
+  }
+  void swap(committed_descriptor& other) noexcept {
+    std::swap(params, other.params);
+    std::swap(queue_, other.queue_);
+    std::swap(plan_, other.plan_);
+  }
+
   using scalar_type = Scalar;
   using complex_type = std::complex<Scalar>;
 
@@ -57,9 +76,14 @@ class committed_descriptor {
   const descriptor<Scalar, Domain>& get_descriptor() const noexcept { return params; }
   /// Level chosen for one dimension (thread / warp / block / multi-kernel).
   detail::level get_level(std::size_t dimension = 0) const {
-    return static_cast<detail::level>(pfft_plan_level(st_->plan, dimension));
+    return static_cast<detail::level>(pfft_plan_level(plan_, dimension));
   }
-  std::size_t get_workspace_bytes() const { return pfft_workspace_bytes(st_->plan); }
+  std::size_t get_workspace_bytes() const { return pfft_workspace_bytes(plan_); }
+  /// Extension (no reference counterpart: a SYCL queue may run independent commands concurrently, a CUDA stream is
+  /// in order): the queue this object submits to.  A copy bound to another queue of the same device computes
+  /// concurrently with the original; each owns its workspaces.
+  void set_queue(const queue& q) { queue_ = q; }
+  const queue& get_queue() const noexcept { return queue_; }
 
   // ---- in-place ------------------------------------------------------------------------------------------------
   event compute_forward(complex_type* inout, const std::vector<event>& dependencies = {}) {

@@ -49,6 +49,7 @@ SYMBOLS = {
     "pfft_plan_export": (c_int, [POINTER(pfft_desc), c_int, c_char_p, c_size_t, POINTER(c_size_t)]),
     "pfft_table_host": (c_int, [c_int, c_int, c_size_t, c_size_t, c_void_p]),
     "pfft_commit": (c_int, [POINTER(pfft_desc), c_int, c_void_p, POINTER(c_void_p)]),
+    "pfft_clone": (c_int, [c_void_p, POINTER(c_void_p)]),
     "pfft_commit_guru": (c_int, [POINTER(pfft_desc), c_size_t, POINTER(pfft_batch_dim), c_int, c_int, c_void_p,
                                  POINTER(c_void_p)]),
     "pfft_compute_peer": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, POINTER(c_void_p), POINTER(c_void_p),

@@ -264,6 +264,15 @@ class committed_descriptor:
             _lib.load().pfft_destroy(self._handle)
             self._handle = None
 
+    def copy(self) -> "committed_descriptor":
+        """Copy constructor of the reference (committed_descriptor_impl.hpp:774-803): shares the device tables, owns
+        fresh workspaces (pfft_clone), so the copy may compute concurrently on another stream."""
+        handle = ctypes.c_void_p()
+        _check(_lib.load().pfft_clone(self._handle, ctypes.byref(handle)))
+        return committed_descriptor(self.params, handle, self.device)
+
+    __copy__ = copy
+
     def _dispatch(self, d: direction, args, queue):
         n = len(args)
         split = self.params.complex_storage == complex_storage.SPLIT_COMPLEX

@@ -50,6 +50,7 @@ std::vector<size_t> default_strides(const std::vector<size_t>& lengths) {
 }
 
 int get_layout(const DescHost& d, int dir) {
+  if (d.lengths.empty() || d.strides(dir).size() != d.lengths.size()) return PFFT_LAYOUT_UNPACKED;  // (unvalidated input)
   if (d.strides(dir) == default_strides(d.lengths) && d.distance(dir) == d.flattened_length())
     return PFFT_LAYOUT_PACKED;
   if (d.lengths.size() == 1 && d.distance(dir) == 1 && d.strides(dir).back() == d.number_of_transforms)

@@ -16,6 +16,7 @@
 #include <cstring>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -46,13 +47,29 @@ struct GtwTable {
 
 using namespace pfft;
 
+// Device-resident tables of a plan: immutable after commit, shared (ref-counted) between a plan and its copies
+// (pfft_clone) exactly as the reference's copy constructor shares the twiddles and re-allocates only the scratch
+// (/root/reference/src/portfft/committed_descriptor_impl.hpp:774-803).
+struct PlanTables {
+  int device = 0;
+  std::map<long long, void*> tw;
+  std::map<long long, GtwTable> gtw;
+  std::map<std::pair<int, std::pair<long long, long long>>, void*> mod;  // (ModTable, (L, M)) -> device table
+  std::vector<void*> owned;
+  ~PlanTables() {
+    if (owned.empty()) return;
+    int prev = -1;
+    const bool sw = cudaGetDevice(&prev) == cudaSuccess && prev != device && cudaSetDevice(device) == cudaSuccess;
+    for (void* p : owned) cudaFree(p);
+    if (sw) cudaSetDevice(prev);
+  }
+};
+
 struct pfft_plan {
   PlanHost host;
   int device = 0;
   cudaStream_t stream = nullptr;
-  std::map<long long, void*> tw;
-  std::map<long long, GtwTable> gtw;
-  std::map<std::pair<int, std::pair<long long, long long>>, void*> mod;  // (ModTable, (L, M)) -> device table
+  std::shared_ptr<PlanTables> tables;
   void* scratch = nullptr;
   void* scratch2 = nullptr;
   void* scratch3 = nullptr;
@@ -60,7 +77,6 @@ struct pfft_plan {
   // device staging for pfft_compute_host
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
-  std::vector<void*> owned;
   // pfft_compute_host pipeline: copy streams, per-chunk events, sub-batch plans (number_of_transforms -> plan)
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_up, chunk_done;
@@ -84,7 +100,6 @@ struct pfft_plan {
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
     for (cudaStream_t s : copy_stream)
       if (s) cudaStreamDestroy(s);
-    for (void* p : owned) cudaFree(p);
     if (scratch) cudaFree(scratch);
     if (scratch2) cudaFree(scratch2);
     if (scratch3) cudaFree(scratch3);
@@ -98,7 +113,7 @@ namespace pfft {
 static void* upload(pfft_plan* plan, const void* host, size_t bytes) {
   void* d = nullptr;
   PFFT_CUDA_CHECK(cudaMalloc(&d, bytes));
-  plan->owned.push_back(d);
+  plan->tables->owned.push_back(d);
   PFFT_CUDA_CHECK(cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, plan->stream));
   PFFT_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
   return d;
@@ -106,13 +121,14 @@ static void* upload(pfft_plan* plan, const void* host, size_t bytes) {
 
 template <typename T>
 static void build_tables(pfft_plan* plan) {
+  PlanTables* tb = plan->tables.get();
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
-      if (ps.tw_n > 0 && !plan->tw.count(ps.tw_n)) {
+      if (ps.tw_n > 0 && !tb->tw.count(ps.tw_n)) {
         std::vector<T> t = make_twiddles<T>(ps.tw_n, ps.tw_n, 1);
-        plan->tw[ps.tw_n] = upload(plan, t.data(), t.size() * sizeof(T));
+        tb->tw[ps.tw_n] = upload(plan, t.data(), t.size() * sizeof(T));
       }
-      if (ps.pp.gtw_dim >= 0 && !plan->gtw.count(ps.pp.gtw_n)) {
+      if (ps.pp.gtw_dim >= 0 && !tb->gtw.count(ps.pp.gtw_n)) {
         const long long n = ps.pp.gtw_n;
         int total_bits = 0;
         while ((1LL << total_bits) < n) ++total_bits;
@@ -124,25 +140,23 @@ static void build_tables(pfft_plan* plan) {
         std::vector<T> hi = make_twiddles<T>(n, hi_count, lo_count);
         g.lo = upload(plan, lo.data(), lo.size() * sizeof(T));
         g.hi = upload(plan, hi.data(), hi.size() * sizeof(T));
-        plan->gtw[n] = g;
+        tb->gtw[n] = g;
       }
       for (int kind : {ps.lmod_kind, ps.smod_kind}) {
         const auto key = std::make_pair(kind, std::make_pair(ps.mod_l, ps.mod_m));
-        if (kind != MODT_NONE && !plan->mod.count(key)) {
+        if (kind != MODT_NONE && !tb->mod.count(key)) {
           std::vector<T> t = make_mod_table<T>(kind, ps.mod_l, ps.mod_m);
-          plan->mod[key] = upload(plan, t.data(), t.size() * sizeof(T));
+          tb->mod[key] = upload(plan, t.data(), t.size() * sizeof(T));
         }
       }
     }
   }
 }
 
-static void commit_device(pfft_plan* plan) {
-  PFFT_CUDA_CHECK(cudaSetDevice(plan->device));
-  if (plan->host.desc.is_double)
-    build_tables<double>(plan);
-  else
-    build_tables<float>(plan);
+// workspaces of one plan instance (a copy of a plan owns its own: committed_descriptor_impl.hpp:774-803) and the
+// table / workspace addresses patched into its pass list
+static void attach_device_state(pfft_plan* plan) {
+  PlanTables* tb = plan->tables.get();
   const size_t scalar = plan->host.desc.is_double ? 8 : 4;
   if (plan->l2_chunk == 0 && plan->nd_chunk == 0) {  // (chunked plans run through their sub-plans and own no workspace)
     plan->scratch_bytes = plan->host.scratch_elems * 2 * scalar;
@@ -154,17 +168,27 @@ static void commit_device(pfft_plan* plan) {
   }
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
-      ps.pp.tw = ps.tw_n > 0 ? plan->tw[ps.tw_n] : nullptr;
+      ps.pp.tw = ps.tw_n > 0 ? tb->tw[ps.tw_n] : nullptr;
       if (ps.pp.gtw_dim >= 0) {
-        const GtwTable& g = plan->gtw[ps.pp.gtw_n];
+        const GtwTable& g = tb->gtw[ps.pp.gtw_n];
         ps.pp.gtw_lo = g.lo;
         ps.pp.gtw_hi = g.hi;
         ps.pp.gtw_bits = g.bits;
       }
-      if (ps.lmod_kind != MODT_NONE) ps.pp.lmod = plan->mod[std::make_pair(ps.lmod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
-      if (ps.smod_kind != MODT_NONE) ps.pp.smod = plan->mod[std::make_pair(ps.smod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
+      if (ps.lmod_kind != MODT_NONE) ps.pp.lmod = tb->mod[std::make_pair(ps.lmod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
+      if (ps.smod_kind != MODT_NONE) ps.pp.smod = tb->mod[std::make_pair(ps.smod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
     }
   }
+}
+
+static void commit_device(pfft_plan* plan) {
+  plan->tables = std::make_shared<PlanTables>();
+  plan->tables->device = plan->device;
+  if (plan->host.desc.is_double)
+    build_tables<double>(plan);
+  else
+    build_tables<float>(plan);
+  attach_device_state(plan);
 }
 
 // The kernels of a plan must be launched with the plan's device current (its streams, tables and workspaces live
@@ -172,8 +196,14 @@ static void commit_device(pfft_plan* plan) {
 struct DeviceGuard {
   int prev = -1;
   bool switched = false;
+  bool ok = true;
   explicit DeviceGuard(int device) {
-    if (cudaGetDevice(&prev) == cudaSuccess && prev != device) switched = cudaSetDevice(device) == cudaSuccess;
+    if (cudaGetDevice(&prev) != cudaSuccess) {
+      ok = false;
+    } else if (prev != device) {
+      switched = cudaSetDevice(device) == cudaSuccess;
+      ok = switched;
+    }
   }
   ~DeviceGuard() {
     if (switched) cudaSetDevice(prev);
@@ -330,7 +360,9 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     // storage of each side of this pass: the descriptor's, or interleaved for plan-internal rows of a REAL plan
     const bool il_in = il || (ps.internal_storage & 1), il_out = il || (ps.internal_storage & 2);
     const bool pil = il_in && il_out;  // the transform kernels take one storage for both sides (the planner pairs them)
-    const bool swap = ps.force_swap ? true : (pil && bwd && !real && (p.mod_flags & internal) != internal);
+    // (force_swap: inverse complex passes of a REAL N-D backward plan.)  A pass whose both sides are plan-internal never
+    // swaps, in any kernel family.
+    const bool swap = (ps.force_swap || (pil && bwd && !real)) && (p.mod_flags & internal) != internal;
     if (ps.real_view) {
       // the user's real rows addressed as interleaved complex pairs: needs complex alignment of the first element
       const uintptr_t a = (ps.real_view & 1) ? (uintptr_t)p.in_re + (size_t)p.ioff * 2 * scalar
@@ -458,13 +490,27 @@ static void choose_nd_chunk(pfft_plan* plan) {
   plan->nd_chunk = chunk;
 }
 
-static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, bool allow_l2_chunk) {
-  PFFT_CUDA_CHECK(cudaSetDevice(device));
-  cudaDeviceProp prop;
-  PFFT_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+// SM count and opt-in shared memory of a device, queried once per device (cudaGetDeviceProperties costs ~1 ms)
+static DeviceLimits device_limits(int device) {
+  static std::mutex mu;
+  static std::map<int, DeviceLimits> cache;
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find(device);
+  if (it != cache.end()) return it->second;
   DeviceLimits lim;
-  lim.num_sms = prop.multiProcessorCount;
-  lim.max_smem_per_block = prop.sharedMemPerBlockOptin;
+  int v = 0;
+  PFFT_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device));
+  lim.num_sms = v;
+  PFFT_CUDA_CHECK(cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device));
+  lim.max_smem_per_block = (size_t)v;
+  cache[device] = lim;
+  return lim;
+}
+
+static pfft_plan* make_plan(const DescHost& d, int device, cudaStream_t stream, bool allow_l2_chunk) {
+  DeviceGuard guard(device);  // the caller's current device is restored on return
+  if (!guard.ok) throw PlanError(PFFT_CUDA_ERROR, "cudaSetDevice failed for the plan's device");
+  const DeviceLimits lim = device_limits(device);
   std::unique_ptr<pfft_plan> plan(new pfft_plan);
   plan->host = build_plan(d, lim);
   plan->device = device;
@@ -665,6 +711,24 @@ pfft_status pfft_commit(const pfft_desc* desc, int device, void* stream, pfft_pl
   });
 }
 
+pfft_status pfft_clone(const pfft_plan* plan, pfft_plan** plan_out) {
+  return guarded([&] {
+    if (plan == nullptr || plan_out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null plan");
+    *plan_out = nullptr;
+    DeviceGuard guard(plan->device);
+    std::unique_ptr<pfft_plan> copy(new pfft_plan);
+    copy->host = plan->host;
+    copy->device = plan->device;
+    copy->stream = plan->stream;
+    copy->tables = plan->tables;  // shared, immutable
+    copy->allow_l2_chunk = plan->allow_l2_chunk;
+    copy->l2_chunk = plan->l2_chunk;
+    copy->nd_chunk = plan->nd_chunk;
+    attach_device_state(copy.get());  // own workspaces; staging buffers, copy streams and sub-plans are made on demand
+    *plan_out = copy.release();
+  });
+}
+
 pfft_status pfft_compute(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
                          void* out_imag, void* stream) {
   return guarded([&] {
@@ -727,7 +791,12 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
     if (real && in == out)
       throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION, "pfft_compute_host: REAL-domain transforms take distinct host buffers");
     const bool inplace = in == out;
-    PFFT_CUDA_CHECK(cudaSetDevice(plan->device));
+    // in place on the host = in place on the device: both domains then live in ONE staged buffer, which is only
+    // meaningful when they address it alike (same offset, same plane size)
+    if (inplace && (plane_in != plane_out || d.forward_offset != d.backward_offset))
+      throw PlanError(PFFT_UNSUPPORTED_CONFIGURATION,
+                      "pfft_compute_host: an in-place call needs equal forward / backward offsets and buffer sizes");
+    DeviceGuard guard(plan->device);
     const size_t need[2] = {plane_in * planes_in, inplace ? 0 : plane_out * planes_out};
     for (int i = 0; i < 2; ++i) {
       if (need[i] > plan->stage_bytes[i]) {
@@ -759,7 +828,7 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
 pfft_status pfft_destroy(pfft_plan* plan) {
   return guarded([&] {
     if (plan == nullptr) return;
-    cudaSetDevice(plan->device);
+    DeviceGuard guard(plan->device);
     cudaStreamSynchronize(plan->stream);  // committed_descriptor_impl.hpp:825-828
     delete plan;
   });

@@ -527,17 +527,8 @@ template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS, bool INPLAC
 static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, cudaStream_t stream) {
   using Cfg = ColCfg<T, N1, N2, N3, IN, INPLACE>;
   auto kern = wg_col_kernel<T, N1, N2, N3, IN, OUT_ROWS, INPLACE>;
-  static const int slots = [&] {
-    int occ = 0, dev = 0, sms = 0;
-    if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem) != cudaSuccess) return 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, Cfg::NT, Cfg::kSmem) != cudaSuccess) return 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return occ * sms;
-  }();
+  const int slots = persistent_slots(kern, Cfg::NT, Cfg::kSmem);  // cached per (kernel, device)
   if (slots <= 0) return cudaErrorLaunchOutOfResources;
-  cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem);
-  if (e != cudaSuccess) return e;
   const long long tiles = ((p.nb[0] + Cfg::C - 1) / Cfg::C) * p.nb[1] * p.nb[2] * p.nb[3];
   const int grid = (int)(tiles < slots ? tiles : slots);
   kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);
@@ -603,12 +594,7 @@ static cudaError_t launch_col512(const PassParams& p, bool swap, cudaStream_t st
   memset(&map, 0, sizeof(map));
   if (!make_tensor_map(p, false, Col512::C, 256, &map)) return cudaSuccess;  // caller falls back
   *used = true;
-  static const int sms = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return n;
-  }();
+  const int sms = sm_count();
   if (sms <= 0) return cudaErrorLaunchOutOfResources;
   cudaError_t e = ensure_dynamic_smem(wg_col512_kernel, Col512::kSmem);
   if (e != cudaSuccess) return e;

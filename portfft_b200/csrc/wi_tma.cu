@@ -217,12 +217,7 @@ cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaSt
   if (!make_row_map(in, is_double, lines, one_per_line ? p.ibd[0] * (long long)esz : 128, &in_map)) return cudaSuccess;
   if (!make_row_map(out, is_double, lines, one_per_line ? p.obd[0] * (long long)esz : 128, &out_map)) return cudaSuccess;
   *used = true;
-  static const int sms = [] {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-    return n;
-  }();
+  const int sms = sm_count();
   if (sms <= 0) return cudaErrorLaunchOutOfResources;
   const long long tiles = (lines + wt::kRows - 1) / wt::kRows;
   const int grid = (int)(tiles < 4LL * sms ? tiles : 4LL * sms);

@@ -4,12 +4,18 @@
 // plus the error convention (invalid_configuration from commit, storage mismatch from compute).
 #include <portfft/portfft.hpp>
 
+#include <chrono>
 #include <cmath>
 #include <complex>
 #include <cstdio>
 #include <vector>
 
 using namespace portfft;
+
+template <typename C>
+static void pfft_compute_raw(C& c, const std::complex<float>* in, std::complex<float>* out) {
+  c.compute_forward(in, out);  // (returns its completion event, as the reference does; dropped here)
+}
 
 template <typename T>
 static double check(std::size_t n, std::size_t batch) {
@@ -100,8 +106,106 @@ static double check_real(std::size_t n, std::size_t batch) {
   return std::max(fwd_err, std::sqrt(err / nrm));
 }
 
+// Copies of a committed descriptor own their workspaces (committed_descriptor_impl.hpp:774-803): the original and a
+// copy run a GLOBAL-level plan (N = 65536: two passes through the plan's scratch) concurrently on two streams, many
+// times over; every result must equal the one computed alone.
+static int check_copies() {
+  const std::size_t n = 65536, batch = 6;
+  descriptor<float, domain::COMPLEX> desc({n});
+  desc.number_of_transforms = batch;
+  cudaStream_t s1, s2;
+  cudaStreamCreateWithFlags(&s1, cudaStreamNonBlocking);
+  cudaStreamCreateWithFlags(&s2, cudaStreamNonBlocking);
+  int bad = 0;
+  std::complex<float>*in1, *in2, *out1, *out2, *ref1, *ref2;
+  const std::size_t bytes = sizeof(std::complex<float>) * n * batch;
+  for (auto pp : {&in1, &in2, &out1, &out2, &ref1, &ref2}) cudaMalloc(pp, bytes);
+  std::vector<std::complex<float>> h1(n * batch), h2(n * batch), r(n * batch), o(n * batch);
+  for (std::size_t i = 0; i < h1.size(); ++i) {
+    h1[i] = {float(std::sin(0.11 * i)), float(std::cos(0.7 * i))};
+    h2[i] = {float(std::cos(0.13 * i + 1.0)), float(std::sin(0.3 * i))};
+  }
+  cudaMemcpy(in1, h1.data(), bytes, cudaMemcpyHostToDevice);
+  cudaMemcpy(in2, h2.data(), bytes, cudaMemcpyHostToDevice);
+  {
+    queue q1(s1), q2(s2);
+    auto a = desc.commit(q1);
+    auto b = a;  // copy: shared twiddles, own scratch
+    b.set_queue(q2);
+    if (a.get_workspace_bytes() == 0 || b.get_workspace_bytes() != a.get_workspace_bytes()) ++bad;
+    a.compute_forward(in1, ref1).wait();
+    a.compute_forward(in2, ref2).wait();  // results computed alone, one at a time
+    event last_a, last_b;
+    for (int it = 0; it < 20; ++it) {
+      last_a = a.compute_forward(in1, out1);
+      last_b = b.compute_forward(in2, out2);
+    }
+    event first = last_a;  // events stay valid however many computes follow
+    for (int it = 0; it < 40; ++it) a.compute_forward(in1, out1);
+    first.wait();
+    last_b.wait();
+    q1.wait();
+    for (int k = 0; k < 2; ++k) {
+      cudaMemcpy(r.data(), k ? ref2 : ref1, bytes, cudaMemcpyDeviceToHost);
+      cudaMemcpy(o.data(), k ? out2 : out1, bytes, cudaMemcpyDeviceToHost);
+      for (std::size_t i = 0; i < r.size(); ++i)
+        if (r[i] != o[i]) {
+          ++bad;
+          break;
+        }
+    }
+    auto c = std::move(b);  // moved-from objects release nothing
+    committed_descriptor<float, domain::COMPLEX> d2 = c;
+    d2 = a;
+  }
+  for (auto pp : {in1, in2, out1, out2, ref1, ref2}) cudaFree(pp);
+  cudaStreamDestroy(s1);
+  cudaStreamDestroy(s2);
+  std::printf("copies on two streams: %s\n", bad ? "MISMATCH" : "identical");
+  return bad;
+}
+
+// BASELINE config C1 (N = 64, batch 1024, out of place): host cost of one compute call through the C++ header and
+// the rate at which back-to-back calls retire on the device.
+static void c1_latency() {
+  descriptor<float, domain::COMPLEX> desc({64});
+  desc.number_of_transforms = 1024;
+  cudaStream_t s;
+  cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+  std::complex<float>*in, *out;
+  cudaMalloc(&in, 8 * 65536);
+  cudaMalloc(&out, 8 * 65536);
+  cudaMemset(in, 0, 8 * 65536);
+  {
+    queue q(s);
+    auto c = desc.commit(q);
+    for (int i = 0; i < 200; ++i) pfft_compute_raw(c, in, out);
+    q.wait();
+    const int iters = 5000;
+    auto t0 = std::chrono::steady_clock::now();
+    for (int i = 0; i < iters; ++i) pfft_compute_raw(c, in, out);
+    auto t1 = std::chrono::steady_clock::now();
+    q.wait();
+    auto t2 = std::chrono::steady_clock::now();
+    const double submit = std::chrono::duration<double, std::micro>(t1 - t0).count() / iters;
+    const double total = std::chrono::duration<double, std::micro>(t2 - t0).count() / iters;
+    // one call at a time: submit, wait, repeat (latency of a lone transform as a caller sees it)
+    auto t3 = std::chrono::steady_clock::now();
+    for (int i = 0; i < 500; ++i) c.compute_forward(in, out).wait();
+    auto t4 = std::chrono::steady_clock::now();
+    const double lone = std::chrono::duration<double, std::micro>(t4 - t3).count() / 500;
+    std::printf("C1 n=64 batch=1024: host submit %.2f us/call, back-to-back %.2f us/call, submit+wait %.2f us/call\n",
+                submit, total, lone);
+  }
+  cudaFree(in);
+  cudaFree(out);
+  cudaStreamDestroy(s);
+}
+
 int main() {
   int fails = 0;
+  fails += check_copies();
+  c1_latency();
   for (std::size_t n : {16, 1000, 81}) {
     double ef = check_real<float>(n, 3), ed = check_real<double>(n, 3);
     double bf = 1e-5 * std::log2(double(n)), bd = 1e-13 * std::log2(double(n));

@@ -1,0 +1,266 @@
+"""Parity case grids shared by the GPU suite (tests/test_fft_gpu.py) and the CPU plan emulator
+(tests/test_plan_emulator.py): the reference's FFT test grid (/root/reference/test/unit_test/instantiate_fft_tests.hpp:
+95-319) re-expressed as CaseParams lists, the suites added here (column tiles, Bluestein, REAL,
+steady state), and the seeded random-layout fuzz.  Pure data: no pytest, no CUDA."""
+import itertools
+
+from fft_check import BI, P, U, CaseParams
+
+# placement x layout sets (instantiate_fft_tests.hpp:37-85)
+ALL_LAYOUTS = [("IP", P, P), ("IP", BI, BI), ("OOP", P, P), ("OOP", P, BI), ("OOP", BI, BI), ("OOP", BI, P)]
+MD_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
+GLOBAL_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
+OOP_ALL = [l for l in ALL_LAYOUTS if l[0] == "OOP"]
+BOTH_DIR = ["fwd", "bwd"]
+STORAGES = ["interleaved", "split"]
+SCALARS = ["float", "double"]
+
+
+def basic(layouts, dirs, storages, batches, lengths):
+    out = []
+    for (pl, li, lo), dr, st, b, n, sc in itertools.product(layouts, dirs, storages, batches, lengths, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, b, pl, li, lo, dr, st, sc))
+    return out
+
+
+def layouts(placements, dirs, storages, batches, lps):
+    """layout_params = (len, fwd_stride, bwd_stride[, fwd_dist, bwd_dist]) (fft_test_utils.hpp:52-78)"""
+    out = []
+    for pl, dr, st, b, lp, sc in itertools.product(placements, dirs, storages, batches, lps, SCALARS):
+        fd, bd = (lp[3], lp[4]) if len(lp) == 5 else (None, None)
+        out.append(CaseParams([lp[0]], b, pl, U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
+                              forward_distance=fd, backward_distance=bd))
+    return out
+
+
+def offsets(layouts_, dirs, batches, lengths, offs):
+    out = []
+    for (pl, li, lo), dr, b, n, (fo, bo), sc in itertools.product(layouts_, dirs, batches, lengths, offs, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, b, pl, li, lo, dr, "interleaved", sc, forward_offset=fo, backward_offset=bo))
+    return out
+
+
+def real(dirs, storages, batches, lengths):
+    """REAL domain, out of place, packed rows: forward real -> half spectrum, backward half spectrum -> real.
+    The backward distance is the packed half-spectrum length n // 2 + 1."""
+    out = []
+    for dr, st, b, n, sc in itertools.product(dirs, storages, batches, lengths, SCALARS):
+        out.append(CaseParams([n], b, "OOP", U, U, dr, st, sc, forward_strides=[1], backward_strides=[1],
+                              forward_distance=n, backward_distance=n // 2 + 1, domain="real",
+                              backward_scale=(1.0 / n if dr == "bwd" else None)))
+    return out
+
+
+def real_layouts(dirs, storages, batches, lps):
+    """REAL domain with explicit layouts: (n, fwd_stride, bwd_stride, fwd_dist, bwd_dist, fwd_off, bwd_off)"""
+    out = []
+    for dr, st, b, lp, sc in itertools.product(dirs, storages, batches, lps, SCALARS):
+        out.append(CaseParams([lp[0]], b, "OOP", U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
+                              forward_distance=lp[3], backward_distance=lp[4], forward_offset=lp[5],
+                              backward_offset=lp[6], domain="real"))
+    return out
+
+
+def real_md(dirs, storages, batches, lengths_list, packed):
+    """REAL domain, N-D, out of place.  packed=False: the descriptor's default strides (row-major over `lengths` in
+    both domains, as the reference's constructor sets them: descriptor.hpp:137-144); packed=True: the half spectrum
+    stored densely ([.., n_last // 2 + 1])."""
+    out = []
+    for dr, st, b, lens, sc in itertools.product(dirs, storages, batches, lengths_list, SCALARS):
+        lens = list(lens)
+        if not packed:
+            out.append(CaseParams(lens, b, "OOP", P, P, dr, st, sc, domain="real"))
+            continue
+        cl = lens[:-1] + [lens[-1] // 2 + 1]
+        fs, bs, fa, ba = [0] * len(lens), [0] * len(lens), 1, 1
+        for i in range(len(lens) - 1, -1, -1):
+            fs[i], bs[i] = fa, ba
+            fa, ba = fa * lens[i], ba * cl[i]
+        out.append(CaseParams(lens, b, "OOP", U, U, dr, st, sc, forward_strides=fs, backward_strides=bs,
+                              forward_distance=fa, backward_distance=ba, domain="real"))
+    return out
+
+
+def scaled(dr, lengths, fs, bs):
+    out = []
+    for n, sc in itertools.product(lengths, SCALARS):
+        n = list(n) if isinstance(n, (list, tuple)) else [n]
+        out.append(CaseParams(n, 3, "OOP", P, P, dr, "interleaved", sc, forward_scale=fs, backward_scale=bs))
+    return out
+
+
+SUITES = {
+    "workItemTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 33000], [1, 2, 3, 4, 8]),
+    "workItemOrSubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [16, 32]),
+    "SubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [64, 96, 128]),
+    "SubgroupRegressionTest": basic([("IP", BI, BI)], ["fwd"], ["interleaved"], [44, 100], [80, 100]),
+    "SubgroupOrWorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 131], [256, 512, 1024]),
+    "SubgroupOrWorkgroupRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [1, 131], [1536]),
+    "WorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [2048, 3072, 4096]),
+    "WorkgroupOrGlobal": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 128], [8192, 16384]),
+    "GlobalTest": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [32768, 65536, 131072]),
+    "WorkgroupOrGlobalRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [3], [9800, 15360, 68640]),
+    "BackwardTest": basic(ALL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [8, 9, 16, 32, 64, 4096]),
+    "BackwardGlobalTest": basic(GLOBAL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [32768, 65536]),
+    "MultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                                  [[2, 4], [4, 2], [16, 512], [64, 2048], [2, 3, 6], [2, 3, 2, 3]]),
+    # not in the reference grid: column-tile kernel (TMA tiles with ragged column counts, odd strides -> fallback)
+    "ColumnTileTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                            [[64, 100], [128, 24], [256, 20], [512, 36], [64, 33], [256, 256], [64, 64, 64]]),
+    "ColumnTileOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
+    "ColumnTileOffsetsMatchedTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(3, 3), (16, 16)]),
+    # BASELINE config C4 at full length (one transform) and a 2^20 case: three / two column-tile passes
+    "LargeGlobalTest": basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [1], [1 << 20, 1 << 24]),
+    "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
+    "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
+    "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
+    "OffsetsWIErrorRegressionTest": offsets(OOP_ALL, BOTH_DIR, [33000], [8], [(0, 2049), (2049, 0), (2047, 2049)]),
+    "OffsetsMDErrorRegressionTest": offsets([("OOP", P, P)], ["fwd"], [2], [[4, 4]], [(2, 0)]),
+    "FwdScaledFFTTest": scaled("fwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
+    "BwdScaledFFTTest": scaled("bwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
+    "workItemStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
+                                         [(3, 4, 7), (8, 11, 2), (9, 3, 4, 30, 40)]),
+    "SubgroupStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
+                                         [(64, 1, 7), (64, 4, 7), (75, 3, 2, 300, 200), (104, 3, 4)]),
+    "workItemStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
+                                                      [(8, 33, 99, 1, 3), (8, 33, 2, 1, 16), (8, 2, 66, 16, 2)]),
+    "SubgroupStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
+                                                      [(64, 33, 99, 1, 3), (96, 33, 2, 1, 192), (70, 2, 66, 140, 2)]),
+    "workItemStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(3, 4, 4), (9, 3, 3, 25, 25)]),
+    "SubgroupStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(75, 4, 4), (96, 3, 3, 286, 286)]),
+    "workItemStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
+                                                     [(3, 66, 66, 2, 2), (6, 40, 40, 1, 1)]),
+    "SubgroupStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
+                                                     [(75, 66, 66, 2, 2), (96, 40, 40, 1, 1)]),
+    "StridedStrideEqualsDistance": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [1], [(8, 2, 2, 2, 2), (8, 1, 1, 1, 1)]),
+    "workItemStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [4], [(4, 4, 4, 3, 3)]),
+    "SubgroupStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [13], [(85, 13, 13, 12, 12)]),
+    # not in the reference grid (it rejects these as unsupported): layouts beyond PACKED at the GLOBAL
+    # level and for N-D transforms
+    "GlobalLayoutsTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16384, 32768]),
+    "GlobalStridedTest": layouts(["OOP"], BOTH_DIR, STORAGES, [2],
+                                 [(16384, 2, 3, 40000, 50000), (9800, 3, 1, 30000, 9800)]),
+    # lengths with prime factors > 31 (Bluestein; the reference throws unsupported_configuration):
+    # one CTA per convolution (M <= 8192 fp32 / 4096 fp64) and the multi-pass form
+    "BluesteinTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 5], [37, 67, 1031, 2 * 1031]),
+    "BluesteinGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3], [4099, 65537]),
+    "BluesteinMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [2], [[6, 37], [37, 6], [41, 43]]),
+    "BluesteinOffsetsTest": offsets(OOP_ALL, BOTH_DIR, [3], [131], [(0, 7), (9, 0), (5, 11)]),
+    # REAL domain (the reference reserves the API and throws; expected values = numpy rfft as in its generator,
+    # reference_data_wrangler.hpp:136-137): even lengths on the pair view, odd lengths, every level of the
+    # half-length complex transform, strided / offset layouts through the pack and unpack passes
+    "RealTest": real(BOTH_DIR, STORAGES, [1, 3, 131], [1, 2, 4, 8, 9, 15, 16, 30, 64, 100, 256, 512, 1000, 1024, 4096,
+                                                        8192]),
+    "RealGlobalTest": real(BOTH_DIR, STORAGES, [1, 3], [16384, 65536, 3 * 16384, 1 << 20]),
+    "RealLayoutsTest": real_layouts(BOTH_DIR, STORAGES, [1, 5],
+                                    [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
+                                     (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
+                                     (8, 5, 5, 1, 1, 0, 0)]),
+    # BASELINE config C3's kernel (three compile-time radices, N = 1000) on every layout family and C3's own layout
+    "ThreeRadixTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3, 1031], [1000]),
+    "ThreeRadixC3LayoutTest": [CaseParams([1000], b, "OOP", U, U, dr, "split", sc, forward_strides=[2],
+                                          backward_strides=[1], forward_distance=2048, backward_distance=1024,
+                                          forward_offset=7, backward_offset=3, backward_scale=1e-3)
+                               for b in (5, 1500) for dr in BOTH_DIR for sc in SCALARS],
+    # generic in-place column-tile kernel: batch-interleaved layouts of lengths the TMA tile kernel does not take,
+    # N-D outer dimensions that are not powers of two, non-power-of-two multi-pass lengths (column passes with the
+    # inter-factor twiddle)
+    "ColumnGenericTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [5, 131], [96, 100, 1000, 1536, 1792]),
+    "ColumnGenericMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
+                                               [[96, 40], [100, 100], [1000, 24], [60, 50, 40]]),
+    "ColumnGenericGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [3], [68640, 9800, 3 * 16384, 1 << 17]),
+    # thread-level kernel with TMA tiles in and out (rows of exactly 128 bytes: fp32 N = 16, fp64 N = 8; large batches)
+    "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000, 65536],
+                             [2, 4, 8, 16]),
+    "workItemTmaPaddedRowsTest": layouts(["OOP"], BOTH_DIR, ["interleaved"], [5000], [(16, 1, 1, 20, 18), (8, 1, 1, 8, 10)]),
+    "workItemTmaOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [5000], [16], [(0, 2), (6, 0), (3, 5)]),
+    "RealMultidimensionalTest": real_md(BOTH_DIR, STORAGES, [1, 3],
+                                        [[4, 8], [3, 5], [6, 9], [2, 3, 4], [16, 512], [64, 64, 64], [37, 8]], False),
+    # REAL N-D backward whose outer dimension needs the multi-pass Bluestein form: inverse (swapping) passes around
+    # plan-internal plain-forward transforms (MOD_NO_USER_SWAP_* on every kernel family)
+    "RealBluesteinMultidimensionalTest": real_md(BOTH_DIR, ["interleaved"], [2], [[4099, 8], [37, 16]], False),
+    "RealMultidimensionalPackedTest": real_md(BOTH_DIR, STORAGES, [1, 3],
+                                              [[4, 8], [6, 9], [2, 3, 4], [16, 512], [8, 16384], [128, 128, 128]], True),
+    # steady state of the persistent TMA-ring kernels: more tiles than the persistent grid holds CTAs x ring stages, so
+    # every stage wraps and every mbarrier phase flips many times (the reference's grid goes to batch 33000,
+    # instantiate_fft_tests.hpp:95-192).  wg_cube<16,1> (C2's kernel): > 296 transforms; wg_cube<8,4>: > 2400;
+    # wg_rows3 (1024 / 2048 / 8192); wg_col (64 .. 256 rows and columns); wg_col512 (C5's y / x kernel): > 444 tiles of
+    # 16 columns, two groups x three-stage ring
+    "SteadyStateTest": (basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [3000], [4096]) +
+                        [c for c in basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [20000], [512]) +
+                         basic([("IP", P, P)], ["fwd"], ["interleaved"], [8000], [1024]) +
+                         basic([("OOP", P, P)], ["bwd"], ["interleaved"], [4000], [2048]) +
+                         basic([("OOP", P, P)], ["fwd"], ["interleaved"], [1000], [8192]) +
+                         basic([("IP", P, P)], ["bwd"], ["interleaved"], [1000], [8192]) +
+                         basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [40000], [64, 256])
+                         if c.scalar == "float" or c.lengths[0] <= 2048]),
+    "SteadyStateColumnTest": [c for c in basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [3], [[512, 8192]]) +
+                              basic([("OOP", P, P)], ["fwd"], ["interleaved"], [1], [[512, 512, 64], [256, 256, 128]]) +
+                              basic([("IP", P, P)], ["bwd"], ["interleaved"], [1], [[512, 512, 64]]) +
+                              basic([("OOP", BI, BI)], ["fwd"], ["interleaved"], [30000], [512, 128])
+                              if c.scalar == "float" or c.lengths == [256, 256, 128]],
+}
+
+
+def random_layout(rng, dims, batch):
+    """A valid (overlap-free) strides / distance pair for `dims` x batch: the dimensions and the batch are nested in a
+    random order, each level padded by a random amount."""
+    order = list(range(len(dims) + 1))  # index len(dims) = the batch
+    rng.shuffle(order)
+    strides, distance, acc = [0] * len(dims), 1, 1
+    for k in order:
+        acc += rng.choice([0, 0, 0, 1, 3])
+        if k == len(dims):
+            distance = acc
+            acc *= batch
+        else:
+            strides[k] = acc
+            acc *= dims[k]
+    return strides, distance
+
+
+def fuzz_cases(count=600, seed=5):
+    import random
+
+    rng = random.Random(seed)
+    pool = [1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 25, 27, 30, 32, 37, 49, 64, 96, 100, 101, 128, 243, 256, 500, 512, 1000,
+            1024, 1031, 2048, 4096, 4099, 8192, 10000, 16384, 20000]
+    cases = []
+    while len(cases) < count:
+        rank = rng.choice([1, 1, 1, 2, 2, 3])
+        # (rank > 1: no unit dimensions -- the reference's conservative N-D overlap check rejects a unit dimension
+        # whose stride ties with another one's, descriptor_validation.hpp:123-151)
+        dims = [rng.choice(pool if rank == 1 else pool[1:18]) for _ in range(rank)]
+        n = 1
+        for d in dims:
+            n *= d
+        batch = rng.choice([1, 2, 3, 5, 7])
+        if n * batch > (1 << 16):
+            continue
+        real = rng.random() < 0.3
+        cdims = dims[:-1] + [dims[-1] // 2 + 1] if real else dims
+        if real and any(p > 31 for p in prime_factors(dims[-1] // 2 if dims[-1] % 2 == 0 else dims[-1])):
+            continue  # REAL: the inner half-length transform must be 31-smooth
+        fs, fd = random_layout(rng, dims, batch)
+        bs, bd = random_layout(rng, cdims, batch)
+        tp = CaseParams(dims, batch, "OOP", U, U, rng.choice(["fwd", "bwd"]), rng.choice(["interleaved", "split"]),
+                        rng.choice(["float", "double"]), forward_strides=fs, backward_strides=bs, forward_distance=fd,
+                        backward_distance=bd, forward_offset=rng.choice([0, 0, 1, 6]), backward_offset=rng.choice([0, 0, 2, 5]),
+                        forward_scale=rng.choice([None, 0.5]), backward_scale=rng.choice([None, -2.0]),
+                        domain="real" if real else "complex")
+        cases.append(tp)
+    return cases
+
+
+def prime_factors(n):
+    out, p = [], 2
+    while p * p <= n:
+        while n % p == 0:
+            out.append(p)
+            n //= p
+        p += 1
+    if n > 1:
+        out.append(n)
+    return out

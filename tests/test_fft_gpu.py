@@ -1,189 +1,12 @@
 """GPU parity tests: the reference's FFT test grid (/root/reference/test/unit_test/instantiate_fft_tests.hpp:95-319,
 SURVEY.md App. B) re-expressed in pytest, run through the C ABI against the numpy oracle, for float and double."""
-import itertools
-import os
-
 import pytest
 
 from fft_check import BI, P, U, CaseParams, run_case
+from grid_cases import (ALL_LAYOUTS, BOTH_DIR, GLOBAL_LAYOUTS, MD_LAYOUTS, SCALARS, STORAGES, SUITES, basic, fuzz_cases,
+                        offsets, real, scaled)
 
 pytestmark = pytest.mark.gpu
-
-# placement x layout sets (instantiate_fft_tests.hpp:37-85)
-ALL_LAYOUTS = [("IP", P, P), ("IP", BI, BI), ("OOP", P, P), ("OOP", P, BI), ("OOP", BI, BI), ("OOP", BI, P)]
-MD_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
-GLOBAL_LAYOUTS = [("IP", P, P), ("OOP", P, P)]
-OOP_ALL = [l for l in ALL_LAYOUTS if l[0] == "OOP"]
-BOTH_DIR = ["fwd", "bwd"]
-STORAGES = ["interleaved", "split"]
-SCALARS = ["float", "double"]
-
-
-def basic(layouts, dirs, storages, batches, lengths):
-    out = []
-    for (pl, li, lo), dr, st, b, n, sc in itertools.product(layouts, dirs, storages, batches, lengths, SCALARS):
-        n = list(n) if isinstance(n, (list, tuple)) else [n]
-        out.append(CaseParams(n, b, pl, li, lo, dr, st, sc))
-    return out
-
-
-def layouts(placements, dirs, storages, batches, lps):
-    """layout_params = (len, fwd_stride, bwd_stride[, fwd_dist, bwd_dist]) (fft_test_utils.hpp:52-78)"""
-    out = []
-    for pl, dr, st, b, lp, sc in itertools.product(placements, dirs, storages, batches, lps, SCALARS):
-        fd, bd = (lp[3], lp[4]) if len(lp) == 5 else (None, None)
-        out.append(CaseParams([lp[0]], b, pl, U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
-                              forward_distance=fd, backward_distance=bd))
-    return out
-
-
-def offsets(layouts_, dirs, batches, lengths, offs):
-    out = []
-    for (pl, li, lo), dr, b, n, (fo, bo), sc in itertools.product(layouts_, dirs, batches, lengths, offs, SCALARS):
-        n = list(n) if isinstance(n, (list, tuple)) else [n]
-        out.append(CaseParams(n, b, pl, li, lo, dr, "interleaved", sc, forward_offset=fo, backward_offset=bo))
-    return out
-
-
-def real(dirs, storages, batches, lengths):
-    """REAL domain, out of place, packed rows: forward real -> half spectrum, backward half spectrum -> real.
-    The backward distance is the packed half-spectrum length n // 2 + 1."""
-    out = []
-    for dr, st, b, n, sc in itertools.product(dirs, storages, batches, lengths, SCALARS):
-        out.append(CaseParams([n], b, "OOP", U, U, dr, st, sc, forward_strides=[1], backward_strides=[1],
-                              forward_distance=n, backward_distance=n // 2 + 1, domain="real",
-                              backward_scale=(1.0 / n if dr == "bwd" else None)))
-    return out
-
-
-def real_layouts(dirs, storages, batches, lps):
-    """REAL domain with explicit layouts: (n, fwd_stride, bwd_stride, fwd_dist, bwd_dist, fwd_off, bwd_off)"""
-    out = []
-    for dr, st, b, lp, sc in itertools.product(dirs, storages, batches, lps, SCALARS):
-        out.append(CaseParams([lp[0]], b, "OOP", U, U, dr, st, sc, forward_strides=[lp[1]], backward_strides=[lp[2]],
-                              forward_distance=lp[3], backward_distance=lp[4], forward_offset=lp[5],
-                              backward_offset=lp[6], domain="real"))
-    return out
-
-
-def real_md(dirs, storages, batches, lengths_list, packed):
-    """REAL domain, N-D, out of place.  packed=False: the descriptor's default strides (row-major over `lengths` in
-    both domains, as the reference's constructor sets them: descriptor.hpp:137-144); packed=True: the half spectrum
-    stored densely ([.., n_last // 2 + 1])."""
-    out = []
-    for dr, st, b, lens, sc in itertools.product(dirs, storages, batches, lengths_list, SCALARS):
-        lens = list(lens)
-        if not packed:
-            out.append(CaseParams(lens, b, "OOP", P, P, dr, st, sc, domain="real"))
-            continue
-        cl = lens[:-1] + [lens[-1] // 2 + 1]
-        fs, bs, fa, ba = [0] * len(lens), [0] * len(lens), 1, 1
-        for i in range(len(lens) - 1, -1, -1):
-            fs[i], bs[i] = fa, ba
-            fa, ba = fa * lens[i], ba * cl[i]
-        out.append(CaseParams(lens, b, "OOP", U, U, dr, st, sc, forward_strides=fs, backward_strides=bs,
-                              forward_distance=fa, backward_distance=ba, domain="real"))
-    return out
-
-
-def scaled(dr, lengths, fs, bs):
-    out = []
-    for n, sc in itertools.product(lengths, SCALARS):
-        n = list(n) if isinstance(n, (list, tuple)) else [n]
-        out.append(CaseParams(n, 3, "OOP", P, P, dr, "interleaved", sc, forward_scale=fs, backward_scale=bs))
-    return out
-
-
-SUITES = {
-    "workItemTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 33000], [1, 2, 3, 4, 8]),
-    "workItemOrSubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [16, 32]),
-    "SubgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3, 555], [64, 96, 128]),
-    "SubgroupRegressionTest": basic([("IP", BI, BI)], ["fwd"], ["interleaved"], [44, 100], [80, 100]),
-    "SubgroupOrWorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 131], [256, 512, 1024]),
-    "SubgroupOrWorkgroupRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [1, 131], [1536]),
-    "WorkgroupTest": basic(ALL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [2048, 3072, 4096]),
-    "WorkgroupOrGlobal": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 128], [8192, 16384]),
-    "GlobalTest": basic(GLOBAL_LAYOUTS, ["fwd"], STORAGES, [1, 3], [32768, 65536, 131072]),
-    "WorkgroupOrGlobalRegressionTest": basic([("IP", P, P)], ["fwd"], ["interleaved"], [3], [9800, 15360, 68640]),
-    "BackwardTest": basic(ALL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [8, 9, 16, 32, 64, 4096]),
-    "BackwardGlobalTest": basic(GLOBAL_LAYOUTS, ["bwd"], STORAGES, [1, 3], [32768, 65536]),
-    "MultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
-                                  [[2, 4], [4, 2], [16, 512], [64, 2048], [2, 3, 6], [2, 3, 2, 3]]),
-    # not in the reference grid: column-tile kernel (TMA tiles with ragged column counts, odd strides -> fallback)
-    "ColumnTileTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
-                            [[64, 100], [128, 24], [256, 20], [512, 36], [64, 33], [256, 256], [64, 64, 64]]),
-    "ColumnTileOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [2], [[128, 40]], [(0, 3), (5, 0), (16, 32)]),
-    "ColumnTileOffsetsMatchedTest": offsets(MD_LAYOUTS, BOTH_DIR, [2], [[128, 40]], [(3, 3), (16, 16)]),
-    # BASELINE config C4 at full length (one transform) and a 2^20 case: three / two column-tile passes
-    "LargeGlobalTest": basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [1], [1 << 20, 1 << 24]),
-    "OffsetsMatchedTest": offsets(ALL_LAYOUTS, ["fwd"], [33], [2048], [(8, 8), (67, 67)]),
-    "OffsetsMultiDimensionalTest": offsets(MD_LAYOUTS, ["fwd"], [33], [[16, 512]], [(8, 8), (67, 67)]),
-    "OffsetsMismatchedTest": offsets(OOP_ALL, BOTH_DIR, [33], [2048], [(0, 2049), (2049, 0), (2047, 2049)]),
-    "OffsetsWIErrorRegressionTest": offsets(OOP_ALL, BOTH_DIR, [33000], [8], [(0, 2049), (2049, 0), (2047, 2049)]),
-    "OffsetsMDErrorRegressionTest": offsets([("OOP", P, P)], ["fwd"], [2], [[4, 4]], [(2, 0)]),
-    "FwdScaledFFTTest": scaled("fwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
-    "BwdScaledFFTTest": scaled("bwd", [9, 16, 64, 512, 4096, [16, 512]], -1.0, 2.0),
-    "workItemStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
-                                         [(3, 4, 7), (8, 11, 2), (9, 3, 4, 30, 40)]),
-    "SubgroupStridedOOPInOrder": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 3, 33000],
-                                         [(64, 1, 7), (64, 4, 7), (75, 3, 2, 300, 200), (104, 3, 4)]),
-    "workItemStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
-                                                      [(8, 33, 99, 1, 3), (8, 33, 2, 1, 16), (8, 2, 66, 16, 2)]),
-    "SubgroupStridedOOPLikeBatchInterleaved": layouts(["OOP"], BOTH_DIR, STORAGES, [1, 10, 33],
-                                                      [(64, 33, 99, 1, 3), (96, 33, 2, 1, 192), (70, 2, 66, 140, 2)]),
-    "workItemStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(3, 4, 4), (9, 3, 3, 25, 25)]),
-    "SubgroupStridedIP": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33000], [(75, 4, 4), (96, 3, 3, 286, 286)]),
-    "workItemStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
-                                                     [(3, 66, 66, 2, 2), (6, 40, 40, 1, 1)]),
-    "SubgroupStridedIPLikeBatchInterleaved": layouts(["IP"], BOTH_DIR, STORAGES, [1, 3, 33],
-                                                     [(75, 66, 66, 2, 2), (96, 40, 40, 1, 1)]),
-    "StridedStrideEqualsDistance": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [1], [(8, 2, 2, 2, 2), (8, 1, 1, 1, 1)]),
-    "workItemStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [4], [(4, 4, 4, 3, 3)]),
-    "SubgroupStridedArbitraryInterleaved": layouts(["IP", "OOP"], BOTH_DIR, STORAGES, [13], [(85, 13, 13, 12, 12)]),
-    # not in the reference grid (it rejects these as unsupported): layouts beyond PACKED at the GLOBAL
-    # level and for N-D transforms
-    "GlobalLayoutsTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [3], [16384, 32768]),
-    "GlobalStridedTest": layouts(["OOP"], BOTH_DIR, STORAGES, [2],
-                                 [(16384, 2, 3, 40000, 50000), (9800, 3, 1, 30000, 9800)]),
-    # lengths with prime factors > 31 (Bluestein; the reference throws unsupported_configuration):
-    # one CTA per convolution (M <= 8192 fp32 / 4096 fp64) and the multi-pass form
-    "BluesteinTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 5], [37, 67, 1031, 2 * 1031]),
-    "BluesteinGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3], [4099, 65537]),
-    "BluesteinMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [2], [[6, 37], [37, 6], [41, 43]]),
-    "BluesteinOffsetsTest": offsets(OOP_ALL, BOTH_DIR, [3], [131], [(0, 7), (9, 0), (5, 11)]),
-    # REAL domain (the reference reserves the API and throws; expected values = numpy rfft as in its generator,
-    # reference_data_wrangler.hpp:136-137): even lengths on the pair view, odd lengths, every level of the
-    # half-length complex transform, strided / offset layouts through the pack and unpack passes
-    "RealTest": real(BOTH_DIR, STORAGES, [1, 3, 131], [1, 2, 4, 8, 9, 15, 16, 30, 64, 100, 256, 512, 1000, 1024, 4096,
-                                                        8192]),
-    "RealGlobalTest": real(BOTH_DIR, STORAGES, [1, 3], [16384, 65536, 3 * 16384, 1 << 20]),
-    "RealLayoutsTest": real_layouts(BOTH_DIR, STORAGES, [1, 5],
-                                    [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
-                                     (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),
-                                     (8, 5, 5, 1, 1, 0, 0)]),
-    # BASELINE config C3's kernel (three compile-time radices, N = 1000) on every layout family and C3's own layout
-    "ThreeRadixTest": basic(ALL_LAYOUTS, BOTH_DIR, STORAGES, [1, 3, 1031], [1000]),
-    "ThreeRadixC3LayoutTest": [CaseParams([1000], b, "OOP", U, U, dr, "split", sc, forward_strides=[2],
-                                          backward_strides=[1], forward_distance=2048, backward_distance=1024,
-                                          forward_offset=7, backward_offset=3, backward_scale=1e-3)
-                               for b in (5, 1500) for dr in BOTH_DIR for sc in SCALARS],
-    # generic in-place column-tile kernel: batch-interleaved layouts of lengths the TMA tile kernel does not take,
-    # N-D outer dimensions that are not powers of two, non-power-of-two multi-pass lengths (column passes with the
-    # inter-factor twiddle)
-    "ColumnGenericTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [5, 131], [96, 100, 1000, 1536, 1792]),
-    "ColumnGenericMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
-                                               [[96, 40], [100, 100], [1000, 24], [60, 50, 40]]),
-    "ColumnGenericGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [3], [68640, 9800, 3 * 16384, 1 << 17]),
-    # thread-level kernel with TMA tiles in and out (rows of exactly 128 bytes: fp32 N = 16, fp64 N = 8; large batches)
-    "workItemTmaTest": basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"], [4096 + 77, 33000, 65536],
-                             [2, 4, 8, 16]),
-    "workItemTmaPaddedRowsTest": layouts(["OOP"], BOTH_DIR, ["interleaved"], [5000], [(16, 1, 1, 20, 18), (8, 1, 1, 8, 10)]),
-    "workItemTmaOffsetsTest": offsets([("OOP", P, P)], BOTH_DIR, [5000], [16], [(0, 2), (6, 0), (3, 5)]),
-    "RealMultidimensionalTest": real_md(BOTH_DIR, STORAGES, [1, 3],
-                                        [[4, 8], [3, 5], [6, 9], [2, 3, 4], [16, 512], [64, 64, 64], [37, 8]], False),
-    "RealMultidimensionalPackedTest": real_md(BOTH_DIR, STORAGES, [1, 3],
-                                              [[4, 8], [6, 9], [2, 3, 4], [16, 512], [8, 16384], [128, 128, 128]], True),
-}
 
 CASES = [pytest.param(tp, id=f"{suite}-{tp.ident()}") for suite, tps in SUITES.items() for tp in tps]
 
@@ -269,13 +92,59 @@ def test_real_in_place(n, scalar):
     c.destroy()
 
 
-def _fuzz():
-    from test_plan_emulator import _fuzz_cases
-    return _fuzz_cases(400, 17)
-
-
-@pytest.mark.skipif(not os.environ.get("PFFT_GPU_FUZZ"), reason="opt-in (PFFT_GPU_FUZZ=1): the planner fuzz of "
-                    "tests/test_plan_emulator.py through the CUDA kernels; not yet part of the default GPU suite")
-@pytest.mark.parametrize("tp", _fuzz(), ids=lambda tp: tp.ident())
+@pytest.mark.parametrize("tp", fuzz_cases(400, 17), ids=lambda tp: tp.ident())
 def test_random_layouts(tp):
+    """The planner fuzz of tests/test_plan_emulator.py (random ranks, lengths incl. primes, nested padded layouts in both
+    domains, offsets, scales, storage, precision, complex and REAL) through the CUDA kernels: the GPU coverage of N-D
+    transforms with non-default strides."""
     run_case(tp)
+
+
+@pytest.mark.parametrize("n,scalar", [(65536, "float"), (1 << 20, "double"), (4099, "float"), (8192, "float")])
+def test_copies_compute_concurrently(n, scalar):
+    """pfft_clone (the reference's copy constructor, committed_descriptor_impl.hpp:774-803): a copy shares the twiddles
+    and owns its workspaces.  The original and the copy run multi-pass plans (GLOBAL level, Bluestein, REAL) on two
+    streams at the same time, repeatedly; every result equals the one computed alone."""
+    import torch
+
+    import portfft_b200 as pf
+
+    real = n == 8192
+    d = pf.descriptor([n], scalar, pf.domain.REAL if real else pf.domain.COMPLEX)
+    d.number_of_transforms = 4
+    if real:
+        d.backward_distance = n // 2 + 1
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    a = d.commit(s1, 0)
+    b = a.copy()
+    if not real:
+        assert a.workspace_bytes() > 0 and b.workspace_bytes() == a.workspace_bytes()
+    cdt = torch.complex128 if scalar == "double" else torch.complex64
+    rdt = torch.float64 if scalar == "double" else torch.float32
+    g = torch.Generator(device="cuda")
+    g.manual_seed(3)
+    n_out = 4 * (n // 2 + 1 if real else n)
+
+    def rand():
+        if real:
+            return torch.rand(4 * n, dtype=rdt, device="cuda", generator=g) * 2 - 1
+        return torch.view_as_complex(torch.rand(4 * n, 2, dtype=rdt, device="cuda", generator=g) * 2 - 1)
+
+    x1, x2 = rand(), rand()
+    ref1, ref2 = (torch.empty(n_out, dtype=cdt, device="cuda") for _ in range(2))
+    o1, o2 = (torch.empty(n_out, dtype=cdt, device="cuda") for _ in range(2))
+    torch.cuda.synchronize()
+    a.compute_forward(x1, ref1, queue=s1)
+    s1.synchronize()
+    a.compute_forward(x2, ref2, queue=s1)
+    s1.synchronize()
+    for _ in range(25):
+        a.compute_forward(x1, o1, queue=s1)
+        b.compute_forward(x2, o2, queue=s2)
+    torch.cuda.synchronize()
+    assert torch.equal(o1, ref1) and torch.equal(o2, ref2)
+    b.destroy()
+    a.compute_forward(x1, o1, queue=s1)  # the tables outlive the copy
+    torch.cuda.synchronize()
+    assert torch.equal(o1, ref1)
+    a.destroy()

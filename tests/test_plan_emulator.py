@@ -7,6 +7,7 @@ import pytest
 
 import portfft_oracle as oracle
 from fft_check import BI, P, U, CaseParams, make_descriptors
+from grid_cases import fuzz_cases
 from plan_emulator import run_plan
 
 CASES = [
@@ -112,7 +113,7 @@ def _grid_sample():
     """Every 3rd case of the GPU parity grid (tests/test_fft_gpu.py) whose buffers stay small: the planner's pass lists
     for the reference's own test matrix -- layouts, offsets, scales, storages, N-D, GLOBAL, Bluestein, REAL -- are
     replayed on the CPU, so a planner regression shows up without a GPU."""
-    import test_fft_gpu as grid
+    import grid_cases as grid
 
     out = []
     i = 0
@@ -132,69 +133,7 @@ def test_gpu_grid_sample_on_the_emulator(tp):
     test_exported_plan_matches_oracle(tp)
 
 
-def _random_layout(rng, dims, batch):
-    """A valid (overlap-free) strides / distance pair for `dims` x batch: the dimensions and the batch are nested in a
-    random order, each level padded by a random amount."""
-    order = list(range(len(dims) + 1))  # index len(dims) = the batch
-    rng.shuffle(order)
-    strides, distance, acc = [0] * len(dims), 1, 1
-    for k in order:
-        acc += rng.choice([0, 0, 0, 1, 3])
-        if k == len(dims):
-            distance = acc
-            acc *= batch
-        else:
-            strides[k] = acc
-            acc *= dims[k]
-    return strides, distance
-
-
-def _fuzz_cases(count=600, seed=5):
-    import random
-
-    rng = random.Random(seed)
-    pool = [1, 2, 3, 4, 5, 7, 8, 9, 12, 16, 25, 27, 30, 32, 37, 49, 64, 96, 100, 101, 128, 243, 256, 500, 512, 1000,
-            1024, 1031, 2048, 4096, 4099, 8192, 10000, 16384, 20000]
-    cases = []
-    while len(cases) < count:
-        rank = rng.choice([1, 1, 1, 2, 2, 3])
-        # (rank > 1: no unit dimensions -- the reference's conservative N-D overlap check rejects a unit dimension
-        # whose stride ties with another one's, descriptor_validation.hpp:123-151)
-        dims = [rng.choice(pool if rank == 1 else pool[1:18]) for _ in range(rank)]
-        n = 1
-        for d in dims:
-            n *= d
-        batch = rng.choice([1, 2, 3, 5, 7])
-        if n * batch > (1 << 16):
-            continue
-        real = rng.random() < 0.3
-        cdims = dims[:-1] + [dims[-1] // 2 + 1] if real else dims
-        if real and any(p > 31 for p in _prime_factors(dims[-1] // 2 if dims[-1] % 2 == 0 else dims[-1])):
-            continue  # REAL: the inner half-length transform must be 31-smooth
-        fs, fd = _random_layout(rng, dims, batch)
-        bs, bd = _random_layout(rng, cdims, batch)
-        tp = CaseParams(dims, batch, "OOP", U, U, rng.choice(["fwd", "bwd"]), rng.choice(["interleaved", "split"]),
-                        rng.choice(["float", "double"]), forward_strides=fs, backward_strides=bs, forward_distance=fd,
-                        backward_distance=bd, forward_offset=rng.choice([0, 0, 1, 6]), backward_offset=rng.choice([0, 0, 2, 5]),
-                        forward_scale=rng.choice([None, 0.5]), backward_scale=rng.choice([None, -2.0]),
-                        domain="real" if real else "complex")
-        cases.append(tp)
-    return cases
-
-
-def _prime_factors(n):
-    out, p = [], 2
-    while p * p <= n:
-        while n % p == 0:
-            out.append(p)
-            n //= p
-        p += 1
-    if n > 1:
-        out.append(n)
-    return out
-
-
-@pytest.mark.parametrize("tp", _fuzz_cases(), ids=lambda tp: tp.ident())
+@pytest.mark.parametrize("tp", fuzz_cases(), ids=lambda tp: tp.ident())
 def test_random_layouts_on_the_emulator(tp):
     """Seeded fuzz of the planner: random ranks, lengths (powers of two, mixed radix, primes), nested-and-padded
     layouts in both domains, offsets, scales, storage, precision, complex and REAL domain."""
