@@ -12,7 +12,10 @@ Printed JSON line (rank 0): metric GFLOP/s = 5*N*log2(N)*batch/t (the reference'
 /root/reference/test/bench/utils/ops_estimate.hpp:34-50), device-timed `value`, `e2e` through the C ABI with
 pinned HOST buffers (pfft_compute_host: H2D + compute + D2H per step), `roofline` for the dominant kernel against
 MEASURED_PEAKS.json, `cpu_baseline` = the C oracle port timed on a bounded sample on the host cores.
-Multi-GPU (torchrun): every rank transforms its own shard of the batch, no data-path collective ("weak").
+Multi-GPU (torchrun): the configured batch is sharded over the ranks (65536 / N transforms per GPU for C2: strong
+scaling, BASELINE.json config 2 / SURVEY 8d row "C2 per GPU at 8 GPUs"), no data-path collective; the same run
+also reports the weak-scaling figure (`weak_scaling`: the full batch on every GPU) and the slab-decomposed C5
+(`slab_c5`: 512^3 over the N GPUs, peer-store and NCCL exchange, rel-L2 against numpy.fft.fftn).
 `--impl reference` times the reference's CPU algorithm (oracle port; the SYCL reference cannot be built here).
 """
 from __future__ import annotations
@@ -205,7 +208,8 @@ def cpu_sample_batch(cfg) -> int:
     """bounded sample: about 0.5 GFLOP-equivalents of the port's speed (~10-20 s on 8 cores)"""
     per = flops_of(cfg) / cfg["batch"]
     target_flops = 1.5e10
-    return int(max(1, min(cfg["batch"], target_flops // per)))
+    sample = int(max(1, min(cfg["batch"], target_flops // per)))
+    return cfg["batch"] if sample >= 0.9 * cfg["batch"] else sample  # nearly everything: take the whole workload
 
 
 def run_reference_arm(args, cfg, name):
@@ -229,9 +233,10 @@ def run_reference_arm(args, cfg, name):
     line = {
         "impl": "reference", "metric": "batched_c2c_gflops", "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": t * 1e3, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64" if cfg["scalar"] == "double" else "f32",
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64" if cfg["scalar"] == "double" else "f32",
         "data": "synthetic",
-        "config": {"workload": f"{name}: {cfg['desc']}", "sample": f"{sample} of {cfg['batch']} transforms per step"},
+        "config": {"workload": f"{name}: {cfg['desc']}", "total_batch": cfg["batch"],
+                   "sample": f"{sample} of {cfg['batch']} transforms per step"},
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} transforms of the workload per step, C oracle port of the reference "
                                    f"algorithm (SYCL reference not buildable here)"},
@@ -330,62 +335,85 @@ def run_slab(args, cfg, name, rank, local_rank, world, dev):
     plan.destroy()
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-e2e", action="store_true")
-    ap.add_argument("--graph", action="store_true", help="replay the timed steps from one CUDA graph (launch-bound configs)")
-    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="slab exchange (C5 at --gpus > 1)")
-    args = ap.parse_args()
-    cfg = CONFIGS[args.config]
-    if args.impl == "reference":
-        run_reference_arm(args, cfg, args.config)
-        return
-    args.warmup = max(args.warmup, 3)
-    if args.graph and args.steps % 2:
-        args.steps += 1  # a replay must leave the in-place data where it started
+def scipy_cpu_time(cfg, sample_batch: int):
+    """Second CPU baseline (SURVEY 8d Plan B ii): scipy.fft (pocketfft, the library behind the numpy oracle the
+    reference's tests use) on the same kind of sample, all host cores.  Returns (seconds, cores) or None."""
+    try:
+        import numpy as np
+        import scipy.fft as sfft
+    except Exception:
+        return None
+    dbl = cfg["scalar"] == "double"
+    rng = np.random.Generator(np.random.SFC64(1))
+    shape = [sample_batch] + list(cfg["lengths"])
+    x = (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex128 if dbl else np.complex64)
+    cores = len(os.sched_getaffinity(0))
+    axes = tuple(range(1, len(shape)))
+    sfft.fftn(x[:max(1, min(sample_batch, cores))], axes=axes, workers=cores)  # plan cache warm-up
+    best = float("inf")
+    for _ in range(2):
+        t0 = time.perf_counter()
+        sfft.fftn(x, axes=axes, workers=cores)
+        best = min(best, time.perf_counter() - t0)
+    return best, cores
 
+
+def copy_ceiling(torch, dist, dev, world, h_in, h_out, reps=3):
+    """What the host link allows for one e2e step, all ranks at once: the step's H2D bytes and D2H bytes as two plain
+    pinned cudaMemcpyAsync streams running concurrently (PCIe is full duplex), no kernels.  Seconds, max over ranks."""
+    s_up, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    d_in = [torch.empty_like(t, device=dev) for t in h_in]
+    d_out = d_in if h_out is h_in else [torch.empty_like(t, device=dev) for t in h_out]
+    h_back = [torch.empty_like(t).pin_memory() for t in h_out]  # D2H target distinct from the H2D source
+    best = float("inf")
+    for _ in range(reps + 1):
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s_up):
+            for a, b in zip(d_in, h_in):
+                a.copy_(b, non_blocking=True)
+        with torch.cuda.stream(s_dn):
+            for a, b in zip(h_back, d_out):
+                a.copy_(b, non_blocking=True)
+        torch.cuda.synchronize(dev)
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        best = min(best, float(t.item()))
+    return best
+
+
+def run_batched(args, cfg, name, batch, rank, local_rank, world, dev, steps, warmup, with_e2e, use_graph):
+    """One measurement of the batched path: every rank commits the descriptor for `batch` transforms (its shard; no
+    data-path collective), runs `warmup` + `steps` alternating forward / backward computes, device-timed with CUDA
+    events on the launching stream, max over ranks.  Returns a dict of the raw figures."""
     import numpy as np
     import torch
     import torch.distributed as dist
 
     import portfft_b200 as pf
 
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device("cuda", local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-
-    if args.config == "C5" and world > 1:
-        run_slab(args, cfg, args.config, rank, local_rank, world, dev)
-        dist.destroy_process_group()
-        return
-
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize(dev)
 
-    # ---- descriptor (each rank owns an identical shard: batch-sharded, no data-path collective) ----------------
     n_flat = 1
     for l in cfg["lengths"]:
         n_flat *= l
     d = pf.descriptor(cfg["lengths"], cfg["scalar"])
-    d.number_of_transforms = cfg["batch"]
+    d.number_of_transforms = batch
     d.placement = pf.placement.IN_PLACE if cfg["inplace"] else pf.placement.OUT_OF_PLACE
     d.complex_storage = pf.complex_storage.SPLIT_COMPLEX if cfg["split"] else pf.complex_storage.INTERLEAVED_COMPLEX
     for k in ("forward_strides", "forward_distance", "forward_offset", "backward_strides", "backward_distance",
               "backward_offset", "backward_scale"):
         if k in cfg:
-            setattr(d, k, cfg[k])
+            v = cfg[k]
+            if k.endswith("_strides") and batch != cfg["batch"]:
+                v = [batch if x == cfg["batch"] else x for x in v]  # batch-interleaved shard: stride = local batch
+            setattr(d, k, v)
     if "backward_scale" not in cfg:
         d.backward_scale = 1.0 / n_flat
     stream = torch.cuda.current_stream(dev)
@@ -405,22 +433,21 @@ def main():
     bwd_buf = fwd_buf if cfg["inplace"] else alloc(n_bwd)
     orig = [t.clone() for t in fwd_buf] if n_fwd * (16 if fdt == torch.float64 else 8) <= (8 << 30) else None
 
-    def step(i):
+    def step(i, q=stream):
         if i % 2 == 0:
             if cfg["inplace"]:
-                plan.compute_forward(*fwd_buf, queue=stream)
+                plan.compute_forward(*fwd_buf, queue=q)
             else:
-                plan.compute_forward(*fwd_buf, *bwd_buf, queue=stream)
+                plan.compute_forward(*fwd_buf, *bwd_buf, queue=q)
         else:
             if cfg["inplace"]:
-                plan.compute_backward(*fwd_buf, queue=stream)
+                plan.compute_backward(*fwd_buf, queue=q)
             else:
-                plan.compute_backward(*bwd_buf, *fwd_buf, queue=stream)
+                plan.compute_backward(*bwd_buf, *fwd_buf, queue=q)
 
-    total_steps = args.warmup + args.steps
-    if total_steps % 2 == 1:
-        args.warmup += 1  # even number of steps: the data ends where it started (round-trip check below)
-    for i in range(args.warmup):
+    if (warmup + steps) % 2 == 1:
+        warmup += 1  # even number of steps: the data ends where it started (round-trip check below)
+    for i in range(warmup):
         step(i)
     barrier()
     sampler = ClockSampler(local_rank)
@@ -429,7 +456,7 @@ def main():
     launches0 = pf.total_launches()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     graph = None
-    if args.graph:
+    if use_graph:
         # launch-bound workloads: the K steps are captured once into a CUDA graph (stream capture of the same C-ABI
         # calls) and the timed region replays it; the work on the device is identical
         side = torch.cuda.Stream(dev)
@@ -437,16 +464,11 @@ def main():
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph, stream=side):
             cap = torch.cuda.current_stream(dev)
-            for i in range(args.steps):
-                if i % 2 == 0:
-                    (plan.compute_forward(*fwd_buf, queue=cap) if cfg["inplace"]
-                     else plan.compute_forward(*fwd_buf, *bwd_buf, queue=cap))
-                else:
-                    (plan.compute_backward(*fwd_buf, queue=cap) if cfg["inplace"]
-                     else plan.compute_backward(*bwd_buf, *fwd_buf, queue=cap))
+            for i in range(steps):
+                step(warmup + i, cap)
         stream.wait_stream(side)
         with torch.cuda.stream(stream):
-            graph.replay()  # warm replay
+            graph.replay()  # warm replay (an even number of steps: the data is back where it started)
         barrier()
     barrier()
     ev0.record(stream)
@@ -454,63 +476,34 @@ def main():
         with torch.cuda.stream(stream):
             graph.replay()
     else:
-        for i in range(args.steps):
-            step(args.warmup + i)
+        for i in range(steps):
+            step(warmup + i)
     ev1.record(stream)
     barrier()
     ms = ev0.elapsed_time(ev1)
     launches = pf.total_launches() - launches0
     if graph is not None:  # the replayed graph holds the launches counted at capture time
-        launches = args.steps * plan.num_launches(pf.direction.FORWARD)
+        launches = steps * plan.num_launches(pf.direction.FORWARD)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
     tmax = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-    ms = float(tmax.item())
-    ms_per_step = ms / args.steps
-    flops_total = flops_of(cfg) * world
-    value = flops_total / (ms_per_step * 1e-3) / 1e9
-    hbm_gbs = bytes_of(cfg) * world / (ms_per_step * 1e-3) / 1e9
+    res = {"ms_per_step": float(tmax.item()) / steps, "steps": steps, "warmup": warmup, "launches": int(launches),
+           "clocks": sampler.summary() if rank == 0 else None, "batch": batch,
+           "n_pass": plan.num_launches(pf.direction.FORWARD), "l2_chunk": plan.l2_chunk(), "roundtrip": None,
+           "e2e": None}
 
     # ---- round-trip identity at full size (size-independent parity property) ------------------------------------
-    roundtrip = None
     if orig is not None:
         num = sum(float(torch.linalg.vector_norm((a - b).reshape(-1)).item()) ** 2 for a, b in zip(fwd_buf, orig))
         den = sum(float(torch.linalg.vector_norm(b.reshape(-1)).item()) ** 2 for b in orig)
-        if "forward_strides" not in cfg:  # strided layouts hold untouched padding in between: norm still valid
-            pass
-        roundtrip = math.sqrt(num / den)
+        res["roundtrip"] = math.sqrt(num / den)
         del orig
 
-    # ---- roofline of the dominant kernel (one launch per step for single-pass plans) ---------------------------
-    peak, peak_src = measured_peak()
-    n_pass = plan.num_launches(pf.direction.FORWARD)
-    l2_chunk = plan.l2_chunk()
-    # Multi-pass plans that run L2 resident (the batch in chunks whose workspace stays in L2)
-    # touch HBM once per element and direction whatever their pass count: their roofline is that of the whole step.
-    hbm_passes = 1 if l2_chunk else n_pass
-    per_launch_ms = ms_per_step / hbm_passes
-    achieved = bytes_of(cfg) / (per_launch_ms * 1e-3) / 1e9  # algorithmic bytes of ONE pass over the data / launch
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            traffic = json.load(open(tpath)).get(args.config)
-        except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src, "kernel_launches_per_step": launches // args.steps,
-                "passes_per_transform": n_pass, "l2_chunk_transforms": l2_chunk,
-                "note": ("achieved = 1 read + 1 write of every element per step / step time (CUDA events): the plan runs "
-                         "L2 resident, its intermediate passes do not reach HBM" if l2_chunk else
-                         "achieved = 1 read + 1 write of every element per launch / mean launch time (CUDA events)")}
-
     # ---- e2e through the C ABI with pinned host buffers ----------------------------------------------------------
-    e2e = None
-    if not args.no_e2e:
-        scalar_np = np.float64 if cfg["scalar"] == "double" else np.float32
+    if with_e2e:
         esz = (2 if not cfg["split"] else 1)
         h_in = [torch.empty(n_fwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
         h_out = h_in if cfg["inplace"] else [torch.empty(n_bwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
@@ -519,7 +512,7 @@ def main():
         for t in h_out:
             if t is not h_in[0]:
                 t.zero_()
-        e_steps = max(1, min(args.steps, 4))
+        e_steps = max(1, min(steps, 4))
 
         def e2e_step():
             a = [t.data_ptr() for t in h_in] + [None] * (2 - planes)
@@ -538,36 +531,239 @@ def main():
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         te = float(tt.item())
         bpe = (16 if cfg["scalar"] == "double" else 8)
-        e2e = {"value": flops_total / te / 1e9, "unit": "GFLOP/s", "h2d_bytes_per_step": n_fwd * bpe,
-               "d2h_bytes_per_step": n_bwd * bpe, "steps": e_steps, "ms_per_step": te * 1e3,
-               "api": "pfft_compute_host (C ABI, pinned host buffers)"}
+        del fwd_buf, bwd_buf
+        torch.cuda.empty_cache()
+        tc = copy_ceiling(torch, dist, dev, world, h_in, h_out)
+        res["e2e"] = {"seconds": te, "h2d_bytes_per_step": n_fwd * bpe, "d2h_bytes_per_step": n_bwd * bpe,
+                      "steps": e_steps, "copy_only_seconds": tc}
         del h_in, h_out
+    plan.destroy()
+    torch.cuda.empty_cache()
+    return res
 
-    # ---- CPU baseline (rank 0, N=1 only) ---------------------------------------------------------------------
-    cpu = None
+
+def run_slab_check(args, rank, local_rank, world, dev):
+    """C5 (3-D fp32 512^3) slab-decomposed over the N ranks, both exchanges, inside the default multi-GPU run: timing
+    (CUDA events, max over ranks), bytes over NVLink against the measured 770 GB/s, and a real parity check --
+    rank 0 draws the input (SFC64(0), uniform(-1,1), as the reference's generator), scatters the x-slabs, gathers the
+    y-slabs of the spectrum and compares them with numpy.fft.fftn in complex128 (128^3 and 512^3)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    from portfft_b200.distributed import slab_fft3d
+
+    out = {}
+    for exchange in ("peer", "nccl"):
+        entry = {}
+        try:
+            for n in (128, 512):
+                plan = slab_fft3d([n, n, n], "float", exchange=exchange, device=dev)
+                g = plan.geom
+                x = torch.empty(g.xl, n, n, dtype=torch.complex64, device=dev)
+                ref = None
+                if rank == 0:
+                    rng = np.random.Generator(np.random.SFC64(0))
+                    re = rng.uniform(-1, 1, (n, n, n)).astype(np.float32)
+                    full = (re + 1j * rng.uniform(-1, 1, (n, n, n)).astype(np.float32)).astype(np.complex64)
+                    del re
+                    parts = [torch.from_numpy(full[r * g.xl:(r + 1) * g.xl]).to(dev) for r in range(world)]
+                    dist.scatter(x, parts, src=0)
+                    del parts
+                    ref = np.fft.fftn(full.astype(np.complex128))
+                    del full
+                else:
+                    dist.scatter(x, None, src=0)
+                y = plan.forward(x).contiguous()
+                torch.cuda.synchronize(dev)
+                got = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
+                dist.gather(y, got, dst=0)
+                if rank == 0:
+                    num = den = 0.0
+                    for r in range(world):
+                        want = ref[:, r * g.yb:(r + 1) * g.yb, :]
+                        diff = got[r].cpu().numpy().astype(np.complex128) - want
+                        num += float(np.vdot(diff, diff).real)
+                        den += float(np.vdot(want, want).real)
+                    entry[f"rel_l2_{n}"] = math.sqrt(num / den)
+                    entry[f"rel_l2_bound_{n}"] = 1e-5 * math.log2(n ** 3)
+                    del ref, got
+                if n == 512:
+                    for _ in range(3):
+                        plan.forward(x)
+                    torch.cuda.synchronize(dev)
+                    dist.barrier()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 20
+                    e0.record()
+                    for _ in range(reps):
+                        plan.forward(x)
+                    e1.record()
+                    torch.cuda.synchronize(dev)
+                    tm = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
+                    dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+                    ms = float(tm.item())
+                    nv = (world - 1) * g.block_elems * 8
+                    entry.update({"ms": ms, "gflops": 5.0 * n ** 3 * math.log2(n ** 3) / (ms * 1e-3) / 1e9,
+                                  "nvlink_bytes_sent_per_gpu": nv, "nvlink_gbs": nv / (ms * 1e-3) / 1e9,
+                                  "nvlink_frac_of_770": nv / (ms * 1e-3) / 1e9 / 770.0})
+                plan.destroy()
+                del x, y
+                torch.cuda.empty_cache()
+        except Exception as exc:  # reported, never silently dropped
+            entry["error"] = repr(exc)[:300]
+        out[exchange] = entry
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--config", default="C2", choices=sorted(CONFIGS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay the timed steps from one CUDA graph (launch-bound configs)")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"], help="slab exchange (C5 at --gpus > 1)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="--gpus > 1: strong = the configured batch sharded over the GPUs (BASELINE.json config 2), "
+                         "weak = the configured batch on every GPU")
+    ap.add_argument("--no-extras", action="store_true", help="--gpus > 1: skip the weak-scaling and C5 slab extras")
+    args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    if args.impl == "reference":
+        run_reference_arm(args, cfg, args.config)
+        return
+    args.warmup = max(args.warmup, 3)
+    if args.graph and args.steps % 2:
+        args.steps += 1  # a replay must leave the in-place data where it started
+
+    import torch
+    import torch.distributed as dist
+
+    import portfft_b200 as pf  # noqa: F401  (fails loudly when the CUDA library is missing)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    if args.config == "C5" and world > 1:
+        run_slab(args, cfg, args.config, rank, local_rank, world, dev)
+        dist.destroy_process_group()
+        return
+
+    # ---- the measurement: the configured batch, sharded over the ranks (strong) or replicated (weak) -------------
+    strong = args.scaling == "strong" or world == 1
+    if strong and cfg["batch"] % world:
+        raise SystemExit(f"batch {cfg['batch']} does not divide over {world} GPUs")
+    batch = cfg["batch"] // world if strong else cfg["batch"]
+    total_batch = batch * world
+    r = run_batched(args, cfg, args.config, batch, rank, local_rank, world, dev, args.steps, args.warmup,
+                    not args.no_e2e, args.graph)
+    ms_per_step = r["ms_per_step"]
+    per_gpu_flops = flops_of(cfg) * batch / cfg["batch"]
+    per_gpu_bytes = bytes_of(cfg) * batch / cfg["batch"]
+    value = per_gpu_flops * world / (ms_per_step * 1e-3) / 1e9
+    hbm_gbs = per_gpu_bytes * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- roofline of the dominant kernel (one launch per step for single-pass plans) ---------------------------
+    peak, peak_src = measured_peak()
+    n_pass, l2_chunk = r["n_pass"], r["l2_chunk"]
+    # Multi-pass plans that run L2 resident touch HBM once per element and direction whatever their pass count: their
+    # roofline is that of the whole step.
+    hbm_passes = 1 if l2_chunk else n_pass
+    per_launch_ms = ms_per_step / hbm_passes
+    achieved = per_gpu_bytes / (per_launch_ms * 1e-3) / 1e9  # algorithmic bytes of ONE pass over the data / launch
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            traffic = json.load(open(tpath)).get(args.config)
+        except Exception:
+            traffic = None
+    if traffic is not None and batch != cfg["batch"]:
+        traffic = traffic * batch / cfg["batch"]
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic,
+                "traffic_source": "static: dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture of "
+                                  "this kernel on this workload (profiles/traffic.json), scaled to the per-GPU batch; "
+                                  "not re-measured in this run",
+                "peak_source": peak_src, "kernel_launches_per_step": r["launches"] // r["steps"],
+                "passes_per_transform": n_pass, "l2_chunk_transforms": l2_chunk,
+                "note": ("achieved = 1 read + 1 write of every element per step / step time (CUDA events): the plan runs "
+                         "L2 resident, its intermediate passes do not reach HBM" if l2_chunk else
+                         "achieved = 1 read + 1 write of every element per launch / mean launch time (CUDA events)")}
+
+    e2e = None
+    if r["e2e"] is not None:
+        e = r["e2e"]
+        moved = e["h2d_bytes_per_step"] + e["d2h_bytes_per_step"]
+        e2e = {"value": per_gpu_flops * world / e["seconds"] / 1e9, "unit": "GFLOP/s",
+               "h2d_bytes_per_step": e["h2d_bytes_per_step"], "d2h_bytes_per_step": e["d2h_bytes_per_step"],
+               "steps": e["steps"], "ms_per_step": e["seconds"] * 1e3,
+               "api": "pfft_compute_host (C ABI, pinned host buffers)",
+               "roofline": {"bound": "host_link", "unit": "GB/s per GPU (H2D + D2H bytes of one step / time)",
+                            "achieved": moved / e["seconds"] / 1e9, "peak": moved / e["copy_only_seconds"] / 1e9,
+                            "frac": e["copy_only_seconds"] / e["seconds"],
+                            "peak_source": "measured in this run: the same bytes as two concurrent pinned "
+                                           "cudaMemcpyAsync streams (H2D || D2H), all ranks at once, no kernels",
+                            "copy_only_ms": e["copy_only_seconds"] * 1e3}}
+
+    # ---- extras of the multi-GPU run: weak-scaling figure, C5 slab ------------------------------------------------
+    weak = slab = None
+    if world > 1 and strong and not args.no_extras:
+        w = run_batched(args, cfg, args.config, cfg["batch"], rank, local_rank, world, dev, max(4, min(args.steps, 20)),
+                        args.warmup, False, False)
+        weak = {"value": flops_of(cfg) * world / (w["ms_per_step"] * 1e-3) / 1e9, "unit": "GFLOP/s",
+                "ms_per_step": w["ms_per_step"], "per_gpu_batch": cfg["batch"], "steps": w["steps"],
+                "roundtrip_rel_l2": w["roundtrip"]}
+        if args.config == "C2":
+            slab = run_slab_check(args, rank, local_rank, world, dev)
+
+    # ---- CPU baselines (rank 0, N=1 only) ---------------------------------------------------------------------
+    cpu = cpu2 = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = cpu_sample_batch(cfg)
         t, cores = cpu_port_time(cfg, sample)
-        cpu = {"value": flops_of(cfg) / cfg["batch"] * sample / t / 1e9, "unit": "GFLOP/s", "cores": cores,
+        per = flops_of(cfg) / cfg["batch"]
+        cpu = {"value": per * sample / t / 1e9, "unit": "GFLOP/s", "cores": cores,
                "kind": "port", "sample": f"{sample} of {cfg['batch']} transforms, C oracle port of the reference "
                                           f"algorithm, {t:.2f} s"}
+        sample2 = sample
+        sc = scipy_cpu_time(cfg, sample2)
+        if sc is not None:
+            cpu2 = {"value": per * sample2 / sc[0] / 1e9, "unit": "GFLOP/s", "cores": sc[1], "kind": "pocketfft",
+                    "sample": f"{sample2} of {cfg['batch']} transforms, scipy.fft.fftn(workers={sc[1]}) -- the library "
+                              f"behind the numpy oracle of the reference's tests, {sc[0]:.2f} s"}
 
     if rank == 0:
         line = {
-            "metric": "batched_c2c_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "metric": "batched_c2c_gflops", "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": r["steps"],
+            "warmup": r["warmup"], "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "strong" if strong else "weak",
             "vs_baseline": None, "dtype": "f64" if cfg["scalar"] == "double" else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.config}: {cfg['desc']}", "per_gpu_batch": cfg["batch"],
+            "config": {"workload": f"{args.config}: {cfg['desc']}", "total_batch": total_batch, "per_gpu_batch": batch,
                        "direction": "alternating compute_forward / compute_backward (backward_scale 1/N)",
-                       "l2": "per-GPU working set %.0f MiB >> 126 MB L2 (no flush needed)" % (bytes_of(cfg) / 2 / 2**20)
-                       if bytes_of(cfg) / 2 > 4 * 126e6 else "working set fits L2: launch-latency bound",
-                       "sharding": "batch-sharded, one plan per GPU, no collective"},
+                       "l2": "per-GPU working set %.0f MiB > 126 MB L2, rewritten by every step (no flush needed)"
+                             % (per_gpu_bytes / 2 / 2**20)
+                       if per_gpu_bytes / 2 > 1.5 * 126e6 else "working set fits L2: launch-latency bound",
+                       "sharding": "batch-sharded: %d transforms per GPU, one plan per GPU, no collective" % batch},
             "hbm_gbs": hbm_gbs, "hbm_frac_of_measured": hbm_gbs / world / peak,
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": sampler.summary(), "roundtrip_rel_l2": roundtrip, "cuda_graph": bool(args.graph),
+            "roofline": roofline, "cpu_baseline": cpu, "cpu_baseline_pocketfft": cpu2, "e2e": e2e,
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "roundtrip_rel_l2": r["roundtrip"],
+            "cuda_graph": bool(args.graph),
         }
+        if weak is not None:
+            line["weak_scaling"] = weak
+        if slab is not None:
+            line["slab_c5"] = slab
         print(json.dumps(line), flush=True)
-    plan.destroy()
     if world > 1:
         dist.destroy_process_group()
 
