@@ -567,17 +567,20 @@ def run_slab_check(args, rank, local_rank, world, dev):
                     re = rng.uniform(-1, 1, (n, n, n)).astype(np.float32)
                     full = (re + 1j * rng.uniform(-1, 1, (n, n, n)).astype(np.float32)).astype(np.complex64)
                     del re
-                    parts = [torch.from_numpy(full[r * g.xl:(r + 1) * g.xl]).to(dev) for r in range(world)]
-                    dist.scatter(x, parts, src=0)
+                    parts = [torch.view_as_real(torch.from_numpy(full[r * g.xl:(r + 1) * g.xl]).to(dev))
+                             for r in range(world)]  # (NCCL moves real views: it has no complex type)
+                    dist.scatter(torch.view_as_real(x), parts, src=0)
                     del parts
                     ref = np.fft.fftn(full.astype(np.complex128))
                     del full
                 else:
-                    dist.scatter(x, None, src=0)
-                y = plan.forward(x).contiguous()
+                    dist.scatter(torch.view_as_real(x), None, src=0)
+                y = torch.view_as_real(plan.forward(x).contiguous())
                 torch.cuda.synchronize(dev)
                 got = [torch.empty_like(y) for _ in range(world)] if rank == 0 else None
                 dist.gather(y, got, dst=0)
+                if rank == 0:
+                    got = [torch.view_as_complex(t) for t in got]
                 if rank == 0:
                     num = den = 0.0
                     for r in range(world):

@@ -52,6 +52,27 @@ cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, 
 size_t colg_smem_bytes(int n, int columns, bool is_double);
 cudaError_t launch_wg_colg(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
+// GLOBAL level, two consecutive 256-point passes fused into one persistent kernel with the intermediate result in an
+// L2-resident ring (wg_fused.cu).  FusedGeom: chunking decided at commit time; FusedArgs: per-launch arguments.
+struct FusedGeom {
+  int mode = 0;              // how pass b enumerates its rows (0: rows in batch dim 0, 1: rows in batch dim 1)
+  int group = 0;             // chunk = `group` consecutive values of the chunk index (pass a's batch dimension 1)
+  int lead = 1, slots = 3;   // pass a runs `lead` chunks ahead of pass b; ring slots
+  long long num_chunks = 0, unit = 0, tiles_a = 0, tiles_b = 0;
+  size_t ring_bytes = 0;
+};
+struct FusedArgs {
+  void* ring;
+  unsigned long long* done_a;  // per chunk: tiles of pass a completed (monotone over launches)
+  unsigned long long* done_b;
+  unsigned long long epoch;    // 1-based launch count of this plan: the counters reach epoch * tiles
+  int group, lead, slots;
+  long long num_chunks, unit, tiles_a, tiles_b;
+};
+bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double, FusedGeom* g);
+cudaError_t launch_wg_fused2(const PassParams& a, const PassParams& b, const FusedArgs& fa, int mode, bool is_double,
+                             bool swap_a, bool swap_b, cudaStream_t stream, bool* used);
+
 // element-wise pass with modifiers (ew.cu): n == 1, modifier index = index along batch dimension 0
 cudaError_t launch_ew(const PassParams& p, bool is_double, bool interleaved_in, bool interleaved_out, bool swap, int grid,
                       cudaStream_t stream);

@@ -77,6 +77,16 @@ struct pfft_plan {
   // device staging for pfft_compute_host
   void* stage[2] = {nullptr, nullptr};
   size_t stage_bytes[2] = {0, 0};
+  // pairs of consecutive GLOBAL-level passes that run as ONE persistent kernel with their intermediate result in an
+  // L2-resident ring (wg_fused.cu): index of the first pass, chunk geometry, ring + arrival counters, launch count
+  struct FusedPair {
+    size_t first = 0;
+    FusedGeom geom;
+    void* ring = nullptr;
+    unsigned long long* counters = nullptr;  // [2 * num_chunks]: done_a, done_b
+    unsigned long long epoch = 0;
+  };
+  std::vector<FusedPair> fused[2];
   // pfft_compute_host pipeline: copy streams, per-chunk events, sub-batch plans (number_of_transforms -> plan)
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_up, chunk_done;
@@ -100,6 +110,11 @@ struct pfft_plan {
     for (cudaEvent_t e : chunk_done) cudaEventDestroy(e);
     for (cudaStream_t s : copy_stream)
       if (s) cudaStreamDestroy(s);
+    for (auto& v : fused)
+      for (FusedPair& f : v) {
+        if (f.ring) cudaFree(f.ring);
+        if (f.counters) cudaFree(f.counters);
+      }
     if (scratch) cudaFree(scratch);
     if (scratch2) cudaFree(scratch2);
     if (scratch3) cudaFree(scratch3);
@@ -177,6 +192,31 @@ static void attach_device_state(pfft_plan* plan) {
       }
       if (ps.lmod_kind != MODT_NONE) ps.pp.lmod = tb->mod[std::make_pair(ps.lmod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
       if (ps.smod_kind != MODT_NONE) ps.pp.smod = tb->mod[std::make_pair(ps.smod_kind, std::make_pair(ps.mod_l, ps.mod_m))];
+    }
+    // fusable pairs: pass i writes a workspace that only pass i + 1 reads
+    std::vector<PassHost>& ps = plan->host.passes[dir];
+    plan->fused[dir].clear();
+    for (size_t i = 0; i + 1 < ps.size(); ++i) {
+      const PassHost &a = ps[i], &b = ps[i + 1];
+      if (a.kernel != KERNEL_WG_COL || b.kernel != KERNEL_WG_COL || a.dst != b.src) continue;
+      if (a.dst != BUF_SCRATCH && a.dst != BUF_SCRATCH2) continue;
+      if (a.internal_storage != b.internal_storage || a.real_view || b.real_view) continue;
+      bool read_later = false;
+      for (size_t j = i + 2; j < ps.size() && !read_later; ++j) {
+        if (ps[j].src == a.dst) read_later = true;
+        if (ps[j].dst == a.dst) break;
+      }
+      if (read_later) continue;
+      pfft_plan::FusedPair f;
+      f.first = i;
+      if (!fused2_plan(a.pp, a.variant, b.pp, b.variant, plan->host.desc.is_double, &f.geom)) continue;
+      PFFT_CUDA_CHECK(cudaMalloc(&f.ring, f.geom.ring_bytes));
+      const size_t cbytes = (size_t)2 * f.geom.num_chunks * sizeof(unsigned long long);
+      PFFT_CUDA_CHECK(cudaMalloc((void**)&f.counters, cbytes));
+      PFFT_CUDA_CHECK(cudaMemsetAsync(f.counters, 0, cbytes, plan->stream));
+      PFFT_CUDA_CHECK(cudaStreamSynchronize(plan->stream));
+      plan->fused[dir].push_back(f);
+      ++i;  // a pass belongs to one pair at most
     }
   }
 }
@@ -339,8 +379,14 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   void* s_im = il ? nullptr : (void*)((char*)plan->scratch + plan->host.scratch_elems * scalar);
   void* s2_re = plan->scratch2;
   void* s2_im = il ? nullptr : (void*)((char*)plan->scratch2 + plan->host.scratch2_elems * scalar);
-  for (const PassHost& ps : plan->host.passes[dir]) {
-    PassParams p = ps.pp;
+  struct Prepared {
+    PassParams p;
+    bool swap, il_in, il_out, pil;
+  };
+  auto prepare = [&](const PassHost& ps) {
+    Prepared r;
+    PassParams& p = r.p;
+    p = ps.pp;
     switch (ps.src) {
       case BUF_IN: p.in_re = uin_re; p.in_im = uin_im; break;
       case BUF_OUT: p.in_re = uout_re; p.in_im = uout_im; break;
@@ -358,11 +404,12 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
     // (Bluestein's inner transforms) always run the plain forward transform
     const int internal = MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
     // storage of each side of this pass: the descriptor's, or interleaved for plan-internal rows of a REAL plan
-    const bool il_in = il || (ps.internal_storage & 1), il_out = il || (ps.internal_storage & 2);
-    const bool pil = il_in && il_out;  // the transform kernels take one storage for both sides (the planner pairs them)
+    r.il_in = il || (ps.internal_storage & 1);
+    r.il_out = il || (ps.internal_storage & 2);
+    r.pil = r.il_in && r.il_out;  // the transform kernels take one storage for both sides (the planner pairs them)
     // (force_swap: inverse complex passes of a REAL N-D backward plan.)  A pass whose both sides are plan-internal never
     // swaps, in any kernel family.
-    const bool swap = (ps.force_swap || (pil && bwd && !real)) && (p.mod_flags & internal) != internal;
+    r.swap = (ps.force_swap || (r.pil && bwd && !real)) && (p.mod_flags & internal) != internal;
     if (ps.real_view) {
       // the user's real rows addressed as interleaved complex pairs: needs complex alignment of the first element
       const uintptr_t a = (ps.real_view & 1) ? (uintptr_t)p.in_re + (size_t)p.ioff * 2 * scalar
@@ -383,7 +430,50 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         p.out_tab_im[i] = im;
       }
     }
+    return r;
+  };
+  std::vector<PassHost>& passes = plan->host.passes[dir];
+  std::vector<pfft_plan::FusedPair>& fused = plan->fused[dir];
+  size_t next_fused = 0;
+  for (size_t pi = 0; pi < passes.size(); ++pi) {
+    const PassHost& ps = passes[pi];
+    const Prepared pr = prepare(ps);
+    const PassParams& p = pr.p;
+    const bool swap = pr.swap, il_in = pr.il_in, il_out = pr.il_out, pil = pr.pil;
     cudaError_t e = cudaSuccess;
+    while (next_fused < fused.size() && fused[next_fused].first < pi) ++next_fused;
+    if (next_fused < fused.size() && fused[next_fused].first == pi) {
+      // this pass and the next one as ONE persistent kernel, the data between them in an L2-resident ring.  The source
+      // of the first must not be the destination of the second (an in-place transform through the workspace): the
+      // second pass of a chunk would overwrite what the first pass of a later chunk still has to read.
+      pfft_plan::FusedPair& f = fused[next_fused];
+      const Prepared pb = prepare(passes[pi + 1]);
+      if (pil && pb.pil && p.in_re != pb.p.out_re && pr.swap == pb.swap) {
+        FusedArgs fa;
+        fa.ring = f.ring;
+        fa.done_a = f.counters;
+        fa.done_b = f.counters + f.geom.num_chunks;
+        fa.epoch = f.epoch + 1;
+        fa.group = f.geom.group;
+        fa.lead = f.geom.lead;
+        fa.slots = f.geom.slots;
+        fa.num_chunks = f.geom.num_chunks;
+        fa.unit = f.geom.unit;
+        fa.tiles_a = f.geom.tiles_a;
+        fa.tiles_b = f.geom.tiles_b;
+        bool used = false;
+        // swap of the pair: on the load of the first pass and the store of the second (what lies between is internal)
+        e = launch_wg_fused2(p, pb.p, fa, f.geom.mode, d.is_double, pr.swap, pb.swap, stream, &used);
+        if (e != cudaSuccess)
+          throw PlanError(PFFT_CUDA_ERROR, std::string("kernel launch failed: ") + cudaGetErrorString(e));
+        if (used) {
+          ++f.epoch;
+          g_total_launches.fetch_add(1, std::memory_order_relaxed);
+          ++pi;
+          continue;
+        }
+      }
+    }
     switch (ps.kernel) {
       case KERNEL_WG_GENERIC:
         e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);

@@ -26,6 +26,7 @@
 #include <cstdlib>
 #include <cstring>
 
+#include "col_common.cuh"
 #include "device_utils.cuh"
 #include "io.cuh"
 #include "kernels.h"
@@ -33,56 +34,6 @@
 
 namespace pfft {
 
-namespace col {
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  do {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(smem_u32(bar)), "r"(parity)
-        : "memory");
-  } while (!ok);
-}
-__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
-__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
-// TMA tile load: box {C columns, rows, 1, 1, 1} at coordinates (c0, r0, b1, b2, b3)
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, int c0, int r0, int b1, int b2, int b3,
-                                            uint64_t* bar) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4, %5, "
-      "%6}], [%7];" ::"r"(smem_u32(dst)),
-      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(b1), "r"(b2), "r"(b3), "r"(smem_u32(bar))
-      : "memory");
-}
-
-__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                   smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(smem_u32(bar))
-               : "memory");
-}
-
-template <typename T>
-__host__ __device__ constexpr int pad(int i) {
-  return i + (i >> (sizeof(T) == 4 ? 4 : 3));
-}
-template <typename T>
-__host__ __device__ constexpr int pitch(int n) {
-  return (pad<T>(n - 1) + 1) | 1;
-}
-constexpr int cmin(int a, int b) { return a < b ? a : b; }
-constexpr int cmax(int a, int b) { return a > b ? a : b; }
-
-}  // namespace col
 
 // IN: how a tile of C transforms reaches the CTA
 enum : int {
@@ -488,7 +439,7 @@ static EncodeTiledFn encode_fn() {
 
 // 5-D view of the pass input: (column, row j, b1, b2, b3); element = one complex number described as 2 scalars
 // folded into the innermost dimension (so that fp32 and fp64 both use a native TMA data type)
-static bool make_tensor_map(const PassParams& p, bool is_double, int C, int box_rows, CUtensorMap* map) {
+bool col_make_tensor_map(const PassParams& p, bool is_double, int C, int box_rows, CUtensorMap* map) {
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) return false;
   const size_t sc = is_double ? 8 : 4, esz = 2 * sc;
@@ -553,7 +504,7 @@ static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cud
   memset(&map, 0, sizeof(map));
   if (in == IN_COLS_TMA) {
     using Cfg = ColCfg<T, N1, N2, N3, IN_COLS_TMA>;
-    if (!make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
+    if (!col_make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
   }
   if (in == IN_ROWS_BULK) {
     const uintptr_t base = reinterpret_cast<uintptr_t>(p.in_re) + (size_t)p.ioff * 2 * sizeof(T);
@@ -592,7 +543,7 @@ static cudaError_t launch_col512(const PassParams& p, bool swap, cudaStream_t st
   *used = false;
   CUtensorMap map;
   memset(&map, 0, sizeof(map));
-  if (!make_tensor_map(p, false, Col512::C, 256, &map)) return cudaSuccess;  // caller falls back
+  if (!col_make_tensor_map(p, false, Col512::C, 256, &map)) return cudaSuccess;  // caller falls back
   *used = true;
   const int sms = sm_count();
   if (sms <= 0) return cudaErrorLaunchOutOfResources;
