@@ -69,7 +69,9 @@ struct FusedArgs {
   int group, lead, slots;
   long long num_chunks, unit, tiles_a, tiles_b;
 };
-bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double, FusedGeom* g);
+int fused2_grid(bool is_double);  // persistent grid on the current device (0: the kernel cannot run)
+bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double, int grid,
+                 FusedGeom* g);
 cudaError_t launch_wg_fused2(const PassParams& a, const PassParams& b, const FusedArgs& fa, int mode, bool is_double,
                              bool swap_a, bool swap_b, cudaStream_t stream, bool* used);
 

@@ -209,7 +209,9 @@ static void attach_device_state(pfft_plan* plan) {
       if (read_later) continue;
       pfft_plan::FusedPair f;
       f.first = i;
-      if (!fused2_plan(a.pp, a.variant, b.pp, b.variant, plan->host.desc.is_double, &f.geom)) continue;
+      if (a.pp.n != 256 || b.pp.n != 256) continue;
+      const int fgrid = fused2_grid(plan->host.desc.is_double);
+      if (fgrid <= 0 || !fused2_plan(a.pp, a.variant, b.pp, b.variant, plan->host.desc.is_double, fgrid, &f.geom)) continue;
       PFFT_CUDA_CHECK(cudaMalloc(&f.ring, f.geom.ring_bytes));
       const size_t cbytes = (size_t)2 * f.geom.num_chunks * sizeof(unsigned long long);
       PFFT_CUDA_CHECK(cudaMalloc((void**)&f.counters, cbytes));

@@ -24,6 +24,7 @@
 // batch group, here arrival counters inside one launch.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -45,6 +46,40 @@ __device__ __forceinline__ unsigned long long ld_acquire(const unsigned long lon
 __device__ __forceinline__ void red_release_add(unsigned long long* p, unsigned long long v) {
   asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+// L2 eviction priorities: the source and the destination stream through once (evict first), the ring must stay
+// resident until its slot is rewritten (evict last) -- otherwise every dirty ring line is written back to HBM after its
+// only use (measured without hints: 2.0 GB written for 1.07 GB of output on 65536 x 2048)
+__device__ __forceinline__ uint64_t policy_evict_first() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ uint64_t policy_evict_last() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void st_hint(cx<float>* a, cx<float> v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f32 [%0], {%1, %2}, %3;" ::"l"(a), "f"(v.x), "f"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void st_hint(cx<double>* a, cx<double> v, uint64_t pol) {
+  asm volatile("st.global.L2::cache_hint.v2.f64 [%0], {%1, %2}, %3;" ::"l"(a), "d"(v.x), "d"(v.y), "l"(pol) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_hint(void* dst, const CUtensorMap* map, int c0, int r0, int b1, int b2, int b3,
+                                                 uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1, {%2, "
+      "%3, %4, %5, %6}], [%7], %8;" ::"r"(col::smem_u32(dst)),
+      "l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(r0), "r"(b1), "r"(b2), "r"(b3), "r"(col::smem_u32(bar)), "l"(pol)
+      : "memory");
+}
+__device__ __forceinline__ void bulk_g2s_hint(void* dst, const void* src, uint32_t bytes, uint64_t* bar, uint64_t pol) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::"r"(
+          col::smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(col::smem_u32(bar)), "l"(pol)
+      : "memory");
+}
 // generic-proxy writes (other CTAs' stores, made visible by the acquire above) -> async-proxy reads (TMA) and back
 __device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 }  // namespace fz
@@ -53,142 +88,179 @@ template <typename T>
 struct FusedCfg {
   static constexpr int N = 256, N1 = 16, N2 = 16, B1 = N / N1;
   static constexpr int C = 128 / (2 * (int)sizeof(T));  // transforms per tile: one 128-byte line per row segment
-  static constexpr int TPC = 16, NT = C * TPC;
-  static constexpr int PITCH = col::pitch<T>(N);
+  static constexpr int TPC = 16;
+  static constexpr int NC = C * TPC;      // consumer (butterfly) threads
+  static constexpr int NT = NC + 32;      // + one service warp (loads, dependencies, completion signals)
+  static constexpr int NW = NC / 32;      // consumer warps
   static constexpr int RING = 2;
-  static constexpr size_t kStageBytes = (size_t)N * C * 2 * sizeof(T);  // 32 KiB for both precisions
-  static constexpr size_t kSmem = RING * kStageBytes + (size_t)C * PITCH * 2 * sizeof(T) + 64;
+  // Pass B keeps each contiguous row at a padded pitch and exchanges in place: 16-byte aligned rows for cp.async.bulk,
+  // and a pitch of 4 banks (mod 32) so that the quarter-warp wavefronts of the 128-bit second-pass loads (lanes along
+  // the rows) fall on distinct banks.  Pass A uses the same stage as [row j][column] without padding.
+  static constexpr int PB = N + (sizeof(T) == 4 ? 2 : 1);
+  static constexpr size_t kTileBytes = (size_t)N * C * 2 * sizeof(T);   // 32 KiB of payload for both precisions
+  static constexpr size_t kStageBytes = (size_t)PB * C * 2 * sizeof(T);  // 33 024 / 32 896 bytes
+  static constexpr size_t kSmem = RING * kStageBytes + 128;
   static constexpr int kBoxRows = 256;
+  static constexpr int kMinBlocks = 3;
 };
 
+namespace fz {
+__device__ __forceinline__ void consumer_sync(int threads) { asm volatile("bar.sync 1, %0;" ::"r"(threads) : "memory"); }
+__device__ __forceinline__ unsigned ld_acquire_cta(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.cta.shared.u32 %0, [%1];" : "=r"(v) : "r"(col::smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void red_release_cta(unsigned* p) {
+  asm volatile("red.release.cta.shared.add.u32 [%0], 1;" ::"r"(col::smem_u32(p)) : "memory");
+}
+}  // namespace fz
+
+// Work of one CTA: items blockIdx.x + k * gridDim.x of the list.  The SERVICE warp (one lane) never blocks: it polls
+// (1) completion counts of the consumer warps and turns them into release-increments of the per-chunk arrival
+// counters, (2) free stages, posting the load of the next item as soon as its dependency is satisfied.  The CONSUMER
+// warps wait only on the stage mbarriers.  Nothing in a CTA waits for another CTA except the service lane's polling,
+// and that never holds back a completion signal: the earliest unfinished item of the whole list can always proceed.
 template <typename T, int B_MODE>
-__global__ void __launch_bounds__(FusedCfg<T>::NT, 2)
+__global__ void __launch_bounds__(FusedCfg<T>::NT, FusedCfg<T>::kMinBlocks)
     wg_fused2_kernel(const PassParams pa, const PassParams pb, const __grid_constant__ CUtensorMap tmap_a,
                      const FusedArgs fa, const bool swap_a, const bool swap_b) {
   using Cfg = FusedCfg<T>;
-  constexpr int N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, B1 = Cfg::B1, C = Cfg::C, TPC = Cfg::TPC, PITCH = Cfg::PITCH;
+  constexpr int N = Cfg::N, N1 = Cfg::N1, N2 = Cfg::N2, B1 = Cfg::B1, C = Cfg::C, TPC = Cfg::TPC, PB = Cfg::PB;
   constexpr int RING = Cfg::RING;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   unsigned char* stage0 = smem_raw;
-  cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + RING * Cfg::kStageBytes);
-  uint64_t* full = reinterpret_cast<uint64_t*>(E + (size_t)C * PITCH);
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + RING * Cfg::kStageBytes);
+  unsigned* rel_cnt = reinterpret_cast<unsigned*>(full + RING);  // consumer warps that handed a stage back, ever
+  unsigned* done_cnt = rel_cnt + 1;                              // consumer warps that finished a tile, ever
+  int4* info = reinterpret_cast<int4*>(rel_cnt + 4);             // per stage: phase, chunk, local tile
   const int tid = threadIdx.x;
-  const int cc = tid % C, tc = tid / C;    // lanes along the transform index (column accesses)
-  const int cr = tid / TPC, tr = tid % TPC;  // lanes along the element index (row accesses)
   cx<T>* ring = reinterpret_cast<cx<T>*>(fa.ring);
-  const long long per = fa.tiles_a + fa.tiles_b;
-  const long long total_items = fa.num_chunks * per;
-  const long long head = (long long)fa.lead * fa.tiles_a;  // prologue: A(0) .. A(lead-1)
-  const long long body_chunks = fa.num_chunks - fa.lead;   // then (A(m), B(m - lead)) pairs
-  const int tca = (int)((pa.nb[0] + C - 1) / C);           // column tiles of pass A per chunk index q
-
-  // item -> (phase, chunk, local tile)
-  auto decode = [&](long long i, int& phase, long long& chunk, long long& local) {
-    if (i < head) {
-      phase = 0;
-      chunk = i / fa.tiles_a;
-      local = i - chunk * fa.tiles_a;
-      return;
-    }
-    const long long r = i - head;
-    const long long m = r / per;
-    if (m < body_chunks) {
-      const long long rem = r - m * per;
-      if (rem < fa.tiles_a) {
-        phase = 0;
-        chunk = m + fa.lead;
-        local = rem;
-      } else {
-        phase = 1;
-        chunk = m;
-        local = rem - fa.tiles_a;
-      }
-      return;
-    }
-    const long long r2 = r - body_chunks * per;  // epilogue: B(NC - lead) .. B(NC - 1)
-    phase = 1;
-    chunk = body_chunks + r2 / fa.tiles_b;
-    local = r2 % fa.tiles_b;
-  };
-  auto slot_base = [&](long long chunk) { return (chunk % fa.slots) * (long long)fa.group * fa.unit; };
-  auto ready = [&](int phase, long long chunk) -> bool {
-    if (phase == 0) {
-      if (chunk < fa.slots) return true;
-      return fz::ld_acquire(fa.done_b + (chunk - fa.slots)) >= fa.epoch * (unsigned long long)fa.tiles_b;
-    }
-    return fz::ld_acquire(fa.done_a + chunk) >= fa.epoch * (unsigned long long)fa.tiles_a;
-  };
-  // load of one item into stage s (thread 0; the item's dependency is satisfied)
-  auto issue = [&](int phase, long long chunk, long long local, int s) {
-    unsigned char* dst = stage0 + s * Cfg::kStageBytes;
-    fz::fence_proxy_async_all();
-    col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
-    if (phase == 0) {
-      const int ct = (int)(local % tca);
-      const long long q = chunk * fa.group + local / tca;
-      col::tma_load_5d(dst, &tmap_a, 2 * ct * C, 0, (int)q, 0, 0, &full[s]);  // innermost coordinate counts scalars
-    } else if (B_MODE == 0) {
-      // rows of one chunk index q: C consecutive rows = one contiguous run
-      const int tcb = (int)(pb.nb[0] / C);
-      const long long ql = local / tcb;  // q - chunk * group
-      const int r0 = (int)(local - ql * tcb) * C;
-      const cx<T>* src = ring + slot_base(chunk) + ql * fa.unit + (long long)r0 * N;
-      col::bulk_g2s(dst, src, (uint32_t)Cfg::kStageBytes, &full[s]);
-    } else {
-      // row r of C consecutive chunk indices q
-      const int gpc = fa.group / C;
-      const long long r = local / gpc;
-      const int g8 = (int)(local - r * gpc);
-      const cx<T>* src = ring + slot_base(chunk) + (long long)g8 * C * fa.unit + r * N;
-#pragma unroll 1
-      for (int j = 0; j < C; ++j)
-        col::bulk_g2s(dst + (size_t)j * N * sizeof(cx<T>), src + (long long)j * fa.unit, (uint32_t)(N * sizeof(cx<T>)),
-                      &full[s]);
-    }
-  };
+  const unsigned per = (unsigned)(fa.tiles_a + fa.tiles_b), ta = (unsigned)fa.tiles_a, tb = (unsigned)fa.tiles_b;
+  const unsigned total_items = (unsigned)fa.num_chunks * per;
+  const unsigned my_items = total_items > blockIdx.x ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+  const unsigned tca = (unsigned)((pa.nb[0] + C - 1) / C);  // column tiles of pass A per chunk index q
+  auto slot_base = [&](int chunk) { return (long long)(chunk % fa.slots) * fa.group * fa.unit; };
 
   if (tid == 0) {
     for (int s = 0; s < RING; ++s) col::mbar_init(&full[s], 1);
+    *rel_cnt = 0;
+    *done_cnt = 0;
     col::fence_mbar_init();
     col::fence_proxy_async();
   }
   __syncthreads();
 
-  // number of items of this CTA, and the issue pump (thread 0 only): `next` = sequence number of the next item to
-  // load, `released` = items whose stage has been handed back
-  const long long my_items = total_items > blockIdx.x ? (total_items - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
-  long long next = 0, released = 0;
-  auto pump = [&](bool block_for, long long k_block) {
-    while (next < my_items && next < released + RING) {
-      int ph;
-      long long ch, lo;
-      decode(blockIdx.x + next * gridDim.x, ph, ch, lo);
-      if (!ready(ph, ch)) {
-        if (!(block_for && next == k_block)) return;
-        while (!ready(ph, ch)) __nanosleep(64);
+  if (tid >= Cfg::NC) {
+    // =========================== service warp ================================================================
+    if (tid != Cfg::NC) return;
+    const unsigned head = (unsigned)fa.lead * ta;            // prologue: A(0) .. A(lead-1)
+    const unsigned body_chunks = (unsigned)(fa.num_chunks - fa.lead);  // then (A(m), B(m - lead)) pairs
+    auto decode = [&](unsigned i, int& phase, int& chunk, int& local) {
+      if (i < head) {
+        phase = 0;
+        chunk = (int)(i / ta);
+        local = (int)(i - chunk * ta);
+        return;
       }
-      issue(ph, ch, lo, (int)(next % RING));
-      ++next;
+      const unsigned r = i - head, m = r / per;
+      if (m < body_chunks) {
+        const unsigned rem = r - m * per;
+        phase = rem < ta ? 0 : 1;
+        chunk = (int)(rem < ta ? m + fa.lead : m);
+        local = (int)(rem < ta ? rem : rem - ta);
+        return;
+      }
+      const unsigned r2 = r - body_chunks * per;  // epilogue: B(NC - lead) .. B(NC - 1)
+      phase = 1;
+      chunk = (int)(body_chunks + r2 / tb);
+      local = (int)(r2 % tb);
+    };
+    auto ready = [&](int phase, int chunk) -> bool {
+      if (phase == 0) {
+        if (chunk < fa.slots) return true;
+        return fz::ld_acquire(fa.done_b + (chunk - fa.slots)) >= fa.epoch * (unsigned long long)tb;
+      }
+      return fz::ld_acquire(fa.done_a + chunk) >= fa.epoch * (unsigned long long)ta;
+    };
+    const uint64_t pol_stream = fz::policy_evict_first(), pol_ring = fz::policy_evict_last();
+    auto issue = [&](int phase, int chunk, int local, int s) {
+      unsigned char* dst = stage0 + s * Cfg::kStageBytes;
+      info[s] = make_int4(phase, chunk, local, 0);
+      fz::fence_proxy_async_all();
+      col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kTileBytes);
+      if (phase == 0) {
+        const int ct = (int)((unsigned)local % tca);
+        const int q = chunk * fa.group + (int)((unsigned)local / tca);
+        fz::tma_load_5d_hint(dst, &tmap_a, 2 * ct * C, 0, q, 0, 0, &full[s], pol_stream);  // innermost: scalars
+      } else {
+        // C rows of N contiguous elements each, to the padded row pitch of the stage
+        const cx<T>* src;
+        long long step;
+        if (B_MODE == 0) {  // consecutive rows of one chunk index q
+          const unsigned tcb = (unsigned)(pb.nb[0] / C);
+          const unsigned ql = (unsigned)local / tcb;  // q - chunk * group
+          const unsigned r0 = ((unsigned)local - ql * tcb) * C;
+          src = ring + slot_base(chunk) + (long long)ql * fa.unit + (long long)r0 * N;
+          step = N;
+        } else {  // row r of C consecutive chunk indices q
+          const unsigned gpc = (unsigned)fa.group / C;
+          const unsigned r = (unsigned)local / gpc, g8 = (unsigned)local - r * gpc;
+          src = ring + slot_base(chunk) + (long long)g8 * C * fa.unit + (long long)r * N;
+          step = fa.unit;
+        }
+#pragma unroll 1
+        for (int j = 0; j < C; ++j)
+          fz::bulk_g2s_hint(dst + (size_t)j * PB * sizeof(cx<T>), src + (long long)j * step, (uint32_t)(N * sizeof(cx<T>)),
+                            &full[s], pol_ring);
+      }
+    };
+    unsigned next = 0, sig = 0;
+    int nph = 0, nch = 0, nlo = 0;  // decoded item `next`
+    if (my_items) decode(blockIdx.x, nph, nch, nlo);
+    while (sig < my_items) {
+      bool progress = false;
+      if (fz::ld_acquire_cta(done_cnt) >= (sig + 1) * (unsigned)Cfg::NW) {
+        // tile `sig` is complete: every consumer warp's stores precede its count (release.cta), the fence makes them
+        // visible at gpu scope (and to the async proxy of the consumer CTA) before the arrival counter moves
+        int ph, ch, lo;
+        decode(blockIdx.x + sig * gridDim.x, ph, ch, lo);
+        __threadfence();
+        fz::fence_proxy_async_all();
+        fz::red_release_add((ph == 0 ? fa.done_a : fa.done_b) + ch, 1ULL);
+        ++sig;
+        progress = true;
+      }
+      if (next < my_items && fz::ld_acquire_cta(rel_cnt) >= (next < RING ? 0u : (next - RING + 1) * (unsigned)Cfg::NW) &&
+          ready(nph, nch)) {
+        issue(nph, nch, nlo, (int)(next % RING));
+        ++next;
+        if (next < my_items) decode(blockIdx.x + next * gridDim.x, nph, nch, nlo);
+        progress = true;
+      }
+      if (!progress) __nanosleep(32);
     }
-  };
-  if (tid == 0) pump(true, 0);
+    return;
+  }
 
+  // =========================== consumer warps ==================================================================
+  const int cc = tid % C, tc = tid / C;      // lanes along the transform index (column accesses)
+  const int cr = tid / TPC, tr = tid % TPC;  // lanes along the element index (row accesses)
+  const int lane = tid & 31;
   const T scale_b = T(pb.scale);
-  const IoFlags fl_b{true, swap_b};
   const long long gmask = (1LL << pa.gtw_bits) - 1;
+  const uint64_t pol_stream = fz::policy_evict_first(), pol_ring = fz::policy_evict_last();
 
-  for (long long k = 0; k < my_items; ++k) {
-    int phase;
-    long long chunk, local;
-    decode(blockIdx.x + k * gridDim.x, phase, chunk, local);
+  for (unsigned k = 0; k < my_items; ++k) {
     const int st = (int)(k % RING);
     cx<T>* S = reinterpret_cast<cx<T>*>(stage0 + st * Cfg::kStageBytes);
-    if (tid == 0 && next <= k) pump(true, k);  // head of the list and not yet loaded: wait for its dependency
     col::mbar_wait(&full[st], (uint32_t)((k / RING) & 1));
+    const int4 inf = info[st];
+    const int phase = inf.x, chunk = inf.y, local = inf.z;
     if (phase == 0) {
       // ---- pass A: strided columns (stage [row][column]), radix 16 x 16 exchanged inside the stage ----------------
-      const int ct = (int)(local % tca);
-      const long long ql = local / tca;
+      const int ct = (int)((unsigned)local % tca);
+      const int ql = (int)((unsigned)local / tca);
       {
         const int j = tc;  // B1 == TPC: one first-pass butterfly per thread
         cx<T> v[N1];
@@ -202,23 +274,20 @@ __global__ void __launch_bounds__(FusedCfg<T>::NT, 2)
 #pragma unroll
         for (int r = 0; r < N1; ++r) S[(j + B1 * r) * C + cc] = v[r];
       }
-      __syncthreads();
+      fz::consumer_sync(Cfg::NC);
       cx<T> v[N2];
       const int j = tc;
 #pragma unroll
       for (int r = 0; r < N2; ++r) v[r] = S[(r + B1 * j) * C + cc];
-      __syncthreads();  // every thread has taken its inputs: the stage is free
-      if (tid == 0) {
-        ++released;
-        pump(false, 0);
-      }
+      __syncwarp();
+      if (lane == 0) fz::red_release_cta(rel_cnt);  // this warp has taken its inputs out of the stage
 #pragma unroll
       for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(pa.tw, j * r));
       DFT<N2, T>::run(v);
       const int col_idx = ct * C + cc;
       if (col_idx < pa.nb[0]) {
         // inter-factor twiddle w_M^{column * k}, k = j + 16 r (fp64: running product from two look-ups, see wg_col.cu)
-        cx<T>* out = ring + slot_base(chunk) + ql * fa.unit + col_idx;
+        cx<T>* out = ring + slot_base(chunk) + (long long)ql * fa.unit + col_idx;
         cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
         const long long gidx = col_idx;
         if (sizeof(T) == 8) {
@@ -237,69 +306,74 @@ __global__ void __launch_bounds__(FusedCfg<T>::NT, 2)
             const long long m = gidx * kk;
             o = cmul(o, cmul(ldg_cx<T>(pa.gtw_hi, m >> pa.gtw_bits), ldg_cx<T>(pa.gtw_lo, m & gmask)));
           }
-          out[(long long)kk * pa.os] = o;  // plan-internal data: no swap, no scale (both belong to the last pass)
+          fz::st_hint(out + (long long)kk * pa.os, o, pol_ring);  // plan-internal data: no swap, no scale
         }
       }
-      __syncthreads();  // all stores of the tile are issued
-      if (tid == 0) {
-        __threadfence();
-        fz::fence_proxy_async_all();
-        fz::red_release_add(fa.done_a + chunk, 1ULL);
-      }
     } else {
-      // ---- pass B: contiguous rows (stage [row][j]), radix 16, exchange through E, radix 16, column store ---------
+      // ---- pass B: contiguous rows (stage [row][j] at pitch PB), radix 16 x 16 exchanged inside the stage ----------
       {
         const int j = tr;
         cx<T> v[N1];
 #pragma unroll
-        for (int r = 0; r < N1; ++r) v[r] = S[cr * N + j + B1 * r];
+        for (int r = 0; r < N1; ++r) v[r] = S[cr * PB + j + B1 * r];
         DFT<N1, T>::run(v);
 #pragma unroll
-        for (int r = 0; r < N1; ++r) E[cr * PITCH + col::pad<T>(j * N1 + r)] = v[r];
+        for (int r = 0; r < N1; ++r) S[cr * PB + j + B1 * r] = v[r];  // output r of butterfly j: element j + 16 r
       }
-      __syncthreads();  // the stage is consumed, E is complete
-      if (tid == 0) {
-        ++released;
-        pump(false, 0);
-      }
+      fz::consumer_sync(Cfg::NC);
       long long ob;
       bool live;
       if (B_MODE == 0) {
-        const int tcb = (int)(pb.nb[0] / C);
-        const long long ql = local / tcb;
-        const int r0 = (int)(local - ql * tcb) * C;
-        const long long q = chunk * fa.group + ql;
+        const unsigned tcb = (unsigned)(pb.nb[0] / C);
+        const unsigned ql = (unsigned)local / tcb;
+        const int r0 = (int)(((unsigned)local - ql * tcb) * C);
+        const long long q = (long long)chunk * fa.group + ql;
         live = r0 + cc < pb.nb[0];
         ob = pb.ooff + (long long)(r0 + cc) * pb.obd[0] + q * pb.obd[1];
       } else {
-        const int gpc = fa.group / C;
-        const long long r = local / gpc;
-        const int g8 = (int)(local - r * gpc);
-        const long long q0 = chunk * fa.group + (long long)g8 * C;  // first chunk index of the tile
-        const long long qh = q0 / pb.nb[0], qlow = q0 - qh * pb.nb[0];
+        const unsigned gpc = (unsigned)fa.group / C;
+        const unsigned r = (unsigned)local / gpc, g8 = (unsigned)local - r * gpc;
+        const unsigned q0 = (unsigned)chunk * fa.group + g8 * C;  // first chunk index of the tile
+        const unsigned qh = q0 / (unsigned)pb.nb[0], qlow = q0 - qh * (unsigned)pb.nb[0];
         live = true;
-        ob = pb.ooff + (qlow + cc) * pb.obd[0] + r * pb.obd[1] + qh * pb.obd[2];
+        ob = pb.ooff + (long long)(qlow + cc) * pb.obd[0] + (long long)r * pb.obd[1] + (long long)qh * pb.obd[2];
       }
       {
+        // butterfly j of row cc takes output j of every first-pass butterfly: 16 consecutive elements from 16 j on
         const int j = tc;
         cx<T> v[N2];
+        if (sizeof(T) == 4) {
+          const float4* src = reinterpret_cast<const float4*>(S + cc * PB + B1 * j);
 #pragma unroll
-        for (int r = 0; r < N2; ++r) v[r] = E[cc * PITCH + col::pad<T>(j + B1 * r)];
+          for (int r = 0; r < N2 / 2; ++r) {
+            const float4 t = src[r];
+            v[2 * r] = cx<T>{(T)t.x, (T)t.y};
+            v[2 * r + 1] = cx<T>{(T)t.z, (T)t.w};
+          }
+        } else {
+#pragma unroll
+          for (int r = 0; r < N2; ++r) v[r] = S[cc * PB + B1 * j + r];
+        }
+        __syncwarp();
+        if (lane == 0) fz::red_release_cta(rel_cnt);  // this warp has taken its inputs out of the stage
 #pragma unroll
         for (int r = 1; r < N2; ++r) v[r] = cmul(v[r], ldg_cx<T>(pb.tw, j * r));
         DFT<N2, T>::run(v);
         if (live) {
+          cx<T>* out = reinterpret_cast<cx<T>*>(pb.out_re);
 #pragma unroll
           for (int r = 0; r < N2; ++r) {
             cx<T> o = v[r];
             if (pb.apply_scale) o = cscale(o, scale_b);
-            gstore<T>(pb, fl_b, ob + (long long)(j + N1 * r) * pb.os, o);
+            if (swap_b) o = cx<T>{o.y, o.x};
+            fz::st_hint(out + ob + (long long)(j + N1 * r) * pb.os, o, pol_stream);
           }
         }
       }
-      __syncthreads();  // E is rewritten by the next B tile; the ring slot has been read completely
-      if (tid == 0) fz::red_release_add(fa.done_b + chunk, 1ULL);
     }
+    // this warp's stores of the tile are issued (A: ring slot written; B: ring slot read, destination written)
+    __syncwarp();
+    if (lane == 0) fz::red_release_cta(done_cnt);
   }
 }
 
@@ -313,7 +387,7 @@ static int env_int(const char* name, int dflt) {
 
 // Can passes (a, b) of a plan run fused?  a: 256-point TMA column pass with inter-factor twiddle writing packed
 // columns of the workspace, b: 256-point row pass reading exactly those rows.  Fills the chunk geometry.
-bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double,
+bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double, int grid,
                  FusedGeom* g) {
   if (env_int("PFFT_NO_FUSE", 0)) return false;
   const int C = is_double ? 8 : 16;
@@ -338,13 +412,23 @@ bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int va
   // grid about once (the dependency of B(c) is then long satisfied when its turn comes) while `slots` chunks stay a
   // small part of the L2.
   const long long esz = is_double ? 16 : 8;
-  const long long target = (long long)env_int("PFFT_FUSE_CHUNK_KB", 8192) * 1024;
+  const long long target = (long long)env_int("PFFT_FUSE_CHUNK_KB", 4096) * 1024;
   long long group = mode == 1 ? C : 1;  // (mode 1: a tile takes C consecutive chunk indices)
   const long long qdiv = mode == 1 ? b.nb[0] : Q;  // a chunk must not straddle dimension 2 of pass b
   while (group * 2 * unit * esz <= target && qdiv % (group * 2) == 0) group *= 2;
   if (qdiv % group != 0) return false;
   const long long chunks = Q / group;
-  const int lead = env_int("PFFT_FUSE_LEAD", 1), slots = lead + 2;
+  // pass a runs `lead` chunks ahead of pass b.  A CTA loads its items RING deals ahead; the load of a B(c) tile can be
+  // posted that early only if A(c) is complete by then, i.e. if more than RING deals of the grid lie between the two
+  // segments (measured with lead = 1 and segments shorter than the grid: every B tile loaded late, 1.21 ms against
+  // 0.82 ms unfused on 65536 x 2048).
+  const long long tiles_a = group * (W / C);
+  const long long dist = (long long)env_int("PFFT_FUSE_LEAD_TENTHS", 20) * grid / 10;  // items between the segments
+  int lead = env_int("PFFT_FUSE_LEAD", 0);
+  if (lead <= 0) lead = (int)std::max<long long>(1, (dist + tiles_a - 1) / tiles_a);
+  // ring slots: A(c) overwrites the slot of chunk c - slots, whose B tiles must be long finished as well
+  const long long tiles_b = mode == 0 ? group * (b.nb[0] / C) : (group / C) * b.nb[1];
+  const int slots = lead + 1 + (int)std::max<long long>(1, (dist + tiles_a + tiles_b - 1) / (tiles_a + tiles_b));
   if (chunks < 2 * slots) return false;  // too little work for the pipeline to matter
   g->mode = mode;
   g->group = (int)group;
@@ -352,11 +436,23 @@ bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int va
   g->slots = slots;
   g->num_chunks = chunks;
   g->unit = unit;
-  g->tiles_a = group * (W / C);
-  g->tiles_b = mode == 0 ? group * (b.nb[0] / C) : (group / C) * b.nb[1];
+  g->tiles_a = tiles_a;
+  g->tiles_b = tiles_b;
   g->ring_bytes = (size_t)slots * group * unit * esz;
   return true;
 }
+
+template <typename T>
+static int fused_grid_t() {
+  using Cfg = FusedCfg<T>;
+  int slots = persistent_slots(wg_fused2_kernel<T, 0>, Cfg::NT, Cfg::kSmem);
+  const int cap = env_int("PFFT_FUSE_CTAS_PER_SM", 0);
+  if (cap > 0) slots = std::min(slots, cap * sm_count());
+  return slots;
+}
+
+// persistent grid of the fused kernel on the current device (both row modes have the same footprint)
+int fused2_grid(bool is_double) { return is_double ? fused_grid_t<double>() : fused_grid_t<float>(); }
 
 template <typename T, int B_MODE>
 static cudaError_t launch_fused_t(const PassParams& a, const PassParams& b, const FusedArgs& fa, bool swap_a, bool swap_b,
@@ -367,10 +463,10 @@ static cudaError_t launch_fused_t(const PassParams& a, const PassParams& b, cons
   memset(&map, 0, sizeof(map));
   if (!col_make_tensor_map(a, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller runs the passes apart
   auto kern = wg_fused2_kernel<T, B_MODE>;
-  int slots = persistent_slots(kern, Cfg::NT, Cfg::kSmem);
+  const int slots = fused_grid_t<T>();
   if (slots <= 0) return cudaErrorLaunchOutOfResources;
-  const int cap = env_int("PFFT_FUSE_CTAS_PER_SM", 0);
-  if (cap > 0) slots = std::min(slots, cap * sm_count());
+  cudaError_t es = ensure_dynamic_smem(kern, Cfg::kSmem);
+  if (es != cudaSuccess) return es;
   const long long items = fa.num_chunks * (fa.tiles_a + fa.tiles_b);
   const int grid = (int)(items < slots ? items : slots);
   *used = true;

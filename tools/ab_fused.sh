@@ -16,14 +16,11 @@ except Exception as e:
 PY
 }
 run L1D_unfused L1D PFFT_NO_FUSE=1
-run L1D_fused_8M L1D X=1
-run L1D_fused_4M L1D PFFT_FUSE_CHUNK_KB=4096
-run L1D_fused_16M L1D PFFT_FUSE_CHUNK_KB=16384
-run L1D_fused_2M L1D PFFT_FUSE_CHUNK_KB=2048
-run L1D_fused_8M_lead2 L1D PFFT_FUSE_LEAD=2
-run L1D_fused_8M_1cta L1D PFFT_FUSE_CTAS_PER_SM=1
+for kb in 2048 8192; do for t in 10 20 30; do
+run L1D_fused_${kb}K_t${t} L1D PFFT_FUSE_CHUNK_KB=$kb PFFT_FUSE_LEAD_TENTHS=$t
+done; done
+run L1D_fused_2cta L1D PFFT_FUSE_CTAS_PER_SM=2
 run C4_unfused C4 PFFT_NO_FUSE=1
-run C4_fused_8M C4 X=1
-run C4_fused_16M C4 PFFT_FUSE_CHUNK_KB=16384
-run C4_fused_4M C4 PFFT_FUSE_CHUNK_KB=4096
-run C4_fused_8M_lead2 C4 PFFT_FUSE_LEAD=2
+for kb in 8192; do for t in 10 20; do
+run C4_fused_${kb}K_t${t} C4 PFFT_FUSE_CHUNK_KB=$kb PFFT_FUSE_LEAD_TENTHS=$t
+done; done
