@@ -6,7 +6,7 @@ import os
 from ctypes import POINTER, c_char_p, c_double, c_int, c_size_t, c_ulonglong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libpfft_b200.so")
+LIB_PATH = os.environ.get("PFFT_LIB") or os.path.join(_HERE, "lib", "libpfft_b200.so")  # PFFT_LIB: A/B builds
 
 
 class pfft_desc(ctypes.Structure):

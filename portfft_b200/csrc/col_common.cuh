@@ -5,6 +5,7 @@
 
 #include <cstdint>
 
+#include "device_utils.cuh"
 #include "pass.h"
 
 namespace pfft {
@@ -63,5 +64,13 @@ constexpr int cmin(int a, int b) { return a < b ? a : b; }
 constexpr int cmax(int a, int b) { return a > b ? a : b; }
 
 }  // namespace col
+
+// inter-factor twiddle w_M^m, m = g * k < M <= 2^40, from the two-level table: one 32 x 32 -> 64 bit multiply
+template <typename T>
+__device__ __forceinline__ cx<T> gtw_lookup(const PassParams& p, unsigned g, unsigned k, unsigned long long gmask) {
+  const unsigned long long m = (unsigned long long)g * k;
+  return cmul(ldg_cx<T>(p.gtw_hi, (long long)(m >> p.gtw_bits)), ldg_cx<T>(p.gtw_lo, (long long)(m & gmask)));
+}
+
 
 }  // namespace pfft

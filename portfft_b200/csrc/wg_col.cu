@@ -22,6 +22,7 @@
 //     fused into that store.
 #include <cuda.h>
 
+#include <algorithm>
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
@@ -40,6 +41,50 @@ enum : int {
   IN_COLS_TMA = 0,    // strided columns: TMA tensor tiles into the stage ring, stage layout [row j][column]
   IN_ROWS_DIRECT = 1, // contiguous rows: direct global loads (no staging, latency hidden by resident CTAs)
   IN_ROWS_BULK = 2    // contiguous rows, 16-byte aligned: cp.async.bulk (TMA 1-D) into the ring, layout [row][j]
+};
+
+// Tile coordinates (column tile, batch indices 1..3) of a persistent CTA, advanced by the grid size with carries
+// instead of being re-derived from the linear tile index: the 64-bit divisions of that decode were ~300 of the ~1200
+// instructions a thread spent per tile (SASS: 12 division subroutine calls per kernel).
+struct TileCursor {
+  int ct, b1, b2, b3;
+  int s_ct, s_b1, s_b2, s_b3;
+  int tiles_c, nb1, nb2;
+  __device__ __forceinline__ void init(long long first, long long step, long long tiles_c_, long long nb1_, long long nb2_) {
+    tiles_c = (int)tiles_c_;
+    nb1 = (int)nb1_;
+    nb2 = (int)nb2_;
+    split(first, ct, b1, b2, b3);
+    split(step, s_ct, s_b1, s_b2, s_b3);
+  }
+  __device__ __forceinline__ void split(long long t, int& c, int& x1, int& x2, int& x3) const {
+    long long q = t / tiles_c;
+    c = (int)(t - q * tiles_c);
+    long long q2 = q / nb1;
+    x1 = (int)(q - q2 * nb1);
+    long long q3 = q2 / nb2;
+    x2 = (int)(q2 - q3 * nb2);
+    x3 = (int)q3;
+  }
+  __device__ __forceinline__ void set(long long tile) { split(tile, ct, b1, b2, b3); }
+  __device__ __forceinline__ void advance() {
+    ct += s_ct;
+    if (ct >= tiles_c) {
+      ct -= tiles_c;
+      ++b1;
+    }
+    b1 += s_b1;
+    if (b1 >= nb1) {
+      b1 -= nb1;
+      ++b2;
+    }
+    b2 += s_b2;
+    if (b2 >= nb2) {
+      b2 -= nb2;
+      ++b3;
+    }
+    b3 += s_b3;
+  }
 };
 
 // INPLACE (strided columns in and out, two passes, one last-pass butterfly per thread): the exchange between the two
@@ -70,7 +115,10 @@ struct ColCfg {
                 "in-place exchange: TMA column tiles, two passes, one last-pass butterfly per thread");
   static constexpr int kBoxRows = N < 256 ? N : 256;
   // resident CTAs per SM the register allocation is bounded for (in place, fp32 N = 256: three 64 KiB rings per SM)
-  static constexpr int kMinBlocks = INPLACE && sizeof(T) == 4 && N == 256 ? 3 : 1;
+  // (the other fp32 variants spend 190-210 registers with the lean index arithmetic = one CTA per SM; bounding them
+  // to two CTAs per SM was measured slower: 65536 x 2048 0.720 -> 0.772 ms)
+  static constexpr int kMinBlocks =
+      INPLACE && sizeof(T) == 4 && N == 256 ? 3 : 1;
 };
 
 template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS, bool INPLACE = false>
@@ -86,7 +134,6 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
   unsigned char* stage0 = smem_raw;
   cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + Cfg::STAGES * Cfg::kStageBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(E + (INPLACE ? 0 : (size_t)C * PITCH));  // in place: no exchange buffer
-  const IoFlags fl{true, swap};
   const int tid = threadIdx.x;
   // column mapping: lanes run along the transform index (used where memory is contiguous across transforms)
   const int cc = tid % C, tc = tid / C;
@@ -97,21 +144,25 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
   const long long tiles_c = (p.nb[0] + C - 1) / C;
   const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
   const T scale = T(p.scale);
-  const long long gmask = (1LL << p.gtw_bits) - 1;
+  const unsigned long long gmask = (1ULL << p.gtw_bits) - 1;
   const bool in_contig = p.ibd[0] == N;  // IN_ROWS_BULK: the C rows of a tile are one contiguous run
 
-  auto decode = [&](long long tile, int& c0, int& b1, int& b2, int& b3) {
-    long long q = tile / tiles_c;
-    c0 = (int)(tile - q * tiles_c) * C;
-    long long q2 = q / p.nb[1];
-    b1 = (int)(q - q2 * p.nb[1]);
-    long long q3 = q2 / p.nb[2];
-    b2 = (int)(q2 - q3 * p.nb[2]);
-    b3 = (int)q3;
-  };
-  auto issue = [&](long long tile, int s) {
-    int c0, b1, b2, b3;
-    decode(tile, c0, b1, b2, b3);
+  // fp32: tile coordinates advance incrementally and results leave through a running pointer (-14 % / -6 % on the two
+  // passes of 65536 x 2048).  fp64 keeps the per-tile decode and per-element address arithmetic: measured on C4, every
+  // reduction of the instruction count made these DRAM-paced kernels (8 warps per SM) slower, 772 -> 802 us and
+  // 741 -> 762 us per pass with the lean form, 835 / 809 us with the pass twiddles held in registers as well
+  // (profiles/r2_ab_variants.txt).
+  constexpr bool kLean = sizeof(T) == 4;
+  TileCursor cur, icur;  // tile being transformed / next tile to load (thread 0)
+  cur.init(blockIdx.x, gridDim.x, tiles_c, p.nb[1], p.nb[2]);
+  icur = cur;
+  long long icur_tile = blockIdx.x;
+  auto issue = [&](int s) {  // loads the tile under `icur` into stage s and moves the cursor on
+    const int c0 = icur.ct * C, b1 = icur.b1, b2 = icur.b2, b3 = icur.b3;
+    if (kLean)
+      icur.advance();
+    else
+      icur.set(icur_tile += gridDim.x);
     unsigned char* dst = stage0 + s * Cfg::kStageBytes;
     if (IN == IN_COLS_TMA) {
       col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
@@ -144,14 +195,18 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
     if (tid == 0) {
       long long t0 = blockIdx.x;
       for (int s = 0; s < Cfg::RING; ++s, t0 += gridDim.x)
-        if (t0 < total_tiles) issue(t0, s);
+        if (t0 < total_tiles) issue(s);
     }
   }
 
   int it = 0;
   for (long long tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-    int c0, b1, b2, b3;
-    decode(tile, c0, b1, b2, b3);
+    if (kLean) {
+      if (it) cur.advance();
+    } else {
+      cur.set(tile);
+    }
+    const int c0 = cur.ct * C, b1 = cur.b1, b2 = cur.b2, b3 = cur.b3;
     // ---- pass 1: radix N1 over x[j + N2*r], result to E[transform][pad(j*N1 + r)] -------------------------------
     {
       const int st = it % Cfg::RING;
@@ -198,7 +253,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
       const long long nxt = tile + (long long)Cfg::RING * gridDim.x;
       if (nxt < total_tiles) {
         col::fence_proxy_async();
-        issue(nxt, it % Cfg::RING);
+        issue(it % Cfg::RING);
       }
     }
     if (N3 > 1) {
@@ -236,7 +291,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
             const long long nxt = tile + (long long)Cfg::RING * gridDim.x;
             if (nxt < total_tiles) {
               col::fence_proxy_async();
-              issue(nxt, st);
+              issue(st);
             }
           }
         } else {
@@ -246,15 +301,14 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
 #pragma unroll
         for (int r = 1; r < NL; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, j * r));
         DFT<NL, T>::run(v);
+        if (!kLean) {
         if (live) {
-          // inter-factor twiddle w_M^{g*k}, k = j + NS*r.  fp64: two table look-ups (base w^{g*j}, step w^{g*NS}) and a
-          // running product (error ~ NL * 1.1e-16, far inside the fp64 bound) instead of 2*NL dependent L2 reads;
-          // fp32: the tables are small enough to stay in L1, every element is looked up exactly
+          const IoFlags fl{true, swap};
           cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
           if (p.gtw_dim >= 0 && sizeof(T) == 8) {
             const long long mb = gidx * j, ms = gidx * NS;
-            tw_run = cmul(ldg_cx<T>(p.gtw_hi, mb >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, mb & gmask));
-            tw_step = cmul(ldg_cx<T>(p.gtw_hi, ms >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, ms & gmask));
+            tw_run = cmul(ldg_cx<T>(p.gtw_hi, mb >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, mb & (long long)gmask));
+            tw_step = cmul(ldg_cx<T>(p.gtw_hi, ms >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, ms & (long long)gmask));
           }
 #pragma unroll
           for (int r = 0; r < NL; ++r) {
@@ -266,11 +320,50 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
                 tw_run = cmul(tw_run, tw_step);
               } else {
                 const long long m = gidx * k;
-                o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & gmask)));
+                o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & (long long)gmask)));
               }
             }
             if (p.apply_scale) o = cscale(o, scale);
             gstore<T>(p, fl, ob + (long long)k * p.os, o);
+          }
+        }
+        } else
+        if (live) {
+          // results leave through a running pointer (base + k * os, k = j + NS * r)
+          cx<T>* op = reinterpret_cast<cx<T>*>(p.out_re) + ob + (long long)j * p.os;
+          const long long ostep = (long long)NS * p.os;
+          if (p.gtw_dim >= 0) {
+            // inter-factor twiddle w_M^{g*k}.  fp64: two table look-ups (base w^{g*j}, step w^{g*NS}) and a running
+            // product (error ~ NL * 1.1e-16, far inside the fp64 bound) instead of 2*NL dependent L2 reads; fp32: the
+            // tables are small enough to stay in L1, every element is looked up exactly
+            cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
+            if (sizeof(T) == 8) {
+              tw_run = gtw_lookup<T>(p, (unsigned)gidx, (unsigned)j, gmask);
+              tw_step = gtw_lookup<T>(p, (unsigned)gidx, (unsigned)NS, gmask);
+            }
+#pragma unroll
+            for (int r = 0; r < NL; ++r) {
+              cx<T> o;
+              if (sizeof(T) == 8) {
+                o = cmul(v[r], tw_run);
+                tw_run = cmul(tw_run, tw_step);
+              } else {
+                o = cmul(v[r], gtw_lookup<T>(p, (unsigned)gidx, (unsigned)(j + NS * r), gmask));
+              }
+              if (p.apply_scale) o = cscale(o, scale);
+              if (swap) o = cx<T>{o.y, o.x};
+              *op = o;
+              op += ostep;
+            }
+          } else {
+#pragma unroll
+            for (int r = 0; r < NL; ++r) {
+              cx<T> o = v[r];
+              if (p.apply_scale) o = cscale(o, scale);
+              if (swap) o = cx<T>{o.y, o.x};
+              *op = o;
+              op += ostep;
+            }
           }
         }
       }
@@ -478,8 +571,13 @@ template <typename T, int N1, int N2, int N3, int IN, bool OUT_ROWS, bool INPLAC
 static cudaError_t launch_col_v(const PassParams& p, bool swap, const CUtensorMap& map, cudaStream_t stream) {
   using Cfg = ColCfg<T, N1, N2, N3, IN, INPLACE>;
   auto kern = wg_col_kernel<T, N1, N2, N3, IN, OUT_ROWS, INPLACE>;
-  const int slots = persistent_slots(kern, Cfg::NT, Cfg::kSmem);  // cached per (kernel, device)
+  int slots = persistent_slots(kern, Cfg::NT, Cfg::kSmem);  // cached per (kernel, device)
   if (slots <= 0) return cudaErrorLaunchOutOfResources;
+  static const int cap = [] {  // experiment knob: fewer resident CTAs per SM than the occupancy allows
+    const char* e = std::getenv("PFFT_COL_CTAS_PER_SM");
+    return e ? std::atoi(e) : 0;
+  }();
+  if (cap > 0) slots = std::min(slots, cap * sm_count());
   const long long tiles = ((p.nb[0] + Cfg::C - 1) / Cfg::C) * p.nb[1] * p.nb[2] * p.nb[3];
   const int grid = (int)(tiles < slots ? tiles : slots);
   kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p, map, swap);

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(FusedCfg<T>::NT, FusedCfg<T>::kMinBlocks)
   const int cr = tid / TPC, tr = tid % TPC;  // lanes along the element index (row accesses)
   const int lane = tid & 31;
   const T scale_b = T(pb.scale);
-  const long long gmask = (1LL << pa.gtw_bits) - 1;
+  const unsigned long long gmask = (1ULL << pa.gtw_bits) - 1;
   const uint64_t pol_stream = fz::policy_evict_first(), pol_ring = fz::policy_evict_last();
 
   for (unsigned k = 0; k < my_items; ++k) {
@@ -289,11 +289,10 @@ __global__ void __launch_bounds__(FusedCfg<T>::NT, FusedCfg<T>::kMinBlocks)
         // inter-factor twiddle w_M^{column * k}, k = j + 16 r (fp64: running product from two look-ups, see wg_col.cu)
         cx<T>* out = ring + slot_base(chunk) + (long long)ql * fa.unit + col_idx;
         cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
-        const long long gidx = col_idx;
+        const unsigned gidx = (unsigned)col_idx;
         if (sizeof(T) == 8) {
-          const long long mb = gidx * j, ms = gidx * N1;
-          tw_run = cmul(ldg_cx<T>(pa.gtw_hi, mb >> pa.gtw_bits), ldg_cx<T>(pa.gtw_lo, mb & gmask));
-          tw_step = cmul(ldg_cx<T>(pa.gtw_hi, ms >> pa.gtw_bits), ldg_cx<T>(pa.gtw_lo, ms & gmask));
+          tw_run = gtw_lookup<T>(pa, gidx, (unsigned)j, gmask);
+          tw_step = gtw_lookup<T>(pa, gidx, (unsigned)N1, gmask);
         }
 #pragma unroll
         for (int r = 0; r < N2; ++r) {
@@ -303,8 +302,7 @@ __global__ void __launch_bounds__(FusedCfg<T>::NT, FusedCfg<T>::kMinBlocks)
             o = cmul(o, tw_run);
             tw_run = cmul(tw_run, tw_step);
           } else {
-            const long long m = gidx * kk;
-            o = cmul(o, cmul(ldg_cx<T>(pa.gtw_hi, m >> pa.gtw_bits), ldg_cx<T>(pa.gtw_lo, m & gmask)));
+            o = cmul(o, gtw_lookup<T>(pa, gidx, (unsigned)kk, gmask));
           }
           fz::st_hint(out + (long long)kk * pa.os, o, pol_ring);  // plan-internal data: no swap, no scale
         }
@@ -389,7 +387,12 @@ static int env_int(const char* name, int dflt) {
 // columns of the workspace, b: 256-point row pass reading exactly those rows.  Fills the chunk geometry.
 bool fused2_plan(const PassParams& a, int variant_a, const PassParams& b, int variant_b, bool is_double, int grid,
                  FusedGeom* g) {
-  if (env_int("PFFT_NO_FUSE", 0)) return false;
+  // Opt-in (PFFT_FUSE=1).  Measured on B200 (profiles/r2_ab_variants.txt): the fused kernel halves the DRAM traffic of
+  // 65536 x 2048 fp32 (ncu: 1.11 GB read + 1.50 GB written against 2.15 + 2.06 GB for the two launches) but is not
+  // faster, 0.848 ms against 0.720 ms: the two separate passes already run at 82 % / 98 % of the HBM roofline and the
+  // work per tile is instruction-issue and latency bound (about one 256 x 16 tile per microsecond and SM either way),
+  // so taking DRAM time away buys nothing until the per-tile cost drops.  fp64 2^24 x 8: 2.42 ms fused, 2.27 ms apart.
+  if (!env_int("PFFT_FUSE", 0) || env_int("PFFT_NO_FUSE", 0)) return false;
   const int C = is_double ? 8 : 16;
   if (a.n != 256 || b.n != 256) return false;
   if ((variant_a & 7) != 0 || (variant_b & 7) != 2) return false;  // cols_tma -> cols ; rows_bulk -> cols

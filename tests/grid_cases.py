@@ -196,9 +196,9 @@ SUITES = {
                          basic([("IP", P, P)], ["bwd"], ["interleaved"], [1000], [8192]) +
                          basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [40000], [64, 256])
                          if c.scalar == "float" or c.lengths[0] <= 2048]),
-    # default chunking of the fused GLOBAL-level kernel: 8 MiB chunks, >= 6 chunks
-    "FusedGlobalTest": [c for c in basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [128], [65536])
-                        if c.scalar == "float" or c.dir == "fwd"],
+    # GLOBAL level at a batch deep in the steady state of both passes
+    "GlobalSteadyStateTest": [c for c in basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [128], [65536])
+                              if c.scalar == "float" or c.dir == "fwd"],
     "SteadyStateColumnTest": [c for c in basic(MD_LAYOUTS, BOTH_DIR, ["interleaved"], [3], [[512, 8192]]) +
                               basic([("OOP", P, P)], ["fwd"], ["interleaved"], [1], [[512, 512, 64], [256, 256, 128]]) +
                               basic([("IP", P, P)], ["bwd"], ["interleaved"], [1], [[512, 512, 64]]) +

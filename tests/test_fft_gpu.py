@@ -38,14 +38,15 @@ FORCED = {
                    real(BOTH_DIR, STORAGES, [5], [65536])),
     # two GLOBAL-level passes fused into one persistent kernel with an L2-resident ring (wg_fused.cu): small chunks so
     # that modest batches already run many chunks through the ring slots and both arrival counters
-    "fused_small_chunks": ({"PFFT_FUSE_CHUNK_KB": "512"},
+    "fused_small_chunks": ({"PFFT_FUSE": "1", "PFFT_FUSE_CHUNK_KB": "512"},
                            basic(GLOBAL_LAYOUTS, BOTH_DIR, ["interleaved"], [8, 37], [65536]) +
                            offsets([("OOP", P, P)], BOTH_DIR, [9], [65536], [(0, 6), (4, 0)]) +
                            scaled("fwd", [65536], -1.0, 2.0) + scaled("bwd", [65536], -1.0, 2.0) +
                            basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [2], [1 << 24])),
-    "fused_lead2": ({"PFFT_FUSE_CHUNK_KB": "1024", "PFFT_FUSE_LEAD": "2"},
+    "fused_lead2": ({"PFFT_FUSE": "1", "PFFT_FUSE_CHUNK_KB": "1024", "PFFT_FUSE_LEAD": "2"},
                     basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [40], [65536])),
-    "unfused": ({"PFFT_NO_FUSE": "1"}, basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [8], [65536])),
+    "fused_default_chunks": ({"PFFT_FUSE": "1"}, [c for c in basic([("OOP", P, P)], BOTH_DIR, ["interleaved"], [128], [65536])
+                                                  if c.scalar == "float" or c.dir == "fwd"]),
     "cube_direct_loads": ({"PFFT_CUBE_VARIANT": "1"}, basic([("IP", P, P), ("OOP", P, P)], BOTH_DIR, ["interleaved"],
                                                             [5], [4096])),
 }
