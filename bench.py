@@ -63,6 +63,14 @@ CONFIGS = {
                   desc="1D C2C fp32 N=2048 batch=64Ki out-of-place (packed rows, three-radix kernel 16x16x8)"),
     "M8192": dict(lengths=[8192], batch=16 * 1024, scalar="float", inplace=False, split=False,
                   desc="1D C2C fp32 N=8192 batch=16Ki out-of-place (packed rows, 16x16x32)"),
+    "D512": dict(lengths=[512], batch=128 * 1024, scalar="double", inplace=False, split=False,
+                 desc="1D C2C fp64 N=512 batch=128Ki out-of-place (packed rows, N = 8^3 tile kernel)"),
+    "D1024": dict(lengths=[1024], batch=64 * 1024, scalar="double", inplace=False, split=False,
+                  desc="1D C2C fp64 N=1024 batch=64Ki out-of-place (packed rows, 16x8x8)"),
+    "D2048": dict(lengths=[2048], batch=32 * 1024, scalar="double", inplace=False, split=False,
+                  desc="1D C2C fp64 N=2048 batch=32Ki out-of-place (packed rows, 16x16x8)"),
+    "D4096": dict(lengths=[4096], batch=16 * 1024, scalar="double", inplace=False, split=False,
+                  desc="1D C2C fp64 N=4096 batch=16Ki out-of-place (packed rows, N = 16^3)"),
     "M256": dict(lengths=[256], batch=512 * 1024, scalar="float", inplace=False, split=False,
                  desc="1D C2C fp32 N=256 batch=512Ki out-of-place (reference bench_float medium_small_1d)"),
 }

@@ -462,9 +462,12 @@ void select_specialised(PassHost& ps, const DescHost& d, const DeviceLimits& lim
   if (p.n == 512 && env512 && std::atoi(env512) != 0) return;
   const char* envr3 = std::getenv("PFFT_NO_ROWS3");
   if ((p.n == 1024 || p.n == 2048 || p.n == 8192) && ((envr3 && std::atoi(envr3) != 0) || variant != 0)) return;
+  if (d.is_double && variant != 0) return;  // fp64: the TMA-fed variants only
+  const char* envd = std::getenv("PFFT_NO_CUBE_F64");
+  if (d.is_double && envd && std::atoi(envd) != 0) return;
   if (cube_supported(p.n, d.is_double, &tile, &per_sm) && il && p.is == 1 && p.os == 1 && single_batch_dim &&
       p.gtw_dim < 0 && p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 &&
-      p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0) {
+      (d.is_double || (p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0))) {
     ps.kernel = KERNEL_WG_CUBE;
     ps.variant = variant;
     const long long tiles = (p.batch_total + tile - 1) / tile;

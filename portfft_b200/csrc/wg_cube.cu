@@ -72,7 +72,7 @@ __device__ __forceinline__ constexpr int sw2(int e) {
 }
 
 template <typename T, int R, int F, bool SWAP, bool USE_TMA>
-__global__ void __launch_bounds__(R* R* F, F == 1 ? 2 : 4) wg_cube_kernel(const CubeArgs a) {
+__global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4) wg_cube_kernel(const CubeArgs a) {
   constexpr int NT = R * R;  // threads per transform
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
@@ -396,13 +396,21 @@ static cudaError_t launch_cube_v(const CubeArgs& a, bool swap, bool tma, int gri
 }
 
 bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm) {
-  if (is_double) return false;
   int f = 0, c = 0;
-  if (n == 4096) f = 1, c = 2;
-  if (n == 512) f = kCube512Tile, c = 4;
-  if (n == 1024) f = 4, c = 2;  // wg_rows3_kernel 16 x 8 x 8
-  if (n == 2048) f = 2, c = 2;  // wg_rows3_kernel 16 x 16 x 8
-  if (n == 8192) f = 1, c = 1;  // wg_rows3_kernel 16 x 16 x 32
+  if (is_double) {
+    // same kernels, half the transforms per tile (the tile bytes stay the same); 4096 = 16^3 fills one SM with one
+    // CTA (two 64 KiB stages + the padded exchange buffer)
+    if (n == 4096) f = 1, c = 1;
+    if (n == 512) f = kCube512Tile / 2, c = 4;
+    if (n == 1024) f = 2, c = 2;
+    if (n == 2048) f = 1, c = 2;
+  } else {
+    if (n == 4096) f = 1, c = 2;
+    if (n == 512) f = kCube512Tile, c = 4;
+    if (n == 1024) f = 4, c = 2;  // wg_rows3_kernel 16 x 8 x 8
+    if (n == 2048) f = 2, c = 2;  // wg_rows3_kernel 16 x 16 x 8
+    if (n == 8192) f = 1, c = 1;  // wg_rows3_kernel 16 x 16 x 32
+  }
   if (f == 0) return false;
   if (transforms_per_tile) *transforms_per_tile = f;
   if (ctas_per_sm) *ctas_per_sm = c;
@@ -423,6 +431,14 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   a.scale = p.scale;
   a.apply_scale = p.apply_scale;
   const bool tma = variant == 0;
+  if (is_double) {
+    if (!tma) return cudaErrorInvalidValue;
+    if (p.n == 4096) return launch_cube_v<double, 16, 1>(a, swap, true, grid, stream);
+    if (p.n == 512) return launch_cube_v<double, 8, kCube512Tile / 2>(a, swap, true, grid, stream);
+    if (p.n == 1024) return launch_rows3<double, 16, 8, 8, 2>(a, swap, grid, stream);
+    if (p.n == 2048) return launch_rows3<double, 16, 16, 8, 1>(a, swap, grid, stream);
+    return cudaErrorInvalidValue;
+  }
   if (!is_double && p.n == 4096) return launch_cube_v<float, 16, 1>(a, swap, tma, grid, stream);
   if (!is_double && p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, grid, stream);
   if (!is_double && tma && p.n == 1024) return launch_rows3<float, 16, 8, 8, 4>(a, swap, grid, stream);
