@@ -144,6 +144,88 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
 
 pfft_status pfft_destroy(pfft_plan* plan);
 
+/* ---------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (csrc/multi.cu).  The reference is single-device (one sycl::queue,
+ * src/portfft/committed_descriptor_impl.hpp:109), so these have no reference counterpart beyond the descriptor
+ * vocabulary.  Two shapes of the same thing:
+ *   * batch sharding: the transforms of a descriptor are independent units (overlap is rejected at commit,
+ *     src/portfft/descriptor_validation.hpp:162-204); GPU r of `world` transforms a contiguous batch range.  No
+ *     data-path collective.
+ *   * slab decomposition of ONE 3-D complex transform: three local passes and one exchange step that is fused into
+ *     the stores of the middle pass (peer-mapped memory over NVLink) and closed by a device-side flag barrier.
+ * Both work with one process per GPU (the caller moves 64-byte IPC handles between processes with whatever transport
+ * it has) and with one process driving all GPUs.
+ * --------------------------------------------------------------------------------------------------------------- */
+
+/* Contiguous balanced split of n_items over `world` ranks: the first n_items % world ranks get one extra item. */
+pfft_status pfft_partition(size_t n_items, int world, int rank, size_t* first, size_t* count);
+
+typedef struct pfft_shard_info {
+  size_t first;          /* first transform of the shard within the un-sharded batch */
+  size_t count;          /* transforms in the shard (0: this rank has nothing to do; its plan transforms 1) */
+  size_t forward_start;  /* where the shard begins inside the un-sharded forward-domain buffer, in elements */
+  size_t backward_start; /* ... and inside the backward-domain buffer */
+} pfft_shard_info;
+
+/* pfft_commit of the rank-local shard of `desc`.  Batch-major layouts: the shard is the batch range starting at
+ * first * distance (pass base pointers advanced by *_start, or rank-local buffers).  BATCH_INTERLEAVED layouts
+ * (distance 1, stride == number_of_transforms): the shard is a column range, batch-interleaved with
+ * stride == count in rank-local buffers. */
+pfft_status pfft_commit_shard(const pfft_desc* desc, int world, int rank, int device, void* stream,
+                              pfft_plan** plan_out, pfft_shard_info* info);
+
+/* One process, n_dev GPUs, batch sharded: shard r lives on devices[r] (`streams` may be NULL: the library creates one
+ * non-blocking stream per device; otherwise n_dev cudaStream_t). */
+typedef struct pfft_multi pfft_multi;
+pfft_status pfft_commit_multi(const pfft_desc* desc, int n_dev, const int* devices, void* const* streams,
+                              pfft_multi** multi_out);
+int pfft_multi_size(const pfft_multi* multi);
+pfft_status pfft_multi_shard(const pfft_multi* multi, int r, pfft_shard_info* info, pfft_plan** plan);
+/* Asynchronous: entry r of every pointer table is the rank-local buffer on devices[r] (the *_imag tables may be NULL
+ * for interleaved storage). */
+pfft_status pfft_multi_compute(pfft_multi* multi, int direction, const void* const* in, const void* const* in_imag,
+                               void* const* out, void* const* out_imag);
+/* Un-sharded HOST buffers (batch-major layouts): every GPU runs the pfft_compute_host pipeline on its batch range,
+ * one host thread per GPU; returns when all have finished. */
+pfft_status pfft_multi_compute_host(pfft_multi* multi, int direction, const void* in, const void* in_imag, void* out,
+                                    void* out_imag);
+pfft_status pfft_multi_sync(pfft_multi* multi);
+pfft_status pfft_multi_destroy(pfft_multi* multi);
+
+/* Slab-decomposed 3-D transform: `desc` = COMPLEX, INTERLEAVED_COMPLEX, rank 3, default strides, one transform;
+ * lengths[0] and lengths[1] divisible by `world`.  Rank r holds the x-planes [r*XL, (r+1)*XL) of the input
+ * ([XL][n1][n2], XL = n0 / world) and receives the y-rows [r*YB, (r+1)*YB) of the spectrum ([n0][YB][n2]).
+ * Every rank owns an exchange window in device memory (receive buffer + arrival flags) that its peers map. */
+typedef struct pfft_slab pfft_slab;
+enum { PFFT_IPC_HANDLE_BYTES = 64 };
+pfft_status pfft_slab_commit(const pfft_desc* desc, int world, int rank, int device, void* stream,
+                             pfft_slab** slab_out);
+size_t pfft_slab_elems(const pfft_slab* slab); /* complex elements of every rank-local buffer: n0*n1*n2 / world */
+/* Window plumbing.  Other process: pfft_slab_export here, move the 64 bytes, pfft_slab_import there.  Same process
+ * (or memory that is already mapped, e.g. a symmetric-memory allocation): pfft_slab_window + pfft_slab_attach.
+ * A rank must know the windows of ALL ranks (its own is attached at commit) before the first transform. */
+pfft_status pfft_slab_window(pfft_slab* slab, void** base, size_t* bytes);
+pfft_status pfft_slab_export(pfft_slab* slab, void* ipc_handle);
+pfft_status pfft_slab_import(pfft_slab* slab, int peer_rank, const void* ipc_handle);
+pfft_status pfft_slab_attach(pfft_slab* slab, int peer_rank, void* peer_window);
+/* One process, n_dev GPUs (entries of `devices` may repeat: several ranks on one GPU): commits every rank, enables
+ * peer access and attaches all windows.  slabs_out receives n_dev objects. */
+pfft_status pfft_slab_commit_local(const pfft_desc* desc, int n_dev, const int* devices, void* const* streams,
+                                   pfft_slab** slabs_out);
+/* Exchange through a collective of the caller (e.g. an all-to-all over ncclSend / ncclRecv) instead of peer stores:
+ * fn moves block d (block_bytes each) of `send` to rank d's `recv` at block index = the sender's rank, stream-ordered
+ * on `stream`; returns 0 on success.  NULL restores the peer-store exchange. */
+typedef int (*pfft_alltoall_fn)(void* user, const void* send, void* recv, size_t block_bytes, void* stream);
+pfft_status pfft_slab_set_alltoall(pfft_slab* slab, pfft_alltoall_fn fn, void* user);
+/* Asynchronous on the slab's stream; collective: every rank calls the same sequence.  Forward: x-slab in, *out_yslab =
+ * the y-slab of the spectrum inside the rank's window (valid until the next call).  Backward: y-slab in (may be that
+ * pointer), x-slab out, times backward_scale. */
+pfft_status pfft_slab_forward(pfft_slab* slab, const void* in_xslab, void** out_yslab);
+pfft_status pfft_slab_backward(pfft_slab* slab, const void* in_yslab, void* out_xslab);
+/* Waits for the slab's stream; reports a barrier that timed out (a peer that never arrived) as PFFT_CUDA_ERROR. */
+pfft_status pfft_slab_sync(pfft_slab* slab);
+pfft_status pfft_slab_destroy(pfft_slab* slab);
+
 /* Introspection. */
 size_t pfft_workspace_bytes(const pfft_plan* plan);
 /* Multi-pass plans whose per-transform workspace is small against the L2 run the batch in chunks of this many

@@ -40,8 +40,14 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
 // variant bits 0-1: input mode (0 strided columns via TMA tensor tiles, 1 contiguous rows loaded directly, 2 contiguous
 // rows via cp.async.bulk), bit 2: contiguous output rows (else output columns).
 // *used == false with cudaSuccess: tensor map not encodable for these pointers, run the generic kernel.
+// `cache` (optional, owned by the plan, one per pass): the encoded tensor map of the last call, reused while the input
+// base address is the same (the geometry of a pass never changes after commit) -- no cuTensorMapEncodeTiled per call.
+struct ColMapCache {
+  const void* base = nullptr;  // input address the cached map was encoded for (nullptr: empty)
+  alignas(64) unsigned char map[128];
+};
 cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
-                          bool* used);
+                          bool* used, ColMapCache* cache = nullptr);
 
 // WORKGROUP level, three compile-time radix passes for any layout / storage (wg_r3.cu): n in {1000, 1024, 1536, 2048,
 // 3072, 4096}; geometry = p.ffts_per_block transforms per CTA, r3_supported's threads per transform

@@ -18,6 +18,8 @@ namespace pfft {
 
 // Error carrying a pfft_status; the C ABI maps it to status + thread-local message, the C++ header back to the
 // reference's exception types (src/portfft/common/exceptions.hpp:32-77).
+void set_last_error(const std::string& msg);  // thread-local message behind pfft_last_error (runtime.cu)
+
 struct PlanError : std::runtime_error {
   pfft_status status;
   PlanError(pfft_status s, const std::string& m) : std::runtime_error(m), status(s) {}

@@ -28,6 +28,7 @@
 namespace pfft {
 
 static thread_local std::string g_last_error;
+void set_last_error(const std::string& msg) { g_last_error = msg; }  // for the other translation units of the C ABI
 static std::atomic<unsigned long long> g_total_launches{0};
 
 #define PFFT_CUDA_CHECK(expr)                                                                         \
@@ -87,6 +88,10 @@ struct pfft_plan {
     unsigned long long epoch = 0;
   };
   std::vector<FusedPair> fused[2];
+  // encoded TMA tensor maps of the column-tile passes, [direction][pass]: valid while the caller keeps passing the same
+  // buffers (the usual case), re-encoded when an address changes.  A different box geometry (col512 vs the two-pass
+  // tile kernel) is a different pass, so the address alone identifies the map.
+  std::vector<ColMapCache> col_maps[2];
   // pfft_compute_host pipeline: copy streams, per-chunk events, sub-batch plans (number_of_transforms -> plan)
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_up, chunk_done;
@@ -495,7 +500,9 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         break;
       case KERNEL_WG_COL: {
         bool used = false;
-        e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used);
+        std::vector<ColMapCache>& maps = plan->col_maps[dir];
+        if (maps.size() != passes.size()) maps.assign(passes.size(), ColMapCache());
+        e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used, &maps[pi]);
         if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       }

@@ -593,16 +593,35 @@ static bool inplace_enabled() {
 }
 
 // variant: bits 0-1 = input mode, bit 2 = OUT_ROWS
+// tensor map of the pass input: from the plan's per-pass cache when the base address is the one it was encoded for
+static bool col_tensor_map_cached(const PassParams& p, bool is_double, int C, int box_rows, ColMapCache* cache,
+                                  CUtensorMap* map) {
+  static_assert(sizeof(CUtensorMap) == sizeof(ColMapCache::map), "CUtensorMap is 128 bytes");
+  const void* base = reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * (is_double ? 16 : 8);
+  if (cache != nullptr && cache->base == base) {
+    memcpy(map, cache->map, sizeof(CUtensorMap));
+    return true;
+  }
+  if (!col_make_tensor_map(p, is_double, C, box_rows, map)) return false;
+  if (cache != nullptr) {
+    memcpy(cache->map, map, sizeof(CUtensorMap));
+    cache->base = base;
+  }
+  return true;
+}
+
 template <typename T, int N1, int N2, int N3>
-static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cudaStream_t stream, bool* used) {
+static cudaError_t launch_col_t(const PassParams& p, bool swap, int variant, cudaStream_t stream, bool* used,
+                                ColMapCache* cache) {
   *used = false;
   int in = variant & 3;
   const bool out_rows = (variant & 4) != 0;
   CUtensorMap map;
-  memset(&map, 0, sizeof(map));
   if (in == IN_COLS_TMA) {
     using Cfg = ColCfg<T, N1, N2, N3, IN_COLS_TMA>;
-    if (!col_make_tensor_map(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, &map)) return cudaSuccess;  // caller falls back
+    if (!col_tensor_map_cached(p, sizeof(T) == 8, Cfg::C, Cfg::kBoxRows, cache, &map)) return cudaSuccess;  // caller falls back
+  } else {
+    memset(&map, 0, sizeof(map));
   }
   if (in == IN_ROWS_BULK) {
     const uintptr_t base = reinterpret_cast<uintptr_t>(p.in_re) + (size_t)p.ioff * 2 * sizeof(T);
@@ -637,11 +656,10 @@ static bool col512_groups_enabled() {
   return on;
 }
 
-static cudaError_t launch_col512(const PassParams& p, bool swap, cudaStream_t stream, bool* used) {
+static cudaError_t launch_col512(const PassParams& p, bool swap, cudaStream_t stream, bool* used, ColMapCache* cache) {
   *used = false;
   CUtensorMap map;
-  memset(&map, 0, sizeof(map));
-  if (!col_make_tensor_map(p, false, Col512::C, 256, &map)) return cudaSuccess;  // caller falls back
+  if (!col_tensor_map_cached(p, false, Col512::C, 256, cache, &map)) return cudaSuccess;  // caller falls back
   *used = true;
   const int sms = sm_count();
   if (sms <= 0) return cudaErrorLaunchOutOfResources;
@@ -688,12 +706,12 @@ int col_threads(int n, bool is_double) {
 
 // *used == false on return with cudaSuccess: the tensor map could not be built (alignment); run the generic kernel
 cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
-                          bool* used) {
+                          bool* used, ColMapCache* cache) {
   (void)grid;  // the planner's estimate; the launch sizes the persistent grid from the kernel's actual occupancy
 #define PFFT_COL(NN, A, B, CC)                                                                   \
   case NN:                                                                                       \
-    return is_double ? launch_col_t<double, A, B, CC>(p, swap, variant, stream, used)      \
-                     : launch_col_t<float, A, B, CC>(p, swap, variant, stream, used);
+    return is_double ? launch_col_t<double, A, B, CC>(p, swap, variant, stream, used, cache) \
+                     : launch_col_t<float, A, B, CC>(p, swap, variant, stream, used, cache);
   *used = false;
   switch (p.n) {
     PFFT_COL(64, 8, 8, 1)
@@ -707,10 +725,10 @@ cudaError_t launch_wg_col(const PassParams& p, bool is_double, bool swap, int va
         return e ? std::atoi(e) == 3 : 0;
       }();
       if (!three_pass && !is_double && (variant & 3) == IN_COLS_TMA && (variant & 4) == 0 && col512_groups_enabled())
-        return launch_col512(p, swap, stream, used);
-      if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, stream, used);
-      return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, stream, used)
-                       : launch_col_t<float, 8, 8, 8>(p, swap, variant, stream, used);
+        return launch_col512(p, swap, stream, used, cache);
+      if (!three_pass && !is_double) return launch_col_t<float, 16, 32, 1>(p, swap, variant, stream, used, cache);
+      return is_double ? launch_col_t<double, 8, 8, 8>(p, swap, variant, stream, used, cache)
+                       : launch_col_t<float, 8, 8, 8>(p, swap, variant, stream, used, cache);
     }
     default:
       return cudaErrorInvalidValue;

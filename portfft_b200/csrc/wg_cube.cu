@@ -16,6 +16,7 @@
 //   * per-thread twiddles (w_256^{(t%16) r}, w_4096^{t r}) are loaded once per CTA and stay in registers;
 //   * results leave with coalesced 64-bit stores straight from registers; backward = re/im swap; scale fused.
 #include <cstdint>
+#include <cstdlib>
 
 #include "device_utils.cuh"
 #include "kernels.h"
@@ -214,11 +215,23 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
 // (twiddles from the L1-resident table instead of registers).  TMA ring, padded exchange 1, exchange 2 written back
 // into the consumed stage, coalesced stores from registers -- as above.
 // ---------------------------------------------------------------------------------------------------------------
-template <typename T, int R0, int R1, int R2, int F, bool SWAP>
-__global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg_rows3_kernel(const CubeArgs a) {
+//
+// B1 = radix-16 butterflies per thread in pass 1 (threads per transform NT = N / 16 / B1).  8192 = 16*16*32 runs with
+// B1 = 2: 256 threads, two radix-16 butterflies each in passes 1 and 2 and ONE radix-32 butterfly in pass 3 whose 31
+// twiddles stay in registers (with B1 = 1 half of the 512 threads idle through pass 3 and every radix-32 butterfly
+// fetches its twiddles from the table: 45 % of the HBM roofline).
+template <int R0, int R1, int R2, int F, int B1, typename T>
+constexpr int rows3_min_ctas() {
+  constexpr size_t n = (size_t)R0 * R1 * R2;
+  return (2 * n + n + 2 * (n / 16)) * F * 2 * sizeof(T) + 64 > 113 * 1024 ? 1 : 2;
+}
+
+template <typename T, int R0, int R1, int R2, int F, bool SWAP, int B1 = 1>
+__global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 ? 1 : rows3_min_ctas<R0, R1, R2, F, B1, T>()))
+    wg_rows3_kernel(const CubeArgs a) {
   static_assert(R0 == 16, "pass 1 writes whole padded 16-groups");
   constexpr int N = R0 * R1 * R2;
-  constexpr int NT = N / R0;  // threads per transform
+  constexpr int NT = N / R0 / B1;  // threads per transform
   constexpr int EN = N + 2 * (N / 16);
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);
@@ -235,11 +248,16 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
   // twiddles of the thread's own butterflies, resident in registers for the whole batch loop when they are few
   // (measured: table look-ups inside the passes cost 2048-point rows a third of their bandwidth)
   constexpr int B2 = (N / R1 + NT - 1) / NT, B3 = (N / R2 + NT - 1) / NT;  // butterflies per thread in passes 2, 3
-  constexpr bool TW2REG = B2 * (R1 - 1) <= 16, TW3REG = B3 * (R2 - 1) <= 16;
-  cx<T> tw2[TW2REG ? B2 * (R1 - 1) : 1], tw3[TW3REG ? B3 * (R2 - 1) : 1];
+  // pass-2 twiddles depend on j % R0 only: one set serves all of a thread's butterflies when R0 divides NT
+  constexpr bool TW2SHARED = NT % R0 == 0;
+  constexpr int S2 = TW2SHARED ? 0 : (R1 - 1);  // register offset between the twiddle sets of consecutive butterflies
+  constexpr int NTW2 = (TW2SHARED ? 1 : B2) * (R1 - 1), NTW3 = B3 * (R2 - 1);
+  constexpr int TWMAX = B1 > 1 ? 31 : 16;  // (B1 > 1: 256 threads on a whole SM, 255 registers each)
+  constexpr bool TW2REG = NTW2 <= TWMAX, TW3REG = NTW3 <= TWMAX;
+  cx<T> tw2[TW2REG ? NTW2 : 1], tw3[TW3REG ? NTW3 : 1];
   if (TW2REG) {
 #pragma unroll
-    for (int i = 0; i < B2; ++i)
+    for (int i = 0; i < (TW2SHARED ? 1 : B2); ++i)
 #pragma unroll
       for (int r = 1; r < R1; ++r) tw2[i * (R1 - 1) + r - 1] = ldg_cx<T>(a.tw, ((t + i * NT) % R0) * r * R2);
   }
@@ -283,22 +301,26 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
     // ---- pass 1: x[t + NT r] -> radix 16 -> E[16 t + r'] -------------------------------------------------------
     mbar_wait(&full[it & 1], (it >> 1) & 1);
     if (live) {
-      cx<T> v[R0];
 #pragma unroll
-      for (int r = 0; r < R0; ++r) v[r] = S[t + NT * r];
-      if (SWAP) {
+      for (int i = 0; i < B1; ++i) {
+        const int j = t + i * NT;
+        cx<T> v[R0];
 #pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = cx<T>{v[r].y, v[r].x};
-      }
-      DFT<R0, T>::run(v);
-      cx<T>* dst = Ef + 18 * t;  // epad(16 t + r) = 18 t + r
-      if constexpr (sizeof(T) == 4) {
+        for (int r = 0; r < R0; ++r) v[r] = S[j + (N / R0) * r];
+        if (SWAP) {
 #pragma unroll
-        for (int r = 0; r < R0; r += 2)
-          *reinterpret_cast<float4*>(dst + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
-      } else {
+          for (int r = 0; r < R0; ++r) v[r] = cx<T>{v[r].y, v[r].x};
+        }
+        DFT<R0, T>::run(v);
+        cx<T>* dst = Ef + 18 * j;  // epad(16 j + r) = 18 j + r
+        if constexpr (sizeof(T) == 4) {
 #pragma unroll
-        for (int r = 0; r < R0; ++r) dst[r] = v[r];
+          for (int r = 0; r < R0; r += 2)
+            *reinterpret_cast<float4*>(dst + r) = make_float4(v[r].x, v[r].y, v[r + 1].x, v[r + 1].y);
+        } else {
+#pragma unroll
+          for (int r = 0; r < R0; ++r) dst[r] = v[r];
+        }
       }
     }
     __syncthreads();
@@ -321,7 +343,7 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
         for (int r = 0; r < R1; ++r) v[r] = Ef[epad<R0>(j + (N / R1) * r)];
 #pragma unroll
         for (int r = 1; r < R1; ++r)
-          v[r] = cmul(v[r], TW2REG ? tw2[TW2REG ? i * (R1 - 1) + r - 1 : 0] : ldg_cx<T>(a.tw, k1 * r * R2));
+          v[r] = cmul(v[r], TW2REG ? tw2[TW2REG ? i * S2 + r - 1 : 0] : ldg_cx<T>(a.tw, k1 * r * R2));
         DFT<R1, T>::run(v);
         cx<T>* dst = S + (j - k1) * R1 + k1;
 #pragma unroll
@@ -355,19 +377,19 @@ __global__ void __launch_bounds__((R1 * R2) * F, (R1 * R2) * F > 256 ? 1 : 2) wg
   }
 }
 
-template <typename T, int R0, int R1, int R2, int F>
+template <typename T, int R0, int R1, int R2, int F, int B1 = 1>
 static cudaError_t launch_rows3(const CubeArgs& a, bool swap, int grid, cudaStream_t stream) {
   constexpr int N = R0 * R1 * R2;
   constexpr size_t smem = (2 * (size_t)N + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
   cudaError_t e;
   if (swap) {
-    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, true>, smem);
+    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, true, B1>, smem);
     if (e != cudaSuccess) return e;
-    wg_rows3_kernel<T, R0, R1, R2, F, true><<<grid, (N / R0) * F, smem, stream>>>(a);
+    wg_rows3_kernel<T, R0, R1, R2, F, true, B1><<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
   } else {
-    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, false>, smem);
+    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, false, B1>, smem);
     if (e != cudaSuccess) return e;
-    wg_rows3_kernel<T, R0, R1, R2, F, false><<<grid, (N / R0) * F, smem, stream>>>(a);
+    wg_rows3_kernel<T, R0, R1, R2, F, false, B1><<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
   }
   return cudaGetLastError();
 }
@@ -443,7 +465,14 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   if (!is_double && p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, grid, stream);
   if (!is_double && tma && p.n == 1024) return launch_rows3<float, 16, 8, 8, 4>(a, swap, grid, stream);
   if (!is_double && tma && p.n == 2048) return launch_rows3<float, 16, 16, 8, 2>(a, swap, grid, stream);
-  if (!is_double && tma && p.n == 8192) return launch_rows3<float, 16, 16, 32, 1>(a, swap, grid, stream);
+  if (!is_double && tma && p.n == 8192) {
+    static const bool wide = [] {  // A/B knob: the 512-thread form (one radix-16 butterfly per thread in pass 1)
+      const char* e = std::getenv("PFFT_ROWS8192_WIDE");
+      return e && std::atoi(e) != 0;
+    }();
+    return wide ? launch_rows3<float, 16, 16, 32, 1>(a, swap, grid, stream)
+                : launch_rows3<float, 16, 16, 32, 1, 2>(a, swap, grid, stream);
+  }
   return cudaErrorInvalidValue;
 }
 
