@@ -208,6 +208,10 @@ pfft_status pfft_slab_window(pfft_slab* slab, void** base, size_t* bytes);
 pfft_status pfft_slab_export(pfft_slab* slab, void* ipc_handle);
 pfft_status pfft_slab_import(pfft_slab* slab, int peer_rank, const void* ipc_handle);
 pfft_status pfft_slab_attach(pfft_slab* slab, int peer_rank, void* peer_window);
+/* Replace the rank's own window by caller-owned device memory of at least the size pfft_slab_window reports (e.g. one
+ * buffer of a symmetric-memory allocation that the peers already map); before the first transform only.  The caller
+ * keeps ownership. */
+pfft_status pfft_slab_use_window(pfft_slab* slab, void* base, size_t bytes);
 /* One process, n_dev GPUs (entries of `devices` may repeat: several ranks on one GPU): commits every rank, enables
  * peer access and attaches all windows.  slabs_out receives n_dev objects. */
 pfft_status pfft_slab_commit_local(const pfft_desc* desc, int n_dev, const int* devices, void* const* streams,

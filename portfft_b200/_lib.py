@@ -39,6 +39,15 @@ class pfft_batch_dim(ctypes.Structure):
     _fields_ = [("count", c_size_t), ("forward_distance", c_size_t), ("backward_distance", c_size_t)]
 
 
+class pfft_shard_info(ctypes.Structure):
+    """`pfft_shard_info` (include/pfft.h): where a rank's batch shard lies inside the un-sharded buffers."""
+
+    _fields_ = [("first", c_size_t), ("count", c_size_t), ("forward_start", c_size_t), ("backward_start", c_size_t)]
+
+
+# pfft_alltoall_fn: int fn(void* user, const void* send, void* recv, size_t block_bytes, void* stream)
+ALLTOALL_FN = ctypes.CFUNCTYPE(c_int, c_void_p, c_void_p, c_void_p, c_size_t, c_void_p)
+
 # every symbol include/pfft.h declares: name -> (restype, argtypes)
 SYMBOLS = {
     "pfft_validate": (c_int, [POINTER(pfft_desc)]),
@@ -57,6 +66,31 @@ SYMBOLS = {
     "pfft_compute": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfft_compute_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "pfft_destroy": (c_int, [c_void_p]),
+    # multi-GPU (csrc/multi.cu)
+    "pfft_partition": (c_int, [c_size_t, c_int, c_int, POINTER(c_size_t), POINTER(c_size_t)]),
+    "pfft_commit_shard": (c_int, [POINTER(pfft_desc), c_int, c_int, c_int, c_void_p, POINTER(c_void_p),
+                                  POINTER(pfft_shard_info)]),
+    "pfft_commit_multi": (c_int, [POINTER(pfft_desc), c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p)]),
+    "pfft_multi_size": (c_int, [c_void_p]),
+    "pfft_multi_shard": (c_int, [c_void_p, c_int, POINTER(pfft_shard_info), POINTER(c_void_p)]),
+    "pfft_multi_compute": (c_int, [c_void_p, c_int, POINTER(c_void_p), POINTER(c_void_p), POINTER(c_void_p),
+                                   POINTER(c_void_p)]),
+    "pfft_multi_compute_host": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "pfft_multi_sync": (c_int, [c_void_p]),
+    "pfft_multi_destroy": (c_int, [c_void_p]),
+    "pfft_slab_commit": (c_int, [POINTER(pfft_desc), c_int, c_int, c_int, c_void_p, POINTER(c_void_p)]),
+    "pfft_slab_elems": (c_size_t, [c_void_p]),
+    "pfft_slab_window": (c_int, [c_void_p, POINTER(c_void_p), POINTER(c_size_t)]),
+    "pfft_slab_export": (c_int, [c_void_p, c_void_p]),
+    "pfft_slab_import": (c_int, [c_void_p, c_int, c_void_p]),
+    "pfft_slab_attach": (c_int, [c_void_p, c_int, c_void_p]),
+    "pfft_slab_use_window": (c_int, [c_void_p, c_void_p, c_size_t]),
+    "pfft_slab_commit_local": (c_int, [POINTER(pfft_desc), c_int, POINTER(c_int), POINTER(c_void_p), POINTER(c_void_p)]),
+    "pfft_slab_set_alltoall": (c_int, [c_void_p, ALLTOALL_FN, c_void_p]),
+    "pfft_slab_forward": (c_int, [c_void_p, c_void_p, POINTER(c_void_p)]),
+    "pfft_slab_backward": (c_int, [c_void_p, c_void_p, c_void_p]),
+    "pfft_slab_sync": (c_int, [c_void_p]),
+    "pfft_slab_destroy": (c_int, [c_void_p]),
     "pfft_workspace_bytes": (c_size_t, [c_void_p]),
     "pfft_plan_chunk_transforms": (c_size_t, [c_void_p]),
     "pfft_plan_level": (c_int, [c_void_p, c_size_t]),

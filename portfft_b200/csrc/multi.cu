@@ -134,8 +134,13 @@ struct pfft_multi {
   std::vector<bool> own_stream;
   std::vector<pfft_plan*> plan;
   std::vector<pfft_shard_info> info;
+  // pfft_multi_compute_host on a descriptor with offsets: shards r > 0 start AT their first transform (offset folded
+  // into the base pointer, zero offsets in the plan), so that the host ranges of two shards never overlap
+  std::vector<pfft_plan*> host_plan;
 
   ~pfft_multi() {
+    for (size_t r = 0; r < host_plan.size(); ++r)
+      if (host_plan[r]) pfft_destroy(host_plan[r]);
     for (size_t r = 0; r < plan.size(); ++r)
       if (plan[r]) pfft_destroy(plan[r]);
     for (size_t r = 0; r < stream.size(); ++r)
@@ -210,6 +215,7 @@ struct pfft_slab {
   char* A = nullptr;
   char* S = nullptr;       // exchange buffer of the backward transform and of the caller-collective path
   char* window = nullptr;  // [B: slab_elems complex][flags: kMaxPeers u64]
+  bool own_window = true;
   size_t window_bytes = 0, flags_offset = 0;
   unsigned int* status = nullptr;
   char* peer_window[kMaxPeers] = {};
@@ -233,7 +239,7 @@ struct pfft_slab {
       if (imported[i] && peer_window[i]) cudaIpcCloseMemHandle(peer_window[i]);
     if (A) cudaFree(A);
     if (S) cudaFree(S);
-    if (window) cudaFree(window);
+    if (window && own_window) cudaFree(window);
     if (status) cudaFree(status);
     if (own_stream && stream) cudaStreamDestroy(stream);
     if (prev >= 0) cudaSetDevice(prev);
@@ -503,6 +509,20 @@ pfft_status pfft_multi_compute_host(pfft_multi* multi, int direction, const void
            "use pfft_multi_compute");
     const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
     const size_t ein = element_bytes(d, direction), eout = element_bytes(d, odir);
+    // A shard's host range runs from its base pointer over offset + count * distance elements; with a non-zero offset
+    // the range of shard r would reach into the unaddressed prefix of shard r + 1, which that shard's thread uploads
+    // and writes back concurrently.  Shards r > 0 therefore run zero-offset plans on pointers that include the offset.
+    const bool offsets = d.forward_offset != 0 || d.backward_offset != 0;
+    if (offsets && multi->host_plan.empty()) multi->host_plan.assign(n, nullptr);
+    for (size_t r = 1; offsets && r < n; ++r) {
+      if (multi->host_plan[r] != nullptr || multi->info[r].count == 0) continue;
+      LocalDesc l;
+      make_local(&d, (int)n, (int)r, &l);
+      l.d.forward_offset = l.d.backward_offset = 0;
+      check(pfft_commit(&l.d, multi->device[r], multi->stream[r], &multi->host_plan[r]));
+    }
+    const size_t off_in = direction == PFFT_FORWARD ? d.forward_offset : d.backward_offset;
+    const size_t off_out = direction == PFFT_FORWARD ? d.backward_offset : d.forward_offset;
     std::vector<pfft_status> st(n, PFFT_OK);
     std::vector<std::string> msg(n);
     std::vector<std::thread> workers;
@@ -510,9 +530,10 @@ pfft_status pfft_multi_compute_host(pfft_multi* multi, int direction, const void
       if (multi->info[r].count == 0) continue;
       workers.emplace_back([&, r] {
         const pfft_shard_info& si = multi->info[r];
-        const size_t oi = (direction == PFFT_FORWARD ? si.forward_start : si.backward_start) * ein;
-        const size_t oo = (direction == PFFT_FORWARD ? si.backward_start : si.forward_start) * eout;
-        st[r] = pfft_compute_host(multi->plan[r], direction, (const char*)in + oi, in_imag ? (const char*)in_imag + oi : nullptr,
+        const bool folded = offsets && r > 0;
+        const size_t oi = ((direction == PFFT_FORWARD ? si.forward_start : si.backward_start) + (folded ? off_in : 0)) * ein;
+        const size_t oo = ((direction == PFFT_FORWARD ? si.backward_start : si.forward_start) + (folded ? off_out : 0)) * eout;
+        st[r] = pfft_compute_host(folded ? multi->host_plan[r] : multi->plan[r], direction, (const char*)in + oi, in_imag ? (const char*)in_imag + oi : nullptr,
                                   (char*)out + oo, out_imag ? (char*)out_imag + oo : nullptr);
         if (st[r] != PFFT_OK) msg[r] = pfft_last_error();
       });
@@ -590,6 +611,21 @@ pfft_status pfft_slab_attach(pfft_slab* slab, int peer_rank, void* peer_window) 
     if (slab->imported[peer_rank] && slab->peer_window[peer_rank]) cudaIpcCloseMemHandle(slab->peer_window[peer_rank]);
     slab->imported[peer_rank] = false;
     slab->peer_window[peer_rank] = (char*)peer_window;
+  });
+}
+
+pfft_status pfft_slab_use_window(pfft_slab* slab, void* base, size_t bytes) {
+  return guarded([&] {
+    if (slab == nullptr || base == nullptr) fail(PFFT_INVALID_CONFIGURATION, "null argument");
+    if (bytes < slab->window_bytes) fail(PFFT_INVALID_CONFIGURATION, "slab: the window is too small");
+    if (slab->epoch != 0) fail(PFFT_INVALID_CONFIGURATION, "slab: the window can only be replaced before the first transform");
+    DeviceScope scope(slab->device);
+    MULTI_CUDA(cudaMemsetAsync(base, 0, slab->window_bytes, slab->stream));
+    MULTI_CUDA(cudaStreamSynchronize(slab->stream));
+    if (slab->own_window && slab->window) MULTI_CUDA(cudaFree(slab->window));
+    slab->window = (char*)base;
+    slab->own_window = false;
+    slab->peer_window[slab->rank] = slab->window;
   });
 }
 

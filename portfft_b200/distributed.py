@@ -17,6 +17,11 @@ collective call sites anywhere), so nothing here has a reference counterpart exc
       barrier follows.
   The three local passes are ordinary plans of the C ABI; pass 2 uses the guru batch dimensions of
   `pfft_commit_guru` (destination GPU, plane, row) so that no pack / unpack kernel exists.
+
+The orchestration itself (passes, exchange, device-side flag barrier) is C++ behind the C ABI (`pfft_slab_*`,
+`pfft_commit_shard`, `pfft_multi_*` in include/pfft.h, csrc/multi.cu); `slab_plan` / `slab_fft3d` / `commit_shard`
+below are bindings.  `slab_geometry` and `shard_descriptor` restate the same geometry in Python so that the gloo
+tests can check it on CPU (tests/test_distributed_cpu.py).
 """
 from __future__ import annotations
 
@@ -65,6 +70,25 @@ def shard_descriptor(desc, world_size: int, rank: int) -> BatchShard:
                 desc.number_of_transforms > 1:
             setattr(local, f"{dom}_strides", [max(count, 1)])
     return BatchShard(local, first, count, first * desc.forward_distance, first * desc.backward_distance)
+
+
+def commit_shard(desc, world_size: int, rank: int, device: int = 0, queue=None):
+    """pfft_commit_shard: commit the rank-local shard of `desc` -> (committed_descriptor, BatchShard).  The shard
+    geometry comes from the C library; `shard_descriptor` is its Python restatement (checked equal in the tests)."""
+    import ctypes
+
+    from . import _lib
+    from .api import _check, _stream_handle, committed_descriptor
+
+    c, keep = desc._c_desc()
+    handle = ctypes.c_void_p()
+    info = _lib.pfft_shard_info()
+    _check(_lib.load().pfft_commit_shard(ctypes.byref(c), int(world_size), int(rank), int(device), _stream_handle(queue),
+                                         ctypes.byref(handle), ctypes.byref(info)))
+    sh = shard_descriptor(desc, world_size, rank)
+    assert (sh.first, sh.count, sh.forward_start, sh.backward_start) == \
+        (info.first, info.count, info.forward_start, info.backward_start)
+    return committed_descriptor(sh.desc, handle, device), sh
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -136,15 +160,190 @@ def _make_descriptor(pf, geom: PassGeom, scalar: str):
     return d
 
 
+def _tensor_view(ptr: int, shape, dtype, device):
+    """Zero-copy torch view of device memory owned by the C library (CUDA array interface)."""
+    import torch
+
+    typestr = {torch.complex64: "<c8", torch.complex128: "<c16", torch.uint8: "|u1"}[dtype]
+
+    class _Mem:
+        __cuda_array_interface__ = {"shape": tuple(int(v) for v in shape), "typestr": typestr,
+                                    "data": (int(ptr), False), "version": 2}
+
+    return torch.as_tensor(_Mem(), device=device)
+
+
+class slab_plan:
+    """Binding of `pfft_slab` (include/pfft.h, csrc/multi.cu): one rank's part of a slab-decomposed 3-D transform.
+    All the orchestration -- the three local passes, the exchange fused into the z pass's stores, the device-side flag
+    barrier -- lives behind the C ABI; this class only moves pointers."""
+
+    def __init__(self, handle, lengths, world: int, rank: int, scalar: str, device):
+        import torch
+
+        self._handle = handle
+        self.lengths = tuple(int(v) for v in lengths)
+        self.world, self.rank, self.scalar = world, rank, scalar
+        self.device = torch.device(device)
+        self.cdtype = torch.complex128 if scalar == "double" else torch.complex64
+        self.geom = slab_geometry(self.lengths, world, rank, peer=True)
+        self._keep = []  # ctypes callbacks / symmetric-memory allocations that must outlive the plan
+
+    @classmethod
+    def commit(cls, desc, world: int, rank: int, device, queue=None) -> "slab_plan":
+        import ctypes
+
+        import torch
+
+        from . import _lib
+        from .api import _check, _stream_handle
+
+        device = torch.device(device)
+        c, keep = desc._c_desc()
+        handle = ctypes.c_void_p()
+        _check(_lib.load().pfft_slab_commit(ctypes.byref(c), int(world), int(rank), int(device.index or 0),
+                                            _stream_handle(queue), ctypes.byref(handle)))
+        return cls(handle, desc.lengths, world, rank, desc.scalar, device)
+
+    @classmethod
+    def commit_local(cls, desc, devices: Sequence[int], queues=None) -> List["slab_plan"]:
+        """One process, len(devices) ranks (entries may repeat): pfft_slab_commit_local."""
+        import ctypes
+
+        from . import _lib
+        from .api import _check, _stream_handle
+
+        n = len(devices)
+        c, keep = desc._c_desc()
+        devs = (ctypes.c_int * n)(*[int(d) for d in devices])
+        streams = (ctypes.c_void_p * n)(*[_stream_handle(q) for q in queues]) if queues is not None else None
+        out = (ctypes.c_void_p * n)()
+        _check(_lib.load().pfft_slab_commit_local(ctypes.byref(c), n, devs, streams, out))
+        return [cls(ctypes.c_void_p(out[r]), desc.lengths, n, r, desc.scalar, f"cuda:{int(devices[r])}") for r in range(n)]
+
+    # -- window plumbing ------------------------------------------------------------------------------------------
+    def window(self) -> Tuple[int, int]:
+        import ctypes
+
+        from . import _lib
+        from .api import _check
+
+        base, size = ctypes.c_void_p(), ctypes.c_size_t()
+        _check(_lib.load().pfft_slab_window(self._handle, ctypes.byref(base), ctypes.byref(size)))
+        return int(base.value), int(size.value)
+
+    def export_handle(self) -> bytes:
+        import ctypes
+
+        from . import _lib
+        from .api import _check
+
+        buf = ctypes.create_string_buffer(64)
+        _check(_lib.load().pfft_slab_export(self._handle, buf))
+        return buf.raw
+
+    def import_handle(self, peer_rank: int, handle: bytes) -> None:
+        import ctypes
+
+        from . import _lib
+        from .api import _check
+
+        _check(_lib.load().pfft_slab_import(self._handle, int(peer_rank), ctypes.create_string_buffer(handle, 64)))
+
+    def attach(self, peer_rank: int, window_ptr: int) -> None:
+        from . import _lib
+        from .api import _check
+
+        _check(_lib.load().pfft_slab_attach(self._handle, int(peer_rank), int(window_ptr)))
+
+    def use_window(self, ptr: int, nbytes: int) -> None:
+        from . import _lib
+        from .api import _check
+
+        _check(_lib.load().pfft_slab_use_window(self._handle, int(ptr), int(nbytes)))
+
+    def set_alltoall(self, fn) -> None:
+        """`fn(send_ptr, recv_ptr, block_bytes, stream_handle)` replaces the peer-store exchange (None restores it)."""
+        from . import _lib
+        from .api import _check
+
+        if fn is None:
+            cb = _lib.ALLTOALL_FN()
+        else:
+            def _cb(user, send, recv, block_bytes, stream):
+                try:
+                    fn(int(send), int(recv), int(block_bytes), int(stream or 0))
+                    return 0
+                except Exception:  # reported through the C status (PFFT_NCCL_ERROR)
+                    import traceback
+
+                    traceback.print_exc()
+                    return 1
+
+            cb = _lib.ALLTOALL_FN(_cb)
+        self._keep.append(cb)
+        _check(_lib.load().pfft_slab_set_alltoall(self._handle, cb, None))
+
+    # -- transforms -----------------------------------------------------------------------------------------------
+    def forward(self, x_slab):
+        import ctypes
+
+        from . import _lib
+        from .api import _check, _ptr
+
+        g = self.geom
+        assert x_slab.is_contiguous() and x_slab.numel() == g.slab_elems and x_slab.dtype == self.cdtype
+        out = ctypes.c_void_p()
+        _check(_lib.load().pfft_slab_forward(self._handle, _ptr(x_slab), ctypes.byref(out)))
+        return _tensor_view(out.value, (g.lengths[0], g.yb, g.lengths[2]), self.cdtype, self.device)
+
+    def backward(self, y_slab, out=None):
+        import torch
+
+        from . import _lib
+        from .api import _check, _ptr
+
+        g = self.geom
+        assert y_slab.is_contiguous() and y_slab.numel() == g.slab_elems and y_slab.dtype == self.cdtype
+        if out is None:
+            out = torch.empty(g.xl, g.lengths[1], g.lengths[2], dtype=self.cdtype, device=self.device)
+        _check(_lib.load().pfft_slab_backward(self._handle, _ptr(y_slab), _ptr(out)))
+        return out
+
+    def sync(self) -> None:
+        from . import _lib
+        from .api import _check
+
+        _check(_lib.load().pfft_slab_sync(self._handle))
+
+    def destroy(self) -> None:
+        from . import _lib
+
+        if getattr(self, "_handle", None):
+            _lib.load().pfft_slab_destroy(self._handle)
+            self._handle = None
+        self._keep = []
+
+    def __del__(self):
+        try:
+            self.destroy()
+        except Exception:
+            pass
+
+
 class slab_fft3d:
-    """Forward 3-D C2C transform of `lengths`, slab-decomposed over the ranks of `group` (one GPU per rank).
+    """3-D C2C transform of `lengths`, slab-decomposed over the ranks of `group` (one process and one GPU per rank).
 
         plan = slab_fft3d([512, 512, 512], "float", exchange="peer")
         spectrum_yslab = plan.forward(x_slab)        # x_slab: complex tensor [XL, n1, n2] on this rank's GPU
+        x_again = plan.backward(spectrum_yslab)      # times backward_scale
 
-    `exchange`: "nccl" (all_to_all_single) or "peer" (FFT stores into peer memory + barrier).  "peer" needs
-    symmetric memory (`torch.distributed._symmetric_memory`, NVLink P2P); if it cannot be set up the constructor
-    raises -- there is no silent fallback."""
+    A binding: the transform itself is `pfft_slab_*` (csrc/multi.cu); `torch.distributed` only carries the 64-byte IPC
+    handles of the exchange windows at construction ("peer") or serves as the caller's collective ("nccl":
+    `all_to_all_single` through pfft_slab_set_alltoall).  "peer" maps the windows with CUDA IPC; if that is not
+    possible on this machine the windows are taken from a symmetric-memory allocation instead
+    (`torch.distributed._symmetric_memory`, pfft_slab_use_window) -- both are peer memory over NVLink, and if neither
+    can be set up the constructor raises: there is no silent fallback to another exchange."""
 
     def __init__(self, lengths: Sequence[int], scalar: str = "float", group=None, device=None, exchange: str = "nccl",
                  stream=None, backward_scale: float = 1.0):
@@ -161,94 +360,70 @@ class slab_fft3d:
         self.exchange = exchange
         self.scalar = scalar
         self.cdtype = torch.complex128 if scalar == "double" else torch.complex64
-        self.geom = slab_geometry(lengths, self.world, self.rank, peer=(exchange == "peer"))
         self.stream = stream if stream is not None else torch.cuda.current_stream(self.device)
-        g = self.geom
-        self.A = torch.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
-        self._symm = None
-        if exchange == "peer":
-            import torch.distributed._symmetric_memory as symm_mem
+        d = pf.descriptor([int(v) for v in lengths], scalar)
+        d.backward_scale = backward_scale
+        self.plan = slab_plan.commit(d, self.world, self.rank, self.device, self.stream)
+        self.geom = self.plan.geom
+        self.window_mapping = "local"
+        if exchange == "peer" and self.world > 1:
+            self._map_windows()
+        elif exchange == "nccl":
+            self.plan.set_alltoall(self._all_to_all)
 
-            self.B = symm_mem.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
-            self._symm = symm_mem.rendezvous(self.B, self.group)
-            esize = 16 if scalar == "double" else 8
-            # block from this rank lands at x = rank*XL in every destination's B
-            self.peer_ptrs = [int(p) + self.rank * g.block_elems * esize for p in self._symm.buffer_ptrs]
-            self.S = None
-        else:
-            self.B = torch.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
-            self.S = torch.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
-        self.plans = []
-        for pg in g.passes:
-            d = _make_descriptor(pf, pg, scalar)
-            if pg.name == "y":
-                d.backward_scale = backward_scale  # the y pass runs last in the backward transform
-            self.plans.append(d.commit(self.stream, self.device.index, extra=pg.extra, peer_last=pg.peer_last))
-        self._pz_back = None  # peer mode: the backward z pass reads an ordinary exchange buffer (built on first use)
+    def _map_windows(self):
+        import torch
+        import torch.distributed as dist
+
+        ok = 1
+        try:
+            handles = [None] * self.world
+            dist.all_gather_object(handles, self.plan.export_handle(), group=self.group)
+            for r, h in enumerate(handles):
+                if r != self.rank:
+                    self.plan.import_handle(r, h)
+        except Exception as exc:
+            self._ipc_error = repr(exc)
+            ok = 0
+        flag = torch.tensor([ok], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=self.group)
+        if int(flag.item()) == 1:
+            self.window_mapping = "cuda_ipc"
+            return
+        import torch.distributed._symmetric_memory as symm_mem
+
+        _, nbytes = self.plan.window()
+        buf = symm_mem.empty(nbytes, dtype=torch.uint8, device=self.device)
+        hdl = symm_mem.rendezvous(buf, self.group)
+        self.plan._keep += [buf, hdl]
+        self.plan.use_window(buf.data_ptr(), nbytes)
+        for r in range(self.world):
+            if r != self.rank:
+                self.plan.attach(r, int(hdl.buffer_ptrs[r]))
+        self.window_mapping = "symmetric_memory"
+        dist.barrier(group=self.group)
+
+    def _all_to_all(self, send: int, recv: int, block_bytes: int, stream: int):
+        import torch
+        import torch.distributed as dist
+
+        n = self.world * block_bytes
+        s = _tensor_view(send, (self.world, block_bytes), torch.uint8, self.device)
+        r = _tensor_view(recv, (self.world, block_bytes), torch.uint8, self.device)
+        with torch.cuda.stream(torch.cuda.ExternalStream(stream, device=self.device) if stream else self.stream):
+            dist.all_to_all_single(r, s, group=self.group)
+        del n
 
     def forward(self, x_slab):
-        import torch
-        import torch.distributed as dist
-
-        g = self.geom
-        assert x_slab.is_contiguous() and x_slab.numel() == g.slab_elems and x_slab.dtype == self.cdtype
-        py, pz, px = self.plans
-        with torch.cuda.stream(self.stream):
-            py.compute_forward(x_slab, self.A, queue=self.stream)
-            if self.exchange == "peer":
-                # nobody may still be reading its B (previous call's x pass) when remote stores begin
-                self._symm.barrier(channel=0)
-                pz.compute_forward_peer(self.A, self.peer_ptrs, queue=self.stream)
-                self._symm.barrier(channel=1)  # every block has landed everywhere
-            else:
-                pz.compute_forward(self.A, self.S, queue=self.stream)
-                dist.all_to_all_single(torch.view_as_real(self.B).view(self.world, -1),
-                                       torch.view_as_real(self.S).view(self.world, -1), group=self.group)
-            px.compute_forward(self.B, queue=self.stream)
-        return self.B.view(g.lengths[0], g.yb, g.lengths[2])
+        return self.plan.forward(x_slab)
 
     def backward(self, y_slab, out=None):
-        """Inverse of `forward`: y-slab of the spectrum [n0, YB, n2] in, x-slab [XL, n1, n2] out (times
-        `backward_scale`).  Mirror image of the forward pipeline: x pass, one exchange step, z pass reading the
-        exchange layout through the same guru batch dimensions, y pass."""
-        import torch
-        import torch.distributed as dist
+        return self.plan.backward(y_slab if y_slab.is_contiguous() else y_slab.contiguous(), out)
 
-        import portfft_b200 as pf
-
-        g = self.geom
-        assert y_slab.numel() == g.slab_elems and y_slab.dtype == self.cdtype
-        py, pz, px = self.plans
-        if out is None:
-            out = torch.empty(g.xl, g.lengths[1], g.lengths[2], dtype=self.cdtype, device=self.device)
-        if self.S is None:
-            self.S = torch.empty(g.slab_elems, dtype=self.cdtype, device=self.device)
-        if self.exchange == "peer" and self._pz_back is None:
-            pg = slab_geometry(g.lengths, self.world, self.rank, peer=False).passes[1]
-            self._pz_back = _make_descriptor(pf, pg, self.scalar).commit(self.stream, self.device.index, extra=pg.extra)
-        with torch.cuda.stream(self.stream):
-            if y_slab.data_ptr() != self.B.data_ptr():
-                self.B.copy_(y_slab.reshape(-1))
-            px.compute_backward(self.B, queue=self.stream)
-            if self.exchange == "peer":
-                self._symm.barrier(channel=0)  # every rank's x pass is complete
-                for s in range(self.world):   # pull block `rank` of every peer's B over NVLink
-                    src = self._symm.get_buffer(s, (g.slab_elems,), self.cdtype)
-                    self.S[s * g.block_elems:(s + 1) * g.block_elems].copy_(
-                        src[self.rank * g.block_elems:(self.rank + 1) * g.block_elems], non_blocking=True)
-                self._symm.barrier(channel=1)  # nobody overwrites its B while peers still read it
-                self._pz_back.compute_backward(self.S, self.A, queue=self.stream)
-            else:
-                dist.all_to_all_single(torch.view_as_real(self.S).view(self.world, -1),
-                                       torch.view_as_real(self.B).view(self.world, -1), group=self.group)
-                pz.compute_backward(self.S, self.A, queue=self.stream)
-            py.compute_backward(self.A, out, queue=self.stream)
-        return out
+    def sync(self):
+        self.plan.sync()
 
     def destroy(self):
-        for p in self.plans:
-            p.destroy()
-        if self._pz_back is not None:
-            self._pz_back.destroy()
-            self._pz_back = None
-        self.plans = []
+        if self.plan is not None:
+            self.plan.destroy()
+            self.plan = None

@@ -3,6 +3,7 @@
 // Checks a forward/backward round trip and a naive DFT on the host, in-place interleaved and out-of-place split,
 // plus the error convention (invalid_configuration from commit, storage mismatch from compute).
 #include <portfft/portfft.hpp>
+#include <portfft/distributed.hpp>
 
 #include <chrono>
 #include <cmath>
@@ -202,9 +203,99 @@ static void c1_latency() {
   cudaStreamDestroy(s);
 }
 
+// Multi-GPU header (include/portfft/distributed.hpp) with every rank on the current device: a slab-decomposed 3-D
+// transform and a batch-sharded host-buffer transform, each against the ordinary single-GPU plan.
+static int check_distributed() {
+  using cf = std::complex<float>;
+  int bad = 0;
+  int ngpu = 0;
+  cudaGetDeviceCount(&ngpu);
+  {
+    const std::size_t n0 = 16, n1 = 8, n2 = 32, total = n0 * n1 * n2;
+    const int world = 4;
+    std::vector<int> devices;
+    for (int r = 0; r < world; ++r) devices.push_back(ngpu >= world ? r : 0);  // real GPUs when the box has them
+    descriptor<float, domain::COMPLEX> desc({n0, n1, n2});
+    std::vector<cf> host(total), ref(total), got(total);
+    for (std::size_t i = 0; i < total; ++i) host[i] = {float(std::sin(0.11 * i)), float(std::cos(0.7 * i + 1))};
+    cf *din, *dref;
+    cudaMalloc(&din, total * sizeof(cf));
+    cudaMalloc(&dref, total * sizeof(cf));
+    cudaMemcpy(din, host.data(), total * sizeof(cf), cudaMemcpyHostToDevice);
+    {
+      queue q;
+      auto single = desc.commit(q);
+      single.compute_forward(din, dref).wait();
+    }
+    cudaMemcpy(ref.data(), dref, total * sizeof(cf), cudaMemcpyDeviceToHost);
+    distributed::slab_descriptor<float> slab(desc, devices);
+    const std::size_t xl = n0 / world, yb = n1 / world;
+    std::vector<const cf*> xs;
+    std::vector<cf*> owned;
+    for (int r = 0; r < world; ++r) {
+      cudaSetDevice(devices[r]);
+      cf* p;
+      cudaMalloc(&p, xl * n1 * n2 * sizeof(cf));
+      cudaMemcpy(p, host.data() + r * xl * n1 * n2, xl * n1 * n2 * sizeof(cf), cudaMemcpyHostToDevice);
+      xs.push_back(p);
+      owned.push_back(p);
+    }
+    cudaSetDevice(0);
+    std::vector<cf*> ys = slab.compute_forward(xs);
+    slab.wait();
+    double err = 0, nrm = 0;
+    for (int r = 0; r < world; ++r) {
+      std::vector<cf> part(n0 * yb * n2);
+      cudaMemcpy(part.data(), ys[r], part.size() * sizeof(cf), cudaMemcpyDefault);
+      for (std::size_t x = 0; x < n0; ++x)
+        for (std::size_t y = 0; y < yb; ++y)
+          for (std::size_t z = 0; z < n2; ++z) {
+            const std::complex<double> w = ref[(x * n1 + r * yb + y) * n2 + z], g = part[(x * yb + y) * n2 + z];
+            err += std::norm(g - w);
+            nrm += std::norm(w);
+          }
+    }
+    const double rel = std::sqrt(err / nrm);
+    std::printf("distributed slab %zux%zux%zu over %d ranks (%s): relL2 vs single-GPU plan %.2e\n", n0, n1, n2, world,
+                ngpu >= world ? "one GPU each" : "one GPU", rel);
+    if (!(rel < 1e-6)) ++bad;
+    for (cf* p : owned) cudaFree(p);
+    cudaFree(din);
+    cudaFree(dref);
+  }
+  {
+    const std::size_t n = 1000, batch = 77;
+    descriptor<float, domain::COMPLEX> desc({n});
+    desc.number_of_transforms = batch;
+    std::vector<cf> host(n * batch), ref(n * batch), got(n * batch);
+    for (std::size_t i = 0; i < host.size(); ++i) host[i] = {float(std::sin(0.3 * i)), float(std::cos(0.9 * i))};
+    cf* d;
+    cudaMalloc(&d, host.size() * sizeof(cf));
+    cudaMemcpy(d, host.data(), host.size() * sizeof(cf), cudaMemcpyHostToDevice);
+    {
+      queue q;
+      auto single = desc.commit(q);
+      single.compute_forward(d).wait();
+    }
+    cudaMemcpy(ref.data(), d, host.size() * sizeof(cf), cudaMemcpyDeviceToHost);
+    cudaFree(d);
+    std::vector<int> devices;
+    for (int r = 0; r < 3; ++r) devices.push_back(ngpu >= 3 ? r : 0);
+    distributed::sharded_descriptor<float, domain::COMPLEX> sharded(desc, devices);
+    sharded.compute_forward(host.data(), got.data());
+    std::size_t covered = 0;
+    for (int r = 0; r < sharded.size(); ++r) covered += sharded.get_shard(r).count;
+    const bool same = std::equal(ref.begin(), ref.end(), got.begin());
+    std::printf("distributed batch sharding %zu x %zu over 3 ranks: %s\n", n, batch, same ? "identical" : "MISMATCH");
+    if (!same || covered != batch) ++bad;
+  }
+  return bad;
+}
+
 int main() {
   int fails = 0;
   fails += check_copies();
+  fails += check_distributed();
   c1_latency();
   for (std::size_t n : {16, 1000, 81}) {
     double ef = check_real<float>(n, 3), ed = check_real<double>(n, 3);

@@ -194,7 +194,9 @@ def test_planner_kernel_choices():
     for n in (64, 128, 256):
         assert _kernels(packed(n, 4096)) == ["wg_col"], n                    # TMA tile kernel, rows in and out
     assert _kernels(packed(16, 1 << 20)) == ["wi"] and _kernels(packed(96, 4096)) == ["sg"]
-    assert _kernels(packed(4096, 64, "double")) != ["wg_cube"]               # fp32 only
+    for n in (512, 1024, 2048, 4096):
+        assert _kernels(packed(n, 4096, "double")) == ["wg_cube"], n         # fp64: same kernels, half the tile
+    assert _kernels(packed(8192, 64, "double")) != ["wg_cube"]               # two passes in fp64
     assert _kernels(pf.descriptor([512, 512, 512])) == ["wg_cube", "wg_col", "wg_col"]   # C5: z, y, x
     assert _kernels(packed(1 << 24, 8, "double")) == ["wg_col"] * 3          # C4: 256^3
     c3 = pf.descriptor([1000])                                               # C3: split, stride 2, offsets
