@@ -198,6 +198,7 @@ pfft_status pfft_multi_destroy(pfft_multi* multi);
  * Every rank owns an exchange window in device memory (receive buffer + arrival flags) that its peers map. */
 typedef struct pfft_slab pfft_slab;
 enum { PFFT_IPC_HANDLE_BYTES = 64 };
+/* `stream`: the cudaStream_t every call of this rank is ordered on (NULL: the default stream, as in pfft_commit). */
 pfft_status pfft_slab_commit(const pfft_desc* desc, int world, int rank, int device, void* stream,
                              pfft_slab** slab_out);
 size_t pfft_slab_elems(const pfft_slab* slab); /* complex elements of every rank-local buffer: n0*n1*n2 / world */
@@ -213,7 +214,9 @@ pfft_status pfft_slab_attach(pfft_slab* slab, int peer_rank, void* peer_window);
  * keeps ownership. */
 pfft_status pfft_slab_use_window(pfft_slab* slab, void* base, size_t bytes);
 /* One process, n_dev GPUs (entries of `devices` may repeat: several ranks on one GPU): commits every rank, enables
- * peer access and attaches all windows.  slabs_out receives n_dev objects. */
+ * peer access and attaches all windows.  slabs_out receives n_dev objects.  `streams` NULL (or a NULL entry): the
+ * library creates one non-blocking stream per rank -- ranks of one process must not share a stream, their barriers
+ * wait for each other. */
 pfft_status pfft_slab_commit_local(const pfft_desc* desc, int n_dev, const int* devices, void* const* streams,
                                    pfft_slab** slabs_out);
 /* Exchange through a collective of the caller (e.g. an all-to-all over ncclSend / ncclRecv) instead of peer stores:

@@ -321,7 +321,9 @@ void warm_up(pfft_slab* s) {
   MULTI_CUDA(cudaStreamSynchronize(s->stream));
 }
 
-pfft_slab* slab_commit(const pfft_desc* desc, int world, int rank, int device, cudaStream_t stream) {
+// stream == nullptr: the legacy default stream, as in pfft_commit -- unless `own_stream` asks for a new non-blocking one
+// (several ranks in one process must not share a stream: their barriers wait for each other)
+pfft_slab* slab_commit(const pfft_desc* desc, int world, int rank, int device, cudaStream_t stream, bool own_stream) {
   if (desc == nullptr) fail(PFFT_INVALID_CONFIGURATION, "null descriptor");
   if (world <= 0 || world > kMaxPeers || rank < 0 || rank >= world)
     fail(PFFT_INVALID_CONFIGURATION, "slab: world size must be 1.." + std::to_string(kMaxPeers) + " and 0 <= rank < world");
@@ -345,7 +347,7 @@ pfft_slab* slab_commit(const pfft_desc* desc, int world, int rank, int device, c
   s->rank = rank;
   s->device = device;
   s->stream = stream;
-  if (s->stream == nullptr) {
+  if (s->stream == nullptr && own_stream) {
     MULTI_CUDA(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
     s->own_stream = true;
   }
@@ -562,7 +564,7 @@ pfft_status pfft_slab_commit(const pfft_desc* desc, int world, int rank, int dev
   return guarded([&] {
     if (slab_out == nullptr) fail(PFFT_INVALID_CONFIGURATION, "null slab_out");
     *slab_out = nullptr;
-    *slab_out = slab_commit(desc, world, rank, device, (cudaStream_t)stream);
+    *slab_out = slab_commit(desc, world, rank, device, (cudaStream_t)stream, false);
   });
 }
 
@@ -636,7 +638,7 @@ pfft_status pfft_slab_commit_local(const pfft_desc* desc, int n_dev, const int* 
     std::vector<std::unique_ptr<pfft_slab>> s;
     for (int r = 0; r < n_dev; ++r) slabs_out[r] = nullptr;
     for (int r = 0; r < n_dev; ++r)
-      s.emplace_back(slab_commit(desc, n_dev, r, devices[r], streams ? (cudaStream_t)streams[r] : nullptr));
+      s.emplace_back(slab_commit(desc, n_dev, r, devices[r], streams ? (cudaStream_t)streams[r] : nullptr, true));
     for (int a = 0; a < n_dev; ++a) {
       DeviceScope scope(devices[a]);
       for (int b = 0; b < n_dev; ++b) {
