@@ -13,6 +13,10 @@ namespace pfft {
 // host: 5-D TMA view (column, row j, b1, b2, b3) of a pass input whose fastest batch dimension is contiguous
 // (wg_col.cu); false when the geometry or the pointer alignment cannot be encoded
 bool col_make_tensor_map(const PassParams& p, bool is_double, int C, int box_rows, CUtensorMap* map);
+// the same view over one scalar plane of split storage (scalars = 1) or over interleaved pairs (scalars = 2), `base` =
+// address of element ioff; promo = L2 promotion (0 none, 1 64 B, 2 128 B, 3 256 B)
+bool col_make_tensor_map_plane(const PassParams& p, const void* base, int scalars, bool is_double, int C, int box_rows,
+                               int promo, CUtensorMap* map);
 
 namespace col {
 

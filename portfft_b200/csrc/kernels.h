@@ -56,6 +56,11 @@ cudaError_t launch_wg_r3(const PassParams& p, bool is_double, bool interleaved, 
 // WORKGROUP level, column tiles of any 31-smooth length, in place in shared memory (wg_colg.cu): p.ffts_per_block =
 // columns per tile, p.threads_per_fft = butterfly threads per column; needs ibd[0] == obd[0] == 1
 size_t colg_smem_bytes(int n, int columns, bool is_double);
+// ... and its specialisation with three compile-time radices (wg_colr3.cu; pass variant 1): fixed tile geometry
+// `cache`: four ColMapCache entries of the pass (input planes 0 / 1, output planes 0 / 1), or nullptr
+struct ColMapCache;
+cudaError_t launch_wg_colr3(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream,
+                            ColMapCache* cache);
 cudaError_t launch_wg_colg(const PassParams& p, bool is_double, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
 // GLOBAL level, two consecutive 256-point passes fused into one persistent kernel with the intermediate result in an

@@ -510,6 +510,25 @@ void select_colg(PassHost& ps, const DescHost& d, const DeviceLimits& lim) {
   if (env && std::atoi(env) != 0) return;
   if (p.gtw_dim > 0 || p.peer_dim >= 0 || p.valid_in || p.valid_out || p.n < 2) return;
   if (p.ibd[0] != 1 || p.obd[0] != 1 || p.nb[0] < 2) return;
+  // three compile-time radices, inputs prefetched a tile ahead (wg_colr3.cu): C3b 0.745 -> see profiles/r2_ab_variants.txt
+  {
+    int cols = 0, tpc = 0;
+    size_t smem = 0;
+    const char* e3 = std::getenv("PFFT_NO_COLR3");
+    if (!(e3 && std::atoi(e3) != 0) && p.gtw_dim < 0 && colr3_supported(p.n, d.is_double, &cols, &tpc, &smem) &&
+        smem <= lim.max_smem_per_block && p.nb[0] >= cols) {
+      p.ffts_per_block = cols;
+      p.threads_per_fft = tpc;
+      p.in_mode = p.out_mode = IO_DIRECT;
+      ps.block = cols * tpc;
+      ps.smem = smem;
+      ps.variant = 1;
+      const long long tiles = ((p.nb[0] + cols - 1) / cols) * p.nb[1] * p.nb[2] * p.nb[3];
+      ps.grid = (int)std::min<long long>(tiles, (long long)lim.num_sms);  // one CTA per SM (registers)
+      ps.kernel = KERNEL_WG_COLG;
+      return;
+    }
+  }
   // columns per tile: as wide as shared memory allows, up to one 128-byte row segment.  Measured on C3b (N = 1000,
   // split fp32): 16 columns (128 KB tile, one CTA per SM) 1.61 ms, 8 columns (three CTAs per SM) 1.73 ms -- the
   // kernel is bound by the number of distinct lines per memory instruction, which narrower tiles make worse.

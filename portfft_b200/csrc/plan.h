@@ -107,6 +107,8 @@ bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_p
 size_t colg_smem_bytes(int n, int columns, bool is_double);
 // three-radix kernel (wg_r3.cu)
 bool r3_supported(int n, bool is_double, int* threads_per_fft, int* pitch);
+// wg_colr3.cu: column tiles with three compile-time radices (fixed tile geometry)
+bool colr3_supported(int n, bool is_double, int* columns, int* threads_per_column, size_t* smem);
 
 struct PlanHost {
   DescHost desc;

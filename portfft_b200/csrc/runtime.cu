@@ -91,7 +91,12 @@ struct pfft_plan {
   // encoded TMA tensor maps of the column-tile passes, [direction][pass]: valid while the caller keeps passing the same
   // buffers (the usual case), re-encoded when an address changes.  A different box geometry (col512 vs the two-pass
   // tile kernel) is a different pass, so the address alone identifies the map.
-  std::vector<ColMapCache> col_maps[2];
+  std::vector<ColMapCache> col_maps[2];  // four entries per pass: input planes 0 / 1, output planes 0 / 1
+  ColMapCache* map_cache(int dir, size_t pass) {
+    std::vector<ColMapCache>& m = col_maps[dir];
+    if (m.size() != 4 * host.passes[dir].size()) m.assign(4 * host.passes[dir].size(), ColMapCache());
+    return &m[4 * pass];
+  }
   // pfft_compute_host pipeline: copy streams, per-chunk events, sub-batch plans (number_of_transforms -> plan)
   cudaStream_t copy_stream[2] = {nullptr, nullptr};
   std::vector<cudaEvent_t> chunk_up, chunk_done;
@@ -500,9 +505,7 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         break;
       case KERNEL_WG_COL: {
         bool used = false;
-        std::vector<ColMapCache>& maps = plan->col_maps[dir];
-        if (maps.size() != passes.size()) maps.assign(passes.size(), ColMapCache());
-        e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used, &maps[pi]);
+        e = launch_wg_col(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, &used, plan->map_cache(dir, pi));
         if (e == cudaSuccess && !used) e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       }
@@ -514,7 +517,8 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
           e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_WG_COLG:
-        e = launch_wg_colg(p, d.is_double, pil, swap, ps.grid, stream);
+        e = ps.variant == 1 ? launch_wg_colr3(p, d.is_double, pil, swap, ps.grid, stream, plan->map_cache(dir, pi))
+                            : launch_wg_colg(p, d.is_double, pil, swap, ps.grid, stream);
         break;
       case KERNEL_EW:
         e = launch_ew(p, d.is_double, il_in, il_out, swap, ps.grid, stream);

@@ -533,12 +533,26 @@ static EncodeTiledFn encode_fn() {
 // 5-D view of the pass input: (column, row j, b1, b2, b3); element = one complex number described as 2 scalars
 // folded into the innermost dimension (so that fp32 and fp64 both use a native TMA data type)
 bool col_make_tensor_map(const PassParams& p, bool is_double, int C, int box_rows, CUtensorMap* map) {
+  // L2 promotion of the strided 128-byte row segments (PFFT_COL_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B)
+  static const int promo = [] {
+    const char* e = std::getenv("PFFT_COL_L2PROMO");
+    return e ? std::atoi(e) : 3;  // measured: 256 B is never slower, C4 1.7 % faster (profiles/r1_ab_variants.txt)
+  }();
+  const size_t esz = is_double ? 16 : 8;
+  return col_make_tensor_map_plane(p, reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz, 2, is_double, C,
+                                   box_rows, promo, map);
+}
+
+// The same view over one scalar plane (`scalars` = 1: split storage, element = one scalar) or over interleaved pairs
+// (`scalars` = 2); `base` = address of element ioff.  promo: 0 none, 1 64 B, 2 128 B, 3 256 B.
+bool col_make_tensor_map_plane(const PassParams& p, const void* base_ptr, int scalars, bool is_double, int C,
+                               int box_rows, int promo, CUtensorMap* map) {
   EncodeTiledFn enc = encode_fn();
   if (enc == nullptr) return false;
-  const size_t sc = is_double ? 8 : 4, esz = 2 * sc;
-  const char* base = reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz;
+  const size_t sc = is_double ? 8 : 4, esz = scalars * sc;
+  const char* base = reinterpret_cast<const char*>(base_ptr);
   if (reinterpret_cast<uintptr_t>(base) % 16 != 0) return false;
-  cuuint64_t dims[5] = {(cuuint64_t)p.nb[0] * 2, (cuuint64_t)p.n, (cuuint64_t)p.nb[1], (cuuint64_t)p.nb[2],
+  cuuint64_t dims[5] = {(cuuint64_t)p.nb[0] * scalars, (cuuint64_t)p.n, (cuuint64_t)p.nb[1], (cuuint64_t)p.nb[2],
                         (cuuint64_t)p.nb[3]};
   const long long st[4] = {p.is, p.nb[1] > 1 ? p.ibd[1] : p.is * p.n, p.nb[2] > 1 ? p.ibd[2] : p.is * p.n,
                            p.nb[3] > 1 ? p.ibd[3] : p.is * p.n};
@@ -550,19 +564,15 @@ bool col_make_tensor_map(const PassParams& p, bool is_double, int C, int box_row
   }
   for (int i = 0; i < 5; ++i)
     if (dims[i] == 0 || dims[i] > (1ULL << 32)) return false;
-  cuuint32_t box[5] = {(cuuint32_t)(2 * C), (cuuint32_t)box_rows, 1, 1, 1};
+  cuuint32_t box[5] = {(cuuint32_t)(scalars * C), (cuuint32_t)box_rows, 1, 1, 1};
   cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  // L2 promotion of the strided 128-byte row segments (PFFT_COL_L2PROMO = 0 none, 1 64 B, 2 128 B, 3 256 B)
-  static const CUtensorMapL2promotion promo = [] {
-    const char* e = std::getenv("PFFT_COL_L2PROMO");
-    const int v = e ? std::atoi(e) : 3;  // measured: 256 B is never slower, C4 1.7 % faster (profiles/r1_ab_variants.txt)
-    return v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
-                  : (v == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                            : (v == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
-  }();
+  const CUtensorMapL2promotion pr =
+      promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                 : (promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                               : (promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
   const CUresult r = enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
                          const_cast<char*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                         CU_TENSOR_MAP_SWIZZLE_NONE, pr, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
 }
 

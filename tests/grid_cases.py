@@ -167,7 +167,10 @@ SUITES = {
     # generic in-place column-tile kernel: batch-interleaved layouts of lengths the TMA tile kernel does not take,
     # N-D outer dimensions that are not powers of two, non-power-of-two multi-pass lengths (column passes with the
     # inter-factor twiddle)
-    "ColumnGenericTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [5, 131], [96, 100, 1000, 1536, 1792]),
+    "ColumnGenericTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [5, 131], [96, 100, 1000, 1024, 1536, 1792]),
+    # three-radix column-tile kernel (wg_colr3.cu: 1000, 1024) with more tiles than the grid holds CTAs: the register
+    # prefetch of the next tile and the tile-reuse barrier in their steady state; ragged last tile (3001 = 8 * 375 + 1)
+    "ColumnR3SteadyTest": basic([("IP", BI, BI), ("OOP", BI, BI)], BOTH_DIR, STORAGES, [3001], [1000, 1024]),
     "ColumnGenericMultidimensionalTest": basic(MD_LAYOUTS, BOTH_DIR, STORAGES, [1, 3],
                                                [[96, 40], [100, 100], [1000, 24], [60, 50, 40]]),
     "ColumnGenericGlobalTest": basic(GLOBAL_LAYOUTS, BOTH_DIR, STORAGES, [3], [68640, 9800, 3 * 16384, 1 << 17]),
