@@ -11,14 +11,13 @@
 //   * thread (t, c) owns butterfly t of column c in every pass: decimation-in-frequency, in place in ONE
 //     [row][column] tile, all strides compile-time, row index padded by row / R2 so that the two rows a half-warp
 //     touches fall into different bank halves in all three passes;
-//   * the tile's inputs arrive by TMA (cp.async.bulk.tensor, boxes of 256 rows x one row segment; split storage: one
-//     tensor map per plane) into a two-stage ring one and two tiles AHEAD, guarded by mbarriers: no thread issues a
-//     global load, the LSU queues stay empty and the loads of the next tiles are in flight during all three passes.
-//     Pointers or strides TMA cannot encode: inputs loaded into registers one tile ahead instead (measured on C3b:
-//     0.95 ms -- every warp stalls in the load burst, lg_throttle -- against the TMA ring's figure in
-//     profiles/r2_ab_variants.txt);
-//   * pass 2 stores its outputs to global memory straight from registers in digit-reversed order -- the order costs
-//     nothing because the lanes still run along the columns;
+//   * a tile arrives by ONE tensor load per plane (cp.async.bulk.tensor.5d; the view (column, s, q) with row = R2 q + s
+//     and a box of R2 + 1 rows per group drops the rows straight into the padded layout) and leaves by ONE tensor store
+//     per plane (view (column, r, b1, a) with output row k = a + R0 b1 + R0 R1 r: the digit-reversed tile lands in
+//     natural order); ring of three tile buffers: load in flight / three passes in place / store draining.  No thread
+//     issues a global load or store except the twiddle look-ups;
+//   * pointers, strides or batch shapes TMA cannot encode: the register form (inputs of the next tile loaded into
+//     registers during the passes, per-thread stores in digit-reversed order);
 //   * the generic kernel spends 127 instructions per point on this size (run-time radix list, look-ups, tile
 //     load / store loops with bounds checks); this one about a third of that.
 #include <cstdlib>
@@ -44,16 +43,13 @@ struct ColR3Cfg {
   static constexpr int ROWS = N + N / R2;             // padded rows: [R0][R1][R2 + 1]
   static constexpr size_t kTilePlane = (size_t)ROWS * C * sizeof(T);  // one scalar plane of the tile
   static constexpr size_t kTile = 2 * kTilePlane;
-  static constexpr size_t kSmem = kTile;  // register-prefetch form
-  // TMA form: two stages of whole 256-row boxes (rows beyond N arrive as zeros) + two mbarriers
-  static constexpr int BOX = 256;
-  static constexpr int NBOX = (N + BOX - 1) / BOX;
-  static constexpr size_t kPlane = (size_t)NBOX * BOX * C * sizeof(T);  // one scalar plane of a stage
-  static constexpr size_t kStage = 2 * kPlane;
-  static constexpr size_t kSmemTma = kTile + 2 * kStage + 64;
+  static constexpr size_t kSmem = kTile;  // register-prefetch form: one tile
+  static constexpr int NBUF = 3;          // TMA form: ring of three tiles (load in flight / compute / store draining)
+  static constexpr size_t kSmemTma = NBUF * kTile + 64;
   static_assert(R0 >= R1 && R0 >= R2, "the first radix is the largest: one pass-0 butterfly per thread");
   static_assert(NT <= 1024, "block size");
-  static_assert(kTilePlane % 128 == 0 && kPlane % 128 == 0, "TMA sources / destinations are 128-byte aligned");
+  static_assert(N / R2 <= 256 && R2 + 1 <= 256, "TMA box dimensions");
+  static_assert(kTilePlane % 128 == 0, "TMA sources / destinations are 128-byte aligned");
   __host__ __device__ static constexpr int pad(int row) { return row + row / R2; }
 };
 
@@ -72,48 +68,194 @@ struct ColR3Maps {
   CUtensorMap out0, out1;  // output planes
 };
 
-// I: element-index type of the per-thread global accesses (int when every index of both buffers fits 31 bits).
-// TMA: inputs through the TMA ring; TMAST: outputs by TMA tensor stores from the tile (implies TMA).
-// The tile keeps the storage of the data: interleaved pairs for interleaved storage, two scalar planes for split
-// storage -- so that one tensor store per plane writes it out.
-template <typename T, int R0, int R1, int R2, bool IL, bool SWAP, typename I, bool TMA, bool TMAST>
-__global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1)
-    wg_colr3_kernel(const PassParams p, const __grid_constant__ ColR3Maps maps) {
+// The three passes on one tile buffer.  The tile keeps the storage of the data -- interleaved pairs for interleaved
+// storage, two scalar planes for split storage -- so that tensor loads / stores move it plane by plane.
+template <typename T, int R0, int R1, int R2, bool IL>
+struct ColR3Tile {
   using Cfg = ColR3Cfg<T, R0, R1, R2>;
-  constexpr int N = Cfg::N, TPC = Cfg::TPC, C = Cfg::C;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  unsigned char* stage0 = smem_raw + Cfg::kTile;
-  uint64_t* full = reinterpret_cast<uint64_t*>(stage0 + 2 * Cfg::kStage);
-  const int c = threadIdx.x % C, t = threadIdx.x / C;
-  const long long tiles_c = (p.nb[0] + C - 1) / C;
-  const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
-  const T scale = T(p.scale);
-  const I in_step = (I)(TPC * p.is), out_step = (I)((R0 * R1) * p.os);
-  const I is = (I)p.is, os = (I)p.os;
-
-  // tile element (padded row index * C + c)
-  cx<T>* Sx = reinterpret_cast<cx<T>*>(smem_raw) + c;
-  T* Sre = reinterpret_cast<T*>(smem_raw) + c;
-  T* Sim = reinterpret_cast<T*>(smem_raw + Cfg::kTilePlane) + c;
-  auto tile_ld = [&](int idx) -> cx<T> { return IL ? Sx[idx] : cx<T>{Sre[idx], Sim[idx]}; };
-  auto tile_st = [&](int idx, cx<T> v) {
+  static constexpr int C = Cfg::C, TPC = Cfg::TPC, N = Cfg::N;
+  cx<T>* Sx;
+  T *Sre, *Sim;
+  __device__ __forceinline__ ColR3Tile(unsigned char* raw, int c)
+      : Sx(reinterpret_cast<cx<T>*>(raw) + c), Sre(reinterpret_cast<T*>(raw) + c),
+        Sim(reinterpret_cast<T*>(raw + Cfg::kTilePlane) + c) {}
+  // element at (padded row index * C)
+  __device__ __forceinline__ cx<T> ld(int idx) const { return IL ? Sx[idx] : cx<T>{Sre[idx], Sim[idx]}; }
+  __device__ __forceinline__ void st(int idx, cx<T> v) const {
     if (IL) {
       Sx[idx] = v;
     } else {
       Sre[idx] = v.x;
       Sim[idx] = v.y;
     }
-  };
+  }
+  // pass 0 of butterfly t: outputs (already transformed) times w_N^{t r} into rows t + TPC r
+  // (pad(t + TPC r) = pad(t) + (TPC + R1) r)
+  __device__ __forceinline__ static int row0(int t) { return Cfg::pad(t) * C; }
+  static constexpr int kStep0 = (TPC + R1) * C;
+  // pass 1: radix R1 inside each block of N / R0 rows, in place
+  __device__ __forceinline__ void pass1(const PassParams& p, int t) const {
+#pragma unroll 1
+    for (int b = t; b < N / R1; b += TPC) {
+      const int blk = b / R2, j = b - blk * R2;  // rows blk TPC + j + R2 r: pad = blk (TPC + R1) + j + (R2 + 1) r
+      const int base = (blk * (TPC + R1) + j) * C;
+      cx<T> v[R1];
+#pragma unroll
+      for (int r = 0; r < R1; ++r) v[r] = ld(base + r * (R2 + 1) * C);
+      DFT<R1, T>::run(v);
+      if (R2 > 1) {
+#pragma unroll
+        for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, (long long)j * r * R0));  // w_{N/R0}^{j r}
+      }
+#pragma unroll
+      for (int r = 0; r < R1; ++r) st(base + r * (R2 + 1) * C, v[r]);
+    }
+  }
+};
 
-  // pass-0 twiddles w_N^{t r} stay in registers when the block leaves room; pass 1 needs only R2 * R1 distinct values:
-  // table look-ups (L1 resident)
+// ---------------------------------------------------------------------------------------------------------------
+// TMA form: tensor loads and tensor stores, ring of three tile buffers.  The input view (column, s, q, b1, b2) with
+// row = R2 q + s and the box (C, R2 + 1, N / R2) puts the rows straight into the padded layout (the row s = R2 of
+// every group lies outside the tensor and arrives as zeros); all three passes run in place; the output view
+// (column, r, b1, a, batch) with row k = a + R0 b1 + R0 R1 r and the box (C, R2 + 1, R1, R0) writes the digit-reversed
+// tile out in natural order (the padding rows, outside the tensor, are skipped).  Per tile: one tensor load and one
+// tensor store per plane, three block barriers, no per-thread global access except the twiddle look-ups.
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
+__global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1)
+    wg_colr3_tma_kernel(const PassParams p, const __grid_constant__ ColR3Maps maps) {
+  using Cfg = ColR3Cfg<T, R0, R1, R2>;
+  using Tile = ColR3Tile<T, R0, R1, R2, IL>;
+  constexpr int N = Cfg::N, TPC = Cfg::TPC, C = Cfg::C, NBUF = Cfg::NBUF;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NBUF * Cfg::kTile);
+  const int c = threadIdx.x % C, t = threadIdx.x / C;
+  const long long tiles_c = (p.nb[0] + C - 1) / C;
+  const long long total_tiles = tiles_c * p.nb[1] * p.nb[2];
+  const T scale = T(p.scale);
+
   constexpr bool TW0REG = sizeof(T) == 4 && Cfg::NT <= 512;  // (800 threads leave 72 registers each)
   cx<T> tw0[TW0REG ? R0 : 1];
   if (TW0REG) {
 #pragma unroll
     for (int r = 1; r < R0; ++r) tw0[r] = ldg_cx<T>(p.tw, (long long)t * r);
   }
+  // tile -> first column, batch indices 1 and 2
+  auto coords = [&](long long tl, int& c0, int& b1, int& b2) {
+    long long q = tl / tiles_c;
+    c0 = (int)((tl - q * tiles_c) * C);
+    const long long q2 = q / p.nb[1];
+    b1 = (int)(q - q2 * p.nb[1]);
+    b2 = (int)q2;
+  };
+  auto issue_load = [&](long long tl, int buf) {
+    int c0, b1, b2;
+    coords(tl, c0, b1, b2);
+    unsigned char* dst = smem_raw + (size_t)buf * Cfg::kTile;
+    col::mbar_expect_tx(&full[buf], (uint32_t)Cfg::kTile);
+    col::tma_load_5d(dst, &maps.in0, IL ? 2 * c0 : c0, 0, 0, b1, b2, &full[buf]);
+    if (!IL) col::tma_load_5d(dst + Cfg::kTilePlane, &maps.in1, c0, 0, 0, b1, b2, &full[buf]);
+  };
 
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NBUF; ++s) col::mbar_init(&full[s], 1);
+    col::fence_mbar_init();
+    col::fence_proxy_async();
+  }
+  __syncthreads();
+  long long tile = blockIdx.x;
+  if (threadIdx.x == 0) {
+    if (tile < total_tiles) issue_load(tile, 0);
+    if (tile + gridDim.x < total_tiles) issue_load(tile + gridDim.x, 1);
+  }
+  int buf = 0, phase = 0;  // buffer of the current tile; parity of its mbarrier phase (flips every NBUF tiles)
+  for (; tile < total_tiles; tile += gridDim.x) {
+    unsigned char* raw = smem_raw + (size_t)buf * Cfg::kTile;
+    const Tile S(raw, c);
+    col::mbar_wait(&full[buf], phase);
+    // ---- pass 0: radix R0 on rows t + TPC r, in place -------------------------------------------------------------
+    {
+      cx<T> v[R0];
+      const int base = Tile::row0(t);
+#pragma unroll
+      for (int r = 0; r < R0; ++r) {
+        v[r] = S.ld(base + r * Tile::kStep0);
+        if (IL && SWAP) v[r] = cx<T>{v[r].y, v[r].x};
+      }
+      DFT<R0, T>::run(v);
+#pragma unroll
+      for (int r = 1; r < R0; ++r) v[r] = cmul(v[r], TW0REG ? tw0[TW0REG ? r : 0] : ldg_cx<T>(p.tw, (long long)t * r));
+#pragma unroll
+      for (int r = 0; r < R0; ++r) S.st(base + r * Tile::kStep0, v[r]);
+    }
+    __syncthreads();
+    S.pass1(p, t);
+    __syncthreads();
+    // ---- pass 2: radix R2 on rows b R2 + r, in place: row [a][b1][r] is row k = a + R0 b1 + R0 R1 r of the output ----
+#pragma unroll 1
+    for (int b = t; b < N / R2; b += TPC) {
+      const int base = b * (R2 + 1) * C;  // pad(b R2 + r) = b (R2 + 1) + r
+      cx<T> v[R2];
+#pragma unroll
+      for (int r = 0; r < R2; ++r) v[r] = S.ld(base + r * C);
+      DFT<R2, T>::run(v);
+#pragma unroll
+      for (int r = 0; r < R2; ++r) {
+        cx<T> o = v[r];
+        if (p.apply_scale) o = cscale(o, scale);
+        if (IL && SWAP) o = cx<T>{o.y, o.x};
+        S.st(base + r * C, o);
+      }
+    }
+    col::fence_proxy_async();  // this thread's tile writes become visible to the tensor store
+    // The store of the previous tile has had a whole tile's time to read its buffer: once thread 0 has seen it
+    // complete, that buffer takes the load of the tile after next.
+    if (threadIdx.x == 0) bulk_wait_read_all();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const long long t2 = tile + 2 * (long long)gridDim.x;
+      if (t2 < total_tiles) issue_load(t2, buf == 0 ? NBUF - 1 : buf - 1);
+      int c0, b1, b2;
+      coords(tile, c0, b1, b2);
+      // (the store view has one batch dimension: b2 == 0 here, see colr3_make_store_map)
+      tma_store_5d(&maps.out0, raw, IL ? 2 * c0 : c0, 0, 0, 0, b1);
+      if (!IL) tma_store_5d(&maps.out1, raw + Cfg::kTilePlane, c0, 0, 0, 0, b1);
+      bulk_commit();
+    }
+    if (++buf == NBUF) {
+      buf = 0;
+      phase ^= 1;
+    }
+  }
+  if (threadIdx.x == 0) bulk_wait_all();
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Register form, any pointer alignment / stride / number of batch dimensions: the inputs of the next tile are loaded
+// into registers while the current tile runs its three passes; per-thread stores.  (Measured on C3b: 0.95 ms -- every
+// warp stalls in the burst of loads and stores, lg_throttle -- against 0.44 ms for the TMA form.)
+// I: element-index type (int when every index of both buffers fits 31 bits).
+// ---------------------------------------------------------------------------------------------------------------
+template <typename T, int R0, int R1, int R2, bool IL, bool SWAP, typename I>
+__global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1) wg_colr3_kernel(const PassParams p) {
+  using Cfg = ColR3Cfg<T, R0, R1, R2>;
+  using Tile = ColR3Tile<T, R0, R1, R2, IL>;
+  constexpr int N = Cfg::N, TPC = Cfg::TPC, C = Cfg::C;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  const int c = threadIdx.x % C, t = threadIdx.x / C;
+  const Tile S(smem_raw, c);
+  const long long tiles_c = (p.nb[0] + C - 1) / C;
+  const long long total_tiles = tiles_c * p.nb[1] * p.nb[2] * p.nb[3];
+  const T scale = T(p.scale);
+  const I in_step = (I)(TPC * p.is), out_step = (I)((R0 * R1) * p.os);
+  const I is = (I)p.is, os = (I)p.os;
+
+  constexpr bool TW0REG = sizeof(T) == 4 && Cfg::NT <= 512;
+  cx<T> tw0[TW0REG ? R0 : 1];
+  if (TW0REG) {
+#pragma unroll
+    for (int r = 1; r < R0; ++r) tw0[r] = ldg_cx<T>(p.tw, (long long)t * r);
+  }
   auto load_elem = [&](I idx) -> cx<T> {
     cx<T> v;
     if (IL) {
@@ -143,193 +285,73 @@ __global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1)
     ob_out = (I)ob;
     return col < p.nb[0];
   };
-  // tile -> TMA coordinates: first column, batch indices 1..3
-  auto coords = [&](long long tl, int& c0, int (&bc)[3]) {
-    long long q = tl / tiles_c;
-    c0 = (int)((tl - q * tiles_c) * C);
-#pragma unroll
-    for (int d = 1; d < kMaxBatchDims; ++d) {
-      const long long q2 = q / p.nb[d];
-      bc[d - 1] = (int)(q - q2 * p.nb[d]);
-      q = q2;
-    }
-  };
-  // one thread: TMA loads of tile `tl` into stage `s` (NBOX boxes per plane; the box rows beyond N are zero-filled)
-  auto issue = [&](long long tl, int s) {
-    int c0, bc[3];
-    coords(tl, c0, bc);
-    unsigned char* dst = stage0 + (size_t)s * Cfg::kStage;
-    col::mbar_expect_tx(&full[s], (uint32_t)Cfg::kStage);
-#pragma unroll
-    for (int bx = 0; bx < Cfg::NBOX; ++bx) {
-      if (IL) {  // one map of (re, im) pairs: rows of 2 C scalars
-        col::tma_load_5d(dst + (size_t)bx * Cfg::BOX * C * sizeof(cx<T>), &maps.in0, 2 * c0, bx * Cfg::BOX, bc[0], bc[1],
-                         bc[2], &full[s]);
-      } else {
-        col::tma_load_5d(dst + (size_t)bx * Cfg::BOX * C * sizeof(T), &maps.in0, c0, bx * Cfg::BOX, bc[0], bc[1], bc[2],
-                         &full[s]);
-        col::tma_load_5d(dst + Cfg::kPlane + (size_t)bx * Cfg::BOX * C * sizeof(T), &maps.in1, c0, bx * Cfg::BOX, bc[0],
-                         bc[1], bc[2], &full[s]);
-      }
-    }
-  };
 
   long long tile = blockIdx.x;
   I ib = 0, ob = 0;
   bool live = tile < total_tiles && bases(tile, ib, ob);
-  cx<T> nxt[TMA ? 1 : R0];
-  if (TMA) {
-    if (threadIdx.x == 0) {
-      col::mbar_init(&full[0], 1);
-      col::mbar_init(&full[1], 1);
-      col::fence_mbar_init();
-      col::fence_proxy_async();
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      if (tile < total_tiles) issue(tile, 0);
-      if (tile + gridDim.x < total_tiles) issue(tile + gridDim.x, 1);
-    }
-  } else if (live) {
+  cx<T> nxt[R0];
+  if (live) {
     const I i0 = ib + (I)t * is;
 #pragma unroll
     for (int r = 0; r < R0; ++r) nxt[r] = load_elem(i0 + r * in_step);
   }
-  int it = 0;
-  for (; tile < total_tiles; tile += gridDim.x, ++it) {
+  for (; tile < total_tiles; tile += gridDim.x) {
     const bool cur_live = live;
     const I cur_ob = ob;
-    // ---- pass 0: radix R0 on rows t + TPC r, stage (or registers) -> tile -------------------------------------------
+    // ---- pass 0: radix R0 on rows t + TPC r, registers -> tile ------------------------------------------------------
     {
       cx<T> v[R0];
+#pragma unroll
+      for (int r = 0; r < R0; ++r) v[r] = nxt[r];
+      // inputs of the next tile: in flight while this one runs its three passes
       const long long tn = tile + gridDim.x;
-      if (TMA) {
-        const unsigned char* st = stage0 + (size_t)(it & 1) * Cfg::kStage;
-        col::mbar_wait(&full[it & 1], (it >> 1) & 1);
-        if (IL) {
-          const cx<T>* src = reinterpret_cast<const cx<T>*>(st) + t * C + c;
+      live = tn < total_tiles && bases(tn, ib, ob);
+      if (live) {
+        const I i0 = ib + (I)t * is;
 #pragma unroll
-          for (int r = 0; r < R0; ++r) {
-            v[r] = src[r * TPC * C];
-            if (SWAP) v[r] = cx<T>{v[r].y, v[r].x};
-          }
-        } else {
-          const T* sre = reinterpret_cast<const T*>(st) + t * C + c;
-          const T* sim = reinterpret_cast<const T*>(st + Cfg::kPlane) + t * C + c;
-#pragma unroll
-          for (int r = 0; r < R0; ++r) v[r] = cx<T>{sre[r * TPC * C], sim[r * TPC * C]};
-        }
-        live = tn < total_tiles && bases(tn, ib, ob);
-      } else {
-#pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = nxt[TMA ? 0 : r];
-        // inputs of the next tile: in flight while this one runs its three passes
-        live = tn < total_tiles && bases(tn, ib, ob);
-        if (live) {
-          const I i0 = ib + (I)t * is;
-#pragma unroll
-          for (int r = 0; r < R0; ++r) nxt[TMA ? 0 : r] = load_elem(i0 + r * in_step);
-        }
+        for (int r = 0; r < R0; ++r) nxt[r] = load_elem(i0 + r * in_step);
       }
       if (cur_live) {
         DFT<R0, T>::run(v);
 #pragma unroll
         for (int r = 1; r < R0; ++r) v[r] = cmul(v[r], TW0REG ? tw0[TW0REG ? r : 0] : ldg_cx<T>(p.tw, (long long)t * r));
-      }
-      if (TMAST && it > 0) {
-        // the tensor store of the previous tile must have read the tile buffer before it is overwritten
-        if (threadIdx.x == 0) bulk_wait_read_all();
-        __syncthreads();
-      }
-      if (cur_live) {
-        const int dst = Cfg::pad(t) * C;  // pad(t + TPC r) = pad(t) + (TPC + R1) r
+        const int dst = Tile::row0(t);
 #pragma unroll
-        for (int r = 0; r < R0; ++r) tile_st(dst + r * (TPC + R1) * C, v[r]);
+        for (int r = 0; r < R0; ++r) S.st(dst + r * Tile::kStep0, v[r]);
       }
     }
     __syncthreads();
-    if (TMA && threadIdx.x == 0) {
-      // every thread has taken its inputs out of this stage: refill it with the tile after next
-      const long long t2 = tile + 2 * (long long)gridDim.x;
-      if (t2 < total_tiles) {
-        col::fence_proxy_async();
-        issue(t2, it & 1);
-      }
-    }
-    // ---- pass 1: radix R1 inside each block of N / R0 rows, in place ------------------------------------------------
+    if (cur_live) S.pass1(p, t);
+    __syncthreads();
+    // ---- pass 2: radix R2 on rows b R2 + r; tile -> global ----------------------------------------------------------
     if (cur_live) {
-#pragma unroll 1
-      for (int b = t; b < N / R1; b += TPC) {
-        const int blk = b / R2, j = b - blk * R2;  // rows blk TPC + j + R2 r: pad = blk (TPC + R1) + j + (R2 + 1) r
-        const int base = (blk * (TPC + R1) + j) * C;
-        cx<T> v[R1];
-#pragma unroll
-        for (int r = 0; r < R1; ++r) v[r] = tile_ld(base + r * (R2 + 1) * C);
-        DFT<R1, T>::run(v);
-        if (R2 > 1) {
-#pragma unroll
-          for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, (long long)j * r * R0));  // w_{N/R0}^{j r}
-        }
-#pragma unroll
-        for (int r = 0; r < R1; ++r) tile_st(base + r * (R2 + 1) * C, v[r]);
-      }
-    }
-    __syncthreads();
-    // ---- pass 2: radix R2 on rows b R2 + r; tile -> global, or back into the tile for the tensor store --------------
-    if (cur_live || TMAST) {
 #pragma unroll 1
       for (int b = t; b < N / R2; b += TPC) {
         const int base = b * (R2 + 1) * C;  // pad(b R2 + r) = b (R2 + 1) + r
         cx<T> v[R2];
 #pragma unroll
-        for (int r = 0; r < R2; ++r) v[r] = tile_ld(base + r * C);
+        for (int r = 0; r < R2; ++r) v[r] = S.ld(base + r * C);
         DFT<R2, T>::run(v);
-        if (TMAST) {
-          // in place: row [a][b1][r] of the tile is row k = a + R0 b1 + R0 R1 r of the output (the store's tensor map)
+        // row a N/R0 + b1 R2 + r holds output index k = a + R0 b1 + R0 R1 r (b = a R1 + b1)
+        const int a = b / R1, b1 = b - a * R1;
+        const I o0 = cur_ob + (I)(a + R0 * b1) * os;
 #pragma unroll
-          for (int r = 0; r < R2; ++r) {
-            cx<T> o = v[r];
-            if (p.apply_scale) o = cscale(o, scale);
-            if (IL && SWAP) o = cx<T>{o.y, o.x};
-            tile_st(base + r * C, o);
-          }
-        } else {
-          // row a N/R0 + b1 R2 + r holds output index k = a + R0 b1 + R0 R1 r (b = a R1 + b1)
-          const int a = b / R1, b1 = b - a * R1;
-          const I o0 = cur_ob + (I)(a + R0 * b1) * os;
-#pragma unroll
-          for (int r = 0; r < R2; ++r) {
-            cx<T> o = v[r];
-            if (p.apply_scale) o = cscale(o, scale);
-            const I idx = o0 + r * out_step;
-            if (IL) {
-              if (SWAP) o = cx<T>{o.y, o.x};
-              reinterpret_cast<cx<T>*>(p.out_re)[idx] = o;
-            } else {
-              reinterpret_cast<T*>(p.out_re)[idx] = o.x;
-              reinterpret_cast<T*>(p.out_im)[idx] = o.y;
-            }
+        for (int r = 0; r < R2; ++r) {
+          cx<T> o = v[r];
+          if (p.apply_scale) o = cscale(o, scale);
+          const I idx = o0 + r * out_step;
+          if (IL) {
+            if (SWAP) o = cx<T>{o.y, o.x};
+            reinterpret_cast<cx<T>*>(p.out_re)[idx] = o;
+          } else {
+            reinterpret_cast<T*>(p.out_re)[idx] = o.x;
+            reinterpret_cast<T*>(p.out_im)[idx] = o.y;
           }
         }
       }
     }
-    if (TMAST) {
-      col::fence_proxy_async();  // this thread's tile writes become visible to the tensor store
-      __syncthreads();
-      if (threadIdx.x == 0) {
-        int c0, bc[3];
-        coords(tile, c0, bc);
-        // box (columns, R2 + 1, R1, R0, 1): the padding row r = R2 lies outside the tensor and is not written; neither
-        // are the columns beyond the batch
-        tma_store_5d(&maps.out0, smem_raw, IL ? 2 * c0 : c0, 0, 0, 0, bc[0]);
-        if (!IL) tma_store_5d(&maps.out1, smem_raw + Cfg::kTilePlane, c0, 0, 0, 0, bc[0]);
-        bulk_commit();
-      }
-    } else {
-      __syncthreads();  // the tile is free for the next pass 0
-    }
+    __syncthreads();  // the tile is free for the next pass 0
   }
-  if (TMAST && threadIdx.x == 0) bulk_wait_all();
 }
 
 // largest element index the pass touches on either side
@@ -340,17 +362,6 @@ inline long long colr3_max_index(const PassParams& p) {
     mo += (p.nb[d] - 1) * p.obd[d];
   }
   return mi > mo ? mi : mo;
-}
-
-template <typename T, int R0, int R1, int R2, bool IL, bool SWAP, typename I, bool TMA, bool TMAST>
-cudaError_t launch_colr3_i(const PassParams& p, const ColR3Maps& m, int grid, cudaStream_t stream) {
-  using Cfg = ColR3Cfg<T, R0, R1, R2>;
-  const size_t smem = TMA ? Cfg::kSmemTma : Cfg::kSmem;
-  auto kern = wg_colr3_kernel<T, R0, R1, R2, IL, SWAP, I, TMA, TMAST>;
-  cudaError_t e = ensure_dynamic_smem(kern, smem);
-  if (e != cudaSuccess) return e;
-  kern<<<grid, Cfg::NT, smem, stream>>>(p, m);
-  return cudaGetLastError();
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -369,33 +380,34 @@ EncodeTiledFn colr3_encode_fn() {
   return fn;
 }
 
-// Output view for the tensor store: (column, r, b1, a, batch dimension 1) with output row k = a + R0 b1 + R0 R1 r, so
-// that the dense [a][b1][r (+ 1 padding row)][column] tile lands in natural order.  false: not encodable.
-template <int R0, int R1, int R2>
-bool colr3_make_store_map(const PassParams& p, const void* base_ptr, int scalars, bool is_double, int C, CUtensorMap* map) {
+// 5-D view of one plane: dimension 0 = columns (`scalars` per element), dimensions 1..4 = (size, stride in elements).
+bool colr3_encode(const void* base, int scalars, bool is_double, long long columns, const long long (&size)[4],
+                  const long long (&stride)[4], const int (&box)[5], int promo, CUtensorMap* map) {
   EncodeTiledFn enc = colr3_encode_fn();
-  if (enc == nullptr || p.nb[2] != 1 || p.nb[3] != 1) return false;
-  const size_t sc = is_double ? 8 : 4, esz = scalars * sc;
-  if (reinterpret_cast<uintptr_t>(base_ptr) % 16 != 0) return false;
-  cuuint64_t dims[5] = {(cuuint64_t)p.nb[0] * scalars, (cuuint64_t)R2, (cuuint64_t)R1, (cuuint64_t)R0, (cuuint64_t)p.nb[1]};
-  const long long st[4] = {(long long)R0 * R1 * p.os, (long long)R0 * p.os, p.os, p.nb[1] > 1 ? p.obd[1] : p.os * p.n};
+  if (enc == nullptr || reinterpret_cast<uintptr_t>(base) % 16 != 0) return false;
+  const size_t esz = (size_t)scalars * (is_double ? 8 : 4);
+  cuuint64_t dims[5] = {(cuuint64_t)columns * scalars, 0, 0, 0, 0};
   cuuint64_t strides[4];
   for (int i = 0; i < 4; ++i) {
-    const unsigned long long bytes = (unsigned long long)st[i] * esz;
-    if (st[i] <= 0 || bytes % 16 != 0 || bytes >= (1ULL << 40)) return false;
+    const unsigned long long bytes = (unsigned long long)stride[i] * esz;
+    if (size[i] <= 0 || stride[i] <= 0 || bytes % 16 != 0 || bytes >= (1ULL << 40)) return false;
+    dims[i + 1] = (cuuint64_t)size[i];
     strides[i] = bytes;
   }
-  if (dims[0] > (1ULL << 32) || dims[4] > (1ULL << 32)) return false;
-  cuuint32_t box[5] = {(cuuint32_t)(scalars * C), (cuuint32_t)(R2 + 1), (cuuint32_t)R1, (cuuint32_t)R0, 1};
-  cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  const CUresult r = enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5,
-                         const_cast<void*>(base_ptr), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
+  for (int i = 0; i < 5; ++i)
+    if (dims[i] == 0 || dims[i] > (1ULL << 32)) return false;
+  cuuint32_t bx[5], estr[5] = {1, 1, 1, 1, 1};
+  for (int i = 0; i < 5; ++i) bx[i] = (cuuint32_t)box[i];
+  const CUtensorMapL2promotion pr =
+      promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                 : (promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                               : (promo == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_L2_128B));
+  return enc(map, is_double ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, const_cast<void*>(base),
+             dims, strides, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, pr,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-// PFFT_COLR3_TMA: 0 = register prefetch and per-thread stores; 1..3 = TMA loads with L2 promotion 64 / 128 / 256 B,
-// 4 = none; +8 = per-thread stores instead of tensor stores
+// PFFT_COLR3_TMA: 0 = register form; 1..3 = TMA form with L2 promotion 64 / 128 / 256 B on the loads, 4 = none
 int colr3_mode() {
   static const int mode = [] {
     const char* e = std::getenv("PFFT_COLR3_TMA");
@@ -404,58 +416,72 @@ int colr3_mode() {
   return mode;
 }
 
-// tensor maps of the pass (one per scalar plane for split storage), from the plan's per-pass cache when the base
+// Tensor maps of the pass (one per scalar plane for split storage), from the plan's per-pass cache when the base
 // addresses are the ones they were encoded for.  cache[0..1]: input planes, cache[2..3]: output planes.
+// false: this geometry cannot be expressed (alignment, more than two / one batch dimensions beside the columns).
 template <typename T, int R0, int R1, int R2, bool IL>
-void colr3_tensor_maps(const PassParams& p, ColMapCache* cache, ColR3Maps* m, bool* loads, bool* stores) {
+bool colr3_tensor_maps(const PassParams& p, ColMapCache* cache, ColR3Maps* m) {
   using Cfg = ColR3Cfg<T, R0, R1, R2>;
   const int mode = colr3_mode();
-  *loads = *stores = false;
   memset(m, 0, sizeof(*m));
-  if ((mode & 7) == 0) return;
-  const int promo = (mode & 7) == 4 ? 0 : (mode & 7);
+  if (mode == 0 || p.nb[2] != 1 || p.nb[3] != 1) return false;
+  const int promo = mode == 4 ? 0 : mode;
   const size_t sc = sizeof(T);
   const bool dbl = sizeof(T) == 8;
+  const int scalars = IL ? 2 : 1;
   const void* bases[4] = {reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * (IL ? 2 * sc : sc),
                           IL ? nullptr : reinterpret_cast<const char*>(p.in_im) + (size_t)p.ioff * sc,
                           reinterpret_cast<const char*>(p.out_re) + (size_t)p.ooff * (IL ? 2 * sc : sc),
                           IL ? nullptr : reinterpret_cast<const char*>(p.out_im) + (size_t)p.ooff * sc};
   CUtensorMap* maps[4] = {&m->in0, &m->in1, &m->out0, &m->out1};
-  bool ok[2] = {true, (mode & 8) == 0};
+  const long long whole_in = p.is * p.n, whole_out = p.os * p.n;  // (stride of a dimension of size 1: any valid value)
+  // input: row = R2 q + s                       output: row k = a + R0 b1 + R0 R1 r
+  const long long in_size[4] = {R2, Cfg::N / R2, p.nb[1], 1}, in_stride[4] = {p.is, (long long)R2 * p.is,
+                                                                              p.nb[1] > 1 ? p.ibd[1] : whole_in, whole_in};
+  const long long out_size[4] = {R2, R1, R0, p.nb[1]},
+                  out_stride[4] = {(long long)R0 * R1 * p.os, (long long)R0 * p.os, p.os, p.nb[1] > 1 ? p.obd[1] : whole_out};
+  const int in_box[5] = {scalars * Cfg::C, R2 + 1, Cfg::N / R2, 1, 1}, out_box[5] = {scalars * Cfg::C, R2 + 1, R1, R0, 1};
   for (int i = 0; i < 4; ++i) {
-    if ((IL && (i & 1)) || !ok[i / 2]) continue;
+    if (IL && (i & 1)) continue;
     ColMapCache* ce = cache ? cache + i : nullptr;
     if (ce != nullptr && ce->base == bases[i]) {
       memcpy(maps[i], ce->map, sizeof(CUtensorMap));
       continue;
     }
-    const bool made = i < 2 ? col_make_tensor_map_plane(p, bases[i], IL ? 2 : 1, dbl, Cfg::C, Cfg::BOX, promo, maps[i])
-                            : colr3_make_store_map<R0, R1, R2>(p, bases[i], IL ? 2 : 1, dbl, Cfg::C, maps[i]);
-    if (!made) {
-      ok[i / 2] = false;
-      continue;
-    }
+    const bool made = i < 2 ? colr3_encode(bases[i], scalars, dbl, p.nb[0], in_size, in_stride, in_box, promo, maps[i])
+                            : colr3_encode(bases[i], scalars, dbl, p.nb[0], out_size, out_stride, out_box, 0, maps[i]);
+    if (!made) return false;
     if (ce != nullptr) {
       memcpy(ce->map, maps[i], sizeof(CUtensorMap));
       ce->base = bases[i];
     }
   }
-  *loads = ok[0];
-  *stores = ok[0] && ok[1];
+  return true;
+}
+
+template <typename T, int R0, int R1, int R2, bool IL, bool SWAP, typename I>
+cudaError_t launch_colr3_regs(const PassParams& p, int grid, cudaStream_t stream) {
+  using Cfg = ColR3Cfg<T, R0, R1, R2>;
+  auto kern = wg_colr3_kernel<T, R0, R1, R2, IL, SWAP, I>;
+  cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, Cfg::NT, Cfg::kSmem, stream>>>(p);
+  return cudaGetLastError();
 }
 
 template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
 cudaError_t launch_colr3_v(const PassParams& p, int grid, cudaStream_t stream, ColMapCache* cache) {
+  using Cfg = ColR3Cfg<T, R0, R1, R2>;
   ColR3Maps m;
-  bool loads = false, stores = false;
-  colr3_tensor_maps<T, R0, R1, R2, IL>(p, cache, &m, &loads, &stores);
-  const bool small = colr3_max_index(p) < (1LL << 31) - 1;
-  if (stores) return launch_colr3_i<T, R0, R1, R2, IL, SWAP, int, true, true>(p, m, grid, stream);
-  if (loads)
-    return small ? launch_colr3_i<T, R0, R1, R2, IL, SWAP, int, true, false>(p, m, grid, stream)
-                 : launch_colr3_i<T, R0, R1, R2, IL, SWAP, long long, true, false>(p, m, grid, stream);
-  return small ? launch_colr3_i<T, R0, R1, R2, IL, SWAP, int, false, false>(p, m, grid, stream)
-               : launch_colr3_i<T, R0, R1, R2, IL, SWAP, long long, false, false>(p, m, grid, stream);
+  if (colr3_tensor_maps<T, R0, R1, R2, IL>(p, cache, &m)) {
+    auto kern = wg_colr3_tma_kernel<T, R0, R1, R2, IL, SWAP>;
+    cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmemTma);
+    if (e != cudaSuccess) return e;
+    kern<<<grid, Cfg::NT, Cfg::kSmemTma, stream>>>(p, m);
+    return cudaGetLastError();
+  }
+  if (colr3_max_index(p) < (1LL << 31) - 1) return launch_colr3_regs<T, R0, R1, R2, IL, SWAP, int>(p, grid, stream);
+  return launch_colr3_regs<T, R0, R1, R2, IL, SWAP, long long>(p, grid, stream);
 }
 
 template <typename T, int R0, int R1, int R2>
@@ -473,11 +499,11 @@ cudaError_t launch_colr3_t(const PassParams& p, bool il, bool swap, int grid, cu
 
 bool colr3_supported(int n, bool is_double, int* columns, int* threads_per_column, size_t* smem) {
   switch (n) {
-#define X(NN, A, B, CC)                                                                        \
-  case NN:                                                                                     \
-    if (columns) *columns = is_double ? ColR3Cfg<double, A, B, CC>::C : ColR3Cfg<float, A, B, CC>::C; \
-    if (threads_per_column) *threads_per_column = ColR3Cfg<float, A, B, CC>::TPC;              \
-    if (smem) *smem = ColR3Cfg<float, A, B, CC>::kSmemTma; /* same bytes for both precisions */ \
+#define X(NN, A, B, CC)                                                                                       \
+  case NN:                                                                                                    \
+    if (columns) *columns = is_double ? ColR3Cfg<double, A, B, CC>::C : ColR3Cfg<float, A, B, CC>::C;         \
+    if (threads_per_column) *threads_per_column = ColR3Cfg<float, A, B, CC>::TPC;                             \
+    if (smem) *smem = is_double ? ColR3Cfg<double, A, B, CC>::kSmemTma : ColR3Cfg<float, A, B, CC>::kSmemTma; \
     return true;
     PFFT_COLR3_LIST(X)
 #undef X
