@@ -34,7 +34,9 @@ cudaError_t launch_sg_f32(const PassParams& p, bool interleaved, bool swap, int 
 cudaError_t launch_sg_f64(const PassParams& p, bool interleaved, bool swap, int grid, cudaStream_t stream);
 
 // WORKGROUP level, N = R^3 specialisation with TMA-fed persistent CTAs (wg_cube.cu). variant 0: TMA ring, 1: direct loads
-cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream);
+// real: 0 complex; 1 real-to-complex, 2 complex-to-real fused into the kernel (p.tw2 = w_{2n}^k; TMA variant, no swap)
+cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
+                           int real = 0);
 
 // WORKGROUP level, tiles of 16 (fp32) / 8 (fp64) transforms fed by TMA (wg_col.cu): n in {64,128,256,512}.
 // variant bits 0-1: input mode (0 strided columns via TMA tensor tiles, 1 contiguous rows loaded directly, 2 contiguous

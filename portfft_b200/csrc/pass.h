@@ -49,6 +49,8 @@ struct PassParams {
   int in_mode, out_mode;
   // twiddles w_n^k, k in [0, n), complex<T>, device resident
   const void* tw;
+  // REAL-domain pre / post-processing fused into a transform kernel: w_{2n}^k, k in [0, 2n) (nullptr otherwise)
+  const void* tw2;
   // inter-factor twiddle on store (GLOBAL level): w_{gtw_n}^{b[gtw_dim] * k} = hi[m >> gtw_bits] * lo[m & mask]
   int gtw_dim;  // -1: none
   int gtw_bits;

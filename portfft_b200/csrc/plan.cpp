@@ -941,7 +941,6 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   }
   long long rows = 1;
   for (long long n : row_n) rows *= n;
-  plan.scratch_elems = std::max(plan.scratch_elems, (size_t)(rows * L));
   bool pairs = even && rs == 1 && roff % 2 == 0;
   std::vector<long long> pair_d;
   for (size_t i = 0; i < row_n.size(); ++i) {
@@ -1019,15 +1018,43 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     return outer;
   };
 
+  // Pre / post-processing fused into the TMA-fed tile kernel of the rows (wg_cube.cu): the transform pass itself reads
+  // / writes the user's half spectrum, one HBM round trip instead of two.  Needs the packed-row tile kernel, interleaved
+  // unit-stride complex rows and a single (merged) batch dimension on both sides.
+  const bool il_user = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
+  static const bool fuse_off = [] {
+    const char* e = std::getenv("PFFT_NO_REAL_FUSE");
+    return e && std::atoi(e) != 0;
+  }();
+  auto fusable = [&](const PassHost& ps, const std::vector<BDim>& dims) {
+    return !fuse_off && !d.no_real_fuse && even && pairs && single && il_user && ps.kernel == KERNEL_WG_CUBE &&
+           ps.variant == 0 && dims.size() == 1;
+  };
+  auto set_fused = [&](PassHost& ps, int mode, const std::vector<BDim>& dims) {
+    set_batch_dims(ps.pp, dims);
+    ps.fuse_real = mode;
+    ps.tw2_n = N;
+  };
+
   if (fwd) {
     int zbuf;
+    bool fused = false;
     if (pairs) {
       zbuf = transform(rview, nullptr);
+      const std::vector<BDim> dims = row_dims(rview.dist, row_c);
+      if (passes.size() == 1 && cs == 1 && fusable(passes.back(), dims)) {
+        PassHost& ps = passes.back();
+        set_fused(ps, 1, dims);
+        ps.dst = BUF_OUT;
+        ps.pp.ooff = coff;
+        ps.internal_storage = 0;
+        fused = true;
+      }
     } else {
       passes.push_back(rows_pass(KERNEL_REAL_PACK, BUF_IN, BUF_SCRATCH, rs, roff, row_r, 1, 0, row_s, L));
       zbuf = transform(s1, nullptr);
     }
-    passes.push_back(rows_pass(KERNEL_R2C_POST, zbuf, BUF_OUT, 1, 0, row_s, cs, coff, row_c, H + 1));
+    if (!fused) passes.push_back(rows_pass(KERNEL_R2C_POST, zbuf, BUF_OUT, 1, 0, row_s, cs, coff, row_c, H + 1));
     // the other dimensions: complex passes in place on the half-spectrum output
     std::vector<long long> bst(d.backward_strides.begin(), d.backward_strides.end());
     for (size_t e = D - 1; e > 0; --e) {
@@ -1093,6 +1120,27 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       xoff = 0;
       xd = row_w;
     }
+    bool fused = false;
+    if (pairs && xs == 1) {
+      // try the fused form: plan the transform on packed rows (what the unfused plan runs), then let it read the half
+      // spectrum itself (rows of H + 1 elements at any 8-byte alignment: wg_cube.cu handles the shift)
+      const size_t first = passes.size();
+      transform(s1, &rview);
+      const std::vector<BDim> dims = row_dims(xd, rview.dist);
+      if (passes.size() == first + 1 && fusable(passes.back(), dims)) {
+        PassHost& ps = passes.back();
+        set_fused(ps, 2, dims);
+        ps.src = xbuf;
+        ps.pp.ioff = xoff;
+        ps.internal_storage = xbuf == BUF_IN ? 0 : 1;
+        fused = true;
+      } else {
+        passes.resize(first);
+      }
+    }
+    if (fused) {
+      // (nothing else: the pass reads xbuf and writes the real rows)
+    } else {
     passes.push_back(rows_pass(KERNEL_C2R_PRE, xbuf, BUF_SCRATCH, xs, xoff, xd, 1, 0, row_s, L));
     if (pairs) {
       transform(s1, &rview);
@@ -1100,7 +1148,11 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       const int ybuf = transform(s1, nullptr);
       passes.push_back(rows_pass(KERNEL_REAL_UNPACK, ybuf, BUF_OUT, 1, 0, row_s, rs, roff, row_r, L));
     }
+    }
   }
+  // the packed-row workspace, unless every pass of this direction works on the user's buffers (fused forms)
+  for (const PassHost& ps : passes)
+    if (ps.src == BUF_SCRATCH || ps.dst == BUF_SCRATCH) plan.scratch_elems = std::max(plan.scratch_elems, (size_t)(rows * L));
   // passes that address the user's real buffer as complex pairs
   for (PassHost& ps : passes) {
     if (ps.kernel >= KERNEL_EW && ps.kernel <= KERNEL_REAL_UNPACK) continue;
@@ -1210,6 +1262,7 @@ std::string describe_plan(const PlanHost& plan, int direction) {
          << " valid_out=" << p.valid_out << " mod_flags=" << p.mod_flags << " mod_l=" << ps.mod_l << " mod_m=" << ps.mod_m;
     if (p.apply_scale) ss << " scale=" << p.scale;
     if (ps.real_view) ss << " real_view=" << ps.real_view;
+    if (ps.fuse_real) ss << " fuse_real=" << ps.fuse_real;
     if (ps.force_swap) ss << " force_swap";
     if (ps.kernel >= KERNEL_REAL_PACK && ps.kernel <= KERNEL_REAL_UNPACK) ss << " variant=" << ps.variant;
     ss << "\n";
@@ -1244,7 +1297,7 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
        << ", \"valid_in\": " << p.valid_in << ", \"valid_out\": " << p.valid_out << ", \"mod_flags\": " << p.mod_flags
        << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
        << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
-       << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view
+       << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view << ", \"fuse_real\": " << ps.fuse_real
        << ", \"force_swap\": " << ps.force_swap << "}";
     firstp = false;
   }

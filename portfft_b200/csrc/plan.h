@@ -26,6 +26,7 @@ struct PlanError : std::runtime_error {
 };
 
 struct DescHost {
+  bool no_real_fuse = false;  // plan-internal: build the REAL-domain passes unfused (fallback for unaligned pointers)
   bool is_double = false;
   int domain = PFFT_DOMAIN_COMPLEX;
   std::vector<size_t> lengths;
@@ -88,6 +89,10 @@ struct PassHost {
   int internal_storage = 0;  // bit 0 / bit 1: the input / output side is plan-internal, interleaved complex
   int real_view = 0;
   int force_swap = 0;        // REAL N-D backward: inverse complex pass on the (interleaved) workspace
+  // REAL domain fused into the transform kernel (wg_cube.cu): 1 = the pass also does r2c_post (writes n + 1 outputs per
+  // row), 2 = it also does c2r_pre (reads n + 1 inputs per row); tw2_n = length of the second twiddle table (2 n)
+  int fuse_real = 0;
+  long long tw2_n = 0;
 };
 
 // geometry limits of the thread- and warp-level kernels (wi.cuh, sg.cuh); sg_supports_m lives in sg_f32.cu

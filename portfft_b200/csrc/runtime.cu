@@ -110,10 +110,12 @@ struct pfft_plan {
   size_t nd_chunk = 0;
   std::map<size_t, pfft_plan*> nd_child;     // planes per chunk -> sub-plan over dimensions 1..D-1
   pfft_plan* nd_outer[2] = {nullptr, nullptr};  // [direction]: the pass along dimension 0, in place on the output
+  pfft_plan* unfused = nullptr;  // REAL domain: the plan without kernel fusion, for buffers the fused kernels cannot take
 
   ~pfft_plan() {
     delete nd_outer[0];
     delete nd_outer[1];
+    delete unfused;
     for (auto& kv : nd_child) delete kv.second;
     for (auto& kv : child) delete kv.second;
     for (cudaEvent_t e : chunk_up) cudaEventDestroy(e);
@@ -149,9 +151,11 @@ static void build_tables(pfft_plan* plan) {
   PlanTables* tb = plan->tables.get();
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
-      if (ps.tw_n > 0 && !tb->tw.count(ps.tw_n)) {
-        std::vector<T> t = make_twiddles<T>(ps.tw_n, ps.tw_n, 1);
-        tb->tw[ps.tw_n] = upload(plan, t.data(), t.size() * sizeof(T));
+      for (long long n : {ps.tw_n, ps.tw2_n}) {
+        if (n > 0 && !tb->tw.count(n)) {
+          std::vector<T> t = make_twiddles<T>(n, n, 1);
+          tb->tw[n] = upload(plan, t.data(), t.size() * sizeof(T));
+        }
       }
       if (ps.pp.gtw_dim >= 0 && !tb->gtw.count(ps.pp.gtw_n)) {
         const long long n = ps.pp.gtw_n;
@@ -194,6 +198,7 @@ static void attach_device_state(pfft_plan* plan) {
   for (int dir = 0; dir < 2; ++dir) {
     for (PassHost& ps : plan->host.passes[dir]) {
       ps.pp.tw = ps.tw_n > 0 ? tb->tw[ps.tw_n] : nullptr;
+      ps.pp.tw2 = ps.tw2_n > 0 ? tb->tw[ps.tw2_n] : nullptr;
       if (ps.pp.gtw_dim >= 0) {
         const GtwTable& g = tb->gtw[ps.pp.gtw_n];
         ps.pp.gtw_lo = g.lo;
@@ -368,6 +373,20 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   if ((!in_cplx && in_imag != nullptr) || (!out_cplx && out_imag != nullptr))
     throw PlanError(PFFT_INVALID_CONFIGURATION, "the real side of a REAL-domain transform is a single scalar array");
   if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
+  // REAL-domain passes fused into the TMA tile kernel need 16-byte aligned buffers (complex-to-real input: 8 bytes);
+  // other pointers run the unfused plan (made on first use)
+  for (const PassHost& ps : plan->host.passes[dir]) {
+    if (ps.fuse_real == 0) continue;
+    const uintptr_t need_in = ps.fuse_real == 2 ? (d.is_double ? 16 : 8) : 16;
+    if ((uintptr_t)in % need_in == 0 && (uintptr_t)out % 16 == 0) continue;
+    if (plan->unfused == nullptr) {
+      DescHost du = d;
+      du.no_real_fuse = true;
+      plan->unfused = make_plan(du, plan->device, plan->stream, plan->allow_l2_chunk);
+    }
+    execute(plan->unfused, dir, in, in_imag, out, out_imag, stream, peers);
+    return;
+  }
   if (plan->l2_chunk != 0 && peers == nullptr) {
     execute_chunked(plan, dir, in, in_imag, out, out_imag, stream);
     return;
@@ -510,9 +529,10 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         break;
       }
       case KERNEL_WG_CUBE:
-        // cp.async.bulk needs 16-byte aligned global addresses; otherwise run the generic kernel
-        if (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0)
-          e = launch_wg_cube(p, d.is_double, swap, ps.variant, ps.alt_grid, stream);
+        // cp.async.bulk needs 16-byte aligned global addresses; otherwise run the generic kernel (fused REAL-domain
+        // passes were diverted to the unfused plan above)
+        if (ps.fuse_real != 0 || (((uintptr_t)p.in_re % 16) == 0 && ((uintptr_t)p.out_re % 16) == 0))
+          e = launch_wg_cube(p, d.is_double, swap, ps.variant, ps.alt_grid, stream, ps.fuse_real);
         else
           e = launch_wg_generic(p, d.is_double, pil, swap, ps.grid, stream);
         break;

@@ -17,6 +17,7 @@
 //   * results leave with coalesced 64-bit stores straight from registers; backward = re/im swap; scale fused.
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 
 #include "device_utils.cuh"
 #include "kernels.h"
@@ -63,7 +64,46 @@ struct CubeArgs {
   const void* tw;  // w_N^k, k in [0, N)
   double scale;
   int apply_scale;
+  const void* tw2;  // REAL-domain fusion: w_{2N}^k, k in [0, 2N)
 };
+
+// ---------------------------------------------------------------------------------------------------------------
+// REAL domain fused into the tile kernels (REAL = 1: real-to-complex, 2: complex-to-real; scheme and formulas:
+// real.cu).  The complex transform of N = (real length) / 2 points runs on the real row read / written as interleaved
+// pairs; what real.cu does in a separate pass over HBM happens here on the tile while it is in shared memory:
+//   R2C: pass 3 puts Z back into the stage buffer, one more barrier, then every thread combines its own Z_k with the
+//        partner Z_{N-k} and stores X_k (k = 0..N; rows of N + 1 outputs: plain 64-bit stores);
+//   C2R: the stage receives the N + 1 input elements of a row (the bulk copy starts at the 16-byte boundary at or
+//        below the row: `shift` = 0 or 1 elements), and pass 1 builds its inputs z'_j from X_{N-j} and X_j.
+// The twiddle w_{2N}^k of element k = j + (N / R) r is (one per-thread register) x (the compile-time constant w_{2R}^r).
+// ---------------------------------------------------------------------------------------------------------------
+template <int I, int N, typename F>
+__device__ __forceinline__ void static_for(F&& f) {
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+
+// X_k = E_k + w^k O_k from a = Z_k, b = Z_{N-k}, w = w_{2N}^k
+template <typename T>
+__device__ __forceinline__ cx<T> r2c_combine(cx<T> a, cx<T> b, cx<T> w) {
+  b.y = -b.y;
+  const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
+  const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
+  return ev + cmul(w, od);
+}
+
+// z'_j (the input of the plain forward transform that yields the unnormalised inverse) from a = X_{N-j}, b = X_j,
+// w = w_{2N}^j:  (a + conj b) - i w (a - conj b); j = 0: a = Re X_0, b = Re X_N, (a + b) + i (a - b)
+template <typename T>
+__device__ __forceinline__ cx<T> c2r_combine(cx<T> a, cx<T> b, cx<T> w, bool first) {
+  if (first) return cx<T>{a.x + b.x, a.x - b.x};
+  b.y = -b.y;
+  const cx<T> s = a + b, d = a - b;
+  const cx<T> t = cmul(w, d);
+  return cx<T>{s.x + t.y, s.y - t.x};  // s - i t
+}
 
 // position of element e of the exchange-2 layout inside a stage buffer (a permutation within aligned 16-groups, so
 // that the pass-3 reads of 16 consecutive elements stay conflict free)
@@ -72,15 +112,17 @@ __device__ __forceinline__ constexpr int sw2(int e) {
   return R == 8 ? (e ^ ((e >> 3) & 8)) : e;
 }
 
-template <typename T, int R, int F, bool SWAP, bool USE_TMA>
+template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0>
 __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4) wg_cube_kernel(const CubeArgs a) {
+  static_assert(REAL == 0 || (USE_TMA && !SWAP), "the REAL-domain forms are TMA fed and never swap");
   constexpr int NT = R * R;  // threads per transform
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
+  constexpr int SN = REAL == 2 ? N + 2 : N;  // elements of one transform's slot in a stage (C2R: shift + N + 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);  // TMA: stage 0 ; non-TMA: exchange-2 buffer
-  cx<T>* S1 = S0 + F * N;                          // TMA: stage 1
-  cx<T>* E = USE_TMA ? (S1 + F * N) : (S0 + F * N);  // padded exchange-1 buffer
+  cx<T>* S1 = S0 + F * SN;                         // TMA: stage 1
+  cx<T>* E = USE_TMA ? (S1 + F * SN) : (S0 + F * N);  // padded exchange-1 buffer
   uint64_t* full = reinterpret_cast<uint64_t*>(E + F * EN);
   const int f = F == 1 ? 0 : threadIdx.x / NT;  // transform of the tile
   const int t = F == 1 ? threadIdx.x : threadIdx.x % NT;
@@ -98,10 +140,37 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
     tw3[r - 1] = ldg_cx<T>(a.tw, (long long)t * r);       // w_N^{t r}
   }
   const T scale = T(a.scale);
+  cx<T> wreal{T(1), T(0)};  // REAL: w_{2N}^t
+  if (REAL != 0) wreal = ldg_cx<T>(a.tw2, t);
 
   // one thread: fetch the tile starting at transform k into stage buffer Sd
   auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
     const int rows = (int)min((long long)F, a.batch - k);
+    if constexpr (REAL == 2) {
+      // rows of N + 1 elements at any 8-byte alignment: copy from the 16-byte boundary at or below the row.  An even
+      // row start would read one element past the row: fine inside the buffer, not for its last row, whose element N
+      // is fetched by an ordinary load instead (the arrive below releases it to the waiting threads).
+      uint32_t total = 0;
+      for (int r = 0; r < rows; ++r) {
+        const cx<T>* src = gin + (k + r) * a.idist;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
+        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) {
+          bytes -= 16;
+          Sd[r * SN + shift + N] = src[N];
+        }
+        total += bytes;
+      }
+      mbar_expect_tx(bar, total);
+      for (int r = 0; r < rows; ++r) {
+        const cx<T>* src = gin + (k + r) * a.idist;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
+        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) bytes -= 16;
+        bulk_g2s(Sd + r * SN, src - shift, bytes, bar);
+      }
+      return;
+    }
     mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
     if (F == 1 || contig) {
       bulk_g2s(Sd, gin + k * a.idist, (uint32_t)(rows * N * sizeof(cx<T>)), bar);
@@ -130,15 +199,26 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
   for (long long k0 = (long long)blockIdx.x * F; k0 < a.batch; k0 += stride, ++it) {
     const long long k = k0 + f;
     const bool live = F == 1 || k < a.batch;  // ragged last tile: idle threads still take part in the barriers
-    cx<T>* S = (USE_TMA ? ((it & 1) ? S1 : S0) : S0) + f * N;
+    cx<T>* S = (USE_TMA ? ((it & 1) ? S1 : S0) : S0) + f * SN;
     cx<T>* Ef = E + f * EN;
     cx<T> v[R];
     // ---- pass 1: x[t + NT r] -> radix R -> E[R t + r'] -------------------------------------------------------
     if (USE_TMA) {
       mbar_wait(&full[it & 1], (it >> 1) & 1);
       if (live) {
+        if constexpr (REAL == 2) {
+          // input j = t + NT r of the transform is built from X_{N-j} and X_j of the row (see c2r_combine)
+          const cx<T>* X = S + (int)((reinterpret_cast<uintptr_t>(gin + k * a.idist) & 15) / sizeof(cx<T>));
+          static_for<0, R>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const int j = t + NT * r;
+            const bool first = r == 0 && t == 0;
+            v[r] = c2r_combine(X[first ? 0 : N - j], X[first ? N : j], mul_w<r, 2 * R, T>(wreal), first);
+          });
+        } else {
 #pragma unroll
-        for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
+          for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
+        }
       }
     } else if (live) {
       const cx<T>* src = gin + k * a.idist;
@@ -192,17 +272,42 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw3[r - 1]);
       DFT<R, T>::run(v);
-      cx<T>* dst = gout + k * a.odist;
+      if constexpr (REAL != 1) {
+        cx<T>* dst = gout + k * a.odist;
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        cx<T> o = v[r];
-        if (a.apply_scale) o = cscale(o, scale);
-        if (SWAP) {
-          const T tmp = o.x;
-          o.x = o.y;
-          o.y = tmp;
+        for (int r = 0; r < R; ++r) {
+          cx<T> o = v[r];
+          if (a.apply_scale) o = cscale(o, scale);
+          if (SWAP) {
+            const T tmp = o.x;
+            o.x = o.y;
+            o.y = tmp;
+          }
+          dst[t + NT * r] = o;
         }
-        dst[t + NT * r] = o;
+      } else {
+        // Z back into the stage, in natural order (the positions this thread has just read)
+#pragma unroll
+        for (int r = 0; r < R; ++r) S[sw2<R>(t + NT * r)] = v[r];
+      }
+    }
+    if constexpr (REAL == 1) {
+      __syncthreads();
+      if (live) {
+        cx<T>* dst = gout + k * a.odist;
+        static_for<0, R>([&](auto rc) {
+          constexpr int r = decltype(rc)::value;
+          const int kk = t + NT * r;
+          const cx<T> b = S[sw2<R>(kk == 0 ? 0 : N - kk)];
+          cx<T> o = r2c_combine(v[r], b, mul_w<r, 2 * R, T>(wreal));
+          if (a.apply_scale) o = cscale(o, scale);
+          dst[kk] = o;
+        });
+        if (t == 0) {
+          cx<T> o{v[0].x - v[0].y, T(0)};  // X_N = Re Z_0 - Im Z_0
+          if (a.apply_scale) o = cscale(o, scale);
+          dst[N] = o;
+        }
       }
     }
   }
@@ -226,17 +331,19 @@ constexpr int rows3_min_ctas() {
   return (2 * n + n + 2 * (n / 16)) * F * 2 * sizeof(T) + 64 > 113 * 1024 ? 1 : 2;
 }
 
-template <typename T, int R0, int R1, int R2, int F, bool SWAP, int B1 = 1>
+template <typename T, int R0, int R1, int R2, int F, bool SWAP, int B1 = 1, int REAL = 0>
 __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 ? 1 : rows3_min_ctas<R0, R1, R2, F, B1, T>()))
     wg_rows3_kernel(const CubeArgs a) {
   static_assert(R0 == 16, "pass 1 writes whole padded 16-groups");
+  static_assert(REAL == 0 || !SWAP, "the REAL-domain forms never swap");
   constexpr int N = R0 * R1 * R2;
   constexpr int NT = N / R0 / B1;  // threads per transform
   constexpr int EN = N + 2 * (N / 16);
+  constexpr int SN = REAL == 2 ? N + 2 : N;  // elements of one transform's slot in a stage (C2R: shift + N + 1)
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);
-  cx<T>* S1 = S0 + F * N;
-  cx<T>* E = S1 + F * N;
+  cx<T>* S1 = S0 + F * SN;
+  cx<T>* E = S1 + F * SN;
   uint64_t* full = reinterpret_cast<uint64_t*>(E + F * EN);
   const int f = F == 1 ? 0 : threadIdx.x / NT;
   const int t = F == 1 ? threadIdx.x : threadIdx.x % NT;
@@ -268,8 +375,38 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
       for (int r = 1; r < R2; ++r) tw3[i * (R2 - 1) + r - 1] = ldg_cx<T>(a.tw, ((t + i * NT) % (N / R2)) * r);
   }
 
+  // REAL: w_{2N}^{t + i NT}, the per-thread factor of the twiddles of passes 1 (C2R) and 3 (R2C)
+  constexpr int BR = REAL == 0 ? 1 : (B1 > B3 ? B1 : B3);
+  cx<T> wreal[BR];
+  if (REAL != 0) {
+#pragma unroll
+    for (int i = 0; i < BR; ++i) wreal[i] = ldg_cx<T>(a.tw2, t + i * NT);
+  }
+
   auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
     const int rows = (int)min((long long)F, a.batch - k);
+    if constexpr (REAL == 2) {  // (see wg_cube_kernel)
+      uint32_t total = 0;
+      for (int r = 0; r < rows; ++r) {
+        const cx<T>* src = gin + (k + r) * a.idist;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
+        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) {
+          bytes -= 16;
+          Sd[r * SN + shift + N] = src[N];
+        }
+        total += bytes;
+      }
+      mbar_expect_tx(bar, total);
+      for (int r = 0; r < rows; ++r) {
+        const cx<T>* src = gin + (k + r) * a.idist;
+        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
+        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) bytes -= 16;
+        bulk_g2s(Sd + r * SN, src - shift, bytes, bar);
+      }
+      return;
+    }
     mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
     if (F == 1 || contig) {
       bulk_g2s(Sd, gin + k * a.idist, (uint32_t)(rows * N * sizeof(cx<T>)), bar);
@@ -296,7 +433,7 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
   for (long long k0 = (long long)blockIdx.x * F; k0 < a.batch; k0 += stride, ++it) {
     const long long k = k0 + f;
     const bool live = F == 1 || k < a.batch;
-    cx<T>* S = ((it & 1) ? S1 : S0) + f * N;
+    cx<T>* S = ((it & 1) ? S1 : S0) + f * SN;
     cx<T>* Ef = E + f * EN;
     // ---- pass 1: x[t + NT r] -> radix 16 -> E[16 t + r'] -------------------------------------------------------
     mbar_wait(&full[it & 1], (it >> 1) & 1);
@@ -305,8 +442,18 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
       for (int i = 0; i < B1; ++i) {
         const int j = t + i * NT;
         cx<T> v[R0];
+        if constexpr (REAL == 2) {
+          const cx<T>* X = S + (int)((reinterpret_cast<uintptr_t>(gin + k * a.idist) & 15) / sizeof(cx<T>));
+          static_for<0, R0>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const int jj = j + (N / R0) * r;
+            const bool first = r == 0 && j == 0;
+            v[r] = c2r_combine(X[first ? 0 : N - jj], X[first ? N : jj], mul_w<r, 2 * R0, T>(wreal[i]), first);
+          });
+        } else {
 #pragma unroll
-        for (int r = 0; r < R0; ++r) v[r] = S[j + (N / R0) * r];
+          for (int r = 0; r < R0; ++r) v[r] = S[j + (N / R0) * r];
+        }
         if (SWAP) {
 #pragma unroll
           for (int r = 0; r < R0; ++r) v[r] = cx<T>{v[r].y, v[r].x};
@@ -365,46 +512,81 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
         for (int r = 1; r < R2; ++r)
           v[r] = cmul(v[r], TW3REG ? tw3[TW3REG ? i * (R2 - 1) + r - 1 : 0] : ldg_cx<T>(a.tw, j * r));
         DFT<R2, T>::run(v);
+        if constexpr (REAL == 1) {
+          // Z back into the stage, in natural order (the positions this thread has just read)
 #pragma unroll
-        for (int r = 0; r < R2; ++r) {
-          cx<T> o = v[r];
-          if (a.apply_scale) o = cscale(o, scale);
-          if (SWAP) o = cx<T>{o.y, o.x};
-          dst[j + (N / R2) * r] = o;
+          for (int r = 0; r < R2; ++r) S[j + (N / R2) * r] = v[r];
+        } else {
+#pragma unroll
+          for (int r = 0; r < R2; ++r) {
+            cx<T> o = v[r];
+            if (a.apply_scale) o = cscale(o, scale);
+            if (SWAP) o = cx<T>{o.y, o.x};
+            dst[j + (N / R2) * r] = o;
+          }
+        }
+      }
+    }
+    if constexpr (REAL == 1) {
+      __syncthreads();
+      if (live) {
+        cx<T>* dst = gout + k * a.odist;
+#pragma unroll
+        for (int i = 0; i < B3; ++i) {
+          const int j = t + i * NT;
+          if (j >= N / R2) break;
+          static_for<0, R2>([&](auto rc) {
+            constexpr int r = decltype(rc)::value;
+            const int kk = j + (N / R2) * r;
+            const cx<T> b = S[kk == 0 ? 0 : N - kk];
+            cx<T> o = r2c_combine(S[kk], b, mul_w<r, 2 * R2, T>(wreal[i]));
+            if (a.apply_scale) o = cscale(o, scale);
+            dst[kk] = o;
+          });
+          if (j == 0) {
+            const cx<T> z0 = S[0];
+            cx<T> o{z0.x - z0.y, T(0)};  // X_N = Re Z_0 - Im Z_0
+            if (a.apply_scale) o = cscale(o, scale);
+            dst[N] = o;
+          }
         }
       }
     }
   }
 }
 
-template <typename T, int R0, int R1, int R2, int F, int B1 = 1>
-static cudaError_t launch_rows3(const CubeArgs& a, bool swap, int grid, cudaStream_t stream) {
+template <typename T, int R0, int R1, int R2, int F, int B1, bool SWAP, int REAL>
+static cudaError_t launch_rows3_k(const CubeArgs& a, int grid, cudaStream_t stream) {
   constexpr int N = R0 * R1 * R2;
-  constexpr size_t smem = (2 * (size_t)N + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
-  cudaError_t e;
-  if (swap) {
-    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, true, B1>, smem);
-    if (e != cudaSuccess) return e;
-    wg_rows3_kernel<T, R0, R1, R2, F, true, B1><<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
-  } else {
-    e = ensure_dynamic_smem(wg_rows3_kernel<T, R0, R1, R2, F, false, B1>, smem);
-    if (e != cudaSuccess) return e;
-    wg_rows3_kernel<T, R0, R1, R2, F, false, B1><<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
-  }
+  constexpr int SN = REAL == 2 ? N + 2 : N;
+  constexpr size_t smem = (2 * (size_t)SN + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
+  auto kern = wg_rows3_kernel<T, R0, R1, R2, F, SWAP, B1, REAL>;
+  const cudaError_t e = ensure_dynamic_smem(kern, smem);
+  if (e != cudaSuccess) return e;
+  kern<<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
   return cudaGetLastError();
 }
 
-template <typename T, int R, int F>
-size_t cube_smem_bytes_t(bool use_tma) {
-  constexpr int N = R * R * R;
-  constexpr int EN = N + 2 * (N / 16);
-  return ((use_tma ? 2 : 1) * (size_t)N + EN) * F * sizeof(cx<T>) + 64;
+// real: 0 complex, 1 real-to-complex epilogue, 2 complex-to-real prologue (never with swap)
+template <typename T, int R0, int R1, int R2, int F, int B1 = 1>
+static cudaError_t launch_rows3(const CubeArgs& a, bool swap, int real, int grid, cudaStream_t stream) {
+  if (real == 1) return launch_rows3_k<T, R0, R1, R2, F, B1, false, 1>(a, grid, stream);
+  if (real == 2) return launch_rows3_k<T, R0, R1, R2, F, B1, false, 2>(a, grid, stream);
+  return swap ? launch_rows3_k<T, R0, R1, R2, F, B1, true, 0>(a, grid, stream)
+              : launch_rows3_k<T, R0, R1, R2, F, B1, false, 0>(a, grid, stream);
 }
 
-template <typename T, int R, int F, bool SWAP, bool USE_TMA>
+template <typename T, int R, int F>
+size_t cube_smem_bytes_t(bool use_tma, int real = 0) {
+  constexpr int N = R * R * R;
+  constexpr int EN = N + 2 * (N / 16);
+  return ((use_tma ? 2 : 1) * (size_t)(real == 2 ? N + 2 : N) + EN) * F * sizeof(cx<T>) + 64;
+}
+
+template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0>
 static cudaError_t launch_cube_t(const CubeArgs& a, int grid, cudaStream_t stream) {
-  const size_t smem = cube_smem_bytes_t<T, R, F>(USE_TMA);
-  auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA>;
+  const size_t smem = cube_smem_bytes_t<T, R, F>(USE_TMA, REAL);
+  auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA, REAL>;
   cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, R * R * F, smem, stream>>>(a);
@@ -412,7 +594,9 @@ static cudaError_t launch_cube_t(const CubeArgs& a, int grid, cudaStream_t strea
 }
 
 template <typename T, int R, int F>
-static cudaError_t launch_cube_v(const CubeArgs& a, bool swap, bool tma, int grid, cudaStream_t stream) {
+static cudaError_t launch_cube_v(const CubeArgs& a, bool swap, bool tma, int real, int grid, cudaStream_t stream) {
+  if (real == 1) return launch_cube_t<T, R, F, false, true, 1>(a, grid, stream);
+  if (real == 2) return launch_cube_t<T, R, F, false, true, 2>(a, grid, stream);
   if (tma) return swap ? launch_cube_t<T, R, F, true, true>(a, grid, stream) : launch_cube_t<T, R, F, false, true>(a, grid, stream);
   return swap ? launch_cube_t<T, R, F, true, false>(a, grid, stream) : launch_cube_t<T, R, F, false, false>(a, grid, stream);
 }
@@ -439,8 +623,10 @@ bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_p
   return true;
 }
 
-// p: a single-pass plan entry with n == R^3, interleaved storage, unit strides, one batch dimension
-cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream) {
+// p: a single-pass plan entry with n == R^3, interleaved storage, unit strides, one batch dimension.
+// real: 0 complex transform; 1 / 2: the REAL-domain forms (p.tw2 = w_{2n}^k; never with swap, TMA variant only)
+cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
+                           int real) {
   CubeArgs a;
   a.in = p.in_re;
   a.out = p.out_re;
@@ -450,28 +636,30 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   a.odist = p.obd[0];
   a.batch = p.batch_total;
   a.tw = p.tw;
+  a.tw2 = p.tw2;
   a.scale = p.scale;
   a.apply_scale = p.apply_scale;
   const bool tma = variant == 0;
+  if (real != 0 && (!tma || swap || p.tw2 == nullptr)) return cudaErrorInvalidValue;
   if (is_double) {
     if (!tma) return cudaErrorInvalidValue;
-    if (p.n == 4096) return launch_cube_v<double, 16, 1>(a, swap, true, grid, stream);
-    if (p.n == 512) return launch_cube_v<double, 8, kCube512Tile / 2>(a, swap, true, grid, stream);
-    if (p.n == 1024) return launch_rows3<double, 16, 8, 8, 2>(a, swap, grid, stream);
-    if (p.n == 2048) return launch_rows3<double, 16, 16, 8, 1>(a, swap, grid, stream);
+    if (p.n == 4096) return launch_cube_v<double, 16, 1>(a, swap, true, real, grid, stream);
+    if (p.n == 512) return launch_cube_v<double, 8, kCube512Tile / 2>(a, swap, true, real, grid, stream);
+    if (p.n == 1024) return launch_rows3<double, 16, 8, 8, 2>(a, swap, real, grid, stream);
+    if (p.n == 2048) return launch_rows3<double, 16, 16, 8, 1>(a, swap, real, grid, stream);
     return cudaErrorInvalidValue;
   }
-  if (!is_double && p.n == 4096) return launch_cube_v<float, 16, 1>(a, swap, tma, grid, stream);
-  if (!is_double && p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, grid, stream);
-  if (!is_double && tma && p.n == 1024) return launch_rows3<float, 16, 8, 8, 4>(a, swap, grid, stream);
-  if (!is_double && tma && p.n == 2048) return launch_rows3<float, 16, 16, 8, 2>(a, swap, grid, stream);
-  if (!is_double && tma && p.n == 8192) {
+  if (p.n == 4096) return launch_cube_v<float, 16, 1>(a, swap, tma, real, grid, stream);
+  if (p.n == 512) return launch_cube_v<float, 8, kCube512Tile>(a, swap, tma, real, grid, stream);
+  if (tma && p.n == 1024) return launch_rows3<float, 16, 8, 8, 4>(a, swap, real, grid, stream);
+  if (tma && p.n == 2048) return launch_rows3<float, 16, 16, 8, 2>(a, swap, real, grid, stream);
+  if (tma && p.n == 8192) {
     static const bool wide = [] {  // A/B knob: the 512-thread form (one radix-16 butterfly per thread in pass 1)
       const char* e = std::getenv("PFFT_ROWS8192_WIDE");
       return e && std::atoi(e) != 0;
     }();
-    return wide ? launch_rows3<float, 16, 16, 32, 1>(a, swap, grid, stream)
-                : launch_rows3<float, 16, 16, 32, 1, 2>(a, swap, grid, stream);
+    return wide && real == 0 ? launch_rows3<float, 16, 16, 32, 1>(a, swap, 0, grid, stream)
+                             : launch_rows3<float, 16, 16, 32, 1, 2>(a, swap, real, grid, stream);
   }
   return cudaErrorInvalidValue;
 }

@@ -154,6 +154,12 @@ SUITES = {
     "RealTest": real(BOTH_DIR, STORAGES, [1, 3, 131], [1, 2, 4, 8, 9, 15, 16, 30, 64, 100, 256, 512, 1000, 1024, 4096,
                                                         8192]),
     "RealGlobalTest": real(BOTH_DIR, STORAGES, [1, 3], [16384, 65536, 3 * 16384, 1 << 20]),
+    # pre / post-processing fused into the TMA tile kernels (wg_cube.cu REAL = 1, 2; half lengths 512 .. 8192) in the
+    # steady state of their rings: more rows than the grid holds, odd and even row starts (rows of n / 2 + 1 complex
+    # elements are 8-byte aligned), last row even (the row that must not be over-read)
+    "RealFusedSteadyTest": (real(BOTH_DIR, ["interleaved"], [2501], [1024, 2048]) +
+                            real(BOTH_DIR, ["interleaved"], [1301], [4096, 8192]) +
+                            [c for c in real(BOTH_DIR, ["interleaved"], [700], [16384]) if c.scalar == "float"]),
     "RealLayoutsTest": real_layouts(BOTH_DIR, STORAGES, [1, 5],
                                     [(96, 3, 2, 300, 100, 7, 3), (96, 1, 2, 97, 100, 1, 3), (64, 1, 1, 66, 40, 2, 0),
                                      (81, 2, 3, 170, 130, 0, 5), (32768, 2, 1, 70000, 16385, 0, 0),

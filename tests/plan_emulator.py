@@ -152,6 +152,29 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
             dst[ob[live_out]] = v[live_out].astype(cdt)
             continue
         jv = np.arange(n, dtype=np.int64)
+        if ps.get("fuse_real"):
+            # REAL-domain pre / post-processing fused into the transform kernel (csrc/wg_cube.cu; formulas: real.cu);
+            # n = half the real length
+            h = n
+            w = np.exp(-2j * np.pi * np.arange(h + 1) / (2 * h))
+            s = ps["scale"] if ps["apply_scale"] else 1.0
+            if ps["fuse_real"] == 1:
+                z = np.fft.fft(np.asarray(src[ib[..., None] + jv * ps["is"]], dtype=dt), axis=-1)
+                kk = np.arange(h + 1)
+                a = z[..., np.where(kk == h, 0, kk)]
+                b = np.conj(z[..., np.where(kk == 0, 0, h - kk)])
+                dst[ob[..., None] + kk * ps["os"]] = (((a + b) / 2 + w * (a - b) / 2j) * s).astype(cdt)
+            else:
+                kk = np.arange(h)
+                a = np.asarray(src[ib[..., None] + kk * ps["is"]], dtype=dt)
+                b = np.asarray(src[ib[..., None] + (h - kk) * ps["is"]], dtype=dt)
+                a[..., 0] = a[..., 0].real
+                b[..., 0] = b[..., 0].real
+                b = np.conj(b)
+                zin = np.zeros(ib.shape + (h,), dtype=dt)
+                zin[..., np.where(kk == 0, 0, h - kk)] = (a + b) + 1j * np.conj(w[:h]) * (a - b)
+                dst[ob[..., None] + jv * ps["os"]] = np.fft.fft(zin, axis=-1) * s
+            continue
         vi = ps["valid_in"] or n
         vo = ps["valid_out"] or n
         x = np.zeros(ib.shape + (n,), dtype=dt)

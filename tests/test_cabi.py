@@ -211,8 +211,10 @@ def test_planner_kernel_choices():
     c3b.forward_strides = c3b.backward_strides = [100000]
     c3b.forward_distance = c3b.backward_distance = 1
     assert _kernels(c3b) == ["wg_colg"]
-    r = pf.descriptor([8192], "float", pf.domain.REAL)                       # real: half-length cube + post pass
+    r = pf.descriptor([8192], "float", pf.domain.REAL)                       # real: half-length cube, post / pre fused
     r.number_of_transforms = 1024
+    assert _kernels(r) == ["wg_cube"] and _kernels(r, pf.direction.BACKWARD) == ["wg_cube"]
+    r.complex_storage = pf.complex_storage.SPLIT_COMPLEX                     # split half spectrum: separate passes
     assert _kernels(r) == ["wg_cube", "r2c_post"]
     assert _kernels(r, pf.direction.BACKWARD) == ["c2r_pre", "wg_cube"]
     r = pf.descriptor([8192], "float", pf.domain.REAL)                       # strided real rows: pack pass first
