@@ -1027,10 +1027,25 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     return e && std::atoi(e) != 0;
   }();
   auto fusable = [&](const PassHost& ps, const std::vector<BDim>& dims) {
-    return !fuse_off && !d.no_real_fuse && even && pairs && single && il_user && ps.kernel == KERNEL_WG_CUBE &&
-           ps.variant == 0 && dims.size() == 1;
+    if (fuse_off || d.no_real_fuse || !even || !pairs || !single || !il_user || dims.size() != 1) return false;
+    if (ps.kernel == KERNEL_WG_CUBE) return ps.variant == 0;
+    // half lengths whose complex transform runs elsewhere but whose REAL forms the tile kernel takes (256): the pass
+    // must be what select_specialised would accept
+    const PassParams& p = ps.pp;
+    bool one_dim = true;
+    for (int i = 1; i < kMaxBatchDims; ++i) one_dim = one_dim && p.nb[i] == 1;
+    return cube_real_supported(p.n, dbl, nullptr, nullptr) && p.is == 1 && p.os == 1 && one_dim && p.gtw_dim < 0 &&
+           p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 &&
+           (dbl || (p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0));
   };
   auto set_fused = [&](PassHost& ps, int mode, const std::vector<BDim>& dims) {
+    if (ps.kernel != KERNEL_WG_CUBE) {
+      int tile = 1, per_sm = 1;
+      cube_real_supported(ps.pp.n, dbl, &tile, &per_sm);
+      ps.kernel = KERNEL_WG_CUBE;
+      ps.variant = 0;
+      ps.alt_grid = (int)std::min<long long>((ps.pp.batch_total + tile - 1) / tile, (long long)per_sm * lim.num_sms);
+    }
     set_batch_dims(ps.pp, dims);
     ps.fuse_real = mode;
     ps.tw2_n = N;

@@ -108,6 +108,8 @@ int col_tile_columns(int n, bool is_double);
 // N = R^3 kernel (wg_cube.cu): packed interleaved fp32 4096 (one transform per tile) and 512 (kCube512Tile per tile)
 constexpr int kCube512Tile = 4;
 bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm);
+// ... and the half lengths of REAL-domain transforms it takes (cube_supported's plus 256)
+bool cube_real_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm);
 // generic in-place column-tile kernel (wg_colg.cu)
 size_t colg_smem_bytes(int n, int columns, bool is_double);
 // three-radix kernel (wg_r3.cu)

@@ -623,6 +623,15 @@ bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_p
   return true;
 }
 
+// Half lengths that only the REAL-domain forms run here (their complex transforms belong to the tile kernel of
+// wg_col.cu): 256 = 16 * 4 * 4, eight (fp32) / four (fp64) transforms per 16 KiB tile.
+bool cube_real_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm) {
+  if (n != 256) return cube_supported(n, is_double, transforms_per_tile, ctas_per_sm);
+  if (transforms_per_tile) *transforms_per_tile = is_double ? 4 : 8;
+  if (ctas_per_sm) *ctas_per_sm = 4;
+  return true;
+}
+
 // p: a single-pass plan entry with n == R^3, interleaved storage, unit strides, one batch dimension.
 // real: 0 complex transform; 1 / 2: the REAL-domain forms (p.tw2 = w_{2n}^k; never with swap, TMA variant only)
 cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int variant, int grid, cudaStream_t stream,
@@ -641,6 +650,9 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   a.apply_scale = p.apply_scale;
   const bool tma = variant == 0;
   if (real != 0 && (!tma || swap || p.tw2 == nullptr)) return cudaErrorInvalidValue;
+  if (real != 0 && p.n == 256)
+    return is_double ? launch_rows3<double, 16, 4, 4, 4>(a, false, real, grid, stream)
+                     : launch_rows3<float, 16, 4, 4, 8>(a, false, real, grid, stream);
   if (is_double) {
     if (!tma) return cudaErrorInvalidValue;
     if (p.n == 4096) return launch_cube_v<double, 16, 1>(a, swap, true, real, grid, stream);
