@@ -7,7 +7,7 @@ O=gpurun_out/evidence
 mkdir -p $O
 python bench.py > $O/bench_default_C2.json 2> $O/bench_default_C2.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_C2.json 2>> $O/bench_default_C2.err
-for c in C1 C3 C3B C4 C5 L1D S16 M256 M512 M1024 M2048 M8192; do
+for c in C1 C3 C3B C4 C5 L1D S16 M256 M512 M1024 M2048 M8192 D512 D1024 D2048 D4096; do
   python bench.py --config $c --steps 20 --warmup 4 > $O/bench_$c.json 2> $O/bench_$c.err
 done
 python bench.py --config C1 --graph --steps 200 --warmup 4 --no-cpu-baseline --no-e2e > $O/bench_C1_graph.json 2>> $O/bench_C1.err
@@ -30,6 +30,8 @@ cap m256_wg_col wg_col 3 2 --config M256
 cap c5_all "wg_c" 9 3 --config C5
 cap c4_wg_col wg_col 9 3 --config C4
 cap c3_wg_r3 wg_r3 3 2 --config C3
-cap c3b_wg_colg colg 3 2 --config C3B
+cap c3b_wg_colr3 colr3 3 2 --config C3B
+cap m8192_wg_rows3 wg_rows3 3 2 --config M8192
+cap d4096_wg_cube wg_cube 3 2 --config D4096
 cap s16_wi_tma wi_tma 3 2 --config S16
 ls -la $O

@@ -12,7 +12,15 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "tests"), os.path.join(ROOT, "oracle")):
     sys.path.insert(0, p)
 
-from fft_check import BI, P, CaseParams, run_case  # noqa: E402
+from fft_check import BI, P, U, CaseParams, run_case  # noqa: E402
+
+
+def _real(n, batch, direction, scalar="float"):
+    """REAL domain, packed rows (the layout of the reference's real benchmark set)."""
+    return CaseParams([n], batch, "OOP", U, U, direction, "interleaved", scalar, forward_strides=[1], backward_strides=[1],
+                      forward_distance=n, backward_distance=n // 2 + 1, domain="real",
+                      backward_scale=(1.0 / n if direction == "bwd" else None))
+
 
 CASES = {
     # wg_cube<float,16,1> (C2's kernel): 2 CTAs x 148 SMs x 2 stages = 592 tiles in flight
@@ -38,6 +46,18 @@ CASES = {
     # wi_tma (thread-level, TMA tiles in and out, three stages): 128 lines per tile, 4 x 148 CTAs
     "wi_tma16": CaseParams([16], 400000, "OOP", P, P, "fwd", "interleaved", "float"),
     "wi_tma8_f64": CaseParams([8], 300000, "IP", P, P, "bwd", "interleaved", "double"),
+    # three-radix column tiles (wg_colr3.cu: tensor loads / stores, ring of three tile buffers; C3B's kernel):
+    # 3001 columns = 376 tiles of 8 on <= 148 CTAs, ragged last tile; the register form on an unaligned layout
+    "colr3_1000_split": CaseParams([1000], 3001, "OOP", BI, BI, "fwd", "split", "float"),
+    "colr3_1000_inter": CaseParams([1000], 3001, "IP", BI, BI, "bwd", "interleaved", "float"),
+    "colr3_1024_f64": CaseParams([1024], 1501, "OOP", BI, BI, "fwd", "split", "double"),
+    "colr3_regs": CaseParams([1000], 1203, "OOP", BI, BI, "fwd", "split", "float"),
+    # REAL domain fused into the tile kernels (wg_cube.cu REAL = 1 / 2): odd and even row starts, last row even
+    "r2c_8192": _real(8192, 1301, "fwd"),
+    "c2r_8192": _real(8192, 1301, "bwd"),
+    "r2c_512": _real(512, 10001, "fwd"),
+    "c2r_512": _real(512, 10001, "bwd"),
+    "c2r_2048_f64": _real(2048, 1301, "bwd", "double"),
     # fused two-pass kernel (opt-in; PFFT_FUSE=1 is set below for this case only)
     "fused65536": CaseParams([65536], 24, "OOP", P, P, "fwd", "interleaved", "float"),
 }
