@@ -26,6 +26,9 @@ cudaError_t launch_wi_f64(const PassParams& p, bool interleaved, bool swap, int 
 
 // WORKITEM level, TMA tiles in and out (wi_tma.cu): packed interleaved rows of exactly 128 bytes (fp32 N = 16, fp64 N = 8)
 cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaStream_t stream, bool* used);
+// ... with the REAL-domain pre / post-processing in registers (real: 1 real-to-complex, 2 complex-to-real): real rows of
+// exactly one line, dense half-spectrum rows
+cudaError_t launch_wi_tma_real(const PassParams& p, bool is_double, int real, cudaStream_t stream);
 
 // SUBGROUP level (sg.cuh, sg_f32.cu, sg_f64.cu): n = lanes * m, `lanes` (power of two <= 32) threads per transform,
 // m <= kSgMaxM points per lane, cross-lane stages through __shfl_xor_sync

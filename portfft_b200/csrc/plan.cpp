@@ -1029,6 +1029,13 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
   auto fusable = [&](const PassHost& ps, const std::vector<BDim>& dims) {
     if (fuse_off || d.no_real_fuse || !even || !pairs || !single || !il_user || dims.size() != 1) return false;
     if (ps.kernel == KERNEL_WG_CUBE) return ps.variant == 0;
+    if (ps.kernel == KERNEL_WI) {
+      // thread-level TMA kernel, one real row per 128-byte line (wi_tma.cu): half-spectrum rows that do not overlap,
+      // 16-byte aligned start (dense rows move by bulk copies)
+      const long long spec_dist = fwd ? dims[0].out : dims[0].in, spec_off = fwd ? coff : (D > 1 ? 0 : coff);
+      return ps.variant == 1 && wi_tma_real_supported(ps.pp.n, dbl) && (dims[0].n == 1 || spec_dist >= H + 1) &&
+             (spec_off * (dbl ? 16 : 8)) % 16 == 0;
+    }
     // half lengths whose complex transform runs elsewhere but whose REAL forms the tile kernel takes (256): the pass
     // must be what select_specialised would accept
     const PassParams& p = ps.pp;
@@ -1039,7 +1046,7 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
            (dbl || (p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0));
   };
   auto set_fused = [&](PassHost& ps, int mode, const std::vector<BDim>& dims) {
-    if (ps.kernel != KERNEL_WG_CUBE) {
+    if (ps.kernel != KERNEL_WG_CUBE && ps.kernel != KERNEL_WI) {
       int tile = 1, per_sm = 1;
       cube_real_supported(ps.pp.n, dbl, &tile, &per_sm);
       ps.kernel = KERNEL_WG_CUBE;
@@ -1048,7 +1055,7 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     }
     set_batch_dims(ps.pp, dims);
     ps.fuse_real = mode;
-    ps.tw2_n = N;
+    ps.tw2_n = ps.kernel == KERNEL_WG_CUBE ? N : 0;  // (the thread-level kernel's twiddles are compile-time constants)
   };
 
   if (fwd) {

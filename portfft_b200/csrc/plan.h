@@ -100,6 +100,7 @@ constexpr int kWiMaxNFloat = 32, kWiMaxNDouble = 16, kWiBlock = 128;
 constexpr int kSgMaxMFloat = 32, kSgMaxMDouble = 16, kSgBlock = 256;
 bool sg_supports_m(int m, bool is_double);
 bool wi_tma_supported(int n, bool is_double);  // wi_tma.cu
+bool wi_tma_real_supported(int n, bool is_double);  // wi_tma.cu: half lengths of the fused REAL forms
 // column-tile kernel (wg_col.cu): supported lengths, shared memory and block size
 bool col_supported(int n, bool is_double, int* n1, int* n2);
 size_t col_smem_bytes(int n, bool is_double, bool ring);

@@ -511,6 +511,10 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
         break;
       case KERNEL_WI: {
         bool used = false;
+        if (ps.fuse_real != 0) {
+          e = launch_wi_tma_real(p, d.is_double, ps.fuse_real, stream);
+          break;
+        }
         if (ps.variant == 1) e = launch_wi_tma(p, d.is_double, swap, stream, &used);
         if (e == cudaSuccess && !used)
           e = d.is_double ? launch_wi_f64(p, pil, swap, ps.grid, stream) : launch_wi_f32(p, pil, swap, ps.grid, stream);

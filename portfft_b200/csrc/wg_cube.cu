@@ -22,6 +22,7 @@
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "launch_utils.h"
+#include "real_fuse.cuh"
 
 namespace pfft {
 
@@ -77,34 +78,6 @@ struct CubeArgs {
 //        below the row: `shift` = 0 or 1 elements), and pass 1 builds its inputs z'_j from X_{N-j} and X_j.
 // The twiddle w_{2N}^k of element k = j + (N / R) r is (one per-thread register) x (the compile-time constant w_{2R}^r).
 // ---------------------------------------------------------------------------------------------------------------
-template <int I, int N, typename F>
-__device__ __forceinline__ void static_for(F&& f) {
-  if constexpr (I < N) {
-    f(std::integral_constant<int, I>{});
-    static_for<I + 1, N>(f);
-  }
-}
-
-// X_k = E_k + w^k O_k from a = Z_k, b = Z_{N-k}, w = w_{2N}^k
-template <typename T>
-__device__ __forceinline__ cx<T> r2c_combine(cx<T> a, cx<T> b, cx<T> w) {
-  b.y = -b.y;
-  const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
-  const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
-  return ev + cmul(w, od);
-}
-
-// z'_j (the input of the plain forward transform that yields the unnormalised inverse) from a = X_{N-j}, b = X_j,
-// w = w_{2N}^j:  (a + conj b) - i w (a - conj b); j = 0: a = Re X_0, b = Re X_N, (a + b) + i (a - b)
-template <typename T>
-__device__ __forceinline__ cx<T> c2r_combine(cx<T> a, cx<T> b, cx<T> w, bool first) {
-  if (first) return cx<T>{a.x + b.x, a.x - b.x};
-  b.y = -b.y;
-  const cx<T> s = a + b, d = a - b;
-  const cx<T> t = cmul(w, d);
-  return cx<T>{s.x + t.y, s.y - t.x};  // s - i t
-}
-
 // position of element e of the exchange-2 layout inside a stage buffer (a permutation within aligned 16-groups, so
 // that the pass-3 reads of 16 consecutive elements stay conflict free)
 template <int R>

@@ -20,6 +20,7 @@
 #include "device_utils.cuh"
 #include "kernels.h"
 #include "launch_utils.h"
+#include "real_fuse.cuh"
 
 namespace pfft {
 
@@ -153,6 +154,174 @@ __global__ void __launch_bounds__(wt::kRows) wi_tma_kernel(const __grid_constant
   if (t == 0) wt::bulk_wait_read<0>();  // shared memory must outlive the last store's reads
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// REAL domain fused into the thread-level kernel: real rows of 2 N scalars = exactly one 128-byte line (fp32 real
+// length 32 -- the reference's real `small_1d` benchmark, reference_dft_set.hpp -- and fp64 real length 16), dense half
+// spectrum rows of N + 1 elements.  MODE 1 (real-to-complex): the line arrives by the swizzled tensor load as above,
+// the thread transforms its N pairs and combines Z_k with Z_{N-k} in registers (all indices and twiddles compile
+// time), writes the N + 1 outputs to a [row][N + 1] staging buffer (136-byte pitch: conflict free for 64-bit stores)
+// and the whole tile -- contiguous in global memory when the half-spectrum rows are dense -- leaves by ONE
+// cp.async.bulk (rows further apart: the threads copy the tile out, lanes along the row elements).  MODE 2 (complex-to-real): the
+// mirror image: bulk load of the tile's half spectra, pre-processing and transform in registers, tensor store of the
+// lines.  (An odd number of fp32 rows in the last tile is not a multiple of 16 bytes: its last row moves by ordinary
+// loads / stores.)
+// ---------------------------------------------------------------------------------------------------------------
+namespace wt {
+__device__ __forceinline__ void bulk_s2g(void* dst, const void* src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(smem_u32(src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+template <typename T, int N>
+struct RealCfg {
+  static constexpr int kSpecRow = (N + 1) * 2 * (int)sizeof(T);              // bytes of one half-spectrum row
+  static constexpr int kSpecBytes = (kRows * kSpecRow + 127) / 128 * 128;    // staging buffer of one tile
+  static constexpr size_t kSmem = 2 * (size_t)kStageBytes + 2 * (size_t)kSpecBytes + 1024 + 64;
+};
+}  // namespace wt
+
+template <typename T, int N, int MODE>
+__global__ void __launch_bounds__(wt::kRows) wi_tma_real_kernel(const __grid_constant__ CUtensorMap line_map,
+                                                                cx<T>* spec, const long long spec_dist,
+                                                                const long long batch, const int apply_scale, const T scale) {
+  using Cfg = wt::RealCfg<T, N>;
+  // dense half-spectrum rows (distance N + 1): a tile is contiguous in global memory and moves by one bulk copy;
+  // otherwise the threads move it between global memory and the staging buffer, lanes along the row elements
+  const bool dense = spec_dist == N + 1;
+  static_assert(N * 2 * sizeof(T) == 128, "one transform per 128-byte line");
+  extern __shared__ unsigned char smem_dyn[];
+  unsigned char* base = smem_dyn + ((1024 - (wt::smem_u32(smem_dyn) & 1023)) & 1023);  // line stages (swizzle period)
+  unsigned char* sbase = base + 2 * wt::kStageBytes;                                     // half-spectrum staging
+  uint64_t* full = reinterpret_cast<uint64_t*>(sbase + 2 * Cfg::kSpecBytes);
+  const int t = threadIdx.x;
+  const long long tiles = (batch + wt::kRows - 1) / wt::kRows;
+  // rows of a tile and how many of them move by the bulk copy (a whole number of 16-byte units)
+  auto tile_rows = [&](long long tile) { return (int)min((long long)wt::kRows, batch - tile * wt::kRows); };
+  auto bulk_rows = [&](int rows) { return !dense || (rows * Cfg::kSpecRow) % 16 == 0 ? rows : rows - 1; };
+  auto issue = [&](long long tile, int s) {
+    if (MODE == 1) {
+      wt::mbar_expect_tx(&full[s], wt::kStageBytes);
+      wt::tma_load_2d(base + s * wt::kStageBytes, &line_map, 0, (int)(tile * wt::kRows), &full[s]);
+    } else if (dense) {
+      const uint32_t bytes = (uint32_t)(bulk_rows(tile_rows(tile)) * Cfg::kSpecRow);
+      wt::mbar_expect_tx(&full[s], bytes);
+      if (bytes) wt::bulk_g2s(sbase + s * Cfg::kSpecBytes, spec + tile * wt::kRows * (N + 1), bytes, &full[s]);
+    }
+  };
+
+  if (t == 0) {
+    wt::mbar_init(&full[0], 1);
+    wt::mbar_init(&full[1], 1);
+    wt::fence_mbar_init();
+    wt::fence_proxy_async();
+  }
+  __syncthreads();
+  if (t == 0) {
+    long long tile = blockIdx.x;
+    for (int s = 0; s < 2; ++s, tile += gridDim.x)
+      if (tile < tiles) issue(tile, s);
+  }
+  int it = 0;
+  for (long long tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    const int s = it & 1;
+    const int rows = tile_rows(tile), brows = bulk_rows(rows);
+    unsigned char* line = base + s * wt::kStageBytes + t * 128;
+    cx<T>* stile = reinterpret_cast<cx<T>*>(sbase + s * Cfg::kSpecBytes);
+    cx<T>* srow = stile + t * (N + 1);
+    cx<T>* grow = spec + (tile * wt::kRows + t) * spec_dist;
+    if (MODE == 1 || dense) {
+      wt::mbar_wait(&full[s], (uint32_t)((it >> 1) & 1));
+    } else {
+      for (int idx = t; idx < rows * (N + 1); idx += wt::kRows) {
+        const int r = idx / (N + 1);
+        stile[idx] = spec[(tile * wt::kRows + r) * spec_dist + (idx - r * (N + 1))];
+      }
+      __syncthreads();
+    }
+    cx<T> v[N];
+    if (MODE == 1) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const T* src = reinterpret_cast<const T*>(line + ((c ^ (t & 7)) << 4));
+        if constexpr (sizeof(T) == 4) {
+          const float4 q = *reinterpret_cast<const float4*>(src);
+          v[2 * c] = cx<T>{q.x, q.y};
+          v[2 * c + 1] = cx<T>{q.z, q.w};
+        } else {
+          const double2 q = *reinterpret_cast<const double2*>(src);
+          v[c] = cx<T>{q.x, q.y};
+        }
+      }
+      DFT<N, T>::run(v);
+      cx<T> x[N + 1];
+      static_for<0, N>([&](auto kc) {
+        constexpr int k = decltype(kc)::value;
+        x[k] = r2c_combine(v[k], v[k == 0 ? 0 : N - k], const_w<k, 2 * N, T>());
+      });
+      x[N] = cx<T>{v[0].x - v[0].y, T(0)};
+      const bool direct = t >= brows && t < rows;  // the row the bulk copy cannot take
+#pragma unroll
+      for (int k = 0; k <= N; ++k) {
+        const cx<T> o = apply_scale ? cscale(x[k], scale) : x[k];
+        if (direct)
+          grow[k] = o;
+        else
+          srow[k] = o;
+      }
+    } else {
+      cx<T> x[N + 1];
+      const bool direct = t >= brows && t < rows;
+#pragma unroll
+      for (int k = 0; k <= N; ++k) x[k] = direct ? grow[k] : srow[k];
+      static_for<0, N>([&](auto jc) {
+        constexpr int j = decltype(jc)::value;
+        v[j] = c2r_combine(x[j == 0 ? 0 : N - j], x[j == 0 ? N : j], const_w<j, 2 * N, T>(), j == 0);
+      });
+      DFT<N, T>::run(v);
+      if (apply_scale) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) v[j] = cscale(v[j], scale);
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        T* dst = reinterpret_cast<T*>(line + ((c ^ (t & 7)) << 4));
+        if constexpr (sizeof(T) == 4)
+          *reinterpret_cast<float4*>(dst) = make_float4(v[2 * c].x, v[2 * c].y, v[2 * c + 1].x, v[2 * c + 1].y);
+        else
+          *reinterpret_cast<double2*>(dst) = make_double2(v[c].x, v[c].y);
+      }
+    }
+    wt::fence_proxy_async();  // what this thread wrote to shared memory must be visible to the bulk / tensor store
+    // the store issued one iteration ago has finished reading the OTHER output buffer (it had a whole iteration)
+    if (t == 0) wt::bulk_wait_read<0>();
+    __syncthreads();
+    if (MODE == 1 && !dense) {
+      for (int idx = t; idx < rows * (N + 1); idx += wt::kRows) {
+        const int r = idx / (N + 1);
+        spec[(tile * wt::kRows + r) * spec_dist + (idx - r * (N + 1))] = stile[idx];
+      }
+    }
+    if (t == 0) {
+      if (MODE == 1) {
+        if (dense && brows > 0)
+          wt::bulk_s2g(spec + tile * wt::kRows * (N + 1), sbase + s * Cfg::kSpecBytes, (uint32_t)(brows * Cfg::kSpecRow));
+      } else {
+        wt::tma_store_2d(&line_map, 0, (int)(tile * wt::kRows), base + s * wt::kStageBytes);
+      }
+      wt::bulk_commit();
+      // every thread has taken its inputs out of input buffer s: refill it with the tile two ahead
+      const long long nxt = tile + 2LL * gridDim.x;
+      if (nxt < tiles) issue(nxt, s);
+    }
+  }
+  if (t == 0) wt::bulk_wait_read<0>();  // shared memory must outlive the last store's reads
+}
+
 typedef CUresult (*EncodeTiledFnW)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -236,6 +405,53 @@ cudaError_t launch_wi_tma(const PassParams& p, bool is_double, bool swap, cudaSt
     }
   }
   return cudaErrorInvalidValue;
+}
+
+// REAL domain fused (see wi_tma_real_kernel).  real: 1 real-to-complex (p reads the real rows as pairs, writes rows of
+// n + 1 elements), 2 complex-to-real.  The planner guarantees one transform per line, dense half-spectrum rows and a
+// single batch dimension; the runtime diverts unaligned buffers to the unfused plan.
+bool wi_tma_real_supported(int n, bool is_double) { return is_double ? n == 8 : n == 16; }
+
+template <typename T, int N>
+static cudaError_t launch_wi_tma_real_n(const CUtensorMap& map, void* spec, long long spec_dist, int real,
+                                        const PassParams& p, int grid, cudaStream_t stream) {
+  using Cfg = wt::RealCfg<T, N>;
+  if (real == 1) {
+    cudaError_t e = ensure_dynamic_smem(wi_tma_real_kernel<T, N, 1>, Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    wi_tma_real_kernel<T, N, 1><<<grid, wt::kRows, Cfg::kSmem, stream>>>(map, reinterpret_cast<cx<T>*>(spec), spec_dist,
+                                                                         p.batch_total, p.apply_scale, (T)p.scale);
+  } else {
+    cudaError_t e = ensure_dynamic_smem(wi_tma_real_kernel<T, N, 2>, Cfg::kSmem);
+    if (e != cudaSuccess) return e;
+    wi_tma_real_kernel<T, N, 2><<<grid, wt::kRows, Cfg::kSmem, stream>>>(map, reinterpret_cast<cx<T>*>(spec), spec_dist,
+                                                                         p.batch_total, p.apply_scale, (T)p.scale);
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_wi_tma_real(const PassParams& p, bool is_double, int real, cudaStream_t stream) {
+  const size_t esz = is_double ? 16 : 8;
+  if (!wi_tma_real_supported(p.n, is_double) || (real != 1 && real != 2)) return cudaErrorInvalidValue;
+  // the line side: the real rows (pairs); the other side: dense rows of n + 1 elements
+  const char* lines = real == 1 ? reinterpret_cast<const char*>(p.in_re) + (size_t)p.ioff * esz
+                                : reinterpret_cast<const char*>(p.out_re) + (size_t)p.ooff * esz;
+  char* spec = real == 1 ? reinterpret_cast<char*>(p.out_re) + (size_t)p.ooff * esz
+                         : const_cast<char*>(reinterpret_cast<const char*>(p.in_re)) + (size_t)p.ioff * esz;
+  const long long line_pitch = (real == 1 ? p.ibd[0] : p.obd[0]) * (long long)esz;
+  long long spec_dist = real == 1 ? p.obd[0] : p.ibd[0];
+  if (p.batch_total == 1) spec_dist = p.n + 1;
+  if (spec_dist < p.n + 1) return cudaErrorInvalidValue;
+  // (dense rows move by bulk copies, which need the 16-byte alignment the runtime guarantees for fused passes)
+  CUtensorMap map;
+  memset(&map, 0, sizeof(map));
+  if (!make_row_map(lines, is_double, p.batch_total, line_pitch, &map)) return cudaErrorInvalidValue;
+  const int sms = sm_count();
+  if (sms <= 0) return cudaErrorLaunchOutOfResources;
+  const long long tiles = (p.batch_total + wt::kRows - 1) / wt::kRows;
+  const int grid = (int)(tiles < 3LL * sms ? tiles : 3LL * sms);
+  return is_double ? launch_wi_tma_real_n<double, 8>(map, spec, spec_dist, real, p, grid, stream)
+                   : launch_wi_tma_real_n<float, 16>(map, spec, spec_dist, real, p, grid, stream);
 }
 
 }  // namespace pfft

@@ -157,7 +157,11 @@ SUITES = {
     # pre / post-processing fused into the TMA tile kernels (wg_cube.cu REAL = 1, 2; half lengths 512 .. 8192) in the
     # steady state of their rings: more rows than the grid holds, odd and even row starts (rows of n / 2 + 1 complex
     # elements are 8-byte aligned), last row even (the row that must not be over-read)
-    "RealFusedSteadyTest": (real(BOTH_DIR, ["interleaved"], [10001], [512]) +
+    "RealFusedSteadyTest": (real(BOTH_DIR, ["interleaved"], [70001, 69888, 4097], [16, 32]) +  # thread-level kernel
+                            # ... with the descriptor's default half-spectrum distance (= n) and a padded one
+                            real_layouts(BOTH_DIR, ["interleaved"], [70001],
+                                         [(32, 1, 1, 32, 32, 0, 0), (16, 1, 1, 16, 16, 0, 0), (32, 1, 1, 32, 20, 0, 2)]) +
+                            real(BOTH_DIR, ["interleaved"], [10001], [512]) +
                             real(BOTH_DIR, ["interleaved"], [2501], [1024, 2048]) +
                             real(BOTH_DIR, ["interleaved"], [1301], [4096, 8192]) +
                             [c for c in real(BOTH_DIR, ["interleaved"], [700], [16384]) if c.scalar == "float"]),
