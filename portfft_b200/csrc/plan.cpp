@@ -1163,7 +1163,7 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
     if (fused) {
       // (nothing else: the pass reads xbuf and writes the real rows)
     } else {
-    passes.push_back(rows_pass(KERNEL_C2R_PRE, xbuf, BUF_SCRATCH, xs, xoff, xd, 1, 0, row_s, L));
+    passes.push_back(rows_pass(KERNEL_C2R_PRE, xbuf, BUF_SCRATCH, xs, xoff, xd, 1, 0, row_s, even ? H / 2 + 1 : (N + 1) / 2));
     if (pairs) {
       transform(s1, &rview);
     } else {

@@ -104,9 +104,12 @@ __global__ void __launch_bounds__(256) real_unpack_kernel(const PassParams p, co
 
 // Input: packed interleaved rows (variant 0: Z of length n/2; variant 1: the full-length transform Y).  Output: the
 // half spectrum X_k, k = 0..n/2, in the user's layout (element stride os, descriptor's storage).
+// Variant 0 works on PAIRS (k, H - k), k = 0..H/2: with t = w^k O_k,  X_k = E_k + t  and  X_{H-k} = conj(E_k - t)
+// (E_{H-k} = conj E_k, O_{H-k} = conj O_k, w^{H-k} = -conj w^k), so that every input element is read once and one
+// twiddle serves two outputs (the element-wise form read each Z twice and ran at half the HBM rate on long rows).
 template <typename T>
 __global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const int variant, const bool il) {
-  const int h = p.n / 2, count = h + 1;
+  const int h = p.n / 2, count = variant == 0 ? h / 2 + 1 : h + 1;
   const cx<T>* in = reinterpret_cast<const cx<T>*>(p.in_re);
   const IoFlags fl{il, false};
   const T scale = p.apply_scale ? T(p.scale) : T(1);
@@ -114,29 +117,30 @@ __global__ void __launch_bounds__(256) r2c_post_kernel(const PassParams p, const
     const int k = (int)ku;
     long long ib, ob;
     row_bases(p, g, ib, ob);
-    {
-      cx<T> o;
-      if (variant == 0) {
-        const cx<T> a = in[ib + (k == h ? 0 : k)];
-        cx<T> b = in[ib + (k == 0 ? 0 : h - k)];
-        b.y = -b.y;  // conj Z_{H-k}
-        const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
-        const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
-        o = ev + cmul(ldg_cx<T>(p.tw, k), od);
-      } else {
-        o = in[ib + k];
-      }
-      gstore<T>(p, fl, ob + (long long)k * p.os, cscale(o, scale));
+    if (variant == 0) {
+      const int m = h - k;  // partner (k = 0: Z_H = Z_0)
+      const cx<T> a = in[ib + k];
+      cx<T> b = in[ib + (k == 0 ? 0 : m)];
+      b.y = -b.y;  // conj Z_{H-k}
+      const cx<T> ev{(a.x + b.x) * T(0.5), (a.y + b.y) * T(0.5)};
+      const cx<T> od{(a.y - b.y) * T(0.5), -(a.x - b.x) * T(0.5)};  // (a - b) / (2i)
+      const cx<T> t = cmul(ldg_cx<T>(p.tw, k), od);
+      gstore<T>(p, fl, ob + (long long)k * p.os, cscale(ev + t, scale));
+      if (m != k) gstore<T>(p, fl, ob + (long long)m * p.os, cscale(cx<T>{ev.x - t.x, -(ev.y - t.y)}, scale));
+    } else {
+      gstore<T>(p, fl, ob + (long long)k * p.os, cscale(in[ib + k], scale));
     }
   }
 }
 
 // Input: the half spectrum in the user's layout (element stride is, descriptor's storage).  Output: packed
 // interleaved rows, index-reversed (see the header): variant 0 length n/2, variant 1 the Hermitian extension, length n.
+// Variant 0 works on pairs as above: with s = X_k + conj X_{H-k}, t = conj(w^k) (X_k - conj X_{H-k}):
+// Z'_k = s + i t,  Z'_{H-k} = conj(s) + i conj(t).
 template <typename T>
 __global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const int variant, const bool il) {
   const int n = p.n, h = n / 2;
-  const int count = variant == 0 ? h : (n + 1) / 2;
+  const int count = variant == 0 ? h / 2 + 1 : (n + 1) / 2;
   cx<T>* out = reinterpret_cast<cx<T>*>(p.out_re);
   const IoFlags fl{il, false};
   PFFT_FOR_ROW_ELEMS(p, count, g, ku) {
@@ -147,14 +151,16 @@ __global__ void __launch_bounds__(256) c2r_pre_kernel(const PassParams p, const 
       cx<T> a = gload<T>(p, fl, ib + (long long)k * p.is);
       if (k == 0) a.y = T(0);  // the imaginary parts of X_0 (and X_{N/2}) do not enter a real inverse (numpy.fft.irfft)
       if (variant == 0) {
-        cx<T> b = gload<T>(p, fl, ib + (long long)(h - k) * p.is);
+        const int m = h - k;
+        cx<T> b = gload<T>(p, fl, ib + (long long)m * p.is);
         if (k == 0) b.y = T(0);
         b.y = -b.y;  // conj X_{H-k}
         const cx<T> s = a + b, d = a - b;
         cx<T> w = ldg_cx<T>(p.tw, k);
         w.y = -w.y;  // conj(w^k)
         const cx<T> t = cmul(w, d);
-        out[ob + (k == 0 ? 0 : h - k)] = cx<T>{s.x - t.y, s.y + t.x};  // s + i t
+        out[ob + (k == 0 ? 0 : m)] = cx<T>{s.x - t.y, s.y + t.x};        // Z'_k = s + i t, stored at (H - k) mod H
+        if (k != 0 && m != k) out[ob + k] = cx<T>{s.x + t.y, t.x - s.y};  // Z'_{H-k} = conj(s) + i conj(t), stored at k
       } else {
         // reversed Hermitian extension: row[k] = conj X_k, row[n - k] = X_k
         out[ob + k] = cx<T>{a.x, -a.y};
