@@ -35,8 +35,14 @@ struct R3Cfg {
   static constexpr int RMAX = r3::cmax(R0, r3::cmax(R1, R2));
   static constexpr int TPF = N / RMAX;                      // threads per transform
   static constexpr bool ONE = (R0 == R1 && R1 == R2);       // one butterfly per thread and pass: register twiddles
-  static constexpr int PITCH = (N + N / R0 + 1) | 1;
+  // Second exchange buffer: pass 1 writes index R0 R1 a + k + R0 r' (k = lane % R0), i.e. groups of R0 lanes that are
+  // G = R0 R1 + R1 padded elements apart.  A half-warp of 16 lanes spans two or three groups unless R0 is a multiple
+  // of 16, and they collide in the banks unless G = R0 (mod 16): XPAD extra elements per R0 R1 make it so (radix 10:
+  // G = 110 = 14 (mod 16) put lanes 10..15 onto the banks of lanes 0..3; 12 more per group remove the overlap).
+  static constexpr int XPAD = R0 % 16 == 0 ? 0 : (((R0 - (R0 * R1 + R1)) % 16) + 16) % 16;
+  static constexpr int PITCH = (N + N / R0 + XPAD * R2 + 1) | 1;
   __host__ __device__ static constexpr int pad(int i) { return i + i / R0; }
+  __host__ __device__ static constexpr int pad1(int i) { return i + i / R0 + XPAD * (i / (R0 * R1)); }
 };
 
 template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
@@ -68,7 +74,7 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
   // + r * (compile-time stride) -- the padding i + i/R0 is affine in r because every stride is a multiple of R0 or
   // smaller than R0 -- and every global address is (per-transform pointer) + r * (one 64-bit step).
   constexpr int S1 = N / R1 + N / (R1 * R0);  // pad(j + r N/R1) = pad(j) + r S1
-  constexpr int S2 = N / R2 + N / (R2 * R0);  // pad(j + r N/R2) = pad(j) + r S2
+  constexpr int S2 = N / R2 + N / (R2 * R0) + Cfg::XPAD;  // pad1(j + r N/R2) = pad1(j) + r S2  (N / R2 = R0 R1)
   const long long in_step = (long long)(N / R0) * p.is, out_step = (long long)(R0 * R1) * p.os;
   auto load_elem = [&](long long idx) -> cx<T> {
     cx<T> v;
@@ -143,7 +149,7 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
 #pragma unroll
         for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], TWREG ? tw1[r] : ldg_cx<T>(p.tw, (long long)k * r * R2));
         DFT<R1, T>::run(v);
-        cx<T>* dst = b1 + Cfg::pad((j - k) * R1 + k);  // (j - k) R1 is a multiple of R0: pad(. + r R0) = pad(.) + r (R0 + 1)
+        cx<T>* dst = b1 + Cfg::pad1((j - k) * R1 + k);  // (j - k) R1 is a multiple of R0 R1: pad1(. + r R0) = pad1(.) + r (R0 + 1)
 #pragma unroll
         for (int r = 0; r < R1; ++r) dst[r * (R0 + 1)] = v[r];
       }
@@ -158,7 +164,7 @@ __global__ void __launch_bounds__(512) wg_r3_kernel(const PassParams p) {
       for (int j = t; j < N / R2; j += TPF) {
         const int k = j % (R0 * R1);
         cx<T> v[R2];
-        const cx<T>* src = b1 + Cfg::pad(j);
+        const cx<T>* src = b1 + Cfg::pad1(j);
 #pragma unroll
         for (int r = 0; r < R2; ++r) v[r] = src[r * S2];
 #pragma unroll
