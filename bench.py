@@ -73,6 +73,16 @@ CONFIGS = {
                   desc="1D C2C fp64 N=4096 batch=16Ki out-of-place (packed rows, N = 16^3)"),
     "M256": dict(lengths=[256], batch=512 * 1024, scalar="float", inplace=False, split=False,
                  desc="1D C2C fp32 N=256 batch=512Ki out-of-place (reference bench_float medium_small_1d)"),
+    # REAL domain: the reference's registered real benchmark set (test/bench/utils/reference_dft_set.hpp), dense half
+    # spectrum (backward_distance = N/2 + 1).  forward = real-to-complex, backward = complex-to-real.
+    "R32": dict(lengths=[32], batch=8 * 1024 * 1024, scalar="float", inplace=False, split=False, real=True,
+                desc="1D R2C/C2R fp32 N=32 batch=8Mi out-of-place, dense half spectrum (reference real small_1d)"),
+    "R512": dict(lengths=[512], batch=512 * 1024, scalar="float", inplace=False, split=False, real=True,
+                 desc="1D R2C/C2R fp32 N=512 batch=512Ki out-of-place, dense half spectrum (reference real medium_small_1d)"),
+    "R8192": dict(lengths=[8192], batch=32 * 1024, scalar="float", inplace=False, split=False, real=True,
+                  desc="1D R2C/C2R fp32 N=8192 batch=32Ki out-of-place, dense half spectrum (reference real medium_large_1d)"),
+    "R131072": dict(lengths=[131072], batch=2048, scalar="float", inplace=False, split=False, real=True,
+                    desc="1D R2C/C2R fp32 N=131072 batch=2Ki out-of-place, dense half spectrum (reference real large_1d)"),
 }
 
 
@@ -80,14 +90,18 @@ def flops_of(cfg) -> float:
     n = 1
     for l in cfg["lengths"]:
         n *= l
-    return 5.0 * n * math.log2(n) * cfg["batch"]
+    # (REAL: half the complex count, the convention of the reference's ops estimate for real transforms)
+    return (2.5 if cfg.get("real") else 5.0) * n * math.log2(n) * cfg["batch"]
 
 
 def bytes_of(cfg) -> float:
     n = 1
     for l in cfg["lengths"]:
         n *= l
-    return 2.0 * n * cfg["batch"] * (16 if cfg["scalar"] == "double" else 8)
+    sc = 8 if cfg["scalar"] == "double" else 4
+    if cfg.get("real"):  # one read of the real row + one write of the n/2 + 1 complex outputs (or the reverse)
+        return (n * sc + (n // 2 + 1) * 2 * sc) * cfg["batch"]
+    return 2.0 * n * cfg["batch"] * 2 * sc
 
 
 def measured_peak():
@@ -354,14 +368,19 @@ def scipy_cpu_time(cfg, sample_batch: int):
     dbl = cfg["scalar"] == "double"
     rng = np.random.Generator(np.random.SFC64(1))
     shape = [sample_batch] + list(cfg["lengths"])
-    x = (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex128 if dbl else np.complex64)
+    if cfg.get("real"):
+        x = rng.uniform(-1, 1, shape).astype(np.float64 if dbl else np.float32)
+        fn = sfft.rfftn
+    else:
+        x = (rng.uniform(-1, 1, shape) + 1j * rng.uniform(-1, 1, shape)).astype(np.complex128 if dbl else np.complex64)
+        fn = sfft.fftn
     cores = len(os.sched_getaffinity(0))
     axes = tuple(range(1, len(shape)))
-    sfft.fftn(x[:max(1, min(sample_batch, cores))], axes=axes, workers=cores)  # plan cache warm-up
+    fn(x[:max(1, min(sample_batch, cores))], axes=axes, workers=cores)  # plan cache warm-up
     best = float("inf")
     for _ in range(2):
         t0 = time.perf_counter()
-        sfft.fftn(x, axes=axes, workers=cores)
+        fn(x, axes=axes, workers=cores)
         best = min(best, time.perf_counter() - t0)
     return best, cores
 
@@ -411,8 +430,11 @@ def run_batched(args, cfg, name, batch, rank, local_rank, world, dev, steps, war
     n_flat = 1
     for l in cfg["lengths"]:
         n_flat *= l
-    d = pf.descriptor(cfg["lengths"], cfg["scalar"])
+    real = bool(cfg.get("real"))
+    d = pf.descriptor(cfg["lengths"], cfg["scalar"], pf.domain.REAL if real else pf.domain.COMPLEX)
     d.number_of_transforms = batch
+    if real:
+        d.backward_distance = n_flat // 2 + 1
     d.placement = pf.placement.IN_PLACE if cfg["inplace"] else pf.placement.OUT_OF_PLACE
     d.complex_storage = pf.complex_storage.SPLIT_COMPLEX if cfg["split"] else pf.complex_storage.INTERLEAVED_COMPLEX
     for k in ("forward_strides", "forward_distance", "forward_offset", "backward_strides", "backward_distance",
@@ -437,7 +459,7 @@ def run_batched(args, cfg, name, batch, rank, local_rank, world, dev, steps, war
             return [torch.rand(count, dtype=fdt, device=dev, generator=g) * 2 - 1 for _ in range(2)]
         return [torch.view_as_complex((torch.rand(count, 2, dtype=fdt, device=dev, generator=g) * 2 - 1))]
 
-    fwd_buf = alloc(n_fwd)
+    fwd_buf = [torch.rand(n_fwd, dtype=fdt, device=dev, generator=g) * 2 - 1] if real else alloc(n_fwd)
     bwd_buf = fwd_buf if cfg["inplace"] else alloc(n_bwd)
     orig = [t.clone() for t in fwd_buf] if n_fwd * (16 if fdt == torch.float64 else 8) <= (8 << 30) else None
 
@@ -513,7 +535,7 @@ def run_batched(args, cfg, name, batch, rank, local_rank, world, dev, steps, war
     # ---- e2e through the C ABI with pinned host buffers ----------------------------------------------------------
     if with_e2e:
         esz = (2 if not cfg["split"] else 1)
-        h_in = [torch.empty(n_fwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
+        h_in = [torch.empty(n_fwd * (1 if real else esz), dtype=fdt).pin_memory() for _ in range(planes)]
         h_out = h_in if cfg["inplace"] else [torch.empty(n_bwd * esz, dtype=fdt).pin_memory() for _ in range(planes)]
         for t in h_in:
             t.uniform_(-1, 1)
@@ -542,7 +564,7 @@ def run_batched(args, cfg, name, batch, rank, local_rank, world, dev, steps, war
         del fwd_buf, bwd_buf
         torch.cuda.empty_cache()
         tc = copy_ceiling(torch, dist, dev, world, h_in, h_out)
-        res["e2e"] = {"seconds": te, "h2d_bytes_per_step": n_fwd * bpe, "d2h_bytes_per_step": n_bwd * bpe,
+        res["e2e"] = {"seconds": te, "h2d_bytes_per_step": n_fwd * (bpe // 2 if real else bpe), "d2h_bytes_per_step": n_bwd * bpe,
                       "steps": e_steps, "copy_only_seconds": tc}
         del h_in, h_out
     plan.destroy()
@@ -739,7 +761,16 @@ def main():
 
     # ---- CPU baselines (rank 0, N=1 only) ---------------------------------------------------------------------
     cpu = cpu2 = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and cfg.get("real"):
+        # (the C port restates the reference's complex algorithm: the reference has no real transform to port)
+        sample = cpu_sample_batch(cfg)
+        sc = scipy_cpu_time(cfg, sample)
+        if sc is not None:
+            per = flops_of(cfg) / cfg["batch"]
+            cpu = {"value": per * sample / sc[0] / 1e9, "unit": "GFLOP/s", "cores": sc[1], "kind": "pocketfft",
+                   "sample": f"{sample} of {cfg['batch']} transforms, scipy.fft.rfft(workers={sc[1]}), {sc[0]:.2f} s; the "
+                             f"reference implements no REAL transform, so there is no port of it"}
+    elif rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample = cpu_sample_batch(cfg)
         t, cores = cpu_port_time(cfg, sample)
         per = flops_of(cfg) / cfg["batch"]

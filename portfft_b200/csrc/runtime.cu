@@ -663,9 +663,18 @@ static HostDomain host_domain(const DescHost& d, int dir) {
   h.dist = d.distance(dir);
   h.off = d.offset(dir);
   h.extent = 1;
-  for (size_t i = 0; i < d.lengths.size(); ++i) h.extent += (d.lengths[i] - 1) * d.strides(dir)[i];
+  const std::vector<size_t> len = d.domain_lengths(dir);  // (REAL: n / 2 + 1 along the last dimension of the backward domain)
+  for (size_t i = 0; i < len.size(); ++i) h.extent += (len[i] - 1) * d.strides(dir)[i];
   h.count = d.buffer_count(dir);
   return h;
+}
+
+// every element of the buffer on side `dir` is addressed by the descriptor (nothing to preserve around the results)
+static bool dense_domain(const DescHost& d, int dir) {
+  const std::vector<size_t> len = d.domain_lengths(dir);
+  size_t total = 1;
+  for (size_t l : len) total *= l;
+  return d.offset(dir) == 0 && d.strides(dir) == default_strides(len) && d.distance(dir) == total;
 }
 
 static void compute_host_monolithic(pfft_plan* plan, int direction, const void* in, const void* in_imag, void* out,
@@ -681,7 +690,7 @@ static void compute_host_monolithic(pfft_plan* plan, int direction, const void* 
   PFFT_CUDA_CHECK(cudaMemcpyAsync(din, in, plane_in, cudaMemcpyHostToDevice, s));
   if (in2) PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in, in_imag, plane_in, cudaMemcpyHostToDevice, s));
   // elements of the output buffer that the descriptor does not address must survive the round trip
-  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0 && !d.is_real();
+  const bool out_dense = dense_domain(d, odir);
   if (!inplace && !out_dense) {
     PFFT_CUDA_CHECK(cudaMemcpyAsync(dout, out, plane_out, cudaMemcpyHostToDevice, s));
     if (out2) PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out, out_imag, plane_out, cudaMemcpyHostToDevice, s));
@@ -699,9 +708,14 @@ static void compute_host_pipelined(pfft_plan* plan, int direction, const void* i
   const bool il = d.complex_storage == PFFT_INTERLEAVED_COMPLEX;
   const int odir = direction == PFFT_FORWARD ? PFFT_BACKWARD : PFFT_FORWARD;
   const bool inplace = in == out;
-  const size_t esz = (d.is_double ? 8 : 4) * (il ? 2 : 1);  // bytes of one addressed unit of a plane
+  // bytes of one addressed unit of a plane, per side (REAL descriptors: the forward domain counts real scalars in ONE
+  // plane whatever the complex storage)
+  const size_t sc = d.is_double ? 8 : 4;
+  const bool in_real = d.is_real() && direction == PFFT_FORWARD, out_real = d.is_real() && direction == PFFT_BACKWARD;
+  const size_t esz_in = in_real ? sc : sc * (il ? 2 : 1), esz_out = out_real ? sc : sc * (il ? 2 : 1);
+  const bool in2 = !il && !in_real, out2 = !il && !out_real;  // a second (imaginary) plane on that side
   const HostDomain hi = host_domain(d, direction), ho = host_domain(d, odir);
-  const bool out_dense = get_layout(d, odir) == PFFT_LAYOUT_PACKED && d.offset(odir) == 0;
+  const bool out_dense = dense_domain(d, odir);
   const size_t batch = d.number_of_transforms;
   const size_t per = (batch + chunks - 1) / chunks;
   chunks = (batch + per - 1) / per;
@@ -724,24 +738,24 @@ static void compute_host_pipelined(pfft_plan* plan, int direction, const void* i
       sub = make_plan(dc, plan->device, s);
     }
     // byte ranges of this chunk in the input and output planes
-    const size_t i0 = c == 0 ? 0 : (hi.off + b0 * hi.dist) * esz, i1 = b1 == batch ? plane_in : (hi.off + b1 * hi.dist) * esz;
-    const size_t o0 = c == 0 ? 0 : (ho.off + b0 * ho.dist) * esz, o1 = b1 == batch ? plane_out : (ho.off + b1 * ho.dist) * esz;
+    const size_t i0 = c == 0 ? 0 : (hi.off + b0 * hi.dist) * esz_in, i1 = b1 == batch ? plane_in : (hi.off + b1 * hi.dist) * esz_in;
+    const size_t o0 = c == 0 ? 0 : (ho.off + b0 * ho.dist) * esz_out, o1 = b1 == batch ? plane_out : (ho.off + b1 * ho.dist) * esz_out;
     PFFT_CUDA_CHECK(cudaMemcpyAsync(din + i0, (const char*)in + i0, i1 - i0, cudaMemcpyHostToDevice, s_up));
-    if (!il)
+    if (in2)
       PFFT_CUDA_CHECK(cudaMemcpyAsync(din + plane_in + i0, (const char*)in_imag + i0, i1 - i0, cudaMemcpyHostToDevice, s_up));
     if (!inplace && !out_dense) {
       PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + o0, (const char*)out + o0, o1 - o0, cudaMemcpyHostToDevice, s_up));
-      if (!il)
+      if (out2)
         PFFT_CUDA_CHECK(cudaMemcpyAsync(dout + plane_out + o0, (const char*)out_imag + o0, o1 - o0, cudaMemcpyHostToDevice, s_up));
     }
     PFFT_CUDA_CHECK(cudaEventRecord(plan->chunk_up[c], s_up));
     PFFT_CUDA_CHECK(cudaStreamWaitEvent(s, plan->chunk_up[c], 0));
-    const size_t pi = b0 * hi.dist * esz, po = b0 * ho.dist * esz;  // the sub-plan keeps the descriptor's offsets
-    execute(sub, direction, din + pi, il ? nullptr : din + plane_in + pi, dout + po, il ? nullptr : dout + plane_out + po, s);
+    const size_t pi = b0 * hi.dist * esz_in, po = b0 * ho.dist * esz_out;  // the sub-plan keeps the descriptor's offsets
+    execute(sub, direction, din + pi, in2 ? din + plane_in + pi : nullptr, dout + po, out2 ? dout + plane_out + po : nullptr, s);
     PFFT_CUDA_CHECK(cudaEventRecord(plan->chunk_done[c], s));
     PFFT_CUDA_CHECK(cudaStreamWaitEvent(s_dn, plan->chunk_done[c], 0));
     PFFT_CUDA_CHECK(cudaMemcpyAsync((char*)out + o0, dout + o0, o1 - o0, cudaMemcpyDeviceToHost, s_dn));
-    if (!il)
+    if (out2)
       PFFT_CUDA_CHECK(cudaMemcpyAsync((char*)out_imag + o0, dout + plane_out + o0, o1 - o0, cudaMemcpyDeviceToHost, s_dn));
   }
   PFFT_CUDA_CHECK(cudaStreamSynchronize(s_dn));
@@ -940,7 +954,7 @@ pfft_status pfft_compute_host(pfft_plan* plan, int direction, const void* in, co
     const HostDomain hi = host_domain(d, direction), ho = host_domain(d, odir);
     const size_t batch = d.number_of_transforms;
     size_t chunks = 1;
-    if (batch >= 2 && hi.extent <= hi.dist && ho.extent <= ho.dist && !real) {
+    if (batch >= 2 && hi.extent <= hi.dist && ho.extent <= ho.dist) {
       const char* env = std::getenv("PFFT_HOST_CHUNK_BYTES");
       const size_t target = env ? (size_t)std::atoll(env) : ((size_t)32 << 20);
       chunks = std::min<size_t>(std::min<size_t>(batch, 64), std::max<size_t>(1, (plane_in * planes_in) / std::max<size_t>(1, target)));

@@ -31,6 +31,16 @@ CASES = [
     CaseParams([4096], 21, "OOP", P, P, "bwd", "split", "float", domain="real", backward_scale=1.0 / 4096),
     CaseParams([30], 77, "OOP", P, P, "fwd", "split", "double", domain="real"),
     CaseParams([6, 16], 5, "OOP", P, P, "bwd", "interleaved", "double", domain="real"),
+    # REAL through the chunk pipeline: dense half spectrum (rows of n / 2 + 1: the fused kernels, 8-byte aligned chunk
+    # starts), split half spectrum (one real plane in, two planes out)
+    CaseParams([8192], 301, "OOP", U, U, "fwd", "interleaved", "float", forward_strides=[1], backward_strides=[1],
+               forward_distance=8192, backward_distance=4097, domain="real"),
+    CaseParams([8192], 301, "OOP", U, U, "bwd", "interleaved", "float", forward_strides=[1], backward_strides=[1],
+               forward_distance=8192, backward_distance=4097, domain="real", backward_scale=1.0 / 8192),
+    CaseParams([512], 1001, "OOP", U, U, "fwd", "split", "float", forward_strides=[1], backward_strides=[1],
+               forward_distance=512, backward_distance=257, domain="real"),
+    CaseParams([512], 1001, "OOP", U, U, "bwd", "split", "double", forward_strides=[1], backward_strides=[1],
+               forward_distance=512, backward_distance=257, domain="real", backward_scale=1.0 / 512),
 ]
 
 

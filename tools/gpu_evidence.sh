@@ -7,7 +7,7 @@ O=gpurun_out/evidence
 mkdir -p $O
 python bench.py > $O/bench_default_C2.json 2> $O/bench_default_C2.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_C2.json 2>> $O/bench_default_C2.err
-for c in C1 C3 C3B C4 C5 L1D S16 M256 M512 M1024 M2048 M8192 D512 D1024 D2048 D4096; do
+for c in C1 C3 C3B C4 C5 L1D S16 M256 M512 M1024 M2048 M8192 D512 D1024 D2048 D4096 R32 R512 R8192 R131072; do
   python bench.py --config $c --steps 20 --warmup 4 > $O/bench_$c.json 2> $O/bench_$c.err
 done
 python bench.py --config C1 --graph --steps 200 --warmup 4 --no-cpu-baseline --no-e2e > $O/bench_C1_graph.json 2>> $O/bench_C1.err
