@@ -1036,14 +1036,15 @@ void build_real_direction(PlanHost& plan, int dir, const DeviceLimits& lim) {
       return ps.variant == 1 && wi_tma_real_supported(ps.pp.n, dbl) && (dims[0].n == 1 || spec_dist >= H + 1) &&
              (spec_off * (dbl ? 16 : 8)) % 16 == 0;
     }
-    // half lengths whose complex transform runs elsewhere but whose REAL forms the tile kernel takes (256): the pass
-    // must be what select_specialised would accept
+    // The pass was planned for another kernel: a half length whose complex transform runs elsewhere (256), or rows
+    // that are only 8-byte aligned (in-place layouts: rows of n + 2 reals = n/2 + 1 pairs apart) -- the REAL forms
+    // of the tile kernel take both (their bulk copies start at the 16-byte boundary below the row, wg_cube.cu).
     const PassParams& p = ps.pp;
     bool one_dim = true;
     for (int i = 1; i < kMaxBatchDims; ++i) one_dim = one_dim && p.nb[i] == 1;
     return cube_real_supported(p.n, dbl, nullptr, nullptr) && p.is == 1 && p.os == 1 && one_dim && p.gtw_dim < 0 &&
-           p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 &&
-           (dbl || (p.ioff % 2 == 0 && p.ooff % 2 == 0 && p.ibd[0] % 2 == 0 && p.obd[0] % 2 == 0));
+           p.peer_dim < 0 && p.valid_in == 0 && p.valid_out == 0 && dims[0].in >= p.n + (fwd ? 0 : 1) &&
+           dims[0].out >= p.n + (fwd ? 1 : 0);
   };
   auto set_fused = [&](PassHost& ps, int mode, const std::vector<BDim>& dims) {
     if (ps.kernel != KERNEL_WG_CUBE && ps.kernel != KERNEL_WI) {

@@ -373,12 +373,12 @@ static void execute(pfft_plan* plan, int dir, const void* in, const void* in_ima
   if ((!in_cplx && in_imag != nullptr) || (!out_cplx && out_imag != nullptr))
     throw PlanError(PFFT_INVALID_CONFIGURATION, "the real side of a REAL-domain transform is a single scalar array");
   if (in == nullptr || out == nullptr) throw PlanError(PFFT_INVALID_CONFIGURATION, "null data pointer");
-  // REAL-domain passes fused into the TMA tile kernel need 16-byte aligned buffers (complex-to-real input: 8 bytes);
-  // other pointers run the unfused plan (made on first use)
+  // REAL-domain passes fused into the TMA kernels need 16-byte aligned buffers (their rows may start 8 bytes off such a
+  // boundary: the bulk copies then begin one element early, inside the buffer); other pointers run the unfused plan
+  // (made on first use)
   for (const PassHost& ps : plan->host.passes[dir]) {
     if (ps.fuse_real == 0) continue;
-    const uintptr_t need_in = ps.fuse_real == 2 ? (d.is_double ? 16 : 8) : 16;
-    if ((uintptr_t)in % need_in == 0 && (uintptr_t)out % 16 == 0) continue;
+    if ((uintptr_t)in % 16 == 0 && (uintptr_t)out % 16 == 0) continue;
     if (plan->unfused == nullptr) {
       DescHost du = d;
       du.no_real_fuse = true;

@@ -78,6 +78,38 @@ struct CubeArgs {
 //        below the row: `shift` = 0 or 1 elements), and pass 1 builds its inputs z'_j from X_{N-j} and X_j.
 // The twiddle w_{2N}^k of element k = j + (N / R) r is (one per-thread register) x (the compile-time constant w_{2R}^r).
 // ---------------------------------------------------------------------------------------------------------------
+// One thread: fetch `rows` REAL-domain rows (row k + r of the batch into slot r of the stage) by bulk copies that start
+// at the 16-byte boundary at or below each row.  REAL = 1: rows of N pairs (the real row); REAL = 2: rows of N + 1
+// half-spectrum elements.  Rows are 8-byte aligned in general (in-place layouts: N + 1 elements apart), so a copy
+// begins `shift` = 0 or 1 elements early -- inside the previous row, the buffer's base is 16-byte aligned -- and is
+// rounded up to 16 bytes, which may take one element past the row's data: that is the row's own padding element for
+// REAL = 1 rows that are N + 1 apart, the next row's first element otherwise, and past the buffer only for the last
+// row of the batch, whose last element is fetched by an ordinary load instead (the arrive releases it to the waiters).
+template <typename T, int N, int SN, int REAL>
+__device__ __forceinline__ void real_issue_rows(cx<T>* Sd, const cx<T>* gin, long long k, int rows, long long idist,
+                                                long long batch, uint64_t* bar) {
+  constexpr int LEN = REAL == 2 ? N + 1 : N;  // elements of a row
+  uint32_t total = 0;
+  for (int r = 0; r < rows; ++r) {
+    const cx<T>* src = gin + (k + r) * idist;
+    const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+    uint32_t bytes = (uint32_t)(((shift + LEN) * sizeof(cx<T>) + 15) & ~(size_t)15);
+    if (k + r == batch - 1 && bytes > (shift + LEN) * sizeof(cx<T>)) {
+      bytes -= 16;
+      Sd[r * SN + shift + LEN - 1] = src[LEN - 1];
+    }
+    total += bytes;
+  }
+  mbar_expect_tx(bar, total);
+  for (int r = 0; r < rows; ++r) {
+    const cx<T>* src = gin + (k + r) * idist;
+    const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
+    uint32_t bytes = (uint32_t)(((shift + LEN) * sizeof(cx<T>) + 15) & ~(size_t)15);
+    if (k + r == batch - 1 && bytes > (shift + LEN) * sizeof(cx<T>)) bytes -= 16;
+    if (bytes) bulk_g2s(Sd + r * SN, src - shift, bytes, bar);
+  }
+}
+
 // position of element e of the exchange-2 layout inside a stage buffer (a permutation within aligned 16-groups, so
 // that the pass-3 reads of 16 consecutive elements stay conflict free)
 template <int R>
@@ -91,7 +123,7 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
   constexpr int NT = R * R;  // threads per transform
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
-  constexpr int SN = REAL == 2 ? N + 2 : N;  // elements of one transform's slot in a stage (C2R: shift + N + 1)
+  constexpr int SN = REAL != 0 ? N + 2 : N;  // elements of one transform's slot in a stage (REAL: shift + N (+ 1))
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);  // TMA: stage 0 ; non-TMA: exchange-2 buffer
   cx<T>* S1 = S0 + F * SN;                         // TMA: stage 1
@@ -119,29 +151,8 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
   // one thread: fetch the tile starting at transform k into stage buffer Sd
   auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
     const int rows = (int)min((long long)F, a.batch - k);
-    if constexpr (REAL == 2) {
-      // rows of N + 1 elements at any 8-byte alignment: copy from the 16-byte boundary at or below the row.  An even
-      // row start would read one element past the row: fine inside the buffer, not for its last row, whose element N
-      // is fetched by an ordinary load instead (the arrive below releases it to the waiting threads).
-      uint32_t total = 0;
-      for (int r = 0; r < rows; ++r) {
-        const cx<T>* src = gin + (k + r) * a.idist;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
-        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
-        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) {
-          bytes -= 16;
-          Sd[r * SN + shift + N] = src[N];
-        }
-        total += bytes;
-      }
-      mbar_expect_tx(bar, total);
-      for (int r = 0; r < rows; ++r) {
-        const cx<T>* src = gin + (k + r) * a.idist;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
-        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
-        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) bytes -= 16;
-        bulk_g2s(Sd + r * SN, src - shift, bytes, bar);
-      }
+    if constexpr (REAL != 0) {
+      real_issue_rows<T, N, SN, REAL>(Sd, gin, k, rows, a.idist, a.batch, bar);
       return;
     }
     mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
@@ -188,6 +199,10 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
             const bool first = r == 0 && t == 0;
             v[r] = c2r_combine(X[first ? 0 : N - j], X[first ? N : j], mul_w<r, 2 * R, T>(wreal), first);
           });
+        } else if constexpr (REAL == 1) {
+          const cx<T>* X = S + (int)((reinterpret_cast<uintptr_t>(gin + k * a.idist) & 15) / sizeof(cx<T>));
+#pragma unroll
+          for (int r = 0; r < R; ++r) v[r] = X[t + NT * r];
         } else {
 #pragma unroll
           for (int r = 0; r < R; ++r) v[r] = S[t + NT * r];
@@ -312,7 +327,7 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
   constexpr int N = R0 * R1 * R2;
   constexpr int NT = N / R0 / B1;  // threads per transform
   constexpr int EN = N + 2 * (N / 16);
-  constexpr int SN = REAL == 2 ? N + 2 : N;  // elements of one transform's slot in a stage (C2R: shift + N + 1)
+  constexpr int SN = REAL != 0 ? N + 2 : N;  // elements of one transform's slot in a stage (REAL: shift + N (+ 1))
   extern __shared__ __align__(128) unsigned char smem_raw[];
   cx<T>* S0 = reinterpret_cast<cx<T>*>(smem_raw);
   cx<T>* S1 = S0 + F * SN;
@@ -358,26 +373,8 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
 
   auto issue = [&](long long k, cx<T>* Sd, uint64_t* bar) {
     const int rows = (int)min((long long)F, a.batch - k);
-    if constexpr (REAL == 2) {  // (see wg_cube_kernel)
-      uint32_t total = 0;
-      for (int r = 0; r < rows; ++r) {
-        const cx<T>* src = gin + (k + r) * a.idist;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
-        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
-        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) {
-          bytes -= 16;
-          Sd[r * SN + shift + N] = src[N];
-        }
-        total += bytes;
-      }
-      mbar_expect_tx(bar, total);
-      for (int r = 0; r < rows; ++r) {
-        const cx<T>* src = gin + (k + r) * a.idist;
-        const int shift = (int)((reinterpret_cast<uintptr_t>(src) & 15) / sizeof(cx<T>));
-        uint32_t bytes = (uint32_t)(((shift + N + 1) * sizeof(cx<T>) + 15) & ~(size_t)15);
-        if (k + r == a.batch - 1 && bytes > (shift + N + 1) * sizeof(cx<T>)) bytes -= 16;
-        bulk_g2s(Sd + r * SN, src - shift, bytes, bar);
-      }
+    if constexpr (REAL != 0) {
+      real_issue_rows<T, N, SN, REAL>(Sd, gin, k, rows, a.idist, a.batch, bar);
       return;
     }
     mbar_expect_tx(bar, (uint32_t)(rows * N * sizeof(cx<T>)));
@@ -423,6 +420,10 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
             const bool first = r == 0 && j == 0;
             v[r] = c2r_combine(X[first ? 0 : N - jj], X[first ? N : jj], mul_w<r, 2 * R0, T>(wreal[i]), first);
           });
+        } else if constexpr (REAL == 1) {
+          const cx<T>* X = S + (int)((reinterpret_cast<uintptr_t>(gin + k * a.idist) & 15) / sizeof(cx<T>));
+#pragma unroll
+          for (int r = 0; r < R0; ++r) v[r] = X[j + (N / R0) * r];
         } else {
 #pragma unroll
           for (int r = 0; r < R0; ++r) v[r] = S[j + (N / R0) * r];
@@ -531,7 +532,7 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
 template <typename T, int R0, int R1, int R2, int F, int B1, bool SWAP, int REAL>
 static cudaError_t launch_rows3_k(const CubeArgs& a, int grid, cudaStream_t stream) {
   constexpr int N = R0 * R1 * R2;
-  constexpr int SN = REAL == 2 ? N + 2 : N;
+  constexpr int SN = REAL != 0 ? N + 2 : N;
   constexpr size_t smem = (2 * (size_t)SN + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
   auto kern = wg_rows3_kernel<T, R0, R1, R2, F, SWAP, B1, REAL>;
   const cudaError_t e = ensure_dynamic_smem(kern, smem);
@@ -553,7 +554,7 @@ template <typename T, int R, int F>
 size_t cube_smem_bytes_t(bool use_tma, int real = 0) {
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
-  return ((use_tma ? 2 : 1) * (size_t)(real == 2 ? N + 2 : N) + EN) * F * sizeof(cx<T>) + 64;
+  return ((use_tma ? 2 : 1) * (size_t)(real != 0 ? N + 2 : N) + EN) * F * sizeof(cx<T>) + 64;
 }
 
 template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0>

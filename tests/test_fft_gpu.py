@@ -67,8 +67,10 @@ def test_forced_kernel_paths(env, tp, monkeypatch):
 
 
 @pytest.mark.parametrize("scalar", SCALARS)
-@pytest.mark.parametrize("n", [8, 30, 81, 1000, 4096, 16384])
-def test_real_in_place(n, scalar):
+@pytest.mark.parametrize("n,batch", [(8, 5), (30, 5), (81, 5), (1000, 5), (4096, 5), (16384, 5),
+                                     # fused REAL forms on rows that are only 8-byte aligned, steady state of the ring
+                                     (512, 5001), (1024, 2501), (8192, 1301), (4096, 1300)])
+def test_real_in_place(n, batch, scalar):
     """REAL domain, IN_PLACE (committed_descriptor.hpp:201-206: `compute_forward(Scalar* inout)`): rows padded to
     2 * (n // 2 + 1) reals hold the real input and then the half spectrum; every pass that reads the input finishes
     before the first pass writes the output, so no relation between the two layouts is needed beyond this padding.
@@ -79,7 +81,7 @@ def test_real_in_place(n, scalar):
     import portfft_b200 as pf
     import portfft_oracle as oracle
 
-    batch, h = 5, n // 2 + 1
+    h = n // 2 + 1
     d = pf.descriptor([n], scalar, pf.domain.REAL)
     d.number_of_transforms = batch
     d.placement = pf.placement.IN_PLACE
