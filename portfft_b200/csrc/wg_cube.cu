@@ -117,9 +117,14 @@ __device__ __forceinline__ constexpr int sw2(int e) {
   return R == 8 ? (e ^ ((e >> 3) & 8)) : e;
 }
 
-template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0>
+// EXE: the second exchange goes through the exchange buffer E (one more barrier between pass 2's reads and writes)
+// instead of back into the consumed stage, which is then free right after pass 1: its refill is issued a whole tile
+// earlier, i.e. both stages are always loaded or loading.  For the 64 KiB tiles of fp64 N = 4096 (one CTA of 8 warps
+// per SM: a tile lasts 3.5 us, a refill issued two thirds of a tile ahead arrives late) -- see profiles/r2_ab_variants.txt.
+template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0, bool EXE = false>
 __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4) wg_cube_kernel(const CubeArgs a) {
   static_assert(REAL == 0 || (USE_TMA && !SWAP), "the REAL-domain forms are TMA fed and never swap");
+  static_assert(!EXE || (USE_TMA && REAL == 0 && R == 16), "EXE: complex TMA form of N = 16^3");
   constexpr int NT = R * R;  // threads per transform
   constexpr int N = R * R * R;
   constexpr int EN = N + 2 * (N / 16);
@@ -234,12 +239,16 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
       }
     }
     __syncthreads();
-    if (USE_TMA && threadIdx.x == 0 && it >= 1) {
-      // every thread has finished reading the stage used by iteration it-1 (its pass 3 precedes this barrier)
-      const long long kn = k0 + stride;
+    if (USE_TMA && threadIdx.x == 0 && (EXE || it >= 1)) {
+      // every thread has finished reading the stage used by iteration it-1 (its pass 3 precedes this barrier);
+      // EXE: ... and the stage of THIS iteration (nothing is written back into it): refill it with the tile after next
+      const long long kn = k0 + (EXE ? 2 : 1) * stride;
       if (kn < a.batch) {
         fence_proxy_async();
-        issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
+        if (EXE)
+          issue(kn, (it & 1) ? S1 : S0, &full[it & 1]);
+        else
+          issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
       }
     }
     if (live) {
@@ -249,14 +258,25 @@ __global__ void __launch_bounds__(R* R* F, F == 1 ? (sizeof(T) == 8 ? 1 : 2) : 4
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw2[r - 1]);
       DFT<R, T>::run(v);
+    }
+    if (EXE) __syncthreads();  // every thread holds its inputs: E takes the outputs
+    if (live) {
 #pragma unroll
-      for (int r = 0; r < R; ++r) S[sw2<R>((t - k2) * R + k2 + R * r)] = v[r];
+      for (int r = 0; r < R; ++r) {
+        if (EXE)
+          Ef[epad<R>((t - k2) * R + k2 + R * r)] = v[r];
+        else
+          S[sw2<R>((t - k2) * R + k2 + R * r)] = v[r];
+      }
     }
     __syncthreads();
     if (live) {
       // ---- pass 3: S[t + NT r] * w_N^{t r} -> radix R -> out[t + NT r'] ----------------------------------------
 #pragma unroll
-      for (int r = 0; r < R; ++r) v[r] = S[sw2<R>(t + NT * r)];
+      for (int r = 0; r < R; ++r) v[r] = EXE ? Ef[epad<R>(t + NT * r)] : S[sw2<R>(t + NT * r)];
+    }
+    if (EXE) __syncthreads();  // E is read: the next tile's pass 1 may write it
+    if (live) {
 #pragma unroll
       for (int r = 1; r < R; ++r) v[r] = cmul(v[r], tw3[r - 1]);
       DFT<R, T>::run(v);
@@ -557,10 +577,10 @@ size_t cube_smem_bytes_t(bool use_tma, int real = 0) {
   return ((use_tma ? 2 : 1) * (size_t)(real != 0 ? N + 2 : N) + EN) * F * sizeof(cx<T>) + 64;
 }
 
-template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0>
+template <typename T, int R, int F, bool SWAP, bool USE_TMA, int REAL = 0, bool EXE = false>
 static cudaError_t launch_cube_t(const CubeArgs& a, int grid, cudaStream_t stream) {
   const size_t smem = cube_smem_bytes_t<T, R, F>(USE_TMA, REAL);
-  auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA, REAL>;
+  auto kern = wg_cube_kernel<T, R, F, SWAP, USE_TMA, REAL, EXE>;
   cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, R * R * F, smem, stream>>>(a);
@@ -571,6 +591,15 @@ template <typename T, int R, int F>
 static cudaError_t launch_cube_v(const CubeArgs& a, bool swap, bool tma, int real, int grid, cudaStream_t stream) {
   if (real == 1) return launch_cube_t<T, R, F, false, true, 1>(a, grid, stream);
   if (real == 2) return launch_cube_t<T, R, F, false, true, 2>(a, grid, stream);
+  if constexpr (R == 16 && sizeof(T) == 8) {
+    static const bool exe = [] {  // PFFT_CUBE_EXE=0: exchange 2 back into the stage (the fp32 scheme)
+      const char* e = std::getenv("PFFT_CUBE_EXE");
+      return e ? std::atoi(e) != 0 : true;
+    }();
+    if (tma && exe)
+      return swap ? launch_cube_t<T, R, F, true, true, 0, true>(a, grid, stream)
+                  : launch_cube_t<T, R, F, false, true, 0, true>(a, grid, stream);
+  }
   if (tma) return swap ? launch_cube_t<T, R, F, true, true>(a, grid, stream) : launch_cube_t<T, R, F, false, true>(a, grid, stream);
   return swap ? launch_cube_t<T, R, F, true, false>(a, grid, stream) : launch_cube_t<T, R, F, false, false>(a, grid, stream);
 }
