@@ -339,10 +339,13 @@ constexpr int rows3_min_ctas() {
   return (2 * n + n + 2 * (n / 16)) * F * 2 * sizeof(T) + 64 > 113 * 1024 ? 1 : 2;
 }
 
-template <typename T, int R0, int R1, int R2, int F, bool SWAP, int B1 = 1, int REAL = 0>
+// EXE: as in wg_cube_kernel -- the second exchange goes through E (all of pass 2's reads, a barrier, then its writes;
+// another barrier after pass 3's reads) and the stage is refilled right after pass 1, a whole tile earlier.
+template <typename T, int R0, int R1, int R2, int F, bool SWAP, int B1 = 1, int REAL = 0, bool EXE = false>
 __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 ? 1 : rows3_min_ctas<R0, R1, R2, F, B1, T>()))
     wg_rows3_kernel(const CubeArgs a) {
   static_assert(R0 == 16, "pass 1 writes whole padded 16-groups");
+  static_assert(!EXE || REAL == 0, "EXE: complex form");
   static_assert(REAL == 0 || !SWAP, "the REAL-domain forms never swap");
   constexpr int N = R0 * R1 * R2;
   constexpr int NT = N / R0 / B1;  // threads per transform
@@ -465,14 +468,45 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
       }
     }
     __syncthreads();
-    if (threadIdx.x == 0 && it >= 1) {
-      const long long kn = k0 + stride;
+    if (threadIdx.x == 0 && (EXE || it >= 1)) {
+      const long long kn = k0 + (EXE ? 2 : 1) * stride;
       if (kn < a.batch) {
         fence_proxy_async();
-        issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
+        if (EXE)
+          issue(kn, (it & 1) ? S1 : S0, &full[it & 1]);
+        else
+          issue(kn, (it & 1) ? S0 : S1, &full[(it + 1) & 1]);
       }
     }
-    if (live) {
+    if constexpr (EXE) {
+      // ---- pass 2 through E: all butterflies of the thread read, then (barrier) written ---------------------------
+      cx<T> vv[B2][R1];
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < B2; ++i) {
+          const int j = t + i * NT;
+          if (j >= N / R1) break;
+          const int k1 = j % R0;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) vv[i][r] = Ef[epad<R0>(j + (N / R1) * r)];
+#pragma unroll
+          for (int r = 1; r < R1; ++r)
+            vv[i][r] = cmul(vv[i][r], TW2REG ? tw2[TW2REG ? i * S2 + r - 1 : 0] : ldg_cx<T>(a.tw, k1 * r * R2));
+          DFT<R1, T>::run(vv[i]);
+        }
+      }
+      __syncthreads();
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < B2; ++i) {
+          const int j = t + i * NT;
+          if (j >= N / R1) break;
+          const int k1 = j % R0;
+#pragma unroll
+          for (int r = 0; r < R1; ++r) Ef[epad<R0>((j - k1) * R1 + k1 + R0 * r)] = vv[i][r];
+        }
+      }
+    } else if (live) {
       // ---- pass 2: E[j + (N/R1) r] * w_{R0 R1}^{k1 r} -> radix R1 -> S[(j - k1) R1 + k1 + R0 r'] ------------------
 #pragma unroll
       for (int i = 0; i < B2; ++i) {
@@ -492,7 +526,30 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
       }
     }
     __syncthreads();
-    if (live) {
+    if constexpr (EXE) {
+      // ---- pass 3 from E (one butterfly per thread): read, barrier (E is free for the next tile), compute, store ----
+      static_assert(!EXE || B3 == 1, "EXE: one pass-3 butterfly per thread");
+      cx<T> v[R2];
+      const int j = t;
+      if (live) {
+#pragma unroll
+        for (int r = 0; r < R2; ++r) v[r] = Ef[epad<R0>(j + (N / R2) * r)];
+      }
+      __syncthreads();
+      if (live) {
+        cx<T>* dst = gout + k * a.odist;
+#pragma unroll
+        for (int r = 1; r < R2; ++r) v[r] = cmul(v[r], TW3REG ? tw3[TW3REG ? r - 1 : 0] : ldg_cx<T>(a.tw, j * r));
+        DFT<R2, T>::run(v);
+#pragma unroll
+        for (int r = 0; r < R2; ++r) {
+          cx<T> o = v[r];
+          if (a.apply_scale) o = cscale(o, scale);
+          if (SWAP) o = cx<T>{o.y, o.x};
+          dst[j + (N / R2) * r] = o;
+        }
+      }
+    } else if (live) {
       // ---- pass 3: S[j + (N/R2) r] * w_N^{j r} -> radix R2 -> out[j + (N/R2) r'] -----------------------------------
       cx<T>* dst = gout + k * a.odist;
 #pragma unroll
@@ -549,12 +606,12 @@ __global__ void __launch_bounds__((R1 * R2 / B1) * F, ((R1 * R2 / B1) * F > 256 
   }
 }
 
-template <typename T, int R0, int R1, int R2, int F, int B1, bool SWAP, int REAL>
+template <typename T, int R0, int R1, int R2, int F, int B1, bool SWAP, int REAL, bool EXE = false>
 static cudaError_t launch_rows3_k(const CubeArgs& a, int grid, cudaStream_t stream) {
   constexpr int N = R0 * R1 * R2;
   constexpr int SN = REAL != 0 ? N + 2 : N;
   constexpr size_t smem = (2 * (size_t)SN + (N + 2 * (N / 16))) * F * sizeof(cx<T>) + 64;
-  auto kern = wg_rows3_kernel<T, R0, R1, R2, F, SWAP, B1, REAL>;
+  auto kern = wg_rows3_kernel<T, R0, R1, R2, F, SWAP, B1, REAL, EXE>;
   const cudaError_t e = ensure_dynamic_smem(kern, smem);
   if (e != cudaSuccess) return e;
   kern<<<grid, (N / R0 / B1) * F, smem, stream>>>(a);
@@ -673,6 +730,13 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
       const char* e = std::getenv("PFFT_ROWS8192_WIDE");
       return e && std::atoi(e) != 0;
     }();
+    static const bool exe = [] {  // PFFT_CUBE_EXE=0: exchange 2 back into the stage
+      const char* e = std::getenv("PFFT_CUBE_EXE");
+      return e ? std::atoi(e) != 0 : true;
+    }();
+    if (real == 0 && !wide && exe)
+      return swap ? launch_rows3_k<float, 16, 16, 32, 1, 2, true, 0, true>(a, grid, stream)
+                  : launch_rows3_k<float, 16, 16, 32, 1, 2, false, 0, true>(a, grid, stream);
     return wide && real == 0 ? launch_rows3<float, 16, 16, 32, 1>(a, swap, 0, grid, stream)
                              : launch_rows3<float, 16, 16, 32, 1, 2>(a, swap, real, grid, stream);
   }
