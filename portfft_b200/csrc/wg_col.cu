@@ -108,7 +108,13 @@ struct ColCfg {
   static constexpr size_t kStageBytes = (size_t)N * C * 2 * sizeof(T);
   // in place: one stage when a tile is 64 KiB (the refill then overlaps the last pass's arithmetic and stores and the
   // other CTAs of the SM), two otherwise
-  static constexpr int RING = INPLACE && kStageBytes > 48 * 1024 ? 1 : 2;
+  // fp64 in place (32 KiB stages, one CTA of 8 warps per SM, a tile lasts ~1.7 us): kRingF64 stages, so that a refill
+  // -- issued only when its tile has left the stage -- has two tile times to arrive instead of one
+#ifndef PFFT_COL_RING_F64
+#define PFFT_COL_RING_F64 3
+#endif
+  static constexpr int RING =
+      INPLACE && kStageBytes > 48 * 1024 ? 1 : (INPLACE && sizeof(T) == 8 && N3 == 1 ? PFFT_COL_RING_F64 : 2);
   static constexpr int STAGES = IN == IN_ROWS_DIRECT ? 0 : RING;
   static constexpr size_t kSmem = STAGES * kStageBytes + (INPLACE ? 0 : (size_t)C * PITCH * 2 * sizeof(T)) + 64;
   static_assert(!INPLACE || (IN == IN_COLS_TMA && N3 == 1 && N1 == TPC && (N / N1) % TPC == 0),
