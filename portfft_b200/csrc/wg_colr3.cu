@@ -45,6 +45,15 @@ struct ColR3Cfg {
   static constexpr size_t kTile = 2 * kTilePlane;
   static constexpr size_t kSmem = kTile;  // register-prefetch form: one tile
   static constexpr int NBUF = 3;          // TMA form: ring of three tiles (load in flight / compute / store draining)
+  // TMA form: every thread owns butterfly t of W adjacent columns.  W = 2 (one 64- / 128-bit shared-memory access
+  // serves both columns, shared twiddle look-ups and index arithmetic, 400 threads) was measured SLOWER on C3b than
+  // W = 1 (800 threads): 0.477 ms against 0.431 ms -- with three barriers per tile the kernel needs the warps more
+  // than it needs fewer instructions (profiles/r2_ab_variants.txt section 4).
+#ifndef PFFT_COLR3_W
+#define PFFT_COLR3_W 1
+#endif
+  static constexpr int W = PFFT_COLR3_W;
+  static constexpr int NT_TMA = TPC * C / W;
   static constexpr size_t kSmemTma = NBUF * kTile + 64;
   static_assert(R0 >= R1 && R0 >= R2, "the first radix is the largest: one pass-0 butterfly per thread");
   static_assert(NT <= 1024, "block size");
@@ -89,26 +98,82 @@ struct ColR3Tile {
       Sim[idx] = v.y;
     }
   }
+  // W adjacent columns at once (idx even for W = 2: one vector access per plane)
+  template <int W>
+  __device__ __forceinline__ void ldw(int idx, cx<T> (&o)[W]) const {
+    if constexpr (W == 1) {
+      o[0] = ld(idx);
+    } else if constexpr (IL) {
+      if constexpr (sizeof(T) == 4) {
+        const float4 q = *reinterpret_cast<const float4*>(Sx + idx);
+        o[0] = cx<T>{q.x, q.y};
+        o[1] = cx<T>{q.z, q.w};
+      } else {
+        o[0] = Sx[idx];
+        o[1] = Sx[idx + 1];
+      }
+    } else {
+      using V = typename VecOf<T>::type;  // two scalars
+      const V re = *reinterpret_cast<const V*>(Sre + idx), im = *reinterpret_cast<const V*>(Sim + idx);
+      o[0] = cx<T>{re.x, im.x};
+      o[1] = cx<T>{re.y, im.y};
+    }
+  }
+  template <int W>
+  __device__ __forceinline__ void stw(int idx, const cx<T> (&v)[W]) const {
+    if constexpr (W == 1) {
+      st(idx, v[0]);
+    } else if constexpr (IL) {
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(Sx + idx) = make_float4(v[0].x, v[0].y, v[1].x, v[1].y);
+      } else {
+        Sx[idx] = v[0];
+        Sx[idx + 1] = v[1];
+      }
+    } else {
+      using V = typename VecOf<T>::type;
+      V re, im;
+      re.x = v[0].x, re.y = v[1].x, im.x = v[0].y, im.y = v[1].y;
+      *reinterpret_cast<V*>(Sre + idx) = re;
+      *reinterpret_cast<V*>(Sim + idx) = im;
+    }
+  }
   // pass 0 of butterfly t: outputs (already transformed) times w_N^{t r} into rows t + TPC r
   // (pad(t + TPC r) = pad(t) + (TPC + R1) r)
   __device__ __forceinline__ static int row0(int t) { return Cfg::pad(t) * C; }
   static constexpr int kStep0 = (TPC + R1) * C;
-  // pass 1: radix R1 inside each block of N / R0 rows, in place
+  // pass 1: radix R1 inside each block of N / R0 rows, in place (W adjacent columns per thread)
+  template <int W = 1>
   __device__ __forceinline__ void pass1(const PassParams& p, int t) const {
 #pragma unroll 1
     for (int b = t; b < N / R1; b += TPC) {
       const int blk = b / R2, j = b - blk * R2;  // rows blk TPC + j + R2 r: pad = blk (TPC + R1) + j + (R2 + 1) r
       const int base = (blk * (TPC + R1) + j) * C;
-      cx<T> v[R1];
+      cx<T> v[W][R1];
 #pragma unroll
-      for (int r = 0; r < R1; ++r) v[r] = ld(base + r * (R2 + 1) * C);
-      DFT<R1, T>::run(v);
-      if (R2 > 1) {
+      for (int r = 0; r < R1; ++r) {
+        cx<T> e[W];
+        ldw<W>(base + r * (R2 + 1) * C, e);
 #pragma unroll
-        for (int r = 1; r < R1; ++r) v[r] = cmul(v[r], ldg_cx<T>(p.tw, (long long)j * r * R0));  // w_{N/R0}^{j r}
+        for (int w = 0; w < W; ++w) v[w][r] = e[w];
       }
 #pragma unroll
-      for (int r = 0; r < R1; ++r) st(base + r * (R2 + 1) * C, v[r]);
+      for (int w = 0; w < W; ++w) DFT<R1, T>::run(v[w]);
+      if (R2 > 1) {
+#pragma unroll
+        for (int r = 1; r < R1; ++r) {
+          const cx<T> tw = ldg_cx<T>(p.tw, (long long)j * r * R0);  // w_{N/R0}^{j r}
+#pragma unroll
+          for (int w = 0; w < W; ++w) v[w][r] = cmul(v[w][r], tw);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R1; ++r) {
+        cx<T> e[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) e[w] = v[w][r];
+        stw<W>(base + r * (R2 + 1) * C, e);
+      }
     }
   }
 };
@@ -122,19 +187,19 @@ struct ColR3Tile {
 // tensor store per plane, three block barriers, no per-thread global access except the twiddle look-ups.
 // ---------------------------------------------------------------------------------------------------------------
 template <typename T, int R0, int R1, int R2, bool IL, bool SWAP>
-__global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1)
+__global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT_TMA, 1)
     wg_colr3_tma_kernel(const PassParams p, const __grid_constant__ ColR3Maps maps) {
   using Cfg = ColR3Cfg<T, R0, R1, R2>;
   using Tile = ColR3Tile<T, R0, R1, R2, IL>;
-  constexpr int N = Cfg::N, TPC = Cfg::TPC, C = Cfg::C, NBUF = Cfg::NBUF;
+  constexpr int N = Cfg::N, TPC = Cfg::TPC, C = Cfg::C, NBUF = Cfg::NBUF, W = Cfg::W;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(smem_raw + NBUF * Cfg::kTile);
-  const int c = threadIdx.x % C, t = threadIdx.x / C;
+  const int c = (threadIdx.x % (C / W)) * W, t = threadIdx.x / (C / W);  // first of the thread's W columns
   const long long tiles_c = (p.nb[0] + C - 1) / C;
   const long long total_tiles = tiles_c * p.nb[1] * p.nb[2];
   const T scale = T(p.scale);
 
-  constexpr bool TW0REG = sizeof(T) == 4 && Cfg::NT <= 512;  // (800 threads leave 72 registers each)
+  constexpr bool TW0REG = sizeof(T) == 4 && Cfg::NT_TMA <= 512;  // (800 threads would leave 72 registers each)
   cx<T> tw0[TW0REG ? R0 : 1];
   if (TW0REG) {
 #pragma unroll
@@ -175,36 +240,58 @@ __global__ void __launch_bounds__(ColR3Cfg<T, R0, R1, R2>::NT, 1)
     col::mbar_wait(&full[buf], phase);
     // ---- pass 0: radix R0 on rows t + TPC r, in place -------------------------------------------------------------
     {
-      cx<T> v[R0];
+      cx<T> v[W][R0];
       const int base = Tile::row0(t);
 #pragma unroll
       for (int r = 0; r < R0; ++r) {
-        v[r] = S.ld(base + r * Tile::kStep0);
-        if (IL && SWAP) v[r] = cx<T>{v[r].y, v[r].x};
+        cx<T> e[W];
+        S.template ldw<W>(base + r * Tile::kStep0, e);
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[w][r] = IL && SWAP ? cx<T>{e[w].y, e[w].x} : e[w];
       }
-      DFT<R0, T>::run(v);
 #pragma unroll
-      for (int r = 1; r < R0; ++r) v[r] = cmul(v[r], TW0REG ? tw0[TW0REG ? r : 0] : ldg_cx<T>(p.tw, (long long)t * r));
+      for (int w = 0; w < W; ++w) DFT<R0, T>::run(v[w]);
 #pragma unroll
-      for (int r = 0; r < R0; ++r) S.st(base + r * Tile::kStep0, v[r]);
+      for (int r = 1; r < R0; ++r) {
+        const cx<T> tw = TW0REG ? tw0[TW0REG ? r : 0] : ldg_cx<T>(p.tw, (long long)t * r);
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[w][r] = cmul(v[w][r], tw);
+      }
+#pragma unroll
+      for (int r = 0; r < R0; ++r) {
+        cx<T> e[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) e[w] = v[w][r];
+        S.template stw<W>(base + r * Tile::kStep0, e);
+      }
     }
     __syncthreads();
-    S.pass1(p, t);
+    S.template pass1<W>(p, t);
     __syncthreads();
     // ---- pass 2: radix R2 on rows b R2 + r, in place: row [a][b1][r] is row k = a + R0 b1 + R0 R1 r of the output ----
 #pragma unroll 1
     for (int b = t; b < N / R2; b += TPC) {
       const int base = b * (R2 + 1) * C;  // pad(b R2 + r) = b (R2 + 1) + r
-      cx<T> v[R2];
-#pragma unroll
-      for (int r = 0; r < R2; ++r) v[r] = S.ld(base + r * C);
-      DFT<R2, T>::run(v);
+      cx<T> v[W][R2];
 #pragma unroll
       for (int r = 0; r < R2; ++r) {
-        cx<T> o = v[r];
-        if (p.apply_scale) o = cscale(o, scale);
-        if (IL && SWAP) o = cx<T>{o.y, o.x};
-        S.st(base + r * C, o);
+        cx<T> e[W];
+        S.template ldw<W>(base + r * C, e);
+#pragma unroll
+        for (int w = 0; w < W; ++w) v[w][r] = e[w];
+      }
+#pragma unroll
+      for (int w = 0; w < W; ++w) DFT<R2, T>::run(v[w]);
+#pragma unroll
+      for (int r = 0; r < R2; ++r) {
+        cx<T> e[W];
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          cx<T> o = v[w][r];
+          if (p.apply_scale) o = cscale(o, scale);
+          e[w] = IL && SWAP ? cx<T>{o.y, o.x} : o;
+        }
+        S.template stw<W>(base + r * C, e);
       }
     }
     col::fence_proxy_async();  // this thread's tile writes become visible to the tensor store
@@ -477,7 +564,7 @@ cudaError_t launch_colr3_v(const PassParams& p, int grid, cudaStream_t stream, C
     auto kern = wg_colr3_tma_kernel<T, R0, R1, R2, IL, SWAP>;
     cudaError_t e = ensure_dynamic_smem(kern, Cfg::kSmemTma);
     if (e != cudaSuccess) return e;
-    kern<<<grid, Cfg::NT, Cfg::kSmemTma, stream>>>(p, m);
+    kern<<<grid, Cfg::NT_TMA, Cfg::kSmemTma, stream>>>(p, m);
     return cudaGetLastError();
   }
   if (colr3_max_index(p) < (1LL << 31) - 1) return launch_colr3_regs<T, R0, R1, R2, IL, SWAP, int>(p, grid, stream);
