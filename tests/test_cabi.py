@@ -217,6 +217,22 @@ def test_planner_kernel_choices():
     r.complex_storage = pf.complex_storage.SPLIT_COMPLEX                     # split half spectrum: separate passes
     assert _kernels(r) == ["wg_cube", "r2c_post"]
     assert _kernels(r, pf.direction.BACKWARD) == ["c2r_pre", "wg_cube"]
+    for n, batch, kern in ((512, 4096, "wg_cube"), (1024, 4096, "wg_cube"), (16384, 64, "wg_cube"), (32, 1 << 20, "wi")):
+        r = pf.descriptor([n], "float", pf.domain.REAL)                      # one fused pass in both directions
+        r.number_of_transforms = batch
+        r.backward_distance = n // 2 + 1
+        assert _kernels(r) == [kern] and _kernels(r, pf.direction.BACKWARD) == [kern], n
+    r = pf.descriptor([4096], "float", pf.domain.REAL)                       # in-place layout (rows of n + 2 reals): fused
+    r.number_of_transforms = 100
+    r.placement = pf.placement.IN_PLACE
+    r.forward_distance, r.backward_distance = 4098, 2049
+    assert _kernels(r) == ["wg_cube"] and _kernels(r, pf.direction.BACKWARD) == ["wg_cube"]
+    r = pf.descriptor([131072], "float", pf.domain.REAL)                     # GLOBAL level: two passes + post pass
+    r.number_of_transforms = 8
+    assert _kernels(r) == ["wg_col", "wg_col", "r2c_post"]
+    r = pf.descriptor([1000], "float", pf.domain.REAL)                       # half length 500: no tile kernel, unfused
+    r.number_of_transforms = 64
+    assert _kernels(r)[-1] == "r2c_post"
     r = pf.descriptor([8192], "float", pf.domain.REAL)                       # strided real rows: pack pass first
     r.number_of_transforms = 4
     r.forward_strides, r.forward_distance = [3], 3 * 8192
