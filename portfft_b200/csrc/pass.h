@@ -74,6 +74,10 @@ struct PassParams {
   const void* lmod;
   const void* smod;
   int mod_flags;  // ModFlags
+  // smod_mask != 0 (wg_col.cu only): the store modifier is indexed by the LINEAR position of the output element inside
+  // its packed power-of-two row, (output offset) & smod_mask, instead of by the pass-local index k -- the last pass of a
+  // multi-pass transform multiplies by a table over the whole transform (Bluestein: the transformed chirp)
+  long long smod_mask;
 };
 
 enum ModFlags : int {

@@ -874,9 +874,25 @@ int emit_dim(PlanHost& plan, std::vector<PassHost>& passes, const DescHost& d, c
   const size_t inner0 = passes.size();
   emit_multipass(passes, d, lim, M, row_n, s1, BUF_SCRATCH, s2);
   {
-    PassHost ps = ew(BUF_SCRATCH2, BUF_SCRATCH2, (long long)M, 1, 0, sdist, 1, 0, sdist);
-    mods(ps, MODT_NONE, MODT_CONV, 0, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT);
-    passes.push_back(ps);
+    // times the transformed chirp, (re <-> im) swap: folded into the store of the transform's last pass when that is the
+    // tile kernel reading rows (its store can index a table by the position inside the packed row); else its own pass
+    PassHost& last = passes.back();
+    static const bool fold_off = [] {
+      const char* e = std::getenv("PFFT_NO_BLUESTEIN_FOLD");
+      return e && std::atoi(e) != 0;
+    }();
+    if (!fold_off && last.kernel == KERNEL_WG_COL && (last.variant & 3) != 0 && (last.variant & 4) == 0 &&
+        last.pp.gtw_dim < 0 && (M & (M - 1)) == 0) {
+      last.smod_kind = MODT_CONV;
+      last.mod_l = (long long)L;
+      last.mod_m = (long long)M;
+      last.pp.smod_mask = (long long)M - 1;
+      last.pp.mod_flags |= MOD_SWAP_POST;
+    } else {
+      PassHost ps = ew(BUF_SCRATCH2, BUF_SCRATCH2, (long long)M, 1, 0, sdist, 1, 0, sdist);
+      mods(ps, MODT_NONE, MODT_CONV, 0, 0, MOD_SWAP_POST | MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT);
+      passes.push_back(ps);
+    }
   }
   emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
   for (size_t i = inner0; i < passes.size(); ++i) passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
@@ -1321,6 +1337,7 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
        << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
        << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
        << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view << ", \"fuse_real\": " << ps.fuse_real
+       << ", \"smod_mask\": " << ps.pp.smod_mask
        << ", \"force_swap\": " << ps.force_swap << "}";
     firstp = false;
   }

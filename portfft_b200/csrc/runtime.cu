@@ -216,6 +216,7 @@ static void attach_device_state(pfft_plan* plan) {
       if (a.kernel != KERNEL_WG_COL || b.kernel != KERNEL_WG_COL || a.dst != b.src) continue;
       if (a.dst != BUF_SCRATCH && a.dst != BUF_SCRATCH2) continue;
       if (a.internal_storage != b.internal_storage || a.real_view || b.real_view) continue;
+      if (a.pp.smod_mask != 0 || b.pp.smod_mask != 0) continue;  // (store modifier over the whole transform: wg_col only)
       bool read_later = false;
       for (size_t j = i + 2; j < ps.size() && !read_later; ++j) {
         if (ps[j].src == a.dst) read_later = true;

@@ -330,6 +330,10 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
               }
             }
             if (p.apply_scale) o = cscale(o, scale);
+            if (p.smod_mask != 0) {  // table over the whole (multi-pass) transform, then the modifier's (re <-> im) swap
+              o = cmul(o, ldg_cx<T>(p.smod, (ob + (long long)k * p.os) & p.smod_mask));
+              if (p.mod_flags & MOD_SWAP_POST) o = cx<T>{o.y, o.x};
+            }
             gstore<T>(p, fl, ob + (long long)k * p.os, o);
           }
         }
@@ -360,6 +364,20 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
               if (swap) o = cx<T>{o.y, o.x};
               *op = o;
               op += ostep;
+            }
+          } else if (p.smod_mask != 0) {
+            // last pass of a multi-pass transform with a table over the whole transform (Bluestein: times the
+            // transformed chirp, then the modifier's (re <-> im) swap): index = position inside the packed row
+            long long off = ob + (long long)j * p.os;
+#pragma unroll
+            for (int r = 0; r < NL; ++r) {
+              cx<T> o = cmul(v[r], ldg_cx<T>(p.smod, off & p.smod_mask));
+              if (p.apply_scale) o = cscale(o, scale);
+              if (p.mod_flags & MOD_SWAP_POST) o = cx<T>{o.y, o.x};
+              if (swap) o = cx<T>{o.y, o.x};
+              *op = o;
+              op += ostep;
+              off += ostep;
             }
           } else {
 #pragma unroll

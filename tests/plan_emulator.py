@@ -191,7 +191,10 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
             y = y * np.exp(-2j * np.pi * m / ps["gtw_n"])
         if flags & MOD_SWAP_PRE:
             y = _swap(y)
-        if smod is not None:
+        if smod is not None and ps.get("smod_mask"):
+            # table over the whole multi-pass transform: indexed by the position inside the packed power-of-two row
+            y = y * smod[(ob[..., None] + jv * ps["os"]) & ps["smod_mask"]]
+        elif smod is not None:
             y[..., :vo] = y[..., :vo] * smod[:vo]
         if flags & MOD_SWAP_POST:
             y = _swap(y)
