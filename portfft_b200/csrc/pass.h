@@ -78,6 +78,10 @@ struct PassParams {
   // its packed power-of-two row, (output offset) & smod_mask, instead of by the pass-local index k -- the last pass of a
   // multi-pass transform multiplies by a table over the whole transform (Bluestein: the transformed chirp)
   long long smod_mask;
+  // smod_n1 != 0 (wg_col.cu only; last pass of a two-factor transform writing the user's layout): the store modifier is
+  // indexed by the linear output index (index along batch dimension 0) + smod_n1 * k, and only the elements whose
+  // linear index is below valid_out are written (Bluestein: chirp / M and truncation to the transform length)
+  int smod_n1;
 };
 
 enum ModFlags : int {

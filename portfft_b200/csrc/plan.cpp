@@ -877,9 +877,9 @@ int emit_dim(PlanHost& plan, std::vector<PassHost>& passes, const DescHost& d, c
     // times the transformed chirp, (re <-> im) swap: folded into the store of the transform's last pass when that is the
     // tile kernel reading rows (its store can index a table by the position inside the packed row); else its own pass
     PassHost& last = passes.back();
-    static const bool fold_off = [] {
+    static const bool fold_off = [] {  // PFFT_NO_BLUESTEIN_FOLD: 1 = no fold, 2 = keep this one only, 3 = the other one only
       const char* e = std::getenv("PFFT_NO_BLUESTEIN_FOLD");
-      return e && std::atoi(e) != 0;
+      return e && (std::atoi(e) == 1 || std::atoi(e) == 3);
     }();
     if (!fold_off && last.kernel == KERNEL_WG_COL && (last.variant & 3) != 0 && (last.variant & 4) == 0 &&
         last.pp.gtw_dim < 0 && (M & (M - 1)) == 0) {
@@ -894,9 +894,38 @@ int emit_dim(PlanHost& plan, std::vector<PassHost>& passes, const DescHost& d, c
       passes.push_back(ps);
     }
   }
-  emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
+  // Second transform.  Its last pass can write the user's layout itself -- (re <-> im) swap, times chirp / M,
+  // truncation to the L outputs, scale, backward swap -- when it is the tile kernel reading rows of a two-factor
+  // transform and the user's data is interleaved; otherwise it returns to the workspace and an element-wise pass
+  // finishes.
+  bool folded_out = false;
+  const size_t second0 = passes.size();
+  static const bool fold_off2 = [] {
+    const char* e = std::getenv("PFFT_NO_BLUESTEIN_FOLD");
+    return e && (std::atoi(e) == 1 || std::atoi(e) == 2);
+  }();
+  if (!fold_off2 && d.complex_storage == PFFT_INTERLEAVED_COMPLEX) {
+    const View s2v{BUF_SCRATCH2, 1, 0, sdist};
+    emit_multipass(passes, d, lim, M, outer_n, s2v, BUF_SCRATCH2, vout);
+    PassHost& last = passes.back();
+    if (passes.size() == second0 + 2 && last.kernel == KERNEL_WG_COL && (last.variant & 3) != 0 &&
+        (last.variant & 4) == 0 && last.pp.gtw_dim < 0 && last.pp.nb[0] * (long long)last.pp.n == (long long)M) {
+      last.smod_kind = MODT_CHIRP_OVER_M;
+      last.mod_l = (long long)L;
+      last.mod_m = (long long)M;
+      last.pp.smod_n1 = (int)last.pp.nb[0];
+      last.pp.valid_out = (int)L;
+      last.pp.mod_flags |= MOD_SWAP_PRE;
+      folded_out = true;
+    } else {
+      passes.resize(second0);
+    }
+  }
+  if (!folded_out) emit_multipass(passes, d, lim, M, row_n, s2, BUF_SCRATCH2, s1);
   for (size_t i = inner0; i < passes.size(); ++i) passes[i].pp.mod_flags |= MOD_NO_USER_SWAP_IN | MOD_NO_USER_SWAP_OUT;
-  {
+  if (folded_out) {
+    passes.back().pp.mod_flags &= ~MOD_NO_USER_SWAP_OUT;  // its output is the user's data
+  } else {
     PassHost ps = ew(BUF_SCRATCH, dst_buf, (long long)L, 1, 0, sdist, es_out, off_out, outer_out);
     mods(ps, MODT_NONE, MODT_CHIRP_OVER_M, 0, 0, MOD_SWAP_PRE | MOD_NO_USER_SWAP_IN);
     passes.push_back(ps);
@@ -1337,7 +1366,7 @@ std::string export_plan_json(const PlanHost& plan, int direction) {
        << ", \"lmod\": " << ps.lmod_kind << ", \"smod\": " << ps.smod_kind << ", \"mod_l\": " << ps.mod_l
        << ", \"mod_m\": " << ps.mod_m << ", \"apply_scale\": " << p.apply_scale << ", \"scale\": " << p.scale
        << ", \"variant\": " << ps.variant << ", \"real_view\": " << ps.real_view << ", \"fuse_real\": " << ps.fuse_real
-       << ", \"smod_mask\": " << ps.pp.smod_mask
+       << ", \"smod_mask\": " << ps.pp.smod_mask << ", \"smod_n1\": " << ps.pp.smod_n1
        << ", \"force_swap\": " << ps.force_swap << "}";
     firstp = false;
   }

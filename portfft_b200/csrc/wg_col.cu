@@ -141,6 +141,8 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
   cx<T>* E = reinterpret_cast<cx<T>*>(smem_raw + Cfg::STAGES * Cfg::kStageBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(E + (INPLACE ? 0 : (size_t)C * PITCH));  // in place: no exchange buffer
   const int tid = threadIdx.x;
+  // backward = (re <-> im) swap on the sides that are user data (plan-internal sides run the plain forward transform)
+  const bool swap_in = swap && !(p.mod_flags & MOD_NO_USER_SWAP_IN), swap_out = swap && !(p.mod_flags & MOD_NO_USER_SWAP_OUT);
   // column mapping: lanes run along the transform index (used where memory is contiguous across transforms)
   const int cc = tid % C, tc = tid / C;
   // row mapping: lanes run along the element index (used where each transform is contiguous)
@@ -235,7 +237,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
           for (int r = 0; r < N1; ++r)
             v[r] = live ? reinterpret_cast<const cx<T>*>(p.in_re)[ib + (j + B1 * r)] : cx<T>{T(0), T(0)};
         }
-        if (swap) {
+        if (swap_in) {
 #pragma unroll
           for (int r = 0; r < N1; ++r) {
             const T t = v[r].x;
@@ -309,7 +311,7 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
         DFT<NL, T>::run(v);
         if (!kLean) {
         if (live) {
-          const IoFlags fl{true, swap};
+          const IoFlags fl{true, swap_out};
           cx<T> tw_run{T(1), T(0)}, tw_step{T(1), T(0)};
           if (p.gtw_dim >= 0 && sizeof(T) == 8) {
             const long long mb = gidx * j, ms = gidx * NS;
@@ -329,12 +331,17 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
                 o = cmul(o, cmul(ldg_cx<T>(p.gtw_hi, m >> p.gtw_bits), ldg_cx<T>(p.gtw_lo, m & (long long)gmask)));
               }
             }
-            if (p.apply_scale) o = cscale(o, scale);
-            if (p.smod_mask != 0) {  // table over the whole (multi-pass) transform, then the modifier's (re <-> im) swap
-              o = cmul(o, ldg_cx<T>(p.smod, (ob + (long long)k * p.os) & p.smod_mask));
+            bool keep = true;
+            if (p.smod != nullptr) {  // table over the whole (multi-pass) transform: see PassParams::smod_mask / smod_n1
+              const long long lin = p.smod_mask != 0 ? ((ob + (long long)k * p.os) & p.smod_mask)
+                                                     : (long long)(c0 + c2) + (long long)p.smod_n1 * k;
+              keep = p.smod_mask != 0 || lin < p.valid_out;
+              if (p.mod_flags & MOD_SWAP_PRE) o = cx<T>{o.y, o.x};
+              if (keep) o = cmul(o, ldg_cx<T>(p.smod, lin));
               if (p.mod_flags & MOD_SWAP_POST) o = cx<T>{o.y, o.x};
             }
-            gstore<T>(p, fl, ob + (long long)k * p.os, o);
+            if (p.apply_scale) o = cscale(o, scale);
+            if (keep) gstore<T>(p, fl, ob + (long long)k * p.os, o);
           }
         }
         } else
@@ -361,30 +368,46 @@ __global__ void __launch_bounds__(ColCfg<T, N1, N2, N3, IN, INPLACE>::NT, ColCfg
                 o = cmul(v[r], gtw_lookup<T>(p, (unsigned)gidx, (unsigned)(j + NS * r), gmask));
               }
               if (p.apply_scale) o = cscale(o, scale);
-              if (swap) o = cx<T>{o.y, o.x};
+              if (swap_out) o = cx<T>{o.y, o.x};
               *op = o;
               op += ostep;
             }
-          } else if (p.smod_mask != 0) {
+          } else if (p.smod != nullptr) {
             // last pass of a multi-pass transform with a table over the whole transform (Bluestein: times the
-            // transformed chirp, then the modifier's (re <-> im) swap): index = position inside the packed row
-            long long off = ob + (long long)j * p.os;
+            // transformed chirp and a (re <-> im) swap; or swap, times chirp / M, truncation): see PassParams::smod_mask
+            // (index = position inside the packed row) and PassParams::smod_n1 (index = linear output index)
+            // (the table values are fetched as ONE batch of independent loads, clamped in range, before they are used:
+            // interleaved with the stores their L2 latency was exposed load by load -- 1.7 -> 5.5 ms on the 512-point
+            // pass of N = 65537 x 2048)
+            const long long off = ob + (long long)j * p.os;
+            cx<T> m[NL];
+            if (p.smod_mask != 0) {
+#pragma unroll
+              for (int r = 0; r < NL; ++r) m[r] = ldg_cx<T>(p.smod, (off + r * ostep) & p.smod_mask);
+            } else {
+              const long long l0 = (long long)(c0 + c2) + (long long)p.smod_n1 * j, lstep = (long long)p.smod_n1 * NS;
+#pragma unroll
+              for (int r = 0; r < NL; ++r) m[r] = ldg_cx<T>(p.smod, min(l0 + r * lstep, (long long)p.valid_out - 1));
+            }
+            const long long keep_below = p.smod_mask != 0 ? (1LL << 62) : (long long)p.valid_out;  // linear index bound
+            const long long l0 = (long long)(c0 + c2) + (long long)p.smod_n1 * j, lstep = (long long)p.smod_n1 * NS;
 #pragma unroll
             for (int r = 0; r < NL; ++r) {
-              cx<T> o = cmul(v[r], ldg_cx<T>(p.smod, off & p.smod_mask));
-              if (p.apply_scale) o = cscale(o, scale);
+              cx<T> o = v[r];
+              if (p.mod_flags & MOD_SWAP_PRE) o = cx<T>{o.y, o.x};
+              o = cmul(o, m[r]);
               if (p.mod_flags & MOD_SWAP_POST) o = cx<T>{o.y, o.x};
-              if (swap) o = cx<T>{o.y, o.x};
-              *op = o;
+              if (p.apply_scale) o = cscale(o, scale);
+              if (swap_out) o = cx<T>{o.y, o.x};
+              if (l0 + r * lstep < keep_below) *op = o;
               op += ostep;
-              off += ostep;
             }
           } else {
 #pragma unroll
             for (int r = 0; r < NL; ++r) {
               cx<T> o = v[r];
               if (p.apply_scale) o = cscale(o, scale);
-              if (swap) o = cx<T>{o.y, o.x};
+              if (swap_out) o = cx<T>{o.y, o.x};
               *op = o;
               op += ostep;
             }

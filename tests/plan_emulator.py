@@ -191,9 +191,15 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
             y = y * np.exp(-2j * np.pi * m / ps["gtw_n"])
         if flags & MOD_SWAP_PRE:
             y = _swap(y)
+        lin_keep = None
         if smod is not None and ps.get("smod_mask"):
             # table over the whole multi-pass transform: indexed by the position inside the packed power-of-two row
             y = y * smod[(ob[..., None] + jv * ps["os"]) & ps["smod_mask"]]
+        elif smod is not None and ps.get("smod_n1"):
+            # ... or by the linear output index (index along batch dimension 0) + n1 * k, truncated at valid_out
+            lin = grids[0][..., None] + ps["smod_n1"] * jv
+            lin_keep = lin < ps["valid_out"]
+            y = y * smod[np.minimum(lin, len(smod) - 1)]
         elif smod is not None:
             y[..., :vo] = y[..., :vo] * smod[:vo]
         if flags & MOD_SWAP_POST:
@@ -202,5 +208,9 @@ def run_plan(desc: "pf.descriptor", direction, in_buf: np.ndarray, out_buf: np.n
             y = y * ps["scale"]
         if swap_out:
             y = _swap(y)
-        dst[ob[..., None] + jv[:vo] * ps["os"]] = y[..., :vo].astype(cdt)
+        if lin_keep is not None:
+            addr = ob[..., None] + jv * ps["os"]
+            dst[addr[lin_keep]] = y[lin_keep].astype(cdt)
+        else:
+            dst[ob[..., None] + jv[:vo] * ps["os"]] = y[..., :vo].astype(cdt)
     return out_buf

@@ -151,9 +151,12 @@ def test_planner_levels_for_baseline_configs():
     assert txt.count("pass ") == 2 and txt.count(" n=2048 ") == 2 and "smod=conv" in txt and "lmod=chirp" in txt
     d = pf.descriptor([65537])
     txt = d.describe_plan()
-    # multi-pass Bluestein: chirp pass, two transforms (the multiply by the transformed chirp folded into the store of
-    # the first one's last pass), chirp pass
-    assert _levels(txt) == ["GLOBAL"] and txt.count("kernel=ew") == 2 and "scratch2_elems=262144" in txt
+    # multi-pass Bluestein: chirp pass, then two transforms whose last passes also do the multiply by the transformed
+    # chirp and the final chirp / truncation (5 launches; 7 with separate element-wise passes)
+    assert _levels(txt) == ["GLOBAL"] and txt.count("kernel=ew") == 1 and txt.count("pass ") == 5
+    assert "scratch2_elems=262144" in txt
+    d.complex_storage = pf.complex_storage.SPLIT_COMPLEX       # split user data: the final pass stays element-wise
+    assert d.describe_plan().count("kernel=ew") >= 2
     d = pf.descriptor([(1 << 24) + 1])
     with pytest.raises(pf.unsupported_configuration):
         d.describe_plan()
