@@ -58,6 +58,11 @@ CASES = {
     "r2c_512": _real(512, 10001, "fwd"),
     "c2r_512": _real(512, 10001, "bwd"),
     "c2r_2048_f64": _real(2048, 1301, "bwd", "double"),
+    # Bluestein, multi-pass form: the column kernel's store with a table over the whole transform (position index,
+    # linear index with truncation at L and clamped look-ups), user layout written by the last pass
+    "bluestein_4099": CaseParams([4099], 67, "OOP", P, P, "fwd", "interleaved", "float"),
+    "bluestein_4099_bwd_f64": CaseParams([4099], 33, "OOP", P, P, "bwd", "interleaved", "double"),
+    "bluestein_65537": CaseParams([65537], 3, "OOP", P, P, "fwd", "interleaved", "float"),
     # fused two-pass kernel (opt-in; PFFT_FUSE=1 is set below for this case only)
     "fused65536": CaseParams([65536], 24, "OOP", P, P, "fwd", "interleaved", "float"),
 }
