@@ -983,6 +983,7 @@ size_t pfft_workspace_bytes(const pfft_plan* plan) {
   for (const auto& kv : plan->nd_child) total += pfft_workspace_bytes(kv.second);
   for (const pfft_plan* o : plan->nd_outer)
     if (o) total += pfft_workspace_bytes(o);
+  if (plan->unfused) total += pfft_workspace_bytes(plan->unfused);
   return total;
 }
 
