@@ -684,10 +684,11 @@ bool cube_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_p
 }
 
 // Half lengths that only the REAL-domain forms run here (their complex transforms belong to the tile kernel of
-// wg_col.cu): 256 = 16 * 4 * 4, eight (fp32) / four (fp64) transforms per 16 KiB tile.
+// wg_col.cu): 256 = 16 * 4 * 4, 128 = 16 * 4 * 2, 64 = 16 * 2 * 2; 16 KiB tiles of 8 / 16 / 32 (fp32) or 4 / 8 / 16
+// (fp64) transforms -- the rows of real lengths 512, 256 and 128 (e.g. of 3-D real transforms of those edge lengths).
 bool cube_real_supported(int n, bool is_double, int* transforms_per_tile, int* ctas_per_sm) {
-  if (n != 256) return cube_supported(n, is_double, transforms_per_tile, ctas_per_sm);
-  if (transforms_per_tile) *transforms_per_tile = is_double ? 4 : 8;
+  if (n != 256 && n != 128 && n != 64) return cube_supported(n, is_double, transforms_per_tile, ctas_per_sm);
+  if (transforms_per_tile) *transforms_per_tile = (is_double ? 1024 : 2048) / n;
   if (ctas_per_sm) *ctas_per_sm = 4;
   return true;
 }
@@ -713,6 +714,12 @@ cudaError_t launch_wg_cube(const PassParams& p, bool is_double, bool swap, int v
   if (real != 0 && p.n == 256)
     return is_double ? launch_rows3<double, 16, 4, 4, 4>(a, false, real, grid, stream)
                      : launch_rows3<float, 16, 4, 4, 8>(a, false, real, grid, stream);
+  if (real != 0 && p.n == 128)
+    return is_double ? launch_rows3<double, 16, 4, 2, 8>(a, false, real, grid, stream)
+                     : launch_rows3<float, 16, 4, 2, 16>(a, false, real, grid, stream);
+  if (real != 0 && p.n == 64)
+    return is_double ? launch_rows3<double, 16, 2, 2, 16>(a, false, real, grid, stream)
+                     : launch_rows3<float, 16, 2, 2, 32>(a, false, real, grid, stream);
   if (is_double) {
     if (!tma) return cudaErrorInvalidValue;
     if (p.n == 4096) return launch_cube_v<double, 16, 1>(a, swap, true, real, grid, stream);

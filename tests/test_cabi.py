@@ -222,7 +222,8 @@ def test_planner_kernel_choices():
     r.complex_storage = pf.complex_storage.SPLIT_COMPLEX                     # split half spectrum: separate passes
     assert _kernels(r) == ["wg_cube", "r2c_post"]
     assert _kernels(r, pf.direction.BACKWARD) == ["c2r_pre", "wg_cube"]
-    for n, batch, kern in ((512, 4096, "wg_cube"), (1024, 4096, "wg_cube"), (16384, 64, "wg_cube"), (32, 1 << 20, "wi")):
+    for n, batch, kern in ((128, 4096, "wg_cube"), (256, 4096, "wg_cube"), (512, 4096, "wg_cube"), (1024, 4096, "wg_cube"),
+                           (16384, 64, "wg_cube"), (32, 1 << 20, "wi")):
         r = pf.descriptor([n], "float", pf.domain.REAL)                      # one fused pass in both directions
         r.number_of_transforms = batch
         r.backward_distance = n // 2 + 1
