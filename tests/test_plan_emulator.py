@@ -69,6 +69,26 @@ CASES = [
     CaseParams([37, 8], 2, "OOP", P, P, "bwd", domain="real"),
     CaseParams([8, 16384], 1, "OOP", P, P, "fwd", domain="real"),
     CaseParams([8, 16384], 1, "OOP", P, P, "bwd", domain="real"),
+    # REAL pre / post-processing fused into the transform pass (PassHost::fuse_real): tile-kernel rows (half lengths
+    # 64 .. 8192), dense and default half-spectrum distances, N-D, the
+    # thread-level form needs a large batch (one 128-byte line per row)
+    CaseParams([4096], 5, "OOP", U, U, "fwd", domain="real", forward_strides=[1], backward_strides=[1],
+               forward_distance=4096, backward_distance=2049),
+    CaseParams([4096], 5, "OOP", U, U, "bwd", domain="real", forward_strides=[1], backward_strides=[1],
+               forward_distance=4096, backward_distance=2049, backward_scale=1.0 / 4096),
+    # (rows that are 8-byte aligned only, as in the in-place layout: n + 2 reals = n / 2 + 1 pairs apart; the in-place
+    # call itself aliases a real and a complex view of one buffer and is covered on the GPU, test_real_in_place)
+    CaseParams([1024], 7, "OOP", U, U, "fwd", domain="real", forward_strides=[1], backward_strides=[1],
+               forward_distance=1026, backward_distance=513),
+    CaseParams([1024], 7, "OOP", U, U, "bwd", domain="real", forward_strides=[1], backward_strides=[1],
+               forward_distance=1026, backward_distance=513),
+    CaseParams([128], 9, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([256], 9, "OOP", P, P, "bwd", domain="real", scalar="double"),
+    CaseParams([16, 512], 2, "OOP", P, P, "fwd", domain="real"),
+    CaseParams([16, 512], 2, "OOP", P, P, "bwd", domain="real"),
+    CaseParams([32], 4100, "OOP", U, U, "fwd", domain="real", forward_strides=[1], backward_strides=[1],
+               forward_distance=32, backward_distance=17),
+    CaseParams([32], 4100, "OOP", P, P, "bwd", domain="real"),
 ]
 
 
